@@ -1,0 +1,162 @@
+"""Pin the oracle: the port (oracle/svdb_oracle.c) against the golden vectors the
+reference produced (tests/golden/make_golden.py) and against the compiled reference
+itself (oracle/_ref) on fresh seeded inputs.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import binding
+from oracle.binding import PortDB
+from svdb import synth
+
+NEAREST_CASES = ["nearest_script_k3", "nearest_coarse_k3", "nearest_uniform_k32",
+                 "nearest_normal_k128", "nearest_uniform_k5_d12"]
+
+
+@pytest.mark.parametrize("name", NEAREST_CASES)
+def test_port_tree_matches_golden(port, name):
+    g = load_golden(name)
+    h = port.build(g["rows"], int(g["K"]))
+    ids = port.nearest_batch(h, g["queries"])
+    port.free(h)
+    np.testing.assert_array_equal(ids, g["ids"])
+
+
+@pytest.mark.parametrize("name", NEAREST_CASES)
+def test_port_flat_scan_matches_golden(port, name):
+    """(d, seq) flat order == reference, wherever ties are duplicate-type."""
+    g = load_golden(name)
+    K = int(g["K"])
+    db = PortDB(port, g["rows"].shape[1], K)
+    for r in g["rows"]:
+        db.insert(r)
+    mism = 0
+    for q, want in zip(g["queries"], g["ids"]):
+        seq, idx, d = db.topk(q, 2)
+        if idx[0] != want:
+            # only legal reason: a distinct point at exactly the same distance
+            assert len(d) == 2 and d[0] == d[1], (idx, d, want)
+            assert not np.array_equal(g["rows"][idx[0], :K], g["rows"][int(want), :K])
+            mism += 1
+    if name != "nearest_coarse_k3":
+        assert mism == 0
+    db.close()
+
+
+def test_port_metrics_match_golden_bits(port):
+    g = load_golden("metrics")
+    off = 0
+    for n, want in zip(g["lens"], g["res"]):
+        a, b = g["a"][off:off + n], g["b"][off:off + n]
+        off += n
+        with np.errstate(all="ignore"):
+            got = np.array([port.metric(m, a, b) for m in range(3)], dtype=np.float32)
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_port_delta_semantics_match_golden(port):
+    g = load_golden("delta_ops")
+    db = PortDB(port, int(g["D"]), int(g["K"]))
+    for (code, j), v, q, want, size in zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"]):
+        if code == 0:
+            assert db.insert(v) == j
+        elif code == 1:
+            db.update(int(j), v)
+        else:
+            db.delete(int(j))
+        assert db.size == size
+        assert db.nearest(q) == want
+    db.close()
+
+
+def test_port_ties_match_golden(port):
+    g = load_golden("ties")
+    ro = qo = 0
+    for (n, D, K), want in zip(g["meta"], g["ids"]):
+        rows = g["rows"][ro:ro + n * D].reshape(n, D)
+        q = g["queries"][qo:qo + D]
+        ro += n * D
+        qo += D
+        h = port.build(rows, int(K))
+        assert port.nearest_batch(h, q[None, :])[0] == want
+        port.free(h)
+
+
+def test_empty_tree(port):
+    log = port.lib.orc_log_create(3)
+    q = np.zeros(3)
+    assert port.lib.orc_tree_nearest(log, q.ctypes.data_as(binding._dp)) == binding.NONE
+    port.lib.orc_log_free(log)
+
+
+# ---- against the compiled reference on fresh inputs (skipped without oracle/_ref) ----
+
+@pytest.mark.parametrize("n,D,K,seed", [(5000, 16, 3, 1), (3000, 24, 24, 2), (800, 200, 200, 3), (4000, 5, 1, 4)])
+def test_port_vs_reference_random(port, ref, n, D, K, seed):
+    rows = synth.uniform_rows(seed, n, D)
+    Q = synth.uniform_rows(seed + 100, 200, D)
+    hr, hp = ref.build(rows, K), port.build(rows, K)
+    np.testing.assert_array_equal(ref.nearest_batch(hr, Q, 1), port.nearest_batch(hp, Q, 1))
+    np.testing.assert_array_equal(ref.nearest_batch(hr, Q, 4), port.nearest_batch(hp, Q, 4))
+    i1, i2 = synth.index_pairs(seed, 500, n)
+    for m in range(3):
+        a, b = ref.compare_batch(hr, m, i1, i2, 2), port.compare_batch(hp, m, i1, i2, 2)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    ref.free(hr)
+    port.free(hp)
+
+
+def test_port_vs_reference_script_distribution(port, ref):
+    rows = synth.script_values(77, (6000, 6))
+    Q = synth.script_values(78, (1500, 6))
+    hr, hp = ref.build(rows, 3), port.build(rows, 3)
+    np.testing.assert_array_equal(ref.nearest_batch(hr, Q), port.nearest_batch(hp, Q))
+    ref.free(hr)
+    port.free(hp)
+
+
+def test_reference_O0_equals_O2_nocontract(ref):
+    """The Makefile's flags (-O0) and our timing build (-O2 -ffp-contract=off) agree bit for bit."""
+    r0 = binding.load_ref(o0=True)
+    rows = synth.normal_rows(5, 600, 96)
+    Q = synth.normal_rows(6, 50, 96)
+    h2, h0 = ref.build(rows, 96), r0.build(rows, 96)
+    np.testing.assert_array_equal(ref.nearest_batch(h2, Q), r0.nearest_batch(h0, Q))
+    i1, i2 = synth.index_pairs(5, 300, 600)
+    for m in range(3):
+        np.testing.assert_array_equal(ref.compare_batch(h2, m, i1, i2).view(np.uint32),
+                                      r0.compare_batch(h0, m, i1, i2).view(np.uint32))
+    ref.free(h2)
+    r0.free(h0)
+
+
+def test_reference_dimension_mismatch_sentinel(ref, capfd):
+    """vector_database.c:302-305: -1.0f and a line on stderr."""
+    assert ref.metric(0, np.ones(3), np.ones(4)) == np.float32(-1.0)
+    assert ref.metric(1, np.ones(3), np.ones(4)) == np.float32(-1.0)
+    assert ref.metric(2, np.ones(3), np.ones(4)) == np.float32(-1.0)
+
+
+def test_reference_save_load_roundtrip(ref, tmp_path):
+    """File format of vector_database.c:203-292 (used later by the bulk-load row)."""
+    L = ref.lib
+    db = L.vector_db_init(0, 2)
+    rows = synth.uniform_rows(9, 5, 4)
+    for i, r in enumerate(rows):
+        L.vector_db_insert(db, ref.make_vector(r, uuid=f"id-{i}"))
+    path = str(tmp_path / "db.bin").encode()
+    L.vector_db_save(db, path)
+    raw = open(path, "rb").read()
+    assert len(raw) == 8 + 5 * (37 + 8 + 4 * 8)
+    assert int.from_bytes(raw[:8], "little") == 5
+    db2 = L.vector_db_load(path, 2)
+    assert db2.contents.size == 5
+    q = rows[3].copy()
+    assert L.kdtree_nearest(db2.contents.kdtree, q.ctypes.data_as(binding._dp)) == 3
+    v = L.vector_db_read(db2, 3).contents
+    assert v.uuid == b"id-3" and v.dimension == 4
+    np.testing.assert_array_equal(np.ctypeslib.as_array(v.data, shape=(4,)), rows[3])
+    L.vector_db_free(db)
+    L.vector_db_free(db2)
