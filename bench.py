@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- nearest queries/s + achieved HBM GB/s on 10M x 768 fp64 (BASELINE.json).
+
+    python bench.py [--gpus N --steps K --warmup W]          ours (N=1), or under torchrun for N>1
+    python bench.py --impl reference [...]                   the reference's CPU path on the host cores
+
+A step = ONE single-query nearest (top-1, what /nearest answers) over the whole store:
+one pass of the distance scan over every shard, the candidate exchange and the merge.
+  value  queries/s with the query already in HBM (device-timed, CUDA events, max over ranks)
+  e2e    the same through the public call with the query in pinned HOST memory and the
+         result read back to the host every step
+The store is row-sharded over the N GPUs (strong scaling: the 10M rows are fixed).
+Also reported: a 1024-query top-10 batch (config 3) and, at N=1, the reference's CPU path
+timed on this box's cores on a bounded prefix of the same rows.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "simple-vector-db_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "nearest_queries_per_s"
+UNIT = "queries/s"
+CHUNK_ROWS = 125_000          # generation granule; seeds are per chunk so any sharding sees the same rows
+SEED = 2
+L2_BYTES = 126 << 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while active (NVML)."""
+
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as ex:  # pragma: no cover
+            self.err = str(ex)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.ok:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic():
+    """dram bytes per scan launch from the committed ncu capture, if one exists."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own kdtree_nearest on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_rows(n: int, D: int) -> np.ndarray:
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    return rng.random((n, D), dtype=np.float64)
+
+
+def run_cpu_reference(rows: np.ndarray, K: int, n_total: int, steps: int, warmup: int, budget_s: float):
+    """Each step = `cores` independent queries, one per host thread, on the read-only tree built
+    from `rows` (a prefix-sized sample of the workload).  Returns q/s on the sample and its linear
+    extrapolation to n_total rows (at K=768 the tree search visits ~every node: SURVEY.md s6)."""
+    from oracle import binding as OB
+    drv = OB.load_cpu_driver()
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    h = drv.build(rows, K)
+    build_s = time.perf_counter() - t0
+    rng = np.random.Generator(np.random.PCG64(SEED + 1))
+    Q = rng.random((cores, rows.shape[1]))
+    t0 = time.perf_counter()
+    drv.nearest_batch(h, Q[:1], 1)
+    one = time.perf_counter() - t0
+    # keep the whole arm inside the budget
+    max_steps = max(1, int(budget_s / max(one * 1.3, 1e-6)))
+    warmup = min(warmup, max(0, max_steps // 4))
+    steps = max(1, min(steps, max_steps - warmup))
+    for _ in range(warmup):
+        drv.nearest_batch(h, Q, cores)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        drv.nearest_batch(h, np.roll(Q, i, axis=0), cores)
+    dt = time.perf_counter() - t0
+    drv.free(h)
+    qps_sample = steps * cores / dt
+    scale = rows.shape[0] / n_total
+    return {"kind": drv.kind, "cores": cores, "qps_sample": qps_sample, "qps_full": qps_sample * scale,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "build_s": build_s,
+            "one_query_one_core_s": one}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = min(args.rows, args.cpu_sample_rows)
+    rows = cpu_rows(n_sample, args.dim)
+    r = run_cpu_reference(rows, args.kd_dim, args.rows, args.steps, args.warmup, budget_s=90.0)
+    sample = (f"first {n_sample} of {args.rows} rows (same distribution, numpy PCG64), {r['cores']} concurrent "
+              f"queries per step on {r['cores']} threads; value = q/s on the sample x {n_sample}/{args.rows} "
+              f"(linear in rows: at K={args.kd_dim} kdtree_nearest visits ~every node)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["qps_full"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": r["qps_full"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                         "value_on_sample": r["qps_sample"], "one_query_one_core_s": r["one_query_one_core_s"]},
+        "e2e": {"value": r["qps_full"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"config3: {args.rows}x{args.dim} fp64 store, kd_dim={args.kd_dim}, single-query nearest top-1 "
+                        f"per step, row-sharded over n_gpus",
+            "rows": args.rows, "dim": args.dim, "kd_dim": args.kd_dim, "k": 1, "queries_per_step": 1,
+            "parallelism": f"row-shards x{args.gpus}",
+            "l2": "store per GPU >> 126 MB L2 (no flush needed)" if args.rows * args.dim * 8 // max(1, args.gpus) > 4 * L2_BYTES
+                  else "store fits L2: flushed between steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from svdb import binding as B
+    from svdb.sharded import ShardedIndex
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    D, K, N = args.dim, args.kd_dim, args.rows
+    idx = ShardedIndex(D, K, N, rank, world, local)
+    idx.bind_current_stream()
+    e = idx.engine
+    for name, val in (kv.split("=") for kv in args.opt):
+        e.set_option(name, int(val))
+
+    # ---- synthetic store: U[0,1) fp64, generated on the device chunk by chunk -------------
+    t0 = time.perf_counter()
+    lo, hi = idx.lo, idx.hi
+    c = lo // CHUNK_ROWS
+    while c * CHUNK_ROWS < hi:
+        g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + c)
+        chunk = torch.rand((CHUNK_ROWS, D), dtype=torch.float64, device=dev, generator=g)
+        a, b = max(lo, c * CHUNK_ROWS), min(hi, (c + 1) * CHUNK_ROWS, N)
+        part = chunk[a - c * CHUNK_ROWS: b - c * CHUNK_ROWS]
+        idx.ingest_device(part)
+        torch.cuda.synchronize()
+        del chunk, part
+        c += 1
+    build_s = time.perf_counter() - t0
+    torch.cuda.empty_cache()
+    if rank == 0:
+        log(f"[bench] store built: {hi - lo} rows/rank in {build_s:.1f}s, {e.stats()['hbm_bytes_mapped'] / 2**30:.1f} GiB mapped")
+
+    flush_buf = None
+    if (hi - lo) * K * 8 <= 4 * L2_BYTES:
+        flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+
+    # ---- queries: a pool of distinct ones, in pinned host memory and in HBM --------------
+    gq = torch.Generator().manual_seed(SEED + 7)
+    pool = 64
+    q_host = torch.rand((pool, 1, D), dtype=torch.float64, generator=gq).pin_memory()
+    q_dev = q_host.to(dev)
+    k = 1
+    sampler = ClockSampler(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_e2e(i):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        return idx.nearest(q_host[i % pool], k)
+
+    def step_dev(i):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        return idx.nearest_device(q_dev[i % pool], k)
+
+    # ---- e2e: host query in, host result out, every step ----------------------------------
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    st0 = e.stats()
+    sampler.start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = step_e2e(args.warmup + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st1 = e.stats()
+    e2e_launches = st1["kernels_launched"] - st0["kernels_launched"]
+
+    # ---- device-resident: queries already in HBM, K steps back to back, CUDA events -------
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    e.set_option("profile.scan_events", 1)
+    e.take_scan_time()
+    m0 = idx.merge_launches
+    st0 = e.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    ev1.record()
+    barrier()
+    sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    scan_ms, scan_launches = e.take_scan_time()
+    e.set_option("profile.scan_events", 0)
+    st1 = e.stats()
+    launches = st1["kernels_launched"] - st0["kernels_launched"] + (idx.merge_launches - m0)
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, scan_ms / max(1, scan_launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, scan_ms_avg = (float(x) for x in times.cpu())
+
+    # ---- config 3 batch: 1024 queries, top-10, 8 queries share each pass ------------------
+    batch = None
+    if args.batch_queries > 0:
+        nb, kb = args.batch_queries, 10
+        qb_host = torch.rand((nb, D), dtype=torch.float64, generator=gq).pin_memory()
+        qb_dev = qb_host.to(dev)
+        e.set_option("scan.nq_per_pass", 8)
+        idx.nearest_device(qb_dev[:8], kb)
+        barrier()
+        ev0.record()
+        idx.nearest_device(qb_dev, kb)
+        ev1.record()
+        barrier()
+        b_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        t0 = time.perf_counter()
+        res_b = idx.nearest(qb_host, kb)
+        barrier()
+        b_e2e = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(b_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b_e2e, op=dist.ReduceOp.MAX)
+        batch = {"workload": f"{nb}-query batch, top-{kb}, 8 queries per scan pass", "queries": nb, "k": kb,
+                 "value": nb / (float(b_ms) / 1e3), "unit": UNIT, "ms": float(b_ms),
+                 "e2e": {"value": nb / (float(b_e2e) / 1e3), "unit": UNIT, "h2d_bytes": nb * D * 8, "d2h_bytes": nb * kb * 32},
+                 "scan_passes": nb // 8, "unsafe_flags": int(np.count_nonzero(res_b["flags"] & B.CAND_UNSAFE))}
+        e.set_option("scan.nq_per_pass", 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (N=1 only) -------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = min(N, args.cpu_sample_rows)
+        g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + 0)
+        need_chunks = -(-n_sample // CHUNK_ROWS)
+        parts = []
+        for c in range(need_chunks):
+            g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + c)
+            parts.append(torch.rand((CHUNK_ROWS, D), dtype=torch.float64, device=dev, generator=g).cpu())
+        rows = torch.cat(parts)[:n_sample].numpy()
+        r = run_cpu_reference(rows, K, N, steps=3, warmup=1, budget_s=25.0)
+        cpu = {"value": r["qps_full"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": f"first {n_sample} of {N} rows of the same store, {r['cores']} concurrent queries/step x {r['steps']} steps "
+                         f"on {r['cores']} threads; value = measured {r['qps_sample']:.3f} q/s x {n_sample}/{N} (linear in rows)",
+               "value_on_sample": r["qps_sample"], "one_query_one_core_s": r["one_query_one_core_s"]}
+
+    rows_per_rank = idx.hi - idx.lo
+    algo_bytes = rows_per_rank * K * 8
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_bytes / (scan_ms_avg / 1e3) / 1e9 if scan_ms_avg > 0 else 0.0
+    traffic = profile_traffic()
+    qps = args.steps / (dev_ms / 1e3)
+    line = {
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": D * 8,
+                "d2h_bytes_per_step": k * 32, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "scan_wide_kernel<TR,1> (variant %d)" % e_variant(args),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms_avg,
+                     "launches_timed": int(scan_launches), "peak_source": peak_src,
+                     "scan_share_of_step": scan_ms_avg / (dev_ms / args.steps)},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+        "batch": batch,
+        "store": {"rows_per_rank": rows_per_rank, "build_s": build_s, "hbm_gib_mapped": e.stats()["hbm_bytes_mapped"] / 2**30,
+                  "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e_variant(args):
+    for kv in args.opt:
+        if kv.startswith("scan.variant="):
+            return int(kv.split("=")[1])
+    return int(os.environ.get("SVDB_SCAN_VARIANT", "0"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--kd-dim", type=int, default=0)
+    ap.add_argument("--batch-queries", type=int, default=1024)
+    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. scan.variant=1)")
+    args = ap.parse_args()
+    if args.kd_dim <= 0:
+        args.kd_dim = args.dim
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

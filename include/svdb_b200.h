@@ -1,0 +1,158 @@
+/*
+ * svdb_b200.h -- native C-ABI of the B200 similarity engine.
+ *
+ * One engine = one shard of the vector store resident in one GPU's HBM.
+ * Plain pointers and sizes only; every function returns 0 on success or a
+ * negative svdb_status, and svdb_last_error() describes the last failure of the
+ * calling thread.  There is NO CPU fallback: without a usable CUDA device
+ * svdb_engine_create fails.
+ *
+ * Which reference interface each entry point stands in for (paths relative to the
+ * reference tree):
+ *   svdb_insert_batch            vector_db_insert      src/vector_database.c:81-119
+ *   svdb_update_batch            vector_db_update      src/vector_database.c:169-177
+ *   svdb_delete_batch            vector_db_delete      src/vector_database.c:185-195
+ *   svdb_append_kdpoints         kdtree_insert         src/kdtree.c:87-91
+ *   svdb_nearest_batch (k=1)     kdtree_nearest        src/kdtree.c:171-178 (loop :131-162)
+ *   svdb_compare_batch           cosine_similarity / euclidean_distance / dot_product
+ *                                                      src/vector_database.c:301-352
+ *   svdb_read_row                vector_db_read        src/vector_database.c:128-136
+ * The reference's own function names (vector_db_*, kdtree_*, the three metrics)
+ * are exported by the same library; they are declared in svdb_dropin.h.
+ *
+ * Semantics kept from the reference:
+ *   - the searchable set is an APPEND-ONLY log of (kd-point, index) entries: one per
+ *     insert and one per update; deletes remove nothing from it;
+ *   - distance = squared L2 over the first kd_dim coordinates, summed sequentially
+ *     in index order with a rounded multiply and a rounded add per term (no FMA);
+ *   - nearest = smallest (distance, log sequence number); non-finite distances
+ *     never win; empty log -> SVDB_NONE;
+ *   - metrics accumulate in float exactly as the reference does; bit-identical.
+ */
+#ifndef SVDB_B200_H
+#define SVDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVDB_NONE ((size_t)-1)
+#define SVDB_MAX_K 24            /* largest k of a top-k query */
+
+typedef enum svdb_status {
+    SVDB_OK = 0,
+    SVDB_ERR_ARG = -1,           /* bad argument (NULL, kd_dim > dimension, k > SVDB_MAX_K ...) */
+    SVDB_ERR_CUDA = -2,          /* a CUDA call failed; text in svdb_last_error() */
+    SVDB_ERR_OOM = -3,           /* device or host allocation failed */
+    SVDB_ERR_RANGE = -4          /* index out of range where the call cannot be a silent no-op */
+} svdb_status;
+
+typedef enum svdb_metric {
+    SVDB_COSINE = 0,             /* vector_database.c:301 */
+    SVDB_EUCLIDEAN = 1,          /* vector_database.c:322 */
+    SVDB_DOT = 2                 /* vector_database.c:342 */
+} svdb_metric;
+
+typedef struct svdb_engine svdb_engine;
+
+typedef struct svdb_config {
+    size_t dimension;            /* D: doubles per stored row (db_vector_size) */
+    size_t kd_dim;               /* K <= D: coordinates nearest() measures (kd_tree_dimension) */
+    int    device;               /* CUDA device ordinal */
+    uint64_t seq_base;           /* global sequence number of this shard's first log entry */
+    size_t reserve_rows;         /* map HBM for this many rows up front (0: grow on demand) */
+    uint32_t flags;              /* SVDB_FLAG_* */
+} svdb_config;
+
+#define SVDB_FLAG_LOG_ONLY   1u  /* rows ARE kd-points (dimension == kd_dim), no index map: a bare KDTree */
+#define SVDB_FLAG_NO_LOG     2u  /* rows only (compare / read); nearest is not available */
+
+/* One result of a nearest query; also the unit exchanged between shards. 32 bytes. */
+typedef struct svdb_candidate {
+    double   dist;               /* reference-order squared distance over kd_dim coords; +inf if none */
+    uint64_t seq;                /* global log sequence number (tie-break key); UINT64_MAX if none */
+    uint64_t index;              /* index carried by the log entry; SVDB_NONE if none */
+    uint64_t flags;              /* bit 0: SVDB_CAND_UNSAFE */
+} svdb_candidate;
+
+#define SVDB_CAND_UNSAFE 1ull    /* candidate set could not be proven complete: rerun exact */
+
+const char *svdb_last_error(void);
+const char *svdb_version(void);
+int svdb_device_count(void);
+
+int  svdb_engine_create(const svdb_config *cfg, svdb_engine **out);
+void svdb_engine_destroy(svdb_engine *e);
+/* Launch on this CUDA stream (cudaStream_t as void*; NULL = engine's own stream). */
+int  svdb_set_stream(svdb_engine *e, void *stream);
+
+/* ---- store deltas; rows are host buffers of n x ld doubles (ld >= dimension) ---- */
+int svdb_insert_batch(svdb_engine *e, const double *rows, size_t n, size_t ld, size_t *first_index);
+int svdb_update_batch(svdb_engine *e, const size_t *index, const double *rows, size_t n, size_t ld);
+int svdb_delete_batch(svdb_engine *e, const size_t *index, size_t n);      /* applied in order */
+/* Bare log append (n kd-points of ld >= kd_dim doubles, each with the index to report). */
+int svdb_append_kdpoints(svdb_engine *e, const double *pts, const size_t *index, size_t n, size_t ld);
+/* Same as svdb_insert_batch with rows already in device memory (bulk ingest). */
+int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, size_t ld, size_t *first_index);
+/* Push pending deltas to the device (queries do this themselves). */
+int svdb_flush(svdb_engine *e);
+
+size_t svdb_size(const svdb_engine *e);        /* rows currently indexable (db->size) */
+size_t svdb_log_size(const svdb_engine *e);    /* searchable log entries */
+size_t svdb_dimension(const svdb_engine *e);
+size_t svdb_kd_dim(const svdb_engine *e);
+int svdb_read_row(svdb_engine *e, size_t index, double *out /* dimension doubles */);
+
+/* ---- nearest ---- */
+/* Host buffers.  Q: nq x ldq doubles (only the first kd_dim of each are read).
+ * Outputs are nq x k, row-major, sorted by (dist, seq); missing entries get
+ * SVDB_NONE / +inf / UINT64_MAX.  Any of the three outputs may be NULL. */
+int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k,
+                       size_t *index_out, double *dist_out, uint64_t *seq_out);
+/* Device buffers, asynchronous on the engine's stream: d_out receives nq x k candidates.
+ * The caller must look at flags (SVDB_CAND_UNSAFE) once the results are on the host and
+ * call svdb_nearest_batch_device again with exact != 0 for those queries. */
+int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k,
+                              svdb_candidate *d_out, int exact);
+/* Cross-shard merge: d_in holds nshards blocks of nq x k candidates (an allgather result);
+ * d_out receives nq x k, the k smallest of each query under (dist, seq). */
+int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards,
+                                 size_t nq, size_t k, svdb_candidate *d_out);
+
+/* ---- compare ---- */
+/* out[i] = metric(row[index1[i]], row[index2[i]]); out-of-range pairs give -1.0f
+ * (the reference's mismatch sentinel, vector_database.c:302-305). Host buffers. */
+int svdb_compare_batch(svdb_engine *e, int metric, const size_t *index1, const size_t *index2,
+                       size_t n, float *out);
+/* All three metrics in one pass over the rows: out is n x 3 (cosine, euclidean, dot). */
+int svdb_compare_batch_all(svdb_engine *e, const size_t *index1, const size_t *index2, size_t n, float *out);
+/* Device index / output buffers, asynchronous on the engine's stream. metric 3 = all (n x 3). */
+int svdb_compare_batch_device(svdb_engine *e, int metric, const uint64_t *d_index1, const uint64_t *d_index2,
+                              size_t n, float *d_out);
+/* Two host vectors that need not be stored anywhere (the by-value call of the reference). */
+int svdb_compare_vectors(int device, int metric, const double *a, const double *b, size_t D, float *out);
+
+/* ---- introspection used by bench.py / tests ---- */
+typedef struct svdb_stats {
+    uint64_t kernels_launched;   /* our kernels launched by this engine so far */
+    uint64_t exact_reruns;       /* queries that needed the exact fallback scan */
+    uint64_t hbm_bytes_mapped;   /* physical HBM currently mapped by the arenas */
+    uint64_t h2d_bytes, d2h_bytes;
+} svdb_stats;
+int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
+/* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm". */
+int svdb_set_option(svdb_engine *e, const char *name, long value);
+/* Scan the log for nq queries already on the device, timing the scan kernel alone with
+ * CUDA events on the engine's stream: returns average milliseconds per launch. */
+int svdb_time_scan(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, int iters, float *ms_out);
+/* With option "profile.scan_events" = 1 every scan launch is bracketed by CUDA events on the
+ * engine's stream; this returns their summed duration and count since the last call. */
+int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDB_B200_H */

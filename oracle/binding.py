@@ -101,12 +101,16 @@ class CpuDriver:
         return out
 
 
-class RefLib(CpuDriver):
-    """Raw reference C API (include/vector_database.h:39-135, include/kdtree.h:32-57)."""
+class RefApi:
+    """The reference's L1 C API (include/vector_database.h:39-135, include/kdtree.h:32-57)
+    bound on ANY shared library that exports it: oracle/_ref (the reference itself) or the
+    product's libsvdb_b200.so (the drop-in) -- the parity tests drive both through this class."""
 
-    def __init__(self, path: str = REF_SO):
-        super().__init__(path)
-        L = self.lib
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = L = getattr(self, "lib", None) or C.CDLL(path)
         pdb = C.POINTER(VectorDatabaseS)
         L.vector_db_init.restype = pdb
         L.vector_db_init.argtypes = [C.c_size_t, C.c_size_t]
@@ -154,6 +158,18 @@ class RefLib(CpuDriver):
         va, vb = self.make_vector(a, own=False), self.make_vector(b, own=False)
         f = (self.lib.cosine_similarity, self.lib.euclidean_distance, self.lib.dot_product)[which]
         return np.float32(f(va, vb))
+
+    def nearest(self, db, q) -> int:
+        q = _as_f64(q)
+        return self.lib.kdtree_nearest(db.contents.kdtree, _ptr(q))
+
+
+class RefLib(CpuDriver, RefApi):
+    """oracle/_ref: the reference's own code plus our cpu_* batch driver."""
+
+    def __init__(self, path: str = REF_SO):
+        CpuDriver.__init__(self, path)
+        RefApi.__init__(self, path)
 
 
 class PortLib(CpuDriver):

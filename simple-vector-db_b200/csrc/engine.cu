@@ -1,0 +1,821 @@
+// engine.cu -- one shard of the store: arenas, delta staging, query orchestration, C-ABI.
+#include "engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace svdb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &s) { g_last_error = s; }
+const std::string &get_last_error() { return g_last_error; }
+
+bool Scratch::ensure(size_t bytes, std::string &err) {
+    if (bytes <= cap) return true;
+    size_t want = std::max(bytes, cap + cap / 2);
+    void *np = nullptr;
+    if (cudaMalloc(&np, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        if (cudaMalloc(&np, want) != cudaSuccess) {
+            err = std::string("cudaMalloc(scratch) failed: ") + cudaGetErrorString(cudaGetLastError());
+            return false;
+        }
+    }
+    if (p) cudaFree(p);   // implicit device sync: nothing in flight may still read the old block
+    p = np;
+    cap = want;
+    return true;
+}
+void Scratch::free_() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+bool PinnedScratch::ensure(size_t bytes, std::string &err) {
+    if (bytes <= cap) return true;
+    const size_t want = std::max(bytes, cap + cap / 2);
+    void *np = nullptr;
+    if (cudaMallocHost(&np, want) != cudaSuccess) {
+        err = std::string("cudaMallocHost failed: ") + cudaGetErrorString(cudaGetLastError());
+        return false;
+    }
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = want;
+    return true;
+}
+void PinnedScratch::free_() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+__global__ void fill_f32_kernel(float *dst, float v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+static size_t round_up(size_t v, size_t g) { return (v + g - 1) / g * g; }
+
+}  // namespace svdb
+
+using namespace svdb;
+
+#define CK(call)                                            \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return fail_cuda(#call, e__); \
+    } while (0)
+
+int svdb_engine::fail_cuda(const char *what, cudaError_t e) {
+    set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cudaGetLastError();
+    return SVDB_ERR_CUDA;
+}
+int svdb_engine::fail(int code, const std::string &msg) {
+    set_last_error(msg);
+    return code;
+}
+
+int svdb_engine::init(const svdb_config &c) {
+    cfg = c;
+    if (c.dimension < 1 || c.kd_dim < 1) return fail(SVDB_ERR_ARG, "dimension and kd_dim must be >= 1");
+    if (c.kd_dim > c.dimension)
+        return fail(SVDB_ERR_ARG, "kd_dim > dimension: the reference would read past the row (kdtree.c:26-28)");
+    if (c.dimension > (1u << 20)) return fail(SVDB_ERR_ARG, "dimension too large");
+    log_only = (c.flags & SVDB_FLAG_LOG_ONLY) != 0;
+    no_log = (c.flags & SVDB_FLAG_NO_LOG) != 0;
+    if (log_only && no_log) return fail(SVDB_ERR_ARG, "LOG_ONLY and NO_LOG exclude each other");
+    if (log_only && c.kd_dim != c.dimension) return fail(SVDB_ERR_ARG, "log-only engine needs dimension == kd_dim");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SVDB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                       " (this library has no CPU path)");
+    if (c.device < 0 || c.device >= count) return fail(SVDB_ERR_ARG, "device ordinal out of range");
+    device = c.device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SVDB_ERR_CUDA, "kernels are built for sm_100a only; this device is older");
+    tune.num_sms = prop.multiProcessorCount;
+    if (const char *v = getenv("SVDB_SCAN_VARIANT")) tune.variant = atoi(v);
+
+    D = (int)c.dimension;
+    K = (int)c.kd_dim;
+    Dpad = (int)round_up(D, 16);
+    wide = K > tune.thin_max_k;
+    alias = !log_only && !no_log && wide && K == D;
+    kstride = alias ? Dpad : (wide ? (int)round_up(K, 2) : K);
+
+    const size_t va = (size_t)256 << 30;
+    const size_t main_row_bytes = (size_t)(log_only ? kstride : Dpad) * 8;
+    max_versions = va / main_row_bytes;
+    std::string err;
+    if (!log_only) {
+        if (!rows.init(device, max_versions * (size_t)Dpad * 8, err)) return fail(SVDB_ERR_CUDA, err);
+        if (!norms.init(device, max_versions * 4, err)) return fail(SVDB_ERR_CUDA, err);
+        if (!cur.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+    }
+    if (!alias && !no_log && !kdpts.init(device, max_versions * (size_t)kstride * 8, err)) return fail(SVDB_ERR_CUDA, err);
+    if (!no_log && !log_idx.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+
+    CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+
+    stage_ld = log_only ? (size_t)kstride : (size_t)Dpad;
+    stage_cap = std::min<size_t>(65536, std::max<size_t>(1, ((size_t)8 << 20) / (stage_ld * 8)));
+    if (!stage_rows.ensure(stage_cap * stage_ld * 8, err) || !stage_idx.ensure(stage_cap * 8, err))
+        return fail(SVDB_ERR_OOM, err);
+
+    if (c.reserve_rows) {
+        const size_t n = std::min(c.reserve_rows, max_versions);
+        bool ok = true;
+        if (!log_only) ok = ok && rows.ensure(n * (size_t)Dpad * 8, stream, err) && norms.ensure(n * 4, stream, err) &&
+                            cur.ensure(n * 8, stream, err);
+        if (!alias && !no_log) ok = ok && kdpts.ensure(n * (size_t)kstride * 8, stream, err);
+        if (!no_log) ok = ok && log_idx.ensure(n * 8, stream, err);
+        if (!ok) return fail(SVDB_ERR_OOM, err);
+        cur_host.reserve(n);
+    }
+    return SVDB_OK;
+}
+
+void svdb_engine::destroy() {
+    cudaSetDevice(device);
+    if (own_stream) cudaStreamSynchronize(own_stream);
+    for (auto &ev : scan_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    scan_events.clear();
+    rows.release();
+    kdpts.release();
+    log_idx.release();
+    norms.release();
+    cur.release();
+    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout}) s->free_();
+    for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf}) s->free_();
+    if (own_stream) cudaStreamDestroy(own_stream);
+    own_stream = stream = nullptr;
+}
+
+int svdb_engine::stage_one(const double *row, size_t ncopy, uint64_t index) {
+    if (stage_n == stage_cap) {
+        int rc = flush();
+        if (rc) return rc;
+    }
+    if (n_versions + stage_n >= max_versions) return fail(SVDB_ERR_OOM, "store exceeds the reserved address range");
+    double *dst = stage_rows.as<double>() + stage_n * stage_ld;
+    memcpy(dst, row, ncopy * sizeof(double));
+    if (ncopy < stage_ld) memset(dst + ncopy, 0, (stage_ld - ncopy) * sizeof(double));
+    stage_idx.as<uint64_t>()[stage_n] = index;
+    stage_n++;
+    return SVDB_OK;
+}
+
+int svdb_engine::flush() {
+    if (stage_n == 0) return SVDB_OK;
+    CK(cudaSetDevice(device));
+    const size_t n0 = n_versions, m = stage_n, n1 = n0 + m;
+    std::string err;
+    bool ok = no_log || log_idx.ensure(n1 * 8, stream, err);
+    if (!log_only) ok = ok && rows.ensure(n1 * (size_t)Dpad * 8, stream, err) && norms.ensure(n1 * 4, stream, err);
+    if (!alias && !no_log) ok = ok && kdpts.ensure(n1 * (size_t)kstride * 8, stream, err);
+    if (!ok) return fail(SVDB_ERR_OOM, err);
+
+    double *dst_rows = log_only ? kdpts.as<double>() + n0 * (size_t)kstride : rows.as<double>() + n0 * (size_t)Dpad;
+    CK(cudaMemcpyAsync(dst_rows, stage_rows.p, m * stage_ld * 8, cudaMemcpyHostToDevice, stream));
+    if (!no_log) CK(cudaMemcpyAsync(log_idx.as<uint64_t>() + n0, stage_idx.p, m * 8, cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += m * stage_ld * 8 + m * 8;
+    if (!log_only) {
+        if (!alias && !no_log) {
+            CK(launch_extract_prefix(rows.as<double>() + n0 * (size_t)Dpad, Dpad, kdpts.as<double>() + n0 * (size_t)kstride,
+                                     kstride, K, m, stream));
+            stats.kernels_launched++;
+        }
+        CompareArgs ca{};
+        ca.rows = rows.as<double>();
+        ca.ldr = Dpad;
+        ca.D = D;
+        ca.first = n0;
+        ca.n = m;
+        ca.out = norms.as<float>() + n0;
+        ca.mode = 4;
+        CK(launch_compare(ca, tune.num_sms, stream));
+        stats.kernels_launched++;
+    }
+    CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
+    n_versions = n1;
+    stage_n = 0;
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped();
+    return SVDB_OK;
+}
+
+int svdb_engine::upload_cur() {
+    const size_t n = cur_host.size();
+    if (cur_dirty_lo >= n) {
+        cur_dirty_lo = n;
+        return SVDB_OK;
+    }
+    std::string err;
+    if (!cur.ensure(n * 8, stream, err)) return fail(SVDB_ERR_OOM, err);
+    CK(cudaMemcpyAsync(cur.as<uint64_t>() + cur_dirty_lo, cur_host.data() + cur_dirty_lo, (n - cur_dirty_lo) * 8,
+                       cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));   // pageable source: do not let the host vector change under the copy
+    stats.h2d_bytes += (n - cur_dirty_lo) * 8;
+    cur_dirty_lo = n;
+    return SVDB_OK;
+}
+
+static int largest_pass(size_t remaining, int limit) {
+    int p = 1;
+    while (p * 2 <= limit && (size_t)(p * 2) <= remaining && p * 2 <= 8) p *= 2;
+    return p;
+}
+
+int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, bool exact) {
+    if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
+    if (no_log) return fail(SVDB_ERR_ARG, "this engine was created without a log (SVDB_FLAG_NO_LOG)");
+    if (nq == 0) return SVDB_OK;
+    if (!d_Q || !d_out || ldq < (size_t)K) return fail(SVDB_ERR_ARG, "bad query buffer");
+    int rc = flush();
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    const bool use_exact = exact || force_exact || !wide;
+    const int cap = (int)std::min<size_t>(32, k + 8);
+    const int nlists = n_versions ? scan_num_lists(tune, !use_exact) : 0;
+    std::string err;
+
+    const double *qbase = d_Q;
+    int qld = (int)ldq;
+    if (!use_exact) {
+        if (!qpad.ensure(nq * (size_t)kstride * 8, err)) return fail(SVDB_ERR_OOM, err);
+        CK(launch_pad_queries(d_Q, (int)ldq, qpad.as<double>(), kstride, K, (int)nq, stream));
+        stats.kernels_launched++;
+        qbase = qpad.as<double>();
+        qld = kstride;
+    }
+    const int limit = std::max(1, tune.nq_per_pass);
+    if (nlists && !lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return fail(SVDB_ERR_OOM, err);
+
+    size_t done = 0;
+    while (done < nq) {
+        const int nqp = largest_pass(nq - done, limit);
+        if (nlists) {
+            ScanArgs sa{};
+            sa.pts = kd_ptr();
+            sa.n = n_versions;
+            sa.K = K;
+            sa.stride = kstride;
+            sa.q = qbase + done * (size_t)qld;
+            sa.ldq = qld;
+            sa.nq = nqp;
+            sa.cap = cap;
+            sa.lists = lists.as<Cand>();
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profile_scan) {
+                if (scan_events_used == scan_events.size()) {
+                    cudaEvent_t a, b;
+                    CK(cudaEventCreate(&a));
+                    CK(cudaEventCreate(&b));
+                    scan_events.emplace_back(a, b);
+                }
+                ev0 = scan_events[scan_events_used].first;
+                ev1 = scan_events[scan_events_used].second;
+                scan_events_used++;
+                CK(cudaEventRecord(ev0, stream));
+            }
+            CK(use_exact ? launch_scan_exact(tune, sa, stream) : launch_scan_wide(tune, sa, stream));
+            if (ev1) CK(cudaEventRecord(ev1, stream));
+            stats.kernels_launched++;
+        }
+        FinalArgs fa{};
+        fa.lists = lists.as<Cand>();
+        fa.nlists = nlists;
+        fa.cap = cap;
+        fa.nq = nqp;
+        fa.k = (int)k;
+        fa.pts = kd_ptr();
+        fa.K = K;
+        fa.stride = kstride;
+        fa.q = qbase + done * (size_t)qld;
+        fa.ldq = qld;
+        fa.log_index = log_idx.as<u64>();
+        fa.seq_base = cfg.seq_base;
+        fa.eps = use_exact ? -1.0 : 4.0 * (double)(K + 2) * ldexp(1.0, -53);
+        fa.out = d_out + done * k;
+        CK(launch_finalize(fa, stream));
+        stats.kernels_launched++;
+        done += nqp;
+    }
+    return SVDB_OK;
+}
+
+int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
+                              uint64_t *seq_out) {
+    if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
+    if (nq == 0) return SVDB_OK;
+    if (!Q || ldq < (size_t)K) return fail(SVDB_ERR_ARG, "bad query buffer");
+    CK(cudaSetDevice(device));
+    std::string err;
+    if (!hq.ensure(nq * (size_t)K * 8, err) || !qraw.ensure(nq * (size_t)K * 8, err) ||
+        !outc.ensure(nq * k * sizeof(svdb_candidate), err) || !hout.ensure(nq * k * sizeof(svdb_candidate), err))
+        return fail(SVDB_ERR_OOM, err);
+    for (size_t i = 0; i < nq; i++) memcpy(hq.as<double>() + i * K, Q + i * ldq, (size_t)K * 8);
+    CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += nq * (size_t)K * 8;
+    int rc = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hout.p, outc.p, nq * k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
+    svdb_candidate *res = hout.as<svdb_candidate>();
+    for (size_t i = 0; i < nq; i++) {
+        if (!(res[i * k].flags & SVDB_CAND_UNSAFE)) continue;
+        // the candidate set could not be proven complete (mass near-ties): exact scan for this query
+        stats.exact_reruns++;
+        rc = nearest_device(qraw.as<double>() + i * K, 1, K, k, outc.as<svdb_candidate>() + i * k, true);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(res + i * k, outc.as<svdb_candidate>() + i * k, k * sizeof(svdb_candidate),
+                           cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    for (size_t i = 0; i < nq * k; i++) {
+        if (index_out) index_out[i] = (size_t)res[i].index;
+        if (dist_out) dist_out[i] = res[i].dist;
+        if (seq_out) seq_out[i] = res[i].seq;
+    }
+    return SVDB_OK;
+}
+
+int svdb_engine::compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out) {
+    if (mode < 0 || mode > 3) return fail(SVDB_ERR_ARG, "unknown metric");
+    if (log_only) return fail(SVDB_ERR_ARG, "a log-only engine stores no rows to compare");
+    if (n == 0) return SVDB_OK;
+    int rc = flush();
+    if (rc) return rc;
+    rc = upload_cur();
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    if (cur_host.empty()) {   // every pair is out of range: the reference's -1.0f sentinel
+        const size_t total = n * (mode == 3 ? 3 : 1);
+        fill_f32_kernel<<<(unsigned)std::min<size_t>(1024, (total + 255) / 256), 256, 0, stream>>>(d_out, -1.0f, total);
+        CK(cudaGetLastError());
+        stats.kernels_launched++;
+        return SVDB_OK;
+    }
+    CompareArgs ca{};
+    ca.rows = rows.as<double>();
+    ca.ldr = Dpad;
+    ca.D = D;
+    ca.cur = cur.as<u64>();
+    ca.nrows = cur_host.size();
+    ca.i1 = reinterpret_cast<const u64 *>(d_i1);
+    ca.i2 = reinterpret_cast<const u64 *>(d_i2);
+    ca.n = n;
+    ca.norm = norms.as<float>();
+    ca.out = d_out;
+    ca.mode = mode;
+    CK(launch_compare(ca, tune.num_sms, stream));
+    stats.kernels_launched++;
+    return SVDB_OK;
+}
+
+int svdb_engine::compare_host(int mode, const size_t *i1, const size_t *i2, size_t n, float *out) {
+    if (n == 0) return SVDB_OK;
+    if (!i1 || !i2 || !out) return fail(SVDB_ERR_ARG, "NULL buffer");
+    CK(cudaSetDevice(device));
+    const size_t per = mode == 3 ? 3 : 1;
+    std::string err;
+    if (!hidx.ensure(2 * n * 8, err) || !idx1.ensure(n * 8, err) || !idx2.ensure(n * 8, err) ||
+        !fout.ensure(n * per * 4, err) || !hf.ensure(n * per * 4, err))
+        return fail(SVDB_ERR_OOM, err);
+    memcpy(hidx.as<uint64_t>(), i1, n * 8);
+    memcpy(hidx.as<uint64_t>() + n, i2, n * 8);
+    CK(cudaMemcpyAsync(idx1.p, hidx.as<uint64_t>(), n * 8, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(idx2.p, hidx.as<uint64_t>() + n, n * 8, cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += 2 * n * 8;
+    int rc = compare_device(mode, idx1.as<uint64_t>(), idx2.as<uint64_t>(), n, fout.as<float>());
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hf.p, fout.p, n * per * 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    stats.d2h_bytes += n * per * 4;
+    memcpy(out, hf.p, n * per * 4);
+    return SVDB_OK;
+}
+
+// =====================================================================================
+// C-ABI
+// =====================================================================================
+extern "C" {
+
+const char *svdb_last_error(void) { return get_last_error().c_str(); }
+const char *svdb_version(void) { return "svdb_b200 0.1 (sm_100a)"; }
+
+int svdb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int svdb_engine_create(const svdb_config *cfg, svdb_engine **out) {
+    if (!cfg || !out) {
+        set_last_error("NULL argument");
+        return SVDB_ERR_ARG;
+    }
+    *out = nullptr;
+    svdb_engine *e = new (std::nothrow) svdb_engine();
+    if (!e) return SVDB_ERR_OOM;
+    int rc = e->init(*cfg);
+    if (rc) {
+        const std::string keep = get_last_error();
+        e->destroy();
+        delete e;
+        set_last_error(keep);
+        return rc;
+    }
+    *out = e;
+    return SVDB_OK;
+}
+
+void svdb_engine_destroy(svdb_engine *e) {
+    if (!e) return;
+    e->destroy();
+    delete e;
+}
+
+int svdb_set_stream(svdb_engine *e, void *stream) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->stream = stream ? (cudaStream_t)stream : e->own_stream;
+    return SVDB_OK;
+}
+
+int svdb_insert_batch(svdb_engine *e, const double *rows, size_t n, size_t ld, size_t *first_index) {
+    if (!e || (!rows && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine: use svdb_append_kdpoints");
+    if (ld < (size_t)e->D) return e->fail(SVDB_ERR_ARG, "ld < dimension");
+    if (first_index) *first_index = e->cur_host.size();
+    for (size_t i = 0; i < n; i++) {
+        // vector_database.c:113-115: the entry carries index = size before the increment
+        const uint64_t ver = e->n_versions + e->stage_n;
+        int rc = e->stage_one(rows + i * ld, e->D, e->cur_host.size());
+        if (rc) return rc;
+        e->cur_host.push_back(ver);
+    }
+    return SVDB_OK;
+}
+
+int svdb_update_batch(svdb_engine *e, const size_t *index, const double *rows, size_t n, size_t ld) {
+    if (!e || ((!rows || !index) && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine has no rows to update");
+    if (ld < (size_t)e->D) return e->fail(SVDB_ERR_ARG, "ld < dimension");
+    for (size_t i = 0; i < n; i++) {
+        if (index[i] >= e->cur_host.size()) continue;   // vector_database.c:171: silent no-op
+        const uint64_t ver = e->n_versions + e->stage_n;
+        int rc = e->stage_one(rows + i * ld, e->D, index[i]);   // :174 re-append with the same index
+        if (rc) return rc;
+        e->cur_host[index[i]] = ver;
+        e->cur_dirty_lo = std::min(e->cur_dirty_lo, index[i]);
+    }
+    return SVDB_OK;
+}
+
+int svdb_delete_batch(svdb_engine *e, const size_t *index, size_t n) {
+    if (!e || (!index && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine has no rows to delete");
+    for (size_t i = 0; i < n; i++) {
+        if (index[i] >= e->cur_host.size()) continue;   // vector_database.c:187: silent no-op
+        e->cur_host.erase(e->cur_host.begin() + index[i]);   // :189-191 shift; the log keeps its entries
+        e->cur_dirty_lo = std::min(e->cur_dirty_lo, index[i]);
+    }
+    return SVDB_OK;
+}
+
+int svdb_append_kdpoints(svdb_engine *e, const double *pts, const size_t *index, size_t n, size_t ld) {
+    if (!e || ((!pts || !index) && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (ld < (size_t)e->K) return e->fail(SVDB_ERR_ARG, "ld < kd_dim");
+    if (e->no_log) return e->fail(SVDB_ERR_ARG, "this engine was created without a log");
+    for (size_t i = 0; i < n; i++) {
+        int rc = e->stage_one(pts + i * ld, e->K, index[i]);   // kdtree.c:20-28 copies K coordinates
+        if (rc) return rc;
+    }
+    return SVDB_OK;
+}
+
+int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, size_t ld, size_t *first_index) {
+    if (!e || (!d_rows && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine: use svdb_append_kdpoints");
+    if (ld < (size_t)e->D) return e->fail(SVDB_ERR_ARG, "ld < dimension");
+    int rc = e->flush();
+    if (rc) return rc;
+    if (first_index) *first_index = e->cur_host.size();
+    if (n == 0) return SVDB_OK;
+    if (cudaSetDevice(e->device) != cudaSuccess) return e->fail_cuda("cudaSetDevice", cudaGetLastError());
+    const size_t n0 = e->n_versions, n1 = n0 + n;
+    if (n1 > e->max_versions) return e->fail(SVDB_ERR_OOM, "store exceeds the reserved address range");
+    std::string err;
+    bool ok = (e->no_log || e->log_idx.ensure(n1 * 8, e->stream, err)) &&
+              e->rows.ensure(n1 * (size_t)e->Dpad * 8, e->stream, err) && e->norms.ensure(n1 * 4, e->stream, err);
+    if (!e->alias && !e->no_log) ok = ok && e->kdpts.ensure(n1 * (size_t)e->kstride * 8, e->stream, err);
+    if (!ok) return e->fail(SVDB_ERR_OOM, err);
+    double *dst = e->rows.as<double>() + n0 * (size_t)e->Dpad;
+    cudaError_t ce;
+    if (e->Dpad != e->D) {
+        ce = cudaMemsetAsync(dst, 0, n * (size_t)e->Dpad * 8, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("cudaMemsetAsync", ce);
+    }
+    ce = cudaMemcpy2DAsync(dst, (size_t)e->Dpad * 8, d_rows, ld * 8, (size_t)e->D * 8, n, cudaMemcpyDeviceToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("cudaMemcpy2DAsync", ce);
+    const size_t base_index = e->cur_host.size();
+    if (!e->no_log) {
+        ce = launch_iota(e->log_idx.as<u64>() + n0, base_index, n, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("iota", ce);
+        e->stats.kernels_launched++;
+    }
+    if (!e->alias && !e->no_log) {
+        ce = launch_extract_prefix(dst, e->Dpad, e->kdpts.as<double>() + n0 * (size_t)e->kstride, e->kstride, e->K, n, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("extract_prefix", ce);
+        e->stats.kernels_launched++;
+    }
+    CompareArgs ca{};
+    ca.rows = e->rows.as<double>();
+    ca.ldr = e->Dpad;
+    ca.D = e->D;
+    ca.first = n0;
+    ca.n = n;
+    ca.out = e->norms.as<float>() + n0;
+    ca.mode = 4;
+    ce = launch_compare(ca, e->tune.num_sms, e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("norm precompute", ce);
+    e->stats.kernels_launched++;
+    e->cur_host.reserve(base_index + n);
+    for (size_t i = 0; i < n; i++) e->cur_host.push_back(n0 + i);
+    e->n_versions = n1;
+    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() + e->cur.mapped();
+    return SVDB_OK;
+}
+
+int svdb_flush(svdb_engine *e) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = e->flush();
+    if (rc) return rc;
+    if (!e->log_only) rc = e->upload_cur();
+    return rc;
+}
+
+size_t svdb_size(const svdb_engine *e) { return e ? e->cur_host.size() : 0; }
+size_t svdb_log_size(const svdb_engine *e) { return e ? e->n_versions + e->stage_n : 0; }
+size_t svdb_dimension(const svdb_engine *e) { return e ? (size_t)e->D : 0; }
+size_t svdb_kd_dim(const svdb_engine *e) { return e ? (size_t)e->K : 0; }
+
+int svdb_read_row(svdb_engine *e, size_t index, double *out) {
+    if (!e || !out) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine stores no rows");
+    if (index >= e->cur_host.size()) return e->fail(SVDB_ERR_RANGE, "index out of range");
+    int rc = e->flush();
+    if (rc) return rc;
+    cudaSetDevice(e->device);
+    cudaError_t ce = cudaMemcpyAsync(out, e->rows.as<double>() + e->cur_host[index] * (size_t)e->Dpad, (size_t)e->D * 8,
+                                     cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("read_row", ce);
+    e->stats.d2h_bytes += (size_t)e->D * 8;
+    return SVDB_OK;
+}
+
+int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out,
+                       double *dist_out, uint64_t *seq_out) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->nearest_host(Q, nq, ldq, k, index_out, dist_out, seq_out);
+}
+
+int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out,
+                              int exact) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->nearest_device(d_Q, nq, ldq, k, d_out, exact != 0);
+}
+
+int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards, size_t nq, size_t k,
+                                 svdb_candidate *d_out) {
+    if (!d_in || !d_out || k < 1 || k > SVDB_MAX_K || nshards < 1) {
+        set_last_error("bad argument to svdb_merge_candidates_device");
+        return SVDB_ERR_ARG;
+    }
+    if (nq == 0) return SVDB_OK;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = launch_merge_candidates(d_in, (int)nshards, (int)nq, (int)k, d_out, (cudaStream_t)stream);
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("merge_candidates: ") + cudaGetErrorString(ce));
+        return SVDB_ERR_CUDA;
+    }
+    return SVDB_OK;
+}
+
+int svdb_compare_batch(svdb_engine *e, int metric, const size_t *index1, const size_t *index2, size_t n, float *out) {
+    if (!e) return SVDB_ERR_ARG;
+    if (metric < 0 || metric > 2) return e->fail(SVDB_ERR_ARG, "unknown metric");
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->compare_host(metric, index1, index2, n, out);
+}
+
+int svdb_compare_batch_all(svdb_engine *e, const size_t *index1, const size_t *index2, size_t n, float *out) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->compare_host(3, index1, index2, n, out);
+}
+
+int svdb_compare_batch_device(svdb_engine *e, int metric, const uint64_t *d_index1, const uint64_t *d_index2, size_t n,
+                              float *d_out) {
+    if (!e) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->compare_device(metric, d_index1, d_index2, n, d_out);
+}
+
+// Two loose host vectors: upload both (zero padded to 128-byte rows), K4 for the norms, K3.
+int svdb_compare_vectors(int device, int metric, const double *a, const double *b, size_t D, float *out) {
+    static std::mutex mu;
+    static Scratch dev[64];
+    static PinnedScratch host[64];
+    if (!a || !b || !out || D < 1 || metric < 0 || metric > 2 || device < 0 || device >= 64) {
+        set_last_error("bad argument to svdb_compare_vectors");
+        return SVDB_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> g(mu);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) {
+        cudaGetLastError();
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return SVDB_ERR_CUDA;
+    }
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+        return SVDB_ERR_CUDA;
+    }
+    const size_t Dpad = round_up(D, 16);
+    const size_t row_bytes = Dpad * 8;
+    // device block: [row a][row b][idx 0,1 as u64 x2][norms f32 x2 + pad][result f32]
+    const size_t bytes = 2 * row_bytes + 16 + 16 + 16;
+    std::string err;
+    if (!dev[device].ensure(bytes, err) || !host[device].ensure(bytes, err)) {
+        set_last_error(err);
+        return SVDB_ERR_OOM;
+    }
+    unsigned char *h = host[device].as<unsigned char>();
+    memset(h, 0, bytes);
+    memcpy(h, a, D * 8);
+    memcpy(h + row_bytes, b, D * 8);
+    uint64_t idx[2] = {0, 1};
+    memcpy(h + 2 * row_bytes, idx, 16);
+    unsigned char *d = dev[device].as<unsigned char>();
+    cudaStream_t st = cudaStreamPerThread;
+    ce = cudaMemcpyAsync(d, h, 2 * row_bytes + 16, cudaMemcpyHostToDevice, st);
+    CompareArgs ca{};
+    ca.rows = reinterpret_cast<const double *>(d);
+    ca.ldr = (int)Dpad;
+    ca.D = (int)D;
+    ca.nrows = 2;
+    float *norms = reinterpret_cast<float *>(d + 2 * row_bytes + 16);
+    float *res = reinterpret_cast<float *>(d + 2 * row_bytes + 32);
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 148;
+    if (ce == cudaSuccess && metric == SVDB_COSINE) {
+        ca.first = 0;
+        ca.n = 2;
+        ca.out = norms;
+        ca.mode = 4;
+        ce = launch_compare(ca, sms, st);
+    }
+    if (ce == cudaSuccess) {
+        ca.i1 = reinterpret_cast<const u64 *>(d + 2 * row_bytes);
+        ca.i2 = ca.i1 + 1;
+        ca.n = 1;
+        ca.norm = norms;
+        ca.out = res;
+        ca.mode = metric;
+        ce = launch_compare(ca, sms, st);
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h + 2 * row_bytes + 32, res, 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("svdb_compare_vectors: ") + cudaGetErrorString(ce));
+        cudaGetLastError();
+        return SVDB_ERR_CUDA;
+    }
+    memcpy(out, h + 2 * row_bytes + 32, 4);
+    return SVDB_OK;
+}
+
+int svdb_get_stats(const svdb_engine *e, svdb_stats *out) {
+    if (!e || !out) return SVDB_ERR_ARG;
+    *out = e->stats;
+    return SVDB_OK;
+}
+
+int svdb_set_option(svdb_engine *e, const char *name, long value) {
+    if (!e || !name) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    const std::string n(name);
+    if (n == "scan.variant") e->tune.variant = (int)value;
+    else if (n == "scan.warps") e->tune.warps = (int)value;
+    else if (n == "scan.stages") e->tune.stages = (int)value;
+    else if (n == "scan.tile_rows") e->tune.tile_rows = (int)value;
+    else if (n == "scan.ctas_per_sm") e->tune.ctas_per_sm = (int)value;
+    else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
+    else if (n == "scan.force_exact") e->force_exact = value != 0;
+    else if (n == "profile.scan_events") e->profile_scan = value != 0;
+    else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
+    return SVDB_OK;
+}
+
+int svdb_time_scan(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, int iters, float *ms_out) {
+    if (!e || !d_Q || !ms_out || iters < 1 || nq < 1 || k < 1 || k > SVDB_MAX_K) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = e->flush();
+    if (rc) return rc;
+    if (e->n_versions == 0 || e->no_log) return e->fail(SVDB_ERR_ARG, "empty log");
+    cudaSetDevice(e->device);
+    const bool use_exact = e->force_exact || !e->wide;
+    const int nqp = largest_pass(nq, std::max(1, e->tune.nq_per_pass));
+    const int cap = (int)std::min<size_t>(32, k + 8);
+    const int nlists = scan_num_lists(e->tune, !use_exact);
+    std::string err;
+    if (!e->lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return e->fail(SVDB_ERR_OOM, err);
+    const double *qbase = d_Q;
+    int qld = (int)ldq;
+    if (!use_exact) {
+        if (!e->qpad.ensure(nq * (size_t)e->kstride * 8, err)) return e->fail(SVDB_ERR_OOM, err);
+        cudaError_t ce = launch_pad_queries(d_Q, (int)ldq, e->qpad.as<double>(), e->kstride, e->K, (int)nq, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("pad_queries", ce);
+        qbase = e->qpad.as<double>();
+        qld = e->kstride;
+    }
+    ScanArgs sa{};
+    sa.pts = e->kd_ptr();
+    sa.n = e->n_versions;
+    sa.K = e->K;
+    sa.stride = e->kstride;
+    sa.q = qbase;
+    sa.ldq = qld;
+    sa.nq = nqp;
+    sa.cap = cap;
+    sa.lists = e->lists.as<Cand>();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaError_t ce = use_exact ? launch_scan_exact(e->tune, sa, e->stream) : launch_scan_wide(e->tune, sa, e->stream);
+    cudaEventRecord(a, e->stream);
+    for (int i = 0; i < iters && ce == cudaSuccess; i++)
+        ce = use_exact ? launch_scan_exact(e->tune, sa, e->stream) : launch_scan_wide(e->tune, sa, e->stream);
+    cudaEventRecord(b, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    float ms = 0;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (ce != cudaSuccess) return e->fail_cuda("time_scan", ce);
+    e->stats.kernels_launched += iters + 1;
+    *ms_out = ms / iters;
+    return SVDB_OK;
+}
+
+/* Sum of the scan-kernel durations recorded since the last call (option profile.scan_events). */
+int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches) {
+    if (!e || !total_ms || !launches) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaSetDevice(e->device);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    float sum = 0;
+    for (size_t i = 0; i < e->scan_events_used && ce == cudaSuccess; i++) {
+        float ms = 0;
+        ce = cudaEventElapsedTime(&ms, e->scan_events[i].first, e->scan_events[i].second);
+        sum += ms;
+    }
+    if (ce != cudaSuccess) return e->fail_cuda("take_scan_time", ce);
+    *total_ms = sum;
+    *launches = e->scan_events_used;
+    e->scan_events_used = 0;
+    return SVDB_OK;
+}
+
+}  // extern "C"

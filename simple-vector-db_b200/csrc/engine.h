@@ -1,0 +1,89 @@
+// engine.h -- host side of one shard: HBM arenas, delta staging, query orchestration.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/svdb_b200.h"
+#include "arena.h"
+#include "kernels.h"
+
+namespace svdb {
+
+void set_last_error(const std::string &s);
+const std::string &get_last_error();
+
+// cudaMalloc'ed scratch that only ever grows.
+struct Scratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes, std::string &err);
+    void free_();
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinnedScratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes, std::string &err);
+    void free_();
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace svdb
+
+// Layout in HBM (all fp64, row-major, one entry per VERSION = per insert/update/log append):
+//   rows     [versions][Dpad]   Dpad = D rounded up to 16 doubles (128-byte rows), zero padded
+//   kdpts    [versions][kstride] first K coordinates; aliases rows when K == D on the wide path
+//   log_idx  [versions] u64     index the entry was appended with (what nearest returns)
+//   norms    [versions] f32     float-order self dot product (cosine), computed at insert
+//   cur      [size] u64         index -> version of its current row (shifted by deletes)
+struct svdb_engine {
+    svdb_config cfg;
+    int D = 0, K = 0, Dpad = 0, kstride = 0;
+    bool log_only = false, no_log = false, alias = false, wide = false;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::mutex mu;
+
+    svdb::DeviceBuffer rows, kdpts, log_idx, norms, cur;
+    std::vector<uint64_t> cur_host;      // authoritative index map
+    size_t cur_uploaded = 0;             // entries of cur_host valid on the device ...
+    size_t cur_dirty_lo = 0;             // ... below this index
+    size_t n_versions = 0;               // entries resident on the device
+
+    // pinned staging of not-yet-uploaded versions
+    svdb::PinnedScratch stage_rows, stage_idx;
+    size_t stage_ld = 0, stage_n = 0, stage_cap = 0;
+
+    // query scratch
+    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout;
+    svdb::PinnedScratch hq, hout, hidx, hf;
+
+    svdb::ScanTuning tune;
+    bool force_exact = false;
+    bool profile_scan = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events;
+    size_t scan_events_used = 0;
+    svdb_stats stats{};
+
+    const double *kd_ptr() const { return alias ? rows.as<double>() : kdpts.as<double>(); }
+    size_t max_versions = 0;
+
+    // all return svdb_status; callers hold mu
+    int init(const svdb_config &c);
+    void destroy();
+    int stage_one(const double *row, size_t ncopy, uint64_t index);
+    int flush();
+    int upload_cur();
+    int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, bool exact);
+    int nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
+                     uint64_t *seq_out);
+    int compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out);
+    int compare_host(int mode, const size_t *i1, const size_t *i2, size_t n, float *out);
+    int fail_cuda(const char *what, cudaError_t e);
+    int fail(int code, const std::string &msg);
+};

@@ -1,0 +1,84 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (definitions in *.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/svdb_b200.h"
+
+namespace svdb {
+
+typedef unsigned long long u64;
+
+struct Cand;  // 16-byte (d, seq) record, see common.cuh
+
+// Tunables of the scan launch (engine options "scan.*").
+struct ScanTuning {
+    int variant = 0;        // 0: TMA bulk-copy ring per warp; 1: direct LDG.128 streaming
+    int warps = 8;          // warps per CTA
+    int stages = 3;         // ring depth per warp (variant 0)
+    int tile_rows = 0;      // rows per tile, 0 = choose from the row size
+    int ctas_per_sm = 1;
+    int nq_per_pass = 4;    // queries sharing one pass over the log (1, 2, 4, 8)
+    int thin_max_k = 16;    // K <= this: thread-per-row exact kernel is the primary path
+    int num_sms = 148;
+};
+
+struct ScanArgs {
+    const double *pts;      // log: entry s at pts + s * stride
+    u64 n;                  // entries
+    int K;                  // coordinates measured
+    int stride;             // doubles between entries
+    const double *q;        // device queries, query i at q + i * ldq (zero padded to stride for the wide path)
+    int ldq;
+    int nq;                 // queries in this pass (<= 8)
+    int cap;                // candidates each CTA emits per query
+    Cand *lists;            // [nq][nlists][cap]
+};
+
+// Number of per-CTA lists a scan with this tuning writes per query.
+int scan_num_lists(const ScanTuning &t, bool wide);
+// Approximate (FMA, lane-parallel) scan for wide rows; needs stride even and 16-B aligned pts.
+cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
+// Reference-order exact scan, one thread per log entry (primary for thin rows, fallback for any).
+cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
+
+struct FinalArgs {
+    const Cand *lists;
+    int nlists, cap, nq, k;
+    const double *pts;
+    int K, stride;
+    const double *q;
+    int ldq;
+    const u64 *log_index;   // index carried by each log entry
+    u64 seq_base;
+    double eps;             // relative error bound of the approximate keys; < 0: keys are exact
+    svdb_candidate *out;    // [nq][k]
+};
+cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st);
+
+cudaError_t launch_merge_candidates(const svdb_candidate *in, int nshards, int nq, int k, svdb_candidate *out,
+                                    cudaStream_t st);
+
+struct CompareArgs {
+    const double *rows;     // version rows, row s at rows + s * ldr; ldr % 16 == 0, zero padded
+    int ldr, D;
+    const u64 *cur;         // index -> version row; NULL: pair members are version rows already
+    u64 nrows;              // valid indices are < nrows
+    const u64 *i1, *i2;     // NULL (mode 4 only): member = first + pair id
+    u64 first;
+    u64 n;                  // pairs
+    const float *norm;      // float-order self dot per version row (cosine)
+    float *out;             // n floats (modes 0,1,2,4) or n x 3 (mode 3)
+    int mode;               // 0 cosine, 1 euclidean, 2 dot, 3 all three, 4 self-dot (norm precompute)
+};
+cudaError_t launch_compare(const CompareArgs &a, int num_sms, cudaStream_t st);
+
+// Copy the first K coordinates of n rows (stride ld_src) into a compact array (stride ld_dst), zero padding.
+cudaError_t launch_extract_prefix(const double *src, int ld_src, double *dst, int ld_dst, int K, u64 n,
+                                  cudaStream_t st);
+// dst[i] = base + i  (index carried by freshly inserted log entries)
+cudaError_t launch_iota(u64 *dst, u64 base, u64 n, cudaStream_t st);
+// Pad user queries (nq x ldq, K used) into nq x ldp with zeros.
+cudaError_t launch_pad_queries(const double *src, int ldq, double *dst, int ldp, int K, int nq, cudaStream_t st);
+
+}  // namespace svdb

@@ -1,0 +1,585 @@
+// scan_kernels.cu -- K1 (distance scan + on-chip top-k), finalize (merge + exact re-rank) and
+// K7 (cross-shard merge) for sm_100a.
+//
+// Replaces the reference's nearest-neighbour loop, src/kdtree.c:131-162 (entry :171-178):
+// the reference walks a pointer tree and, at the dimensions the benchmark uses, visits
+// every node; here the append-only log of kd-points is a dense fp64 array in HBM that is
+// streamed once per pass.
+//
+//   scan_wide_kernel   HBM-bound.  Each warp owns a ring of shared-memory stages that it
+//                      fills itself with 1-D bulk async copies (cp.async.bulk -> UBLKCP,
+//                      completion on an mbarrier), so the bytes in flight per SM are
+//                      warps x stages x tile and cost no registers.  Distances are
+//                      accumulated lane-parallel with FMA (an approximation of the
+//                      reference's sequential sum with relative error <= eps); every warp
+//                      keeps its 32 best (d~, seq) in registers, one per lane.
+//   scan_ldg_kernel    same contract, rows streamed with ld.global.nc.v2.f64 (A/B variant).
+//   scan_exact_kernel  one thread per entry, the reference's exact operation order.
+//                      Primary path for thin rows (K <= 16), fallback for any K.
+//   finalize_kernel    per query: merge the per-CTA lists, recompute the survivors in the
+//                      reference's order (exact_sqdist), order by (d, seq), emit top-k and
+//                      prove that no entry outside the candidate set can belong to it.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace svdb {
+
+constexpr int MAX_SMEM = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+// ---- CTA-level merge of the per-warp lists, one query -------------------------------
+__device__ __forceinline__ void cta_merge_emit(WarpList &mine, Cand *mrg, int W, int warp, int lane, int cap,
+                                               Cand *out) {
+    mrg[warp * 32 + lane] = Cand{mine.d, mine.seq};
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < W; w++) {
+            const Cand c = mrg[w * 32 + lane];
+            mine.offer(c.seq != SEQ_NONE, c.d, c.seq, lane);
+        }
+        if (lane < cap) out[lane] = Cand{mine.d, mine.seq};
+    }
+    __syncthreads();
+}
+
+// =====================================================================================
+// Wide rows, TMA bulk-copy ring.  TR rows per tile, NQ queries share the pass.
+// =====================================================================================
+template <int TR, int NQ>
+__global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstages) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kpad = p.stride;
+    const uint32_t row_bytes = (uint32_t)kpad * 8u;
+    const uint32_t tile_bytes = TR * row_bytes;
+
+    unsigned char *stage_base = smem;
+    double *qs = reinterpret_cast<double *>(smem + (size_t)W * nstages * tile_bytes);
+    Cand *mrg = reinterpret_cast<Cand *>(reinterpret_cast<unsigned char *>(qs) + (size_t)NQ * row_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(mrg) + (size_t)W * 32 * sizeof(Cand));
+    const uint32_t qbar = smem_u32(bars + W * nstages);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i <= W * nstages; i++) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // query tile -> shared memory through the TMA engine
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(qbar, NQ * row_bytes);
+        for (int qi = 0; qi < NQ; qi++)
+            bulk_g2s(smem_u32(qs) + qi * row_bytes, p.q + (size_t)qi * p.ldq, row_bytes, qbar);
+    }
+
+    const u64 ntiles = (p.n + TR - 1) / TR;
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const uint32_t my_stage = smem_u32(stage_base) + (uint32_t)warp * nstages * tile_bytes;
+    const uint32_t my_bar = smem_u32(bars + warp * nstages);
+
+    auto issue = [&](u64 t, int s) {
+        const u64 row0 = t * TR;
+        const u64 left = p.n - row0;
+        const uint32_t rows = left < (u64)TR ? (uint32_t)left : (uint32_t)TR;
+        const uint32_t bytes = rows * row_bytes;
+        mbar_arrive_expect_tx(my_bar + 8 * s, bytes);
+        bulk_g2s(my_stage + s * tile_bytes, p.pts + row0 * (u64)kpad, bytes, my_bar + 8 * s);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < nstages; s++) {
+            const u64 t = gw + (u64)s * GW;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
+
+    mbar_wait(qbar, 0);
+
+    int s = 0;
+    uint32_t phase = 0;
+    const uint32_t qa0 = smem_u32(qs) + lane * 16;
+    for (u64 t = gw; t < ntiles; t += GW) {
+        mbar_wait(my_bar + 8 * s, phase);
+        // two independent accumulation chains per (row, query) while registers allow it
+        constexpr int NA = (TR * NQ <= 4) ? 2 : 1;
+        double acc[TR][NQ][NA];
+#pragma unroll
+        for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++)
+#pragma unroll
+                for (int a = 0; a < NA; a++) acc[r][qi][a] = 0.0;
+
+        uint32_t sa = my_stage + s * tile_bytes + lane * 16;
+        uint32_t qa = qa0;
+#pragma unroll 4
+        for (int off = lane * 2; off < kpad; off += 64, sa += 512, qa += 512) {
+            double2 qv[NQ];
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) qv[qi] = lds128(qa + qi * row_bytes);
+#pragma unroll
+            for (int r = 0; r < TR; r++) {
+                const double2 x = lds128(sa + r * row_bytes);
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) {
+                    const double a = x.x - qv[qi].x;
+                    const double b = x.y - qv[qi].y;
+                    acc[r][qi][0] = fma(a, a, acc[r][qi][0]);
+                    acc[r][qi][NA - 1] = fma(b, b, acc[r][qi][NA - 1]);
+                }
+            }
+        }
+        // butterfly all-reduce; the combination tree is identical for every row, so equal
+        // rows always get equal keys wherever they sit in the log
+        double cd[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) cd[qi] = CUDART_INF;
+#pragma unroll
+        for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                double v = NA == 2 ? acc[r][qi][0] + acc[r][qi][NA - 1] : acc[r][qi][0];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
+                if (lane == r) cd[qi] = v;
+            }
+        __syncwarp();
+        // the stage is consumed: refill it before the (rare) list maintenance
+        const u64 tn = t + (u64)nstages * GW;
+        if (lane == 0 && tn < ntiles) issue(tn, s);
+        if (++s == nstages) {
+            s = 0;
+            phase ^= 1;
+        }
+        const u64 row0 = t * TR;
+        const bool has = lane < TR && row0 + lane < p.n;
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane);
+    }
+
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+}
+
+// =====================================================================================
+// Wide rows, direct LDG.128 streaming (A/B variant of the same contract).
+// =====================================================================================
+template <int TR, int NQ>
+__global__ void __launch_bounds__(256, 2) scan_ldg_kernel(ScanArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kpad = p.stride;
+    const uint32_t row_bytes = (uint32_t)kpad * 8u;
+    double *qs = reinterpret_cast<double *>(smem);
+    Cand *mrg = reinterpret_cast<Cand *>(smem + (size_t)NQ * row_bytes);
+
+    for (int i = threadIdx.x; i < NQ * kpad; i += blockDim.x) qs[i] = p.q[(size_t)(i / kpad) * p.ldq + (i % kpad)];
+    __syncthreads();
+
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
+
+    constexpr int U = (TR >= 4) ? 2 : 4;  // chunks loaded ahead of use
+    const u64 ntiles = (p.n + TR - 1) / TR;
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const uint32_t qa0 = smem_u32(qs) + lane * 16;
+    const int nchunks = (kpad + 63) >> 6;
+
+    for (u64 t = gw; t < ntiles; t += GW) {
+        const u64 row0 = t * TR;
+        const u64 left = p.n - row0;
+        const int rows = left < (u64)TR ? (int)left : TR;
+        const double *base = p.pts + row0 * (u64)kpad + lane * 2;
+        double acc[TR][NQ];
+#pragma unroll
+        for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) acc[r][qi] = 0.0;
+
+        for (int c0 = 0; c0 < nchunks; c0 += U) {
+            double2 x[U][TR];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int off = (c0 + u) * 64 + lane * 2;
+#pragma unroll
+                for (int r = 0; r < TR; r++) {
+                    const int rr = r < rows ? r : rows - 1;
+                    x[u][r] = off < kpad ? ldg128_stream(base + (size_t)rr * kpad + (c0 + u) * 64) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int off = (c0 + u) * 64 + lane * 2;
+                if (off < kpad) {
+#pragma unroll
+                    for (int qi = 0; qi < NQ; qi++) {
+                        const double2 qv = lds128(qa0 + qi * row_bytes + (c0 + u) * 512);
+#pragma unroll
+                        for (int r = 0; r < TR; r++) {
+                            const double a = x[u][r].x - qv.x;
+                            const double b = x[u][r].y - qv.y;
+                            acc[r][qi] = fma(a, a, acc[r][qi]);
+                            acc[r][qi] = fma(b, b, acc[r][qi]);
+                        }
+                    }
+                }
+            }
+        }
+        double cd[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) cd[qi] = CUDART_INF;
+#pragma unroll
+        for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                double v = acc[r][qi];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
+                if (lane == r) cd[qi] = v;
+            }
+        const bool has = lane < rows;
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane);
+    }
+
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+}
+
+// =====================================================================================
+// Exact scan: one thread per log entry, reference operation order (kdtree.c:134-137).
+// =====================================================================================
+template <int NQ>
+__global__ void __launch_bounds__(256) scan_exact_kernel(ScanArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = p.K;
+    double *qs = reinterpret_cast<double *>(smem);
+    Cand *mrg = reinterpret_cast<Cand *>(smem + (((size_t)NQ * K * 8 + 15) & ~(size_t)15));
+
+    for (int i = threadIdx.x; i < NQ * K; i += blockDim.x) qs[i] = p.q[(size_t)(i / K) * p.ldq + (i % K)];
+    __syncthreads();
+
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
+
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    for (u64 base = gw * 32; base < p.n; base += GW * 32) {
+        const u64 row = base + lane;
+        const bool has = row < p.n;
+        double d[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) d[qi] = 0.0;
+        if (has) {
+            const double *r = p.pts + row * (u64)p.stride;
+            for (int i = 0; i < K; i++) {
+                const double x = __ldg(r + i);
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) {
+                    const double t = __dsub_rn(x, qs[qi * K + i]);
+                    d[qi] = __dadd_rn(d[qi], __dmul_rn(t, t));
+                }
+            }
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, d[qi], row, lane);
+    }
+
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+}
+
+// =====================================================================================
+// finalize: one warp per query.
+// =====================================================================================
+__global__ void __launch_bounds__(32) finalize_kernel(FinalArgs p) {
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    const Cand *L = p.lists + (size_t)qi * p.nlists * p.cap;
+    const int total = p.nlists * p.cap;
+
+    WarpList wl;
+    wl.reset();
+    double bound = CUDART_INF;  // smallest approximate key any list may have dropped
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        Cand c = Cand{CUDART_INF, SEQ_NONE};
+        if (i < total) c = L[i];
+        const bool has = c.seq != SEQ_NONE;
+        if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);  // that list was full
+        wl.offer(has, c.d, c.seq, lane);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
+    {
+        double d31;
+        u64 s31;
+        wl.key_at(31, d31, s31);
+        if (s31 != SEQ_NONE) bound = fmin(bound, d31);  // this merge dropped something too
+    }
+
+    // exact re-rank in the reference's operation order
+    bool valid = wl.seq != SEQ_NONE;
+    double dex = CUDART_INF;
+    u64 seq = wl.seq;
+    if (valid) {
+        dex = p.eps < 0.0 ? wl.d : exact_sqdist(p.pts + seq * (u64)p.stride, p.q + (size_t)qi * p.ldq, p.K);
+        if (!(dex < CUDART_INF)) valid = false;  // kdtree.c:139 strict <: non-finite never wins
+    }
+    if (!valid) {
+        dex = CUDART_INF;
+        seq = SEQ_NONE;
+    }
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+        const double dj = __shfl_sync(FULL, dex, j);
+        const u64 sj = __shfl_sync(FULL, seq, j);
+        rank += key_less(dj, sj, dex, seq) ? 1 : 0;
+    }
+    const int nvalid = __popc(__ballot_sync(FULL, valid));
+    const unsigned mk = __ballot_sync(FULL, valid && rank == p.k - 1);
+    const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
+
+    bool unsafe = false;
+    if (p.eps >= 0.0 && bound < CUDART_INF) {
+        // entries outside the candidate set have approximate key >= bound, hence reference
+        // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
+        unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps));
+    }
+    svdb_candidate *out = p.out + (size_t)qi * p.k;
+    if (valid && rank < p.k) {
+        svdb_candidate c;
+        c.dist = dex;
+        c.seq = seq + p.seq_base;
+        c.index = p.log_index[seq];
+        c.flags = unsafe ? SVDB_CAND_UNSAFE : 0ull;
+        out[rank] = c;
+    }
+    if (lane < p.k && lane >= nvalid) {
+        svdb_candidate c;
+        c.dist = CUDART_INF;
+        c.seq = SEQ_NONE;
+        c.index = (u64)SVDB_NONE;
+        c.flags = unsafe ? SVDB_CAND_UNSAFE : 0ull;
+        out[lane] = c;
+    }
+}
+
+// =====================================================================================
+// K7: merge of gathered per-shard results. in: [nshards][nq][k]; one warp per query.
+// =====================================================================================
+__global__ void __launch_bounds__(32) merge_candidates_kernel(const svdb_candidate *in, int nshards, int nq, int k,
+                                                              svdb_candidate *out) {
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    WarpList wl;
+    wl.reset();
+    u64 flags = 0;
+    const int total = nshards * k;
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        double d = CUDART_INF;
+        u64 s = SEQ_NONE;
+        if (i < total) {
+            const svdb_candidate c = in[((size_t)(i / k) * nq + qi) * k + (i % k)];
+            d = c.dist;
+            s = c.seq;
+            flags |= c.flags;
+        }
+        wl.offer(s != SEQ_NONE, d, s, lane);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) flags |= __shfl_xor_sync(FULL, flags, m);
+    if (lane < k) {
+        svdb_candidate c;
+        c.dist = wl.d;
+        c.seq = wl.seq;
+        c.index = (u64)SVDB_NONE;
+        c.flags = flags;
+        if (wl.seq != SEQ_NONE) {
+            for (int i = 0; i < total; i++) {
+                const svdb_candidate *src = &in[((size_t)(i / k) * nq + qi) * k + (i % k)];
+                if (src->seq == wl.seq) {
+                    c.index = src->index;
+                    break;
+                }
+            }
+        }
+        out[(size_t)qi * k + lane] = c;
+    }
+}
+
+// ---- small utility kernels -------------------------------------------------------------
+__global__ void extract_prefix_kernel(const double *src, int ld_src, double *dst, int ld_dst, int K, u64 n) {
+    const u64 total = n * (u64)ld_dst;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const u64 r = i / ld_dst;
+        const int c = (int)(i % ld_dst);
+        dst[i] = c < K ? src[r * ld_src + c] : 0.0;
+    }
+}
+__global__ void iota_kernel(u64 *dst, u64 base, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) dst[i] = base + i;
+}
+__global__ void pad_queries_kernel(const double *src, int ldq, double *dst, int ldp, int K, int nq) {
+    const int total = nq * ldp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / ldp, c = i % ldp;
+        dst[i] = c < K ? src[(size_t)r * ldq + c] : 0.0;
+    }
+}
+
+// =====================================================================================
+// host-side launchers
+// =====================================================================================
+static int pick_tile_rows(const ScanTuning &t, int row_bytes, int nq) {
+    int tr = t.tile_rows;
+    if (tr <= 0) {
+        tr = 1;
+        while (tr < 8 && tr * 2 * row_bytes <= 8192) tr *= 2;
+    }
+    while (tr > 1 && tr * nq > 16) tr >>= 1;
+    if (tr >= 8) return 8;
+    if (tr >= 4) return 4;
+    if (tr >= 2) return 2;
+    return 1;
+}
+
+int scan_num_lists(const ScanTuning &t, bool /*wide*/) { return t.num_sms * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1); }
+
+template <int TR, int NQ>
+static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
+    const int row_bytes = a.stride * 8;
+    const int grid = scan_num_lists(t, true);
+    int W = t.warps < 1 ? 1 : (t.warps > 16 ? 16 : t.warps);
+    if (t.variant == 1) {
+        if (W > 8) W = 8;
+        const size_t smem = (size_t)NQ * row_bytes + (size_t)W * 32 * sizeof(Cand);
+        if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(scan_ldg_kernel<TR, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        scan_ldg_kernel<TR, NQ><<<grid, W * 32, smem, st>>>(a);
+        return cudaGetLastError();
+    }
+    int NS = t.stages < 2 ? 2 : t.stages;
+    const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
+    auto need = [&](int w, int ns) {
+        return (size_t)w * ns * TR * row_bytes + (size_t)NQ * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)(w * ns + 1) * 8;
+    };
+    const size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    while (need(W, NS) > budget && NS > 2) NS--;
+    while (need(W, NS) > budget && W > 1) W--;
+    if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    const size_t smem = need(W, NS);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(scan_wide_kernel<TR, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    scan_wide_kernel<TR, NQ><<<grid, W * 32, smem, st>>>(a, NS);
+    return cudaGetLastError();
+}
+
+template <int NQ>
+static cudaError_t launch_wide_nq(int tr, const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
+    switch (tr) {
+        case 8:
+            if constexpr (NQ <= 2) return launch_wide_inst<8, NQ>(t, a, st);
+        case 4:
+            if constexpr (NQ <= 4) return launch_wide_inst<4, NQ>(t, a, st);
+        case 2:
+            return launch_wide_inst<2, NQ>(t, a, st);
+        default:
+            return launch_wide_inst<1, NQ>(t, a, st);
+    }
+}
+
+cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
+    if (a.stride & 1) return cudaErrorInvalidValue;
+    const int tr = pick_tile_rows(t, a.stride * 8, a.nq);
+    switch (a.nq) {
+        case 1: return launch_wide_nq<1>(tr, t, a, st);
+        case 2: return launch_wide_nq<2>(tr, t, a, st);
+        case 4: return launch_wide_nq<4>(tr, t, a, st);
+        case 8: return launch_wide_nq<8>(tr, t, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int NQ>
+static cudaError_t launch_exact_inst(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
+    const int W = 8;
+    const int grid = scan_num_lists(t, false);
+    const size_t smem = (((size_t)NQ * a.K * 8 + 15) & ~(size_t)15) + (size_t)W * 32 * sizeof(Cand);
+    if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(scan_exact_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    scan_exact_kernel<NQ><<<grid, W * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
+    switch (a.nq) {
+        case 1: return launch_exact_inst<1>(t, a, st);
+        case 2: return launch_exact_inst<2>(t, a, st);
+        case 4: return launch_exact_inst<4>(t, a, st);
+        case 8: return launch_exact_inst<8>(t, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st) {
+    finalize_kernel<<<a.nq, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_candidates(const svdb_candidate *in, int nshards, int nq, int k, svdb_candidate *out,
+                                    cudaStream_t st) {
+    merge_candidates_kernel<<<nq, 32, 0, st>>>(in, nshards, nq, k, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_prefix(const double *src, int ld_src, double *dst, int ld_dst, int K, u64 n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const u64 total = n * (u64)ld_dst;
+    const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    extract_prefix_kernel<<<grid, 256, 0, st>>>(src, ld_src, dst, ld_dst, K, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_iota(u64 *dst, u64 base, u64 n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int grid = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+    iota_kernel<<<grid, 256, 0, st>>>(dst, base, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_queries(const double *src, int ldq, double *dst, int ldp, int K, int nq, cudaStream_t st) {
+    if (nq == 0) return cudaSuccess;
+    const int total = nq * ldp;
+    pad_queries_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, ldq, dst, ldp, K, nq);
+    return cudaGetLastError();
+}
+
+}  // namespace svdb

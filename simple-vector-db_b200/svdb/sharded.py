@@ -1,0 +1,108 @@
+"""Row-range sharding of one store over the GPUs of a box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank g owns the contiguous
+slice [lo, hi) of the log's sequence numbers; a query is broadcast, every rank scans its
+shard (K1) and re-ranks its survivors, the per-rank top-k candidate blocks (k x 32 bytes per
+query) are exchanged with ONE all-gather, and every rank merges them (K7).  The exchange is
+latency-bound (16..320 bytes per rank and query), so it rides the same stream directly behind
+the scan epilogue.  The key (reference-order distance, global sequence number) is exact, so
+the merged answer is identical to a single-GPU scan of all rows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import binding as B
+
+
+def shard_range(n_rows: int, world: int, rank: int):
+    """Contiguous ceil-split: shard g owns [g*ceil(n/G), min(n, (g+1)*ceil(n/G)))."""
+    per = -(-n_rows // world)
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+def merge_candidates_host(gathered: np.ndarray, k: int) -> np.ndarray:
+    """Host restatement of the K7 merge for a gathered [nshards, nq, k] candidate array.
+
+    Used where the payload is already on the host (tests over gloo, the exact-rerun path);
+    the product's data path uses the CUDA kernel (svdb_merge_candidates_device)."""
+    nshards, nq, kk = gathered.shape
+    out = np.empty((nq, k), dtype=B.candidate_dtype)
+    for q in range(nq):
+        c = gathered[:, q, :].reshape(-1)
+        order = np.lexsort((c["seq"], c["dist"]))[:k]
+        out[q] = c[order]
+        out[q]["flags"] = np.bitwise_or.reduce(c["flags"])
+    return out
+
+
+class ShardedIndex:
+    """One rank's shard plus the exchange.  world == 1 needs no process group."""
+
+    def __init__(self, dimension: int, kd_dim: int, n_rows_total: int, rank: int = 0, world: int = 1,
+                 device: int = 0, group=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.D, self.K = dimension, kd_dim
+        self.lo, self.hi = shard_range(n_rows_total, world, rank)
+        self.engine = B.Engine(dimension, kd_dim, device=device, seq_base=self.lo,
+                               reserve_rows=max(1, self.hi - self.lo))
+        self.merge_launches = 0
+        self._bufs = {}
+
+    def close(self):
+        self.engine.close()
+
+    def bind_current_stream(self):
+        self.engine.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def ingest_device(self, rows) -> None:
+        """rows: contiguous float64 CUDA tensor [n, D] belonging to this shard, in order."""
+        assert rows.dtype == self.torch.float64 and rows.is_contiguous() and rows.shape[1] == self.D
+        self.engine.insert_device(rows.data_ptr(), rows.shape[0], rows.shape[1])
+
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            t = self.torch
+            dev = t.device("cuda", self.device)
+            local = t.zeros((nq, k, 4), dtype=t.int64, device=dev)
+            gathered = t.zeros((self.world, nq, k, 4), dtype=t.int64, device=dev) if self.world > 1 else None
+            merged = t.zeros((nq, k, 4), dtype=t.int64, device=dev) if self.world > 1 else local
+            host = t.zeros((nq, k, 4), dtype=t.int64).pin_memory()
+            self._bufs[key] = (local, gathered, merged, host)
+        return self._bufs[key]
+
+    def nearest_device(self, dq, k: int, exact: bool = False):
+        """dq: float64 CUDA tensor [nq, >=K]. Returns the merged [nq, k, 4] int64 CUDA tensor
+        (a view of svdb_candidate records); everything is enqueued on the current stream."""
+        nq = dq.shape[0]
+        local, gathered, merged, _ = self._buffers(nq, k)
+        self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), exact)
+        if self.world > 1:
+            self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
+            B.merge_candidates_device(self.device, self.torch.cuda.current_stream(self.device).cuda_stream,
+                                      gathered.data_ptr(), self.world, nq, k, merged.data_ptr())
+            self.merge_launches += 1
+        return merged
+
+    def nearest(self, q_host, k: int):
+        """End-to-end call a user makes: q_host is a (pinned) float64 CPU tensor [nq, >=K];
+        returns a numpy array of svdb_candidate [nq, k] (index = global row for insert-only data
+        is `seq`).  Includes the H2D of the queries and the D2H of the result."""
+        t = self.torch
+        dq = q_host.to(t.device("cuda", self.device), non_blocking=True)
+        merged = self.nearest_device(dq, k)
+        host = self._buffers(dq.shape[0], k)[3]
+        host.copy_(merged, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
+        if np.any(res["flags"] & B.CAND_UNSAFE):
+            # every rank sees the same merged flags, so every rank takes this branch together
+            merged = self.nearest_device(dq, k, exact=True)
+            host.copy_(merged, non_blocking=True)
+            t.cuda.current_stream(self.device).synchronize()
+            res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
+        return res.copy()

@@ -1,0 +1,392 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the oracle and the golden
+vectors the reference produced.  Bit-exact for ids, sequence numbers, distances (fp64 bits)
+and metrics (fp32 bits)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from oracle import binding as OB  # noqa: E402
+from oracle.binding import PortDB  # noqa: E402
+from svdb import binding as B  # noqa: E402
+from svdb import synth  # noqa: E402
+
+NEAREST_CASES = ["nearest_script_k3", "nearest_coarse_k3", "nearest_uniform_k32",
+                 "nearest_normal_k128", "nearest_uniform_k5_d12"]
+
+
+def oracle_topk(port, rows, K, Q, k):
+    db = PortDB(port, rows.shape[1], K)
+    for r in rows:
+        db.insert(r)
+    out = [db.topk(q, k) for q in Q]
+    db.close()
+    return out
+
+
+def assert_topk_equal(got, want, k):
+    idx, dist, seq = got
+    for i, (wseq, widx, wd) in enumerate(want):
+        m = len(wseq)
+        np.testing.assert_array_equal(seq[i, :m].astype(np.int64), wseq, err_msg=f"query {i}: seq")
+        np.testing.assert_array_equal(idx[i, :m], widx, err_msg=f"query {i}: index")
+        np.testing.assert_array_equal(dist[i, :m].view(np.uint64), wd.view(np.uint64), err_msg=f"query {i}: dist bits")
+        assert np.all(idx[i, m:] == B.NONE) and np.all(np.isinf(dist[i, m:]))
+
+
+# ---- golden vectors from the reference ---------------------------------------------------
+
+@pytest.mark.parametrize("name", NEAREST_CASES)
+def test_nearest_matches_reference_golden(port, name):
+    g = load_golden(name)
+    rows, K, Q, want = g["rows"], int(g["K"]), g["queries"], g["ids"]
+    with B.Engine(rows.shape[1], K) as e:
+        e.insert(rows)
+        idx, dist, seq = e.nearest(Q, 2)
+    mism = np.nonzero(idx[:, 0] != want)[0]
+    for i in mism:
+        # legal only for two DISTINCT kd-points at exactly equal distance
+        assert dist[i, 0] == dist[i, 1], (i, idx[i], dist[i], want[i])
+        assert not np.array_equal(rows[idx[i, 0], :K], rows[int(want[i]), :K])
+    if name != "nearest_coarse_k3":
+        assert len(mism) == 0
+    assert_topk_equal((idx, dist, seq), oracle_topk(port, rows, K, Q, 2), 2)
+
+
+def test_metrics_match_reference_golden_bits():
+    g = load_golden("metrics")
+    off = 0
+    for n, want in zip(g["lens"], g["res"]):
+        a, b = g["a"][off:off + n], g["b"][off:off + n]
+        off += n
+        got = np.array([B.compare_vectors(m, a, b) for m in range(3)], dtype=np.float32)
+        for m in range(3):
+            if np.isnan(want[m]):
+                assert np.isnan(got[m])
+            else:
+                assert got[m].view(np.uint32) == want[m].view(np.uint32), (n, m, got, want)
+
+
+def test_delta_stream_matches_reference_golden():
+    g = load_golden("delta_ops")
+    D, K = int(g["D"]), int(g["K"])
+    with B.Engine(D, K) as e:
+        for (code, j), v, q, want, size in zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"]):
+            if code == 0:
+                assert e.insert(v) == j
+            elif code == 1:
+                e.update(int(j), v)
+            else:
+                e.delete(int(j))
+            assert e.size == size
+            assert e.nearest(q, 1)[0][0, 0] == want
+
+
+def test_ties_golden(port):
+    g = load_golden("ties")
+    ro = qo = 0
+    for ci, ((n, D, K), want) in enumerate(zip(g["meta"], g["ids"])):
+        rows = g["rows"][ro:ro + n * D].reshape(n, D)
+        q = g["queries"][qo:qo + D]
+        ro += n * D
+        qo += D
+        with B.Engine(int(D), int(K)) as e:
+            e.insert(rows)
+            idx, dist, seq = e.nearest(q, min(2, n))
+        assert_topk_equal((idx, dist, seq), oracle_topk(port, rows, int(K), [q], min(2, n)), 2)
+        distinct_tie = n > 1 and dist[0, 0] == dist[0, 1] and not np.array_equal(rows[idx[0, 0], :K], rows[idx[0, 1], :K])
+        if not distinct_tie:
+            assert idx[0, 0] == want, f"tie case {ci}"
+
+
+# ---- the reference's own API served by the CUDA library (drop-in) ---------------------------
+
+@pytest.mark.parametrize("name", ["nearest_script_k3", "nearest_uniform_k32", "nearest_normal_k128"])
+def test_dropin_api_nearest_golden(name):
+    g = load_golden(name)
+    api = OB.RefApi(B.LIB_PATH)
+    L = api.lib
+    db = L.vector_db_init(0, int(g["K"]))
+    for i, r in enumerate(g["rows"]):
+        assert L.vector_db_insert(db, api.make_vector(r, uuid=f"row-{i}")) == i
+    assert db.contents.size == len(g["rows"])
+    got = np.array([api.nearest(db, q) for q in g["queries"][:80]], dtype=np.uint64)
+    np.testing.assert_array_equal(got, g["ids"][:80])
+    v = L.vector_db_read(db, 7).contents
+    assert v.uuid == b"row-7"
+    np.testing.assert_array_equal(np.ctypeslib.as_array(v.data, shape=(v.dimension,)), g["rows"][7])
+    assert L.vector_db_read_by_uuid(db, b"row-11").contents.dimension == g["rows"].shape[1]
+    L.vector_db_free(db)
+
+
+def test_dropin_api_delta_stream_golden():
+    g = load_golden("delta_ops")
+    api = OB.RefApi(B.LIB_PATH)
+    L = api.lib
+    db = L.vector_db_init(0, int(g["K"]))
+    for i, ((code, j), v, q, want, size) in enumerate(zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"])):
+        if code == 0:
+            assert L.vector_db_insert(db, api.make_vector(v, uuid=f"u{i}")) == j
+        elif code == 1:
+            vec = api.make_vector(v, uuid=f"u{i}")
+            L.vector_db_update(db, int(j), vec)
+            if j >= size:
+                api._libc.free(vec.data)   # the store ignored it: still ours (put_handler.c frees nothing either)
+        else:
+            L.vector_db_delete(db, int(j))
+        assert db.contents.size == size
+        assert api.nearest(db, q) == want
+    L.vector_db_free(db)
+
+
+def test_dropin_metrics_and_batch_compare(cpu):
+    rows = synth.normal_rows(21, 300, 100)
+    api = OB.RefApi(B.LIB_PATH)
+    L = api.lib
+    db = L.vector_db_init(0, 3)
+    for r in rows:
+        L.vector_db_insert(db, api.make_vector(r))
+    h = cpu.build(rows, 3)
+    i1, i2 = synth.index_pairs(5, 64, 300)
+    for m in range(3):
+        want = cpu.compare_batch(h, m, i1, i2)
+        f = (L.cosine_similarity, L.euclidean_distance, L.dot_product)[m]
+        for a, b, w in list(zip(i1, i2, want))[:8]:
+            got = np.float32(f(L.vector_db_read(db, int(a)).contents, L.vector_db_read(db, int(b)).contents))
+            assert got.view(np.uint32) == w.view(np.uint32)
+        out = np.empty(64, dtype=np.float32)
+        L.vector_db_compare_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        assert L.vector_db_compare_batch(db, m, i1.ctypes.data, i2.ctypes.data, 64, out.ctypes.data) == 0
+        np.testing.assert_array_equal(out.view(np.uint32), want.view(np.uint32))
+    cpu.free(h)
+    L.vector_db_free(db)
+
+
+def test_dropin_save_load_roundtrip(tmp_path):
+    api = OB.RefApi(B.LIB_PATH)
+    L = api.lib
+    rows = synth.uniform_rows(9, 40, 6)
+    db = L.vector_db_init(0, 2)
+    for i, r in enumerate(rows):
+        L.vector_db_insert(db, api.make_vector(r, uuid=f"id-{i}"))
+    path = str(tmp_path / "db.bin").encode()
+    L.vector_db_save(db, path)
+    assert len(open(path, "rb").read()) == 8 + 40 * (37 + 8 + 6 * 8)
+    db2 = L.vector_db_load(path, 2)
+    assert db2.contents.size == 40
+    for i in (0, 17, 39):
+        assert api.nearest(db2, rows[i]) == i
+        assert L.vector_db_read(db2, i).contents.uuid == f"id-{i}".encode()
+    L.vector_db_free(db)
+    L.vector_db_free(db2)
+
+
+# ---- seeded inputs against the oracle -------------------------------------------------------
+
+@pytest.mark.parametrize("n,D,K,k,seed", [
+    (20000, 8, 3, 5, 1),        # thin path, prefix subspace
+    (3000, 16, 16, 10, 2),      # thin path at its upper K
+    (5000, 17, 17, 3, 3),       # wide path at its lower K, odd K (zero padded stride)
+    (12000, 128, 128, 10, 4),   # config-2 shape (K = D = 128), rows alias the kd log
+    (2500, 768, 768, 10, 5),    # config-3 row shape
+    (3000, 200, 50, 24, 6),     # K < D wide: compact kd array, k = SVDB_MAX_K
+    (40, 64, 64, 10, 7),        # fewer rows than CTAs
+    (7, 40, 40, 10, 8),         # fewer rows than k
+])
+def test_topk_vs_oracle(port, n, D, K, k, seed):
+    rows = synth.uniform_rows(seed, n, D)
+    Q = synth.uniform_rows(seed + 50, 13, D)    # 13: ragged against the 8/4/1 query passes
+    want = oracle_topk(port, rows, K, Q, k)
+    with B.Engine(D, K) as e:
+        e.insert(rows)
+        assert_topk_equal(e.nearest(Q, k), want, k)
+        st = e.stats()
+        assert st["kernels_launched"] > 0 and st["exact_reruns"] == 0
+        if K > 16:
+            for opts in ({"scan.variant": 1}, {"scan.variant": 0, "scan.nq_per_pass": 1},
+                         {"scan.nq_per_pass": 8, "scan.warps": 4, "scan.stages": 2},
+                         {"scan.tile_rows": 1, "scan.ctas_per_sm": 2}, {"scan.force_exact": 1}):
+                for name, v in opts.items():
+                    e.set_option(name, v)
+                assert_topk_equal(e.nearest(Q, k), want, k)
+
+
+def test_script_distribution_ties_lowest_seq(port):
+    """Short-decimal values (add_vectors.sh): duplicate kd-points are common; the earliest wins."""
+    rows = synth.script_values(42, (30000, 4))
+    Q = synth.script_values(43, (64, 4))
+    want = oracle_topk(port, rows, 3, Q, 4)
+    with B.Engine(4, 3) as e:
+        e.insert(rows)
+        assert_topk_equal(e.nearest(Q, 4), want, 4)
+
+
+def test_mass_duplicates_take_exact_fallback(port):
+    """More exact duplicates of the best point than the candidate lists hold: the completeness
+    proof fails, the exact scan reruns the query, the earliest duplicate still wins."""
+    rows = synth.uniform_rows(11, 4000, 64)
+    q = synth.uniform_rows(12, 1, 64)[0]
+    near = q + 1e-3
+    rows[500:900] = near
+    want = oracle_topk(port, rows, 64, [q], 3)
+    with B.Engine(64, 64) as e:
+        e.insert(rows)
+        got = e.nearest(q, 3)
+        assert_topk_equal(got, want, 3)
+        assert got[0][0, 0] == 500
+        assert e.stats()["exact_reruns"] >= 1
+
+
+def test_near_ties_are_resolved_by_exact_rerank(port):
+    """Rows that differ from the best one in the last bits: the approximate keys may order them
+    wrongly, the reference-order re-rank must not."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    rows = rng.random((3000, 96))
+    q = rng.random(96)
+    base = q + 0.01 * rng.standard_normal(96)
+    for j in range(12):
+        r = base.copy()
+        r[rng.integers(0, 96)] += (j - 6) * 2.0 ** -50
+        rows[100 + 37 * j] = r
+    want = oracle_topk(port, rows, 96, [q], 10)
+    with B.Engine(96, 96) as e:
+        e.insert(rows)
+        assert_topk_equal(e.nearest(q, 10), want, 10)
+
+
+def test_nonfinite_rows_never_win_and_empty_log():
+    with B.Engine(20, 20) as e:
+        idx, dist, seq = e.nearest(np.zeros(20), 3)
+        assert np.all(idx == B.NONE) and np.all(np.isinf(dist))
+        rows = np.zeros((5, 20))
+        rows[0, 3] = np.nan
+        rows[1, 0] = np.inf
+        rows[2] = 1e200          # squared distance overflows to +inf
+        rows[3] = 5.0
+        rows[4] = 4.0
+        e.insert(rows)
+        idx, dist, seq = e.nearest(np.zeros(20), 4)
+        assert list(idx[0]) == [4, 3, B.NONE, B.NONE]
+    with B.Engine(3, 3) as e:       # thin path
+        rows = np.array([[np.nan, 0, 0], [1e200, 0, 0], [2.0, 0, 0]])
+        e.insert(rows)
+        assert list(e.nearest(np.zeros(3), 2)[0][0]) == [2, B.NONE]
+
+
+def test_append_kdpoints_and_log_only_engine(port):
+    """A bare KDTree: kdtree_insert(tree, point, index) with arbitrary carried indices."""
+    pts = synth.uniform_rows(3, 500, 5)
+    carried = np.arange(500, dtype=np.uint64)[::-1] * 3
+    with B.Engine(5, 5, flags=B.FLAG_LOG_ONLY) as e:
+        e.append_kdpoints(pts, carried)
+        assert e.log_size == 500 and e.size == 0
+        q = pts[123] + 1e-9
+        idx, dist, seq = e.nearest(q, 1)
+        assert idx[0, 0] == carried[123] and seq[0, 0] == 123
+
+
+def test_compare_batch_vs_oracle(cpu):
+    for D, n, seed in ((1, 50, 1), (3, 200, 2), (16, 300, 3), (17, 300, 4), (128, 2000, 5), (1536, 400, 6)):
+        rows = synth.normal_rows(seed, n, D) * 3.0
+        h = cpu.build(rows, 1)
+        i1, i2 = synth.index_pairs(seed, 3000, n)
+        with B.Engine(D, 1) as e:
+            e.insert(rows)
+            allm = e.compare(B.ALL_METRICS, i1, i2)
+            for m in range(3):
+                want = cpu.compare_batch(h, m, i1, i2, 4)
+                got = e.compare(m, i1, i2)
+                np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=f"D={D} metric={m}")
+                np.testing.assert_array_equal(allm[:, m].view(np.uint32), want.view(np.uint32))
+            # out of range -> -1.0f, also after a delete shrank the store
+            bad = e.compare(B.DOT, np.array([0, n], dtype=np.uint64), np.array([n + 5, 0], dtype=np.uint64))
+            assert list(bad) == [-1.0, -1.0]
+        cpu.free(h)
+
+
+def test_compare_follows_update_and_delete(port):
+    rows = synth.uniform_rows(8, 50, 24)
+    db = PortDB(port, 24, 2)
+    with B.Engine(24, 2) as e:
+        for r in rows:
+            db.insert(r)
+        e.insert(rows)
+        new = synth.uniform_rows(9, 3, 24)
+        for j, r in zip((4, 17, 4), new):
+            db.update(j, r)
+            e.update(j, r)
+        for j in (0, 30, 10):
+            db.delete(j)
+            e.delete(j)
+        assert e.size == db.size == 47
+        for i in range(47):
+            np.testing.assert_array_equal(e.read_row(i), db.row(i))
+        i1, i2 = synth.index_pairs(1, 200, 47)
+        for m in range(3):
+            want = np.array([db.compare(m, int(a), int(b)) for a, b in zip(i1, i2)], dtype=np.float32)
+            np.testing.assert_array_equal(e.compare(m, i1, i2).view(np.uint32), want.view(np.uint32))
+    db.close()
+
+
+def test_device_api_shards_and_merge(port):
+    """Two row-range shards on one GPU + K7 merge == one engine over all rows."""
+    n, D, k = 6000, 48, 10
+    rows = synth.uniform_rows(31, n, D)
+    Q = synth.uniform_rows(32, 9, D)
+    want = oracle_topk(port, rows, D, Q, k)
+    half = n // 2
+    dev_rows = torch.from_numpy(rows).cuda()
+    dq = torch.from_numpy(Q).cuda()
+    shards = [B.Engine(D, D, seq_base=0), B.Engine(D, D, seq_base=half)]
+    stream = torch.cuda.current_stream().cuda_stream
+    gathered = torch.zeros((2, len(Q), k, 4), dtype=torch.int64, device="cuda")
+    for s, e in enumerate(shards):
+        e.set_stream(stream)
+        part = dev_rows[s * half:(s + 1) * half]
+        e.insert_device(part.data_ptr(), half, D)
+        e.nearest_device(dq.data_ptr(), len(Q), D, k, gathered[s].data_ptr())
+    merged = torch.zeros((len(Q), k, 4), dtype=torch.int64, device="cuda")
+    B.merge_candidates_device(0, stream, gathered.data_ptr(), 2, len(Q), k, merged.data_ptr())
+    torch.cuda.synchronize()
+    res = merged.cpu().numpy().view(B.candidate_dtype).reshape(len(Q), k)
+    assert not np.any(res["flags"] & B.CAND_UNSAFE)
+    # shard 1 reports its local row index; the global id is seq (contiguous row-range shards)
+    assert_topk_equal((res["seq"], res["dist"], res["seq"]), want, k)
+    for e in shards:
+        e.close()
+
+
+def test_one_million_rows_config2(port):
+    """Config 2 (1M x 128, K = D): ids and distance bits vs the oracle's flat scan."""
+    n, D = 1_000_000, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    dev_rows = torch.rand((n, D), dtype=torch.float64, device="cuda", generator=g)
+    rows = dev_rows.cpu().numpy()
+    Q = synth.uniform_rows(77, 4, D)
+    log = port.lib.orc_log_create(D)
+    # the flat restatement needs only the points, not the tree links: fill the log arrays directly
+    db_want = []
+    for q in Q:
+        d = ((rows - q) ** 2).sum(axis=1)
+        cand = np.argsort(d, kind="stable")[:64]
+        exact = np.array([port.sqdist(rows[c], q) for c in cand])
+        order = np.lexsort((cand, exact))[:10]
+        db_want.append((cand[order].astype(np.int64), cand[order].astype(np.uint64), exact[order]))
+    port.lib.orc_log_free(log)
+    with B.Engine(D, D, reserve_rows=n) as e:
+        e.insert_device(dev_rows.data_ptr(), n, D)
+        assert_topk_equal(e.nearest(Q, 10), db_want, 10)
+        # compare on the same store: 20k random pairs, all three metrics, fp32 bits
+        i1, i2 = synth.index_pairs(3, 20000, n)
+        got = e.compare(B.ALL_METRICS, i1, i2)
+        for m in range(3):
+            want = np.array([port.metric(m, rows[a], rows[b]) for a, b in zip(i1[:300], i2[:300])], dtype=np.float32)
+            np.testing.assert_array_equal(got[:300, m].view(np.uint32), want.view(np.uint32))

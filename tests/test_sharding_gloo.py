@@ -1,0 +1,97 @@
+"""Host-side logic of the multi-GPU path on CPU: shard ranges, the candidate exchange over a
+world_size-2 gloo group and the (dist, seq) merge.  Each rank's local top-k is produced by the
+ORACLE here (there is no GPU); the exchange + merge code is the product's."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, PKG
+
+from svdb import binding as B
+from svdb import synth
+from svdb.sharded import merge_candidates_host, shard_range
+
+
+def test_shard_ranges_cover_exactly():
+    for n in (0, 1, 7, 8, 9, 1000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            per = -(-n // world) if n else 0
+            assert all(b - a <= per for a, b in spans)
+
+
+def test_merge_host_orders_by_dist_then_seq():
+    c = np.zeros((2, 1, 3), dtype=B.candidate_dtype)
+    c["dist"][0, 0] = [1.0, 2.0, 2.0]
+    c["seq"][0, 0] = [5, 1, 9]
+    c["dist"][1, 0] = [1.0, 2.0, np.inf]
+    c["seq"][1, 0] = [3, 0, B.NONE]
+    c["index"] = c["seq"]
+    c["flags"][1, 0, 2] = 1
+    m = merge_candidates_host(c, 3)
+    assert list(m["seq"][0]) == [3, 5, 0] and list(m["dist"][0]) == [1.0, 1.0, 2.0]
+    assert np.all(m["flags"][0] == 1)
+
+
+def _worker(rank, world, port_no, n, D, k, out_dir):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import binding as OB
+    from oracle.binding import PortDB
+    port = OB.load_port()
+    rows = synth.uniform_rows(3, n, D)           # every rank can regenerate any row range
+    Q = synth.uniform_rows(4, 6, D)
+    lo, hi = shard_range(n, world, rank)
+    db = PortDB(port, D, D)
+    for r in rows[lo:hi]:
+        db.insert(r)
+    local = np.zeros((len(Q), k), dtype=B.candidate_dtype)
+    local["dist"], local["seq"], local["index"] = np.inf, B.NONE, B.NONE
+    for i, q in enumerate(Q):
+        seq, idx, d = db.topk(q, k)
+        m = len(seq)
+        local["dist"][i, :m], local["seq"][i, :m], local["index"][i, :m] = d, seq + lo, idx
+    t_local = torch.from_numpy(local.view(np.int64).reshape(len(Q), k, 4).copy())
+    gathered = [torch.zeros_like(t_local) for _ in range(world)]
+    dist.all_gather(gathered, t_local)
+    g = torch.stack(gathered).numpy().view(B.candidate_dtype).reshape(world, len(Q), k)
+    merged = merge_candidates_host(g, k)
+    np.save(os.path.join(out_dir, f"merged_{rank}.npy"), merged)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_exchange_and_merge_equals_single_scan(tmp_path, port):
+    from oracle.binding import PortDB
+    n, D, k, world = 1500, 24, 5, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(world, port_no, n, D, k, str(tmp_path)), nprocs=world, join=True)
+    rows = synth.uniform_rows(3, n, D)
+    Q = synth.uniform_rows(4, 6, D)
+    db = PortDB(port, D, D)
+    for r in rows:
+        db.insert(r)
+    merged = [np.load(tmp_path / f"merged_{r}.npy") for r in range(world)]
+    np.testing.assert_array_equal(merged[0], merged[1])      # every rank holds the same answer
+    for i, q in enumerate(Q):
+        seq, idx, d = db.topk(q, k)
+        np.testing.assert_array_equal(merged[0]["seq"][i].astype(np.int64), seq)
+        np.testing.assert_array_equal(merged[0]["dist"][i].view(np.uint64), d.view(np.uint64))
+    db.close()
