@@ -214,6 +214,8 @@ def ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # one explicit stream carries everything: our kernels, the NCCL exchange, the timing events
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     D, K, N = args.dim, args.kd_dim, args.rows
     idx = ShardedIndex(D, K, N, rank, world, local)

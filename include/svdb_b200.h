@@ -86,7 +86,9 @@ int svdb_device_count(void);
 
 int  svdb_engine_create(const svdb_config *cfg, svdb_engine **out);
 void svdb_engine_destroy(svdb_engine *e);
-/* Launch on this CUDA stream (cudaStream_t as void*; NULL = engine's own stream). */
+/* Launch on this CUDA stream (a cudaStream_t; NULL is CUDA's legacy default stream).
+ * SVDB_STREAM_OWN switches back to the engine's own non-blocking stream (the default). */
+#define SVDB_STREAM_OWN ((void *)(intptr_t)-1)
 int  svdb_set_stream(svdb_engine *e, void *stream);
 
 /* ---- store deltas; rows are host buffers of n x ld doubles (ld >= dimension) ---- */

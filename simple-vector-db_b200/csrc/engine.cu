@@ -457,7 +457,7 @@ void svdb_engine_destroy(svdb_engine *e) {
 int svdb_set_stream(svdb_engine *e, void *stream) {
     if (!e) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    e->stream = stream ? (cudaStream_t)stream : e->own_stream;
+    e->stream = stream == SVDB_STREAM_OWN ? e->own_stream : (cudaStream_t)stream;
     return SVDB_OK;
 }
 

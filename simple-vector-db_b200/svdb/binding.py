@@ -227,7 +227,9 @@ class Engine:
 
     # -- plumbing -----------------------------------------------------------
     def set_stream(self, stream_handle: int | None) -> None:
-        _check(self.L.svdb_set_stream(self.h, C.c_void_p(stream_handle or 0)), "svdb_set_stream")
+        """A cudaStream_t handle (0 = CUDA's legacy default stream); None = the engine's own stream."""
+        h = C.c_void_p(-1) if stream_handle is None else C.c_void_p(stream_handle)
+        _check(self.L.svdb_set_stream(self.h, h), "svdb_set_stream")
 
     def set_option(self, name: str, value: int) -> None:
         _check(self.L.svdb_set_option(self.h, name.encode(), int(value)), "svdb_set_option")

@@ -75,19 +75,33 @@ def test_metrics_match_reference_golden_bits():
                 assert got[m].view(np.uint32) == want[m].view(np.uint32), (n, m, got, want)
 
 
-def test_delta_stream_matches_reference_golden():
+def _assert_same_or_distinct_tie(got_idx, dist2, want, what):
+    """The flat (d, seq) order and the reference agree unless two DISTINCT kd-points sit at
+    exactly the same distance; then the two best distances must be equal."""
+    if got_idx != want:
+        assert len(dist2) >= 2 and dist2[0] == dist2[1], (what, got_idx, want, dist2)
+
+
+def test_delta_stream_matches_reference_golden(port):
     g = load_golden("delta_ops")
     D, K = int(g["D"]), int(g["K"])
+    model = PortDB(port, D, K)      # replays the same stream; its flat top-k is the (d, seq) order
     with B.Engine(D, K) as e:
-        for (code, j), v, q, want, size in zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"]):
+        for i, ((code, j), v, q, want, size) in enumerate(zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"])):
             if code == 0:
-                assert e.insert(v) == j
+                assert e.insert(v) == j == model.insert(v)
             elif code == 1:
                 e.update(int(j), v)
+                model.update(int(j), v)
             else:
                 e.delete(int(j))
+                model.delete(int(j))
             assert e.size == size
-            assert e.nearest(q, 1)[0][0, 0] == want
+            k = min(2, e.log_size)
+            idx, dist, seq = e.nearest(q, k)
+            assert_topk_equal((idx, dist, seq), [model.topk(q, k)], k)
+            _assert_same_or_distinct_tie(idx[0, 0], dist[0], want, f"op {i}")
+    model.close()
 
 
 def test_ties_golden(port):
@@ -127,11 +141,13 @@ def test_dropin_api_nearest_golden(name):
     L.vector_db_free(db)
 
 
-def test_dropin_api_delta_stream_golden():
+def test_dropin_api_delta_stream_golden(port):
     g = load_golden("delta_ops")
     api = OB.RefApi(B.LIB_PATH)
     L = api.lib
+    L.kdtree_nearest_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
     db = L.vector_db_init(0, int(g["K"]))
+    n_ties = 0
     for i, ((code, j), v, q, want, size) in enumerate(zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"])):
         if code == 0:
             assert L.vector_db_insert(db, api.make_vector(v, uuid=f"u{i}")) == j
@@ -139,11 +155,18 @@ def test_dropin_api_delta_stream_golden():
             vec = api.make_vector(v, uuid=f"u{i}")
             L.vector_db_update(db, int(j), vec)
             if j >= size:
-                api._libc.free(vec.data)   # the store ignored it: still ours (put_handler.c frees nothing either)
+                api._libc.free(vec.data)   # the store ignored it: still ours
         else:
             L.vector_db_delete(db, int(j))
         assert db.contents.size == size
-        assert api.nearest(db, q) == want
+        got = api.nearest(db, q)
+        if got != want:
+            idx2 = np.empty(2, dtype=np.uint64)
+            d2 = np.empty(2)
+            assert L.kdtree_nearest_batch(db.contents.kdtree, q.ctypes.data, 1, len(q), 2, idx2.ctypes.data, d2.ctypes.data) == 0
+            _assert_same_or_distinct_tie(got, d2, want, f"op {i}")
+            n_ties += 1
+    assert n_ties < len(g["ops"]) // 4
     L.vector_db_free(db)
 
 
