@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Measurements for the BASELINE.json configs that are not the bench.py headline (1 GPU).
+
+    python scripts/bench_extra.py c1 c2 c4 c5 [--out gpurun_out/extra.jsonl]
+
+Every number is device-timed with CUDA events on the stream the kernels run on, after
+warm-up; GB/s figures divide ALGORITHMIC bytes by that time.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "simple-vector-db_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from svdb import binding as B  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+PEAK = 6542.7
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def fill(e: B.Engine, n: int, D: int, seed: int, chunk: int = 250_000):
+    done = 0
+    c = 0
+    while done < n:
+        m = min(chunk, n - done)
+        g = torch.Generator(device=DEV).manual_seed(seed * 1_000_003 + c)
+        t = torch.rand((m, D), dtype=torch.float64, device=DEV, generator=g)
+        e.insert_device(t.data_ptr(), m, D)
+        torch.cuda.synchronize()
+        del t
+        done += m
+        c += 1
+    torch.cuda.empty_cache()
+
+
+def timed(fn, iters: int, warm: int = 3) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def nearest_case(name, n, D, K, k, nqs, iters=20, extra_opts=()):
+    out = []
+    with B.Engine(D, K, reserve_rows=n) as e:
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        fill(e, n, D, seed=hash(name) % 1000)
+        for o, v in extra_opts:
+            e.set_option(o, v)
+        for nq in nqs:
+            q = torch.rand((nq, D), dtype=torch.float64, device=DEV)
+            res = torch.zeros((nq, k, 4), dtype=torch.int64, device=DEV)
+            e.set_option("scan.nq_per_pass", min(8, nq))
+            ms = timed(lambda: e.nearest_device(q.data_ptr(), nq, D, k, res.data_ptr()), iters)
+            passes = -(-nq // min(8, nq))
+            scan_ms = e.time_scan(q.data_ptr(), nq, D, k, 10)
+            algo = n * K * 8
+            qh = q.cpu().numpy()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                e.nearest(qh, k)
+            e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
+            out.append({"config": name, "rows": n, "dim": D, "kd_dim": K, "k": k, "queries_per_call": nq,
+                        "ms_per_call": ms, "queries_per_s": nq / ms * 1e3, "e2e_queries_per_s": nq / e2e_ms * 1e3,
+                        "scan_ms_per_pass": scan_ms, "scan_passes": passes,
+                        "scan_GBps_algorithmic": algo / scan_ms / 1e6, "frac_of_measured_peak": algo / scan_ms / 1e6 / PEAK})
+            print(json.dumps(out[-1]), flush=True)
+    return out
+
+
+def compare_case(name, n, D, npairs, iters=5):
+    out = []
+    with B.Engine(D, 1, reserve_rows=n, flags=B.FLAG_NO_LOG) as e:
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        fill(e, n, D, seed=7)
+        e.flush()
+        g = torch.Generator(device=DEV).manual_seed(3)
+        i1 = torch.randint(0, n, (npairs,), dtype=torch.int64, device=DEV, generator=g)
+        i2 = torch.randint(0, n, (npairs,), dtype=torch.int64, device=DEV, generator=g)
+        res = torch.zeros((npairs, 3), dtype=torch.float32, device=DEV)
+        for metric, label in ((0, "cosine"), (1, "euclidean"), (2, "dot"), (3, "all3")):
+            ms = timed(lambda: e.compare_device(metric, i1.data_ptr(), i2.data_ptr(), npairs, res.data_ptr()), iters)
+            algo = npairs * 2 * D * 8
+            out.append({"config": name, "rows": n, "dim": D, "pairs": npairs, "metric": label, "ms": ms,
+                        "pairs_per_s": npairs / ms * 1e3, "GBps_algorithmic": algo / ms / 1e6,
+                        "frac_of_measured_peak": algo / ms / 1e6 / PEAK})
+            print(json.dumps(out[-1]), flush=True)
+        # single pair latency through the host call
+        a = np.random.rand(D)
+        b = np.random.rand(D)
+        B.compare_vectors(0, a, b)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            B.compare_vectors(0, a, b)
+        out.append({"config": name, "single_pair_host_call_us": (time.perf_counter() - t0) / 20 * 1e6, "dim": D})
+        print(json.dumps(out[-1]), flush=True)
+    return out
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c2", "c4"]
+    torch.cuda.set_device(0)
+    torch.cuda.set_stream(torch.cuda.Stream(device=DEV))
+    res = []
+    if "c1" in which:   # the reference's own CPU-runnable case: kd_dim 3 prefix of 128-dim rows
+        res += nearest_case("c1_10k_x128_k3", 10_000, 128, 3, 1, (1, 1024), iters=50)
+        res += nearest_case("c1b_100k_x128_k3", 100_000, 128, 3, 1, (1, 1024), iters=50)
+    if "c2" in which:
+        res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50)
+        res += compare_case("c2_compare_1M_x128", 1_000_000, 128, 100_000)
+    if "c4" in which:
+        res += compare_case("c4_compare_1M_x1536", 1_000_000, 1536, 1_000_000)
+    if "c5" in which:
+        res += nearest_case("c5_100M_x128_k128", 100_000_000, 128, 128, 1, (1, 8), iters=5)
+    if "c5k3" in which:
+        res += nearest_case("c5_100M_x128_k3", 100_000_000, 128, 3, 1, (1, 1024), iters=5)
+    out = "gpurun_out/extra.jsonl"
+    for a in sys.argv[1:]:
+        if a.startswith("--out="):
+            out = a.split("=", 1)[1]
+    os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
+    with open(out, "a") as f:
+        for r in res:
+            f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

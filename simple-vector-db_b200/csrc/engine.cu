@@ -255,7 +255,10 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
 
     const double *qbase = d_Q;
     int qld = (int)ldq;
-    if (!use_exact) {
+    // the wide scan stages whole query rows of kstride doubles with 16-byte bulk copies:
+    // use the caller's buffer in place when it already has that shape, else pad a copy
+    const bool q_in_place = K == kstride && (ldq % 2) == 0 && (reinterpret_cast<uintptr_t>(d_Q) % 16) == 0;
+    if (!use_exact && !q_in_place) {
         if (!qpad.ensure(nq * (size_t)kstride * 8, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_pad_queries(d_Q, (int)ldq, qpad.as<double>(), kstride, K, (int)nq, stream));
         stats.kernels_launched++;

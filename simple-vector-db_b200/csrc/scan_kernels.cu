@@ -303,41 +303,118 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(ScanArgs p) {
 }
 
 // =====================================================================================
-// finalize: one warp per query.
+// finalize: one CTA of 8 warps per query.
+//   1. every warp merges a slice of the per-CTA lists into its register list, the slices are
+//      merged through shared memory -> the 32 best approximate keys, plus `bound`, the
+//      smallest approximate key any list may have dropped;
+//   2. only candidates whose approximate key is within the error margin of the k-th can
+//      belong to the exact top-k; those (normally exactly k) are recomputed in the
+//      reference's operation order: the warps fetch each candidate row coalesced and form
+//      the rounded squares t_i = (x_i - q_i)^2 in shared memory, then one lane per
+//      candidate adds them strictly in index order (the serial chain the reference has);
+//   3. rank by (exact distance, seq), emit top-k, prove completeness against `bound`.
 // =====================================================================================
-__global__ void __launch_bounds__(32) finalize_kernel(FinalArgs p) {
-    const int qi = blockIdx.x, lane = threadIdx.x;
+constexpr int FIN_WARPS = 8;
+constexpr int FIN_CH = 256;                       // coordinates re-ranked per round
+constexpr int FIN_LD = FIN_CH + 1;                // odd stride: conflict-free column walks
+constexpr size_t FIN_SMEM = (size_t)32 * FIN_LD * 8 + FIN_WARPS * 32 * sizeof(Cand) + 64 * 8;
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    double *tbuf = reinterpret_cast<double *>(fsm);                                  // [32][FIN_LD]
+    Cand *mrg = reinterpret_cast<Cand *>(fsm + (size_t)32 * FIN_LD * 8);             // [FIN_WARPS][32]
+    double *wbound = reinterpret_cast<double *>(mrg + FIN_WARPS * 32);               // [FIN_WARPS]
+    u64 *cseq = reinterpret_cast<u64 *>(wbound + FIN_WARPS);                         // [32]
+    const int qi = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Cand *L = p.lists + (size_t)qi * p.nlists * p.cap;
     const int total = p.nlists * p.cap;
 
+    // ---- 1. merge ----
     WarpList wl;
     wl.reset();
-    double bound = CUDART_INF;  // smallest approximate key any list may have dropped
-    for (int base = 0; base < total; base += 32) {
-        const int i = base + lane;
-        Cand c = Cand{CUDART_INF, SEQ_NONE};
-        if (i < total) c = L[i];
-        const bool has = c.seq != SEQ_NONE;
-        if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);  // that list was full
-        wl.offer(has, c.d, c.seq, lane);
+    double bound = CUDART_INF;
+    {
+        const int per = ((total + FIN_WARPS - 1) / FIN_WARPS + 31) & ~31;
+        const int lo = warp * per, hi = min(total, lo + per);
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            Cand c = Cand{CUDART_INF, SEQ_NONE};
+            if (i < hi) c = L[i];
+            const bool has = c.seq != SEQ_NONE;
+            if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);   // that list was full
+            wl.offer(has, c.d, c.seq, lane);
+        }
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-    {
+    mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
+    if (lane == 0) wbound[warp] = bound;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < FIN_WARPS; w++) {
+            const Cand c = mrg[w * 32 + lane];
+            // a slice list that is full may itself have dropped keys >= its last one
+            if (lane == 31 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
+            wl.offer(c.seq != SEQ_NONE, c.d, c.seq, lane);
+            bound = fmin(bound, wbound[w]);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
         double d31;
         u64 s31;
         wl.key_at(31, d31, s31);
-        if (s31 != SEQ_NONE) bound = fmin(bound, d31);  // this merge dropped something too
+        if (s31 != SEQ_NONE) bound = fmin(bound, d31);   // the final list is full too
     }
 
-    // exact re-rank in the reference's operation order
-    bool valid = wl.seq != SEQ_NONE;
-    double dex = CUDART_INF;
-    u64 seq = wl.seq;
-    if (valid) {
-        dex = p.eps < 0.0 ? wl.d : exact_sqdist(p.pts + seq * (u64)p.stride, p.q + (size_t)qi * p.ldq, p.K);
-        if (!(dex < CUDART_INF)) valid = false;  // kdtree.c:139 strict <: non-finite never wins
+    // ---- 2. which candidates can still belong to the exact top-k ----
+    int nneed = 0;
+    if (warp == 0) {
+        const bool valid = wl.seq != SEQ_NONE;
+        bool need = valid;
+        if (p.eps >= 0.0) {
+            double dk;
+            u64 sk;
+            wl.key_at(p.k - 1, dk, sk);
+            if (sk != SEQ_NONE) need = valid && wl.d <= dk * (1.0 + 3.0 * p.eps);
+        }
+        nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
+        cseq[lane] = wl.seq;
+        if (lane == 0) cseq[32] = (u64)nneed;
     }
+    __syncthreads();
+    nneed = (int)cseq[32];
+
+    double dex = CUDART_INF;
+    if (p.eps < 0.0) {
+        dex = wl.d;                                     // keys are reference-order already
+    } else {
+        dex = 0.0;
+        const double *qv = p.q + (size_t)qi * p.ldq;
+        for (int c0 = 0; c0 < p.K; c0 += FIN_CH) {
+            const int len = min(FIN_CH, p.K - c0);
+            for (int j = warp; j < nneed; j += FIN_WARPS) {
+                const double *row = p.pts + cseq[j] * (u64)p.stride + c0;
+                double *t = tbuf + j * FIN_LD;
+                for (int i = lane; i < len; i += 32) {
+                    const double df = __dsub_rn(__ldg(row + i), __ldg(qv + c0 + i));
+                    t[i] = __dmul_rn(df, df);
+                }
+            }
+            __syncthreads();
+            if (warp == 0 && lane < nneed) {
+                const double *t = tbuf + lane * FIN_LD;
+#pragma unroll 8
+                for (int i = 0; i < len; i++) dex = __dadd_rn(dex, t[i]);   // kdtree.c:136, in index order
+            }
+            __syncthreads();
+        }
+    }
+    if (warp != 0) return;
+
+    // ---- 3. rank and emit ----
+    bool valid = lane < nneed && wl.seq != SEQ_NONE;
+    u64 seq = wl.seq;
+    if (valid && !(dex < CUDART_INF)) valid = false;    // kdtree.c:139 strict <: non-finite never wins
     if (!valid) {
         dex = CUDART_INF;
         seq = SEQ_NONE;
@@ -550,7 +627,9 @@ cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream
 }
 
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st) {
-    finalize_kernel<<<a.nq, 32, 0, st>>>(a);
+    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM);
+    if (e != cudaSuccess) return e;
+    finalize_kernel<<<a.nq, FIN_WARPS * 32, FIN_SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
