@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, run under torchrun with one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 scripts/check_sharded.py
+
+Every rank owns a row-range shard; the merged answer of the sharded index (scan + NCCL
+all-gather + K7 merge) must be identical -- sequence numbers and distance bits -- to a
+single-engine scan of all rows (done on rank 0's GPU) for top-1 and top-10, host and device
+entry points.  Prints one JSON line from rank 0.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "simple-vector-db_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from svdb import binding as B  # noqa: E402
+from svdb.sharded import ShardedIndex  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    ok = True
+    report = []
+    for (n, D, K) in ((400_003, 128, 128), (50_000, 768, 768), (300_000, 16, 3)):
+        g = torch.Generator().manual_seed(n)
+        rows = torch.rand((n, D), dtype=torch.float64, generator=g)       # same on every rank
+        Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()
+        idx = ShardedIndex(D, K, n, rank, world, local)
+        idx.bind_current_stream()
+        idx.ingest_device(rows[idx.lo:idx.hi].to(dev).contiguous())
+        for k in (1, 10):
+            got = idx.nearest(Q, k)
+            if rank == 0:
+                with B.Engine(D, K, device=local) as e:
+                    e.insert_device(rows.to(dev).data_ptr(), n, D)
+                    _, wdist, wseq = e.nearest(Q.numpy(), k)
+                same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
+                ok &= bool(same)
+                report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "identical_to_single_gpu": bool(same)})
+        idx.close()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({"check": "sharded_vs_single", "world": world, "ok": ok, "cases": report}), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
