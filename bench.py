@@ -374,7 +374,11 @@ def ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "scan_wide_kernel<TR,1> (variant %d)" % e_variant(args),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "frac": achieved / peak,
+                     # ncu dram__bytes_read+write of one launch; the capture streams traffic["rows"] rows,
+                     # this launch streams rows_per_rank (pure streaming: bytes scale with rows)
+                     "traffic": traffic["dram_bytes_per_launch"] * rows_per_rank / traffic["rows"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms_avg,
                      "launches_timed": int(scan_launches), "peak_source": peak_src,
                      "scan_share_of_step": scan_ms_avg / (dev_ms / args.steps)},
