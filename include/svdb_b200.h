@@ -69,6 +69,8 @@ typedef struct svdb_config {
 
 #define SVDB_FLAG_LOG_ONLY   1u  /* rows ARE kd-points (dimension == kd_dim), no index map: a bare KDTree */
 #define SVDB_FLAG_NO_LOG     2u  /* rows only (compare / read); nearest is not available */
+#define SVDB_FLAG_SHARD      4u  /* this engine holds a slice of a larger log: no reference-shaped tree
+                                    (exact distance ties resolve to the lowest sequence number) */
 
 /* One result of a nearest query; also the unit exchanged between shards. 32 bytes. */
 typedef struct svdb_candidate {
@@ -115,10 +117,16 @@ int svdb_read_row(svdb_engine *e, size_t index, double *out /* dimension doubles
 int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k,
                        size_t *index_out, double *dist_out, uint64_t *seq_out);
 /* Device buffers, asynchronous on the engine's stream: d_out receives nq x k candidates.
- * The caller must look at flags (SVDB_CAND_UNSAFE) once the results are on the host and
- * call svdb_nearest_batch_device again with exact != 0 for those queries. */
+ * mode: SVDB_MODE_AUTO   tree traversal for thin kd-points and k = 1, else scan + exact re-rank;
+ *       SVDB_MODE_EXACT  reference-order scan of every entry (no approximation to prove complete);
+ *       SVDB_MODE_TREE   the reference's own traversal on the GPU tree (k = 1 only).
+ * The caller must look at flags (SVDB_CAND_UNSAFE) once the results are on the host and escalate
+ * AUTO -> EXACT -> TREE for those queries (svdb_nearest_batch does exactly that). */
+#define SVDB_MODE_AUTO  0
+#define SVDB_MODE_EXACT 1
+#define SVDB_MODE_TREE  2
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k,
-                              svdb_candidate *d_out, int exact);
+                              svdb_candidate *d_out, int mode);
 /* Cross-shard merge: d_in holds nshards blocks of nq x k candidates (an allgather result);
  * d_out receives nq x k, the k smallest of each query under (dist, seq). */
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards,
@@ -141,6 +149,8 @@ int svdb_compare_vectors(int device, int metric, const double *a, const double *
 typedef struct svdb_stats {
     uint64_t kernels_launched;   /* our kernels launched by this engine so far */
     uint64_t exact_reruns;       /* queries that needed the exact fallback scan */
+    uint64_t tree_reruns;        /* queries that needed the tree traversal as the last resort */
+    uint64_t tree_rounds;        /* level-synchronous insertion rounds run so far (K5) */
     uint64_t hbm_bytes_mapped;   /* physical HBM currently mapped by the arenas */
     uint64_t h2d_bytes, d2h_bytes;
 } svdb_stats;

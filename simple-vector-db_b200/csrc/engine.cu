@@ -116,7 +116,8 @@ int svdb_engine::init(const svdb_config &c) {
 
     const size_t va = (size_t)256 << 30;
     const size_t main_row_bytes = (size_t)(log_only ? kstride : Dpad) * 8;
-    max_versions = va / main_row_bytes;
+    max_versions = std::min<size_t>(va / main_row_bytes, 0xfffffffeull);   // tree links are u32
+    use_tree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !getenv("SVDB_NO_TREE");
     std::string err;
     if (!log_only) {
         if (!rows.init(device, max_versions * (size_t)Dpad * 8, err)) return fail(SVDB_ERR_CUDA, err);
@@ -125,6 +126,10 @@ int svdb_engine::init(const svdb_config &c) {
     }
     if (!alias && !no_log && !kdpts.init(device, max_versions * (size_t)kstride * 8, err)) return fail(SVDB_ERR_CUDA, err);
     if (!no_log && !log_idx.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+    if (use_tree) {
+        if (!child.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+        if (!tree_flag.ensure(16, err) || !tree_hflag.ensure(16, err)) return fail(SVDB_ERR_OOM, err);
+    }
 
     CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
@@ -141,6 +146,7 @@ int svdb_engine::init(const svdb_config &c) {
                             cur.ensure(n * 8, stream, err);
         if (!alias && !no_log) ok = ok && kdpts.ensure(n * (size_t)kstride * 8, stream, err);
         if (!no_log) ok = ok && log_idx.ensure(n * 8, stream, err);
+        if (use_tree) ok = ok && child.ensure(n * 8, stream, err);
         if (!ok) return fail(SVDB_ERR_OOM, err);
         cur_host.reserve(n);
     }
@@ -160,8 +166,9 @@ void svdb_engine::destroy() {
     log_idx.release();
     norms.release();
     cur.release();
-    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout}) s->free_();
-    for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf}) s->free_();
+    child.release();
+    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag}) s->free_();
+    for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
     if (own_stream) cudaStreamDestroy(own_stream);
     own_stream = stream = nullptr;
 }
@@ -177,6 +184,20 @@ int svdb_engine::stage_one(const double *row, size_t ncopy, uint64_t index) {
     if (ncopy < stage_ld) memset(dst + ncopy, 0, (stage_ld - ncopy) * sizeof(double));
     stage_idx.as<uint64_t>()[stage_n] = index;
     stage_n++;
+    return SVDB_OK;
+}
+
+// K5: link log entries [n0, n0+m) into the reference-shaped tree. Their kd-points must be resident.
+int svdb_engine::tree_append(size_t n0, size_t m) {
+    if (!use_tree || m == 0) return SVDB_OK;
+    std::string err;
+    if (!child.ensure((n0 + m) * 8, stream, err) || !tree_pn.ensure(m * 4, err) || !tree_pds.ensure(m * 4, err))
+        return fail(SVDB_ERR_OOM, err);
+    int rounds = 0;
+    CK(launch_tree_insert(kd_ptr(), kstride, K, child.as<uint32_t>(), n0, m, tree_pn.as<uint32_t>(), tree_pds.as<uint32_t>(),
+                          tree_flag.as<unsigned>(), tree_hflag.as<unsigned>(), tune.num_sms, stream, &rounds));
+    stats.tree_rounds += rounds;
+    stats.kernels_launched += rounds + 1;
     return SVDB_OK;
 }
 
@@ -211,10 +232,14 @@ int svdb_engine::flush() {
         CK(launch_compare(ca, tune.num_sms, stream));
         stats.kernels_launched++;
     }
+    {
+        int rc = tree_append(n0, m);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
     n_versions = n1;
     stage_n = 0;
-    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped();
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped();
     return SVDB_OK;
 }
 
@@ -240,7 +265,7 @@ static int largest_pass(size_t remaining, int limit) {
     return p;
 }
 
-int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, bool exact) {
+int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode) {
     if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
     if (no_log) return fail(SVDB_ERR_ARG, "this engine was created without a log (SVDB_FLAG_NO_LOG)");
     if (nq == 0) return SVDB_OK;
@@ -248,7 +273,16 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     int rc = flush();
     if (rc) return rc;
     CK(cudaSetDevice(device));
-    const bool use_exact = exact || force_exact || !wide;
+    if (mode == SVDB_MODE_TREE && (!use_tree || k != 1))
+        return fail(SVDB_ERR_ARG, "tree traversal needs k == 1 and an engine that keeps the tree");
+    // K6: thin kd-points prune well, and the traversal IS the reference's algorithm
+    if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && k == 1 && !force_exact && K <= tree_max_k)) {
+        CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq,
+                               log_idx.as<u64>(), cfg.seq_base, d_out, stream));
+        stats.kernels_launched++;
+        return SVDB_OK;
+    }
+    const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
     const int cap = (int)std::min<size_t>(32, k + 8);
     const int nlists = n_versions ? scan_num_lists(tune, !use_exact) : 0;
     std::string err;
@@ -313,6 +347,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         fa.log_index = log_idx.as<u64>();
         fa.seq_base = cfg.seq_base;
         fa.eps = use_exact ? -1.0 : 4.0 * (double)(K + 2) * ldexp(1.0, -53);
+        fa.child = use_tree ? child.as<uint32_t>() : nullptr;
         fa.out = d_out + done * k;
         CK(launch_finalize(fa, stream));
         stats.kernels_launched++;
@@ -329,26 +364,46 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     CK(cudaSetDevice(device));
     std::string err;
     if (!hq.ensure(nq * (size_t)K * 8, err) || !qraw.ensure(nq * (size_t)K * 8, err) ||
-        !outc.ensure(nq * k * sizeof(svdb_candidate), err) || !hout.ensure(nq * k * sizeof(svdb_candidate), err))
+        !outc.ensure((nq * k + 1) * sizeof(svdb_candidate), err) || !hout.ensure(nq * k * sizeof(svdb_candidate), err))
         return fail(SVDB_ERR_OOM, err);
     for (size_t i = 0; i < nq; i++) memcpy(hq.as<double>() + i * K, Q + i * ldq, (size_t)K * 8);
     CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
     stats.h2d_bytes += nq * (size_t)K * 8;
-    int rc = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), false);
+    int rc = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), SVDB_MODE_AUTO);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hout.p, outc.p, nq * k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
     svdb_candidate *res = hout.as<svdb_candidate>();
+    // Escalation for queries whose answer could not be proven complete:
+    //   AUTO -> EXACT (mass near-ties defeated the approximate candidate set, or the traversal
+    //   stack overflowed) -> TREE (more exactly-tied entries than a candidate list holds; k = 1).
     for (size_t i = 0; i < nq; i++) {
-        if (!(res[i * k].flags & SVDB_CAND_UNSAFE)) continue;
-        // the candidate set could not be proven complete (mass near-ties): exact scan for this query
+        svdb_candidate *r = res + i * k;
+        if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
         stats.exact_reruns++;
-        rc = nearest_device(qraw.as<double>() + i * K, 1, K, k, outc.as<svdb_candidate>() + i * k, true);
+        rc = nearest_device(qraw.as<double>() + i * K, 1, K, k, outc.as<svdb_candidate>() + i * k, SVDB_MODE_EXACT);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(res + i * k, outc.as<svdb_candidate>() + i * k, k * sizeof(svdb_candidate),
-                           cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(r, outc.as<svdb_candidate>() + i * k, k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (!(r[0].flags & SVDB_CAND_UNSAFE) || !use_tree) continue;
+        // more exactly-tied entries than a list holds: ask the tree which one the reference reaches first
+        stats.tree_reruns++;
+        if (!outc.ensure((nq * k + 1) * sizeof(svdb_candidate), err)) return fail(SVDB_ERR_OOM, err);
+        svdb_candidate *d_one = outc.as<svdb_candidate>() + nq * k;
+        svdb_candidate w;
+        rc = nearest_device(qraw.as<double>() + i * K, 1, K, 1, d_one, SVDB_MODE_TREE);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&w, d_one, sizeof w, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (w.flags & SVDB_CAND_UNSAFE) continue;      // traversal stack overflow (degenerate tree): keep (d, seq) order
+        // winner first, the rest stay in (dist, seq) order
+        size_t pos = k - 1;
+        for (size_t j = 0; j < k; j++)
+            if (r[j].seq == w.seq) { pos = j; break; }
+        for (size_t j = pos; j > 0; j--) r[j] = r[j - 1];
+        r[0] = w;
+        for (size_t j = 0; j < k; j++) r[j].flags &= ~SVDB_CAND_UNSAFE;
     }
     for (size_t i = 0; i < nq * k; i++) {
         if (index_out) index_out[i] = (size_t)res[i].index;
@@ -567,10 +622,13 @@ int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, siz
     ce = launch_compare(ca, e->tune.num_sms, e->stream);
     if (ce != cudaSuccess) return e->fail_cuda("norm precompute", ce);
     e->stats.kernels_launched++;
+    rc = e->tree_append(n0, n);
+    if (rc) return rc;
     e->cur_host.reserve(base_index + n);
     for (size_t i = 0; i < n; i++) e->cur_host.push_back(n0 + i);
     e->n_versions = n1;
-    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() + e->cur.mapped();
+    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
+                                e->cur.mapped() + e->child.mapped();
     return SVDB_OK;
 }
 
@@ -612,10 +670,11 @@ int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, s
 }
 
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out,
-                              int exact) {
+                              int mode) {
     if (!e) return SVDB_ERR_ARG;
+    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_TREE) return e->fail(SVDB_ERR_ARG, "unknown mode");
     std::lock_guard<std::mutex> g(e->mu);
-    return e->nearest_device(d_Q, nq, ldq, k, d_out, exact != 0);
+    return e->nearest_device(d_Q, nq, ldq, k, d_out, mode);
 }
 
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards, size_t nq, size_t k,
@@ -746,6 +805,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.ctas_per_sm") e->tune.ctas_per_sm = (int)value;
     else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
     else if (n == "scan.force_exact") e->force_exact = value != 0;
+    else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;

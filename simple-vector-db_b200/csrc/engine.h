@@ -41,15 +41,17 @@ struct PinnedScratch {
 //   log_idx  [versions] u64     index the entry was appended with (what nearest returns)
 //   norms    [versions] f32     float-order self dot product (cosine), computed at insert
 //   cur      [size] u64         index -> version of its current row (shifted by deletes)
+//   child    [versions][2] u32  reference-shaped KD tree links (less / greater-or-equal child), K5
 struct svdb_engine {
     svdb_config cfg;
     int D = 0, K = 0, Dpad = 0, kstride = 0;
-    bool log_only = false, no_log = false, alias = false, wide = false;
+    bool log_only = false, no_log = false, alias = false, wide = false, use_tree = false;
+    int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::mutex mu;
 
-    svdb::DeviceBuffer rows, kdpts, log_idx, norms, cur;
+    svdb::DeviceBuffer rows, kdpts, log_idx, norms, cur, child;
     std::vector<uint64_t> cur_host;      // authoritative index map
     size_t cur_uploaded = 0;             // entries of cur_host valid on the device ...
     size_t cur_dirty_lo = 0;             // ... below this index
@@ -60,8 +62,8 @@ struct svdb_engine {
     size_t stage_ld = 0, stage_n = 0, stage_cap = 0;
 
     // query scratch
-    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout;
-    svdb::PinnedScratch hq, hout, hidx, hf;
+    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag;
+    svdb::PinnedScratch hq, hout, hidx, hf, tree_hflag;
 
     svdb::ScanTuning tune;
     bool force_exact = false;
@@ -79,7 +81,8 @@ struct svdb_engine {
     int stage_one(const double *row, size_t ncopy, uint64_t index);
     int flush();
     int upload_cur();
-    int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, bool exact);
+    int tree_append(size_t n0, size_t m);
+    int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode);
     int nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
                      uint64_t *seq_out);
     int compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out);

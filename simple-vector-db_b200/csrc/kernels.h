@@ -52,12 +52,22 @@ struct FinalArgs {
     const u64 *log_index;   // index carried by each log entry
     u64 seq_base;
     double eps;             // relative error bound of the approximate keys; < 0: keys are exact
+    const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
     svdb_candidate *out;    // [nq][k]
 };
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st);
 
 cudaError_t launch_merge_candidates(const svdb_candidate *in, int nshards, int nq, int k, svdb_candidate *out,
                                     cudaStream_t st);
+
+// K5: insert log entries [n0, n0+m) into the reference-shaped tree (level-synchronous; see tree_kernels.cu).
+// pn/pds: m-entry u32 scratch; d_flag: device word; h_flag_pinned: pinned host word. Synchronizes the stream.
+cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *child, u64 n0, u64 m, uint32_t *pn,
+                               uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
+                               int *rounds_out);
+// K6: the reference's traversal, one thread per query, k = 1.
+cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
+                                int ldq, int nq, const u64 *log_index, u64 seq_base, svdb_candidate *out, cudaStream_t st);
 
 struct CompareArgs {
     const double *rows;     // version rows, row s at rows + s * ldr; ldr % 16 == 0, zero padded

@@ -21,6 +21,7 @@
 //                      prove that no entry outside the candidate set can belong to it.
 #include "common.cuh"
 #include "kernels.h"
+#include "tree.cuh"
 
 namespace svdb {
 
@@ -435,6 +436,43 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         // entries outside the candidate set have approximate key >= bound, hence reference
         // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
         unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps));
+    }
+
+    // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----
+    if (p.child != nullptr && nvalid >= 2) {
+        const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
+        const int l0 = __ffs(m0) - 1;
+        const double e1 = __shfl_sync(FULL, dex, l0);
+        const u64 seq0 = __shfl_sync(FULL, seq, l0);
+        const bool tied = valid && dex == e1;
+        unsigned tmask = __ballot_sync(FULL, tied);
+        const int nt = __popc(tmask);
+        if (nt >= 2) {
+            // a dropped entry could tie as well: exact keys -> bound <= e1; approximate keys are
+            // already covered by the completeness proof above (e1 <= ek < bound(1-eps))
+            if (p.eps < 0.0 && bound <= e1) unsafe = true;
+            // identical kd-points? then the earliest insert is an ancestor of the others and wins
+            bool differs = false;
+            const double *r0 = p.pts + seq0 * (u64)p.stride;
+            for (unsigned tm = tmask; tm; tm &= tm - 1) {
+                const u64 st = __shfl_sync(FULL, seq, __ffs(tm) - 1);
+                const double *rt = p.pts + st * (u64)p.stride;
+                for (int i = lane; i < p.K; i += 32) differs |= rt[i] != r0[i];
+            }
+            if (__any_sync(FULL, differs)) {
+                if (tied) cseq[rank] = seq;            // tied entries hold ranks 0..nt-1
+                __syncwarp();
+                u64 w = 0;
+                if (lane == 0) w = resolve_tie(p.pts, p.stride, p.K, p.child, p.q + (size_t)qi * p.ldq, cseq, nt);
+                w = __shfl_sync(FULL, w, 0);
+                const unsigned mw = __ballot_sync(FULL, tied && seq == w);
+                const int wr = __shfl_sync(FULL, rank, __ffs(mw) - 1);
+                if (tied) {
+                    if (seq == w) rank = 0;
+                    else if (rank < wr) rank++;
+                }
+            }
+        }
     }
     svdb_candidate *out = p.out + (size_t)qi * p.k;
     if (valid && rank < p.k) {

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libsvdb_b200.so")
 NONE = (1 << 64) - 1
 MAX_K = 24
 COSINE, EUCLIDEAN, DOT, ALL_METRICS = 0, 1, 2, 3
-FLAG_LOG_ONLY, FLAG_NO_LOG = 1, 2
+FLAG_LOG_ONLY, FLAG_NO_LOG, FLAG_SHARD = 1, 2, 4
+MODE_AUTO, MODE_EXACT, MODE_TREE = 0, 1, 2
 CAND_UNSAFE = 1
 
 _dp = C.POINTER(C.c_double)
@@ -33,7 +34,8 @@ class Config(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernels_launched", C.c_uint64), ("exact_reruns", C.c_uint64),
+    _fields_ = [("kernels_launched", C.c_uint64), ("exact_reruns", C.c_uint64), ("tree_reruns", C.c_uint64),
+                ("tree_rounds", C.c_uint64),
                 ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -203,8 +205,8 @@ class Engine:
                                          dist.ctypes.data_as(_dp), seq.ctypes.data_as(_u64p)), "svdb_nearest_batch")
         return idx, dist, seq
 
-    def nearest_device(self, q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, exact: bool = False) -> None:
-        _check(self.L.svdb_nearest_batch_device(self.h, C.c_void_p(q_ptr), nq, ldq, k, C.c_void_p(out_ptr), int(exact)),
+    def nearest_device(self, q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, mode: int = 0) -> None:
+        _check(self.L.svdb_nearest_batch_device(self.h, C.c_void_p(q_ptr), nq, ldq, k, C.c_void_p(out_ptr), int(mode)),
                "svdb_nearest_batch_device")
 
     # -- compare ------------------------------------------------------------

@@ -48,7 +48,8 @@ class ShardedIndex:
         self.D, self.K = dimension, kd_dim
         self.lo, self.hi = shard_range(n_rows_total, world, rank)
         self.engine = B.Engine(dimension, kd_dim, device=device, seq_base=self.lo,
-                               reserve_rows=max(1, self.hi - self.lo))
+                               reserve_rows=max(1, self.hi - self.lo),
+                               flags=B.FLAG_SHARD if world > 1 else 0)
         self.merge_launches = 0
         self._bufs = {}
 
@@ -75,12 +76,12 @@ class ShardedIndex:
             self._bufs[key] = (local, gathered, merged, host)
         return self._bufs[key]
 
-    def nearest_device(self, dq, k: int, exact: bool = False):
+    def nearest_device(self, dq, k: int, mode: int = B.MODE_AUTO):
         """dq: float64 CUDA tensor [nq, >=K]. Returns the merged [nq, k, 4] int64 CUDA tensor
         (a view of svdb_candidate records); everything is enqueued on the current stream."""
         nq = dq.shape[0]
         local, gathered, merged, _ = self._buffers(nq, k)
-        self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), exact)
+        self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), mode)
         if self.world > 1:
             self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
             B.merge_candidates_device(self.device, self.torch.cuda.current_stream(self.device).cuda_stream,
@@ -101,7 +102,7 @@ class ShardedIndex:
         res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
         if np.any(res["flags"] & B.CAND_UNSAFE):
             # every rank sees the same merged flags, so every rank takes this branch together
-            merged = self.nearest_device(dq, k, exact=True)
+            merged = self.nearest_device(dq, k, mode=B.MODE_EXACT)
             host.copy_(merged, non_blocking=True)
             t.cuda.current_stream(self.device).synchronize()
             res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)

@@ -44,21 +44,31 @@ def assert_topk_equal(got, want, k):
 
 # ---- golden vectors from the reference ---------------------------------------------------
 
+def oracle_tree_ids(port, rows, K, Q):
+    h = port.build(rows, K)
+    ids = port.nearest_batch(h, Q)
+    port.free(h)
+    return ids
+
+
 @pytest.mark.parametrize("name", NEAREST_CASES)
 def test_nearest_matches_reference_golden(port, name):
+    """Identical ids, distinct-point ties included (nearest_coarse_k3 is full of them)."""
     g = load_golden(name)
     rows, K, Q, want = g["rows"], int(g["K"]), g["queries"], g["ids"]
+    flat = oracle_topk(port, rows, K, Q, 2)
     with B.Engine(rows.shape[1], K) as e:
         e.insert(rows)
-        idx, dist, seq = e.nearest(Q, 2)
-    mism = np.nonzero(idx[:, 0] != want)[0]
-    for i in mism:
-        # legal only for two DISTINCT kd-points at exactly equal distance
-        assert dist[i, 0] == dist[i, 1], (i, idx[i], dist[i], want[i])
-        assert not np.array_equal(rows[idx[i, 0], :K], rows[int(want[i]), :K])
-    if name != "nearest_coarse_k3":
-        assert len(mism) == 0
-    assert_topk_equal((idx, dist, seq), oracle_topk(port, rows, K, Q, 2), 2)
+        idx1, dist1, _ = e.nearest(Q, 1)            # thin K: tree traversal (K6); wide K: scan + re-rank
+        idx2, dist2, _ = e.nearest(Q, 2)            # scan + finalize, ties resolved against the tree
+        e.set_option("nearest.tree_max_k", 0)       # force the scan path for k = 1 as well
+        idx1s, dist1s, _ = e.nearest(Q, 1)
+    np.testing.assert_array_equal(idx1[:, 0], want)
+    np.testing.assert_array_equal(idx1s[:, 0], want)
+    np.testing.assert_array_equal(idx2[:, 0], want)
+    for i, (wseq, widx, wd) in enumerate(flat):
+        assert dist1[i, 0].view(np.uint64) == wd[0].view(np.uint64) == dist1s[i, 0].view(np.uint64)
+        np.testing.assert_array_equal(dist2[i].view(np.uint64), wd.view(np.uint64))
 
 
 def test_metrics_match_reference_golden_bits():
@@ -75,32 +85,30 @@ def test_metrics_match_reference_golden_bits():
                 assert got[m].view(np.uint32) == want[m].view(np.uint32), (n, m, got, want)
 
 
-def _assert_same_or_distinct_tie(got_idx, dist2, want, what):
-    """The flat (d, seq) order and the reference agree unless two DISTINCT kd-points sit at
-    exactly the same distance; then the two best distances must be equal."""
-    if got_idx != want:
-        assert len(dist2) >= 2 and dist2[0] == dist2[1], (what, got_idx, want, dist2)
-
-
 def test_delta_stream_matches_reference_golden(port):
+    """insert / update / delete stream on coarse-grid values: stale entries, index drift and
+    plenty of exact ties; the id after every op is the reference's."""
     g = load_golden("delta_ops")
     D, K = int(g["D"]), int(g["K"])
-    model = PortDB(port, D, K)      # replays the same stream; its flat top-k is the (d, seq) order
-    with B.Engine(D, K) as e:
+    model = PortDB(port, D, K)
+    with B.Engine(D, K) as e, B.Engine(D, K) as e_scan:
+        e_scan.set_option("nearest.tree_max_k", 0)
         for i, ((code, j), v, q, want, size) in enumerate(zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"])):
-            if code == 0:
-                assert e.insert(v) == j == model.insert(v)
-            elif code == 1:
-                e.update(int(j), v)
-                model.update(int(j), v)
-            else:
-                e.delete(int(j))
-                model.delete(int(j))
-            assert e.size == size
-            k = min(2, e.log_size)
+            for eng in (e, e_scan):
+                if code == 0:
+                    assert eng.insert(v) == j
+                elif code == 1:
+                    eng.update(int(j), v)
+                else:
+                    eng.delete(int(j))
+                assert eng.size == size
+            (model.insert(v) if code == 0 else model.update(int(j), v) if code == 1 else model.delete(int(j)))
+            assert e.nearest(q, 1)[0][0, 0] == want, f"op {i} (tree traversal)"
+            assert e_scan.nearest(q, 1)[0][0, 0] == want, f"op {i} (scan + tie resolution)"
+            k = min(3, e.log_size)
             idx, dist, seq = e.nearest(q, k)
-            assert_topk_equal((idx, dist, seq), [model.topk(q, k)], k)
-            _assert_same_or_distinct_tie(idx[0, 0], dist[0], want, f"op {i}")
+            assert idx[0, 0] == want, f"op {i} (top-{k})"
+            np.testing.assert_array_equal(dist[0].view(np.uint64), model.topk(q, k)[2].view(np.uint64))
     model.close()
 
 
@@ -114,11 +122,71 @@ def test_ties_golden(port):
         qo += D
         with B.Engine(int(D), int(K)) as e:
             e.insert(rows)
-            idx, dist, seq = e.nearest(q, min(2, n))
-        assert_topk_equal((idx, dist, seq), oracle_topk(port, rows, int(K), [q], min(2, n)), 2)
-        distinct_tie = n > 1 and dist[0, 0] == dist[0, 1] and not np.array_equal(rows[idx[0, 0], :K], rows[idx[0, 1], :K])
-        if not distinct_tie:
-            assert idx[0, 0] == want, f"tie case {ci}"
+            assert e.nearest(q, 1)[0][0, 0] == want, f"tie case {ci} (tree)"
+            assert e.nearest(q, min(2, n))[0][0, 0] == want, f"tie case {ci} (scan)"
+
+
+def _lattice_ties(K, n_far, seed):
+    """Rows with MANY distinct kd-points at exactly the same distance from the origin
+    (signed permutations of (3,4,0..) and (5,0,0..): d = 25 in exact arithmetic), mixed with
+    farther rows, in a seeded random insertion order."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tied = []
+    for a in range(K):
+        for b in range(K):
+            if a == b:
+                continue
+            for sa in (3.0, -3.0):
+                for sb in (4.0, -4.0):
+                    v = np.zeros(K)
+                    v[a], v[b] = sa, sb
+                    tied.append(v)
+        for s5 in (5.0, -5.0):
+            v = np.zeros(K)
+            v[a] = s5
+            tied.append(v)
+    tied = np.array(tied)
+    far = rng.integers(-9, 10, size=(n_far, K)).astype(np.float64)
+    far = far[(far ** 2).sum(axis=1) > 25]
+    rows = np.concatenate([tied, far])
+    rng.shuffle(rows)
+    return rows
+
+
+@pytest.mark.parametrize("K,n_far", [(2, 300), (3, 2000), (6, 3000), (24, 4000)])
+def test_many_distinct_points_at_equal_distance(port, K, n_far):
+    """12 .. 2256 distinct entries tie for the minimum: more than any candidate list holds.
+    The answer must still be the one the reference's traversal reaches first, whichever path
+    produces it (traversal, scan + resolver, or the escalation EXACT -> TREE)."""
+    rows = _lattice_ties(K, n_far, seed=K)
+    Q = np.zeros((1, K))
+    Q2 = np.concatenate([Q, 1e-3 * synth.normal_rows(K, 5, K)])       # and a few tie-free queries
+    want = oracle_tree_ids(port, rows, K, Q2)
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        np.testing.assert_array_equal(e.nearest(Q2, 1)[0][:, 0], want)
+        e.set_option("nearest.tree_max_k", 0)                          # k = 1 through the scan
+        np.testing.assert_array_equal(e.nearest(Q2, 1)[0][:, 0], want)
+        st = e.stats()
+        assert st["tree_reruns"] >= 1 or K <= 3                        # 12 / 30 ties still fit the lists
+        idx, dist, _ = e.nearest(Q2, 4)
+        np.testing.assert_array_equal(idx[:, 0], want)
+        assert np.all(dist[0] == 25.0)
+
+
+def test_tree_traversal_equals_scan_on_random_data(port):
+    n, D, K = 200_000, 8, 3
+    rows = synth.uniform_rows(17, n, D)
+    Q = synth.uniform_rows(18, 500, D)
+    with B.Engine(D, K) as e:
+        e.insert(rows)
+        a = e.nearest(Q, 1)
+        e.set_option("nearest.tree_max_k", 0)
+        b = e.nearest(Q, 1)
+        assert e.stats()["tree_rounds"] > 0
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a[0][:, 0], oracle_tree_ids(port, rows, K, Q))
 
 
 # ---- the reference's own API served by the CUDA library (drop-in) ---------------------------
@@ -141,13 +209,11 @@ def test_dropin_api_nearest_golden(name):
     L.vector_db_free(db)
 
 
-def test_dropin_api_delta_stream_golden(port):
+def test_dropin_api_delta_stream_golden():
     g = load_golden("delta_ops")
     api = OB.RefApi(B.LIB_PATH)
     L = api.lib
-    L.kdtree_nearest_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
     db = L.vector_db_init(0, int(g["K"]))
-    n_ties = 0
     for i, ((code, j), v, q, want, size) in enumerate(zip(g["ops"], g["vals"], g["queries"], g["ids"], g["sizes"])):
         if code == 0:
             assert L.vector_db_insert(db, api.make_vector(v, uuid=f"u{i}")) == j
@@ -159,14 +225,7 @@ def test_dropin_api_delta_stream_golden(port):
         else:
             L.vector_db_delete(db, int(j))
         assert db.contents.size == size
-        got = api.nearest(db, q)
-        if got != want:
-            idx2 = np.empty(2, dtype=np.uint64)
-            d2 = np.empty(2)
-            assert L.kdtree_nearest_batch(db.contents.kdtree, q.ctypes.data, 1, len(q), 2, idx2.ctypes.data, d2.ctypes.data) == 0
-            _assert_same_or_distinct_tie(got, d2, want, f"op {i}")
-            n_ties += 1
-    assert n_ties < len(g["ops"]) // 4
+        assert api.nearest(db, q) == want, f"op {i}"
     L.vector_db_free(db)
 
 
@@ -242,14 +301,20 @@ def test_topk_vs_oracle(port, n, D, K, k, seed):
                 assert_topk_equal(e.nearest(Q, k), want, k)
 
 
-def test_script_distribution_ties_lowest_seq(port):
-    """Short-decimal values (add_vectors.sh): duplicate kd-points are common; the earliest wins."""
+def test_script_distribution_ties(port):
+    """Short-decimal values (add_vectors.sh): duplicate kd-points are common (earliest wins) and
+    distinct equidistant points can occur (tree order wins)."""
     rows = synth.script_values(42, (30000, 4))
     Q = synth.script_values(43, (64, 4))
-    want = oracle_topk(port, rows, 3, Q, 4)
+    flat = oracle_topk(port, rows, 3, Q, 4)
+    want = oracle_tree_ids(port, rows, 3, Q)
     with B.Engine(4, 3) as e:
         e.insert(rows)
-        assert_topk_equal(e.nearest(Q, 4), want, 4)
+        np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], want)
+        idx, dist, seq = e.nearest(Q, 4)
+        np.testing.assert_array_equal(idx[:, 0], want)
+        for i, (wseq, widx, wd) in enumerate(flat):
+            np.testing.assert_array_equal(dist[i].view(np.uint64), wd.view(np.uint64))
 
 
 def test_mass_duplicates_take_exact_fallback(port):
