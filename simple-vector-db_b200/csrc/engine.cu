@@ -126,6 +126,11 @@ int svdb_engine::init(const svdb_config &c) {
     }
     if (!alias && !no_log && !kdpts.init(device, max_versions * (size_t)kstride * 8, err)) return fail(SVDB_ERR_CUDA, err);
     if (!no_log && !log_idx.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+    if (wide && !no_log) {
+        if (!xnorm.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
+        if (!xnmax.ensure(8, err)) return fail(SVDB_ERR_OOM, err);
+        CK(cudaMemset(xnmax.p, 0, 8));
+    }
     if (use_tree) {
         if (!child.init(device, max_versions * 8, err)) return fail(SVDB_ERR_CUDA, err);
         if (!tree_flag.ensure(16, err) || !tree_hflag.ensure(16, err)) return fail(SVDB_ERR_OOM, err);
@@ -167,7 +172,8 @@ void svdb_engine::destroy() {
     norms.release();
     cur.release();
     child.release();
-    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag}) s->free_();
+    xnorm.release();
+    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
     if (own_stream) cudaStreamDestroy(own_stream);
     own_stream = stream = nullptr;
@@ -189,8 +195,14 @@ int svdb_engine::stage_one(const double *row, size_t ncopy, uint64_t index) {
 
 // K5: link log entries [n0, n0+m) into the reference-shaped tree. Their kd-points must be resident.
 int svdb_engine::tree_append(size_t n0, size_t m) {
-    if (!use_tree || m == 0) return SVDB_OK;
+    if (m == 0) return SVDB_OK;
     std::string err;
+    if (wide && !no_log) {   // |x|^2 for the GEMM-form keys of the batched path (K2)
+        if (!xnorm.ensure((n0 + m) * 8, stream, err)) return fail(SVDB_ERR_OOM, err);
+        CK(launch_rownorm(kd_ptr(), kstride, K, n0, m, xnorm.as<double>(), xnmax.as<unsigned long long>(), tune.num_sms, stream));
+        stats.kernels_launched++;
+    }
+    if (!use_tree) return SVDB_OK;
     if (!child.ensure((n0 + m) * 8, stream, err) || !tree_pn.ensure(m * 4, err) || !tree_pds.ensure(m * 4, err))
         return fail(SVDB_ERR_OOM, err);
     int rounds = 0;
@@ -239,7 +251,7 @@ int svdb_engine::flush() {
     CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
     n_versions = n1;
     stage_n = 0;
-    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped();
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped();
     return SVDB_OK;
 }
 
@@ -284,6 +296,76 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     }
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
     const int cap = (int)std::min<size_t>(32, k + 8);
+    // K2: a batch large enough to be compute-bound goes to the FP64 tensor cores
+    if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
+        const int G = mma_queries_per_group();
+        std::string err;
+        const int ldp = kstride;
+        size_t done = 0;
+        while (done < nq) {
+            const size_t nqp = std::min<size_t>(nq - done, (size_t)G * tune.num_sms);
+            const int ngroups = (int)((nqp + G - 1) / G);
+            const int nstreams = std::max(1, tune.num_sms / ngroups);
+            const size_t nq_pad = (size_t)ngroups * G;
+            if (!qpad.ensure(nq_pad * (size_t)ldp * 8, err) || !qnorm.ensure(nq_pad * 8, err) ||
+                !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err))
+                return fail(SVDB_ERR_OOM, err);
+            CK(launch_prep_queries(d_Q + done * ldq, (int)ldq, K, (int)nqp, (int)nq_pad, qpad.as<double>(), ldp,
+                                   qnorm.as<double>(), stream));
+            MmaArgs ma{};
+            ma.pts = kd_ptr();
+            ma.n = n_versions;
+            ma.K = K;
+            ma.stride = kstride;
+            ma.xnorm = xnorm.as<double>();
+            ma.q = qpad.as<double>();
+            ma.qnorm = qnorm.as<double>();
+            ma.ldq = ldp;
+            ma.nq = (int)nqp;
+            ma.ngroups = ngroups;
+            ma.nstreams = nstreams;
+            ma.cap = cap;
+            ma.lists = lists.as<Cand>();
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profile_scan) {
+                if (scan_events_used == scan_events.size()) {
+                    cudaEvent_t a, b;
+                    CK(cudaEventCreate(&a));
+                    CK(cudaEventCreate(&b));
+                    scan_events.emplace_back(a, b);
+                }
+                ev0 = scan_events[scan_events_used].first;
+                ev1 = scan_events[scan_events_used].second;
+                scan_events_used++;
+                CK(cudaEventRecord(ev0, stream));
+            }
+            CK(launch_scan_mma(ma, stream));
+            if (ev1) CK(cudaEventRecord(ev1, stream));
+            FinalArgs fa{};
+            fa.lists = lists.as<Cand>();
+            fa.nlists = nstreams;
+            fa.cap = cap;
+            fa.nq = (int)nqp;
+            fa.k = (int)k;
+            fa.pts = kd_ptr();
+            fa.K = K;
+            fa.stride = kstride;
+            fa.q = qpad.as<double>();
+            fa.ldq = ldp;
+            fa.log_index = log_idx.as<u64>();
+            fa.seq_base = cfg.seq_base;
+            fa.eps = 0.0;
+            fa.eabs_coef = 8.0 * (double)(K + 8) * ldexp(1.0, -53);
+            fa.qnorm = qnorm.as<double>();
+            fa.xn_max_bits = xnmax.as<unsigned long long>();
+            fa.child = use_tree ? child.as<uint32_t>() : nullptr;
+            fa.out = d_out + done * k;
+            CK(launch_finalize(fa, stream));
+            stats.kernels_launched += 3;
+            done += nqp;
+        }
+        return SVDB_OK;
+    }
     const int nlists = n_versions ? scan_num_lists(tune, !use_exact) : 0;
     std::string err;
 
@@ -628,7 +710,7 @@ int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, siz
     for (size_t i = 0; i < n; i++) e->cur_host.push_back(n0 + i);
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
     return SVDB_OK;
 }
 
@@ -806,6 +888,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
+    else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;

@@ -41,17 +41,19 @@ struct PinnedScratch {
 //   log_idx  [versions] u64     index the entry was appended with (what nearest returns)
 //   norms    [versions] f32     float-order self dot product (cosine), computed at insert
 //   cur      [size] u64         index -> version of its current row (shifted by deletes)
+//   xnorm    [versions] f64     |kd-point|^2 (any order) for the GEMM-form keys of K2; wide engines only
 //   child    [versions][2] u32  reference-shaped KD tree links (less / greater-or-equal child), K5
 struct svdb_engine {
     svdb_config cfg;
     int D = 0, K = 0, Dpad = 0, kstride = 0;
     bool log_only = false, no_log = false, alias = false, wide = false, use_tree = false;
+    int mma_min_q = 16;                  // AUTO: batches of at least this many queries take the DMMA path (K2)
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::mutex mu;
 
-    svdb::DeviceBuffer rows, kdpts, log_idx, norms, cur, child;
+    svdb::DeviceBuffer rows, kdpts, log_idx, norms, cur, child, xnorm;
     std::vector<uint64_t> cur_host;      // authoritative index map
     size_t cur_uploaded = 0;             // entries of cur_host valid on the device ...
     size_t cur_dirty_lo = 0;             // ... below this index
@@ -62,7 +64,7 @@ struct svdb_engine {
     size_t stage_ld = 0, stage_n = 0, stage_cap = 0;
 
     // query scratch
-    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag;
+    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag, qnorm, xnmax;
     svdb::PinnedScratch hq, hout, hidx, hf, tree_hflag;
 
     svdb::ScanTuning tune;

@@ -52,6 +52,9 @@ struct FinalArgs {
     const u64 *log_index;   // index carried by each log entry
     u64 seq_base;
     double eps;             // relative error bound of the approximate keys; < 0: keys are exact
+    double eabs_coef;       // GEMM-form keys (K2): absolute error bound = eabs_coef * (xn_max + |q|^2); 0 otherwise
+    const double *qnorm;    // |q|^2 per query of this launch (K2), else NULL
+    const unsigned long long *xn_max_bits;   // largest |x|^2 in the log, as double bits (K2), else NULL
     const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
     svdb_candidate *out;    // [nq][k]
 };
@@ -59,6 +62,26 @@ cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st);
 
 cudaError_t launch_merge_candidates(const svdb_candidate *in, int nshards, int nq, int k, svdb_candidate *out,
                                     cudaStream_t st);
+
+// K2: batched queries on the FP64 tensor cores (mma_kernels.cu)
+struct MmaArgs {
+    const double *pts;      // log rows, stride doubles apart (even, 16-byte aligned rows, zero padded)
+    u64 n;
+    int K, stride;
+    const double *xnorm;    // |x_r|^2 per log entry
+    const double *q;        // padded queries [ngroups*64][ldq], zeros beyond K and beyond nq
+    const double *qnorm;    // |q|^2 per padded query
+    int ldq, nq;            // nq real queries
+    int ngroups, nstreams;  // grid = ngroups * nstreams CTAs; a group = 64 queries
+    int cap;
+    Cand *lists;            // [ngroups*64][nstreams][cap]
+};
+cudaError_t launch_scan_mma(const MmaArgs &a, cudaStream_t st);
+int mma_queries_per_group();
+cudaError_t launch_rownorm(const double *pts, int stride, int K, u64 first, u64 n, double *out, unsigned long long *max_bits,
+                           int num_sms, cudaStream_t st);
+cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int nq_pad, double *dst, int ldp, double *qnorm,
+                                cudaStream_t st);
 
 // K5: insert log entries [n0, n0+m) into the reference-shaped tree (level-synchronous; see tree_kernels.cu).
 // pn/pds: m-entry u32 scratch; d_flag: device word; h_flag_pinned: pinned host word. Synchronizes the stream.

@@ -1,0 +1,244 @@
+// mma_kernels.cu -- K2: batched-query distance scan on the FP64 tensor cores (DMMA), sm_100a.
+//
+// Same contract as K1 (scan_kernels.cu) -- per-CTA lists of the best approximate keys for each
+// query, finished by finalize_kernel's reference-order re-rank -- for batches large enough that
+// one pass over the log is compute-bound rather than HBM-bound.
+// Replaces src/kdtree.c:134-137 evaluated for Q queries at once.
+//
+//   d~(r, q) = |x_r|^2 + |q|^2 - 2 <x_r, q>
+// The cross term is a [128 rows] x [64 queries] x K GEMM tile per CTA on
+// mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no FP64 kind), 8 warps of 32x32.
+// Row and query chunks of 32 coordinates are staged with 16-byte cp.async into a 3-stage ring,
+// XOR-swizzled per 128-byte line so the m8n8k4 fragment loads hit the 2-wavefront minimum.
+// |x_r|^2 is precomputed at insert (rownorm_kernel), |q|^2 when the batch is padded.
+// After the K loop the 128x64 keys go through shared memory to the warp that owns the query:
+// every warp keeps the register-resident top-32 lists (WarpList) of 8 of the 64 queries.
+//
+// The GEMM form cancels, so its error is ABSOLUTE: |d~ - d_ref| <= E = c (K+8) u (max|x|^2 + |q|^2);
+// finalize_kernel widens its candidate window and its completeness proof by E (FinalArgs::eabs*).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace svdb {
+
+constexpr int MM_ROWS = 128, MM_Q = 64, MM_KC = 32, MM_STAGES = 3, MM_THREADS = 256;
+constexpr int MM_X_BYTES = MM_ROWS * MM_KC * 8;        // 32 KB
+constexpr int MM_Q_BYTES = MM_Q * MM_KC * 8;           // 16 KB
+constexpr int MM_STAGE_BYTES = MM_X_BYTES + MM_Q_BYTES;
+constexpr int MM_DT_LD = MM_ROWS + 2;                  // keys tile [64][130] doubles
+constexpr int MM_DT_BYTES = MM_Q * MM_DT_LD * 8;
+constexpr int MM_SMEM = MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES + (MM_ROWS + MM_Q) * 8;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// byte offset of element (r, c) in a [rows][32 doubles] tile: two 128-byte lines per row, the
+// eight 16-byte chunks of each line XOR-permuted with the row number
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+    return (uint32_t)(r * 256 + (c >> 4) * 128 + ((((c & 15) >> 1) ^ (r & 7)) << 4) + (c & 1) * 8);
+}
+
+__global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.x % p.ngroups, stream = blockIdx.x / p.ngroups;
+    const uint32_t sbase = smem_u32(smem);
+    double *dt = reinterpret_cast<double *>(smem + MM_STAGES * MM_STAGE_BYTES);
+    double *xn_s = reinterpret_cast<double *>(smem + MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES);
+    double *qn_s = xn_s + MM_ROWS;
+
+    const int q0 = group * MM_Q;                       // first query of this CTA's group
+    if (tid < MM_Q) qn_s[tid] = p.qnorm[q0 + tid];
+    const int nchunks = (p.K + MM_KC - 1) / MM_KC;
+    const u64 ntiles = (p.n + MM_ROWS - 1) / MM_ROWS;
+
+    WarpList wl[8];                                    // this warp owns queries warp*8 .. warp*8+7 of the group
+#pragma unroll
+    for (int j = 0; j < 8; j++) wl[j].reset();
+
+    const int wr = warp >> 1, wc = warp & 1;           // warp tile: rows wr*32.., queries wc*32..
+    const int g = lane >> 2, t4 = lane & 3;
+
+    for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
+        const u64 row0 = tile * MM_ROWS;
+        auto issue = [&](int kc, int s) {
+            const uint32_t st = sbase + s * MM_STAGE_BYTES;
+            const int c0 = kc * MM_KC;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {              // rows: 128 x 16 chunks of 16 bytes
+                const int idx = tid + i * MM_THREADS;
+                const int r = idx >> 4, ch = idx & 15;
+                const int col = c0 + ch * 2;
+                const u64 row = row0 + r;
+                const bool ok = row < p.n && col < p.stride;
+                const double *src = ok ? p.pts + row * (u64)p.stride + col : p.pts;
+                cp_async16_zfill(st + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {              // queries: 64 x 16 chunks
+                const int idx = tid + i * MM_THREADS;
+                const int r = idx >> 4, ch = idx & 15;
+                const int col = c0 + ch * 2;
+                const bool ok = col < p.ldq;
+                const double *src = ok ? p.q + (size_t)(q0 + r) * p.ldq + col : p.q;
+                cp_async16_zfill(st + MM_X_BYTES + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            }
+        };
+
+        double acc[4][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+        for (int s = 0; s < MM_STAGES - 1; s++) {
+            if (s < nchunks) issue(s, s);
+            cp_commit();
+        }
+        if (tid < MM_ROWS) xn_s[tid] = row0 + tid < p.n ? p.xnorm[row0 + tid] : 0.0;
+
+        for (int kc = 0; kc < nchunks; kc++) {
+            cp_wait<MM_STAGES - 2>();
+            __syncthreads();                           // chunk kc landed; stage (kc-1)%S is free again
+            if (kc + MM_STAGES - 1 < nchunks) issue(kc + MM_STAGES - 1, (kc + MM_STAGES - 1) % MM_STAGES);
+            cp_commit();
+            const uint32_t xs = sbase + (kc % MM_STAGES) * MM_STAGE_BYTES;
+            const uint32_t qs = xs + MM_X_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < MM_KC / 4; ks++) {
+                const int c = ks * 4 + t4;
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) a[mi] = lds64(xs + swz(wr * 32 + mi * 8 + g, c));
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) b[ni] = lds64(qs + swz(wc * 32 + ni * 8 + g, c));
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        }
+        cp_wait<0>();
+
+        // keys -> shared memory, transposed to [query][row]
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int r = wr * 32 + mi * 8 + g;
+            const double xn = xn_s[r];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int qc = wc * 32 + ni * 8 + t4 * 2 + h;
+                    dt[qc * MM_DT_LD + r] = fma(-2.0, acc[mi][ni][h], xn + qn_s[qc]);
+                }
+            }
+        }
+        __syncthreads();
+        // selection: each warp feeds the lists of its 8 queries
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double *col = dt + (warp * 8 + j) * MM_DT_LD;
+#pragma unroll
+            for (int it = 0; it < MM_ROWS / 32; it++) {
+                const int r = it * 32 + lane;
+                wl[j].offer(row0 + r < p.n, col[r], row0 + r, lane);
+            }
+        }
+        // the next tile's first __syncthreads (inside its K loop) orders these reads before dt is rewritten,
+        // but xn_s / stage buffers are rewritten right away:
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int q = q0 + warp * 8 + j;
+        if (q < p.nq && lane < p.cap)
+            p.lists[((size_t)q * p.nstreams + stream) * p.cap + lane] = Cand{wl[j].d, wl[j].seq};
+    }
+}
+
+cudaError_t launch_scan_mma(const MmaArgs &a, cudaStream_t st) {
+    if (a.ngroups < 1 || a.nstreams < 1 || (a.stride & 1) || (a.ldq & 1)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+    if (e != cudaSuccess) return e;
+    scan_mma_kernel<<<a.ngroups * a.nstreams, MM_THREADS, MM_SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+int mma_queries_per_group() { return MM_Q; }
+
+// ---- |x_r|^2 at insert: one warp per row, any summation order (these feed approximate keys only) ----
+__global__ void __launch_bounds__(256) rownorm_kernel(const double *__restrict__ pts, int stride, int K, u64 first, u64 n,
+                                                      double *__restrict__ out, unsigned long long *max_bits) {
+    const int lane = threadIdx.x & 31;
+    const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, GW = ((u64)gridDim.x * blockDim.x) >> 5;
+    double mx = 0.0;
+    for (u64 r = gw; r < n; r += GW) {
+        const double *row = pts + (first + r) * (u64)stride;
+        double s = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            const double x = row[i];
+            s = fma(x, x, s);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) s += shfl_xor_f64(s, m);
+        if (lane == 0) out[first + r] = s;
+        if (s == s && s > mx) mx = s;                  // NaN rows never win anyway; keep the bound finite
+    }
+    if (lane == 0 && mx > 0.0 && mx < CUDART_INF) atomicMax(max_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+cudaError_t launch_rownorm(const double *pts, int stride, int K, u64 first, u64 n, double *out, unsigned long long *max_bits,
+                           int num_sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const u64 warps = n;
+    u64 grid = (warps + 7) / 8;
+    if (grid > (u64)num_sms * 8) grid = (u64)num_sms * 8;
+    rownorm_kernel<<<(unsigned)grid, 256, 0, st>>>(pts, stride, K, first, n, out, max_bits);
+    return cudaGetLastError();
+}
+
+// Pad a batch of queries to [nq_pad][ldp] (zeros beyond K and beyond nq) and compute |q|^2.
+__global__ void __launch_bounds__(128) prep_queries_kernel(const double *__restrict__ src, int ldq, int K, int nq,
+                                                           double *__restrict__ dst, int ldp, double *__restrict__ qnorm) {
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < ldp; c += blockDim.x) {
+        const double v = (q < nq && c < K) ? src[(size_t)q * ldq + c] : 0.0;
+        dst[(size_t)q * ldp + c] = v;
+        s = fma(v, v, s);
+    }
+    __shared__ double part[4];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += shfl_xor_f64(s, m);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) qnorm[q] = part[0] + part[1] + part[2] + part[3];
+}
+
+cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int nq_pad, double *dst, int ldp, double *qnorm,
+                                cudaStream_t st) {
+    if (nq_pad == 0) return cudaSuccess;
+    prep_queries_kernel<<<nq_pad, 128, 0, st>>>(src, ldq, K, nq, dst, ldp, qnorm);
+    return cudaGetLastError();
+}
+
+}  // namespace svdb

@@ -368,6 +368,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     }
 
     // ---- 2. which candidates can still belong to the exact top-k ----
+    // GEMM-form keys (K2) carry an absolute error on top of the relative one
+    double eabs = 0.0;
+    if (p.eabs_coef > 0.0) eabs = p.eabs_coef * (__longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi]);
     int nneed = 0;
     if (warp == 0) {
         const bool valid = wl.seq != SEQ_NONE;
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
             double dk;
             u64 sk;
             wl.key_at(p.k - 1, dk, sk);
-            if (sk != SEQ_NONE) need = valid && wl.d <= dk * (1.0 + 3.0 * p.eps);
+            if (sk != SEQ_NONE) need = valid && wl.d <= dk * (1.0 + 3.0 * p.eps) + 2.0 * eabs;
         }
         nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
         cseq[lane] = wl.seq;
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     if (p.eps >= 0.0 && bound < CUDART_INF) {
         // entries outside the candidate set have approximate key >= bound, hence reference
         // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
-        unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps));
+        unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
     }
 
     // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----

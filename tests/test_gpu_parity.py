@@ -301,6 +301,42 @@ def test_topk_vs_oracle(port, n, D, K, k, seed):
                 assert_topk_equal(e.nearest(Q, k), want, k)
 
 
+@pytest.mark.parametrize("n,D,K,nq,k,seed", [
+    (20000, 128, 128, 100, 10, 1),     # 100 queries: two groups of 64, the second ragged
+    (9000, 768, 768, 64, 10, 2),       # config-3 rows, exactly one group
+    (6000, 100, 100, 40, 5, 3),        # K not a multiple of the 32-coordinate chunk (zero-filled tail)
+    (5000, 200, 50, 33, 24, 4),        # compact kd array (K < D), k = SVDB_MAX_K
+    (300, 40, 40, 16, 3, 5),           # fewer rows than one 128-row tile per stream
+])
+def test_batched_dmma_path_vs_oracle(port, n, D, K, nq, k, seed):
+    """K2: >= 16 queries per call go through the FP64 tensor-core GEMM-form scan; after the
+    reference-order re-rank the answers are bit-identical to the oracle's."""
+    rows = synth.uniform_rows(seed, n, D)
+    Q = synth.uniform_rows(seed + 70, nq, D)
+    want = oracle_topk(port, rows, K, Q, k)
+    with B.Engine(D, K) as e:
+        e.insert(rows)
+        l0 = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q, k), want, k)
+        assert e.stats()["exact_reruns"] == 0
+        assert e.stats()["kernels_launched"] - l0 <= 8          # prep + DMMA scan + finalize per 148 groups
+        e.set_option("nearest.mma_min_queries", 0)              # same batch through K1, 8 queries per pass
+        assert_topk_equal(e.nearest(Q, k), want, k)
+
+
+def test_batched_dmma_cancellation_falls_back(port):
+    """Rows far from the origin: the GEMM form |x|^2+|q|^2-2<x,q> cancels, its absolute error
+    bound exceeds the gaps between neighbours, the proof fails and the exact scan answers."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    rows = 1.0e6 + rng.random((4000, 64))
+    Q = 1.0e6 + rng.random((20, 64))
+    want = oracle_topk(port, rows, 64, Q, 5)
+    with B.Engine(64, 64) as e:
+        e.insert(rows)
+        assert_topk_equal(e.nearest(Q, 5), want, 5)
+        assert e.stats()["exact_reruns"] > 0
+
+
 def test_script_distribution_ties(port):
     """Short-decimal values (add_vectors.sh): duplicate kd-points are common (earliest wins) and
     distinct equidistant points can occur (tree order wins)."""
