@@ -132,6 +132,20 @@ int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards,
                                  size_t nq, size_t k, svdb_candidate *d_out);
 
+/* Concurrent single-query callers (the server is thread-per-connection, main.c:382, and
+ * kdtree_nearest is called with no lock held, compare_handler.c:403): calls with nq == 1 that
+ * arrive while a pass is running are coalesced into the next pass (no added wait). Same results. */
+
+/* ---- bulk load / save in the reference's file format (vector_database.c:203-292) ----
+ * u64 count, then per row { char uuid[37]; u64 dimension; f64 data[dimension] }, native endian.
+ * load: every row must have the same dimension; rows go straight to HBM (the unaligned records
+ * are unpacked on the device), uuids stay in a host table; indices = file order, as
+ * vector_db_load inserts them (:277-279).  save: current rows in index order. */
+int svdb_engine_load_file(const char *path, size_t kd_dim, int device, uint32_t flags, svdb_engine **out);
+int svdb_save_file(svdb_engine *e, const char *path);
+int svdb_get_uuid(svdb_engine *e, size_t index, char out[37]);
+int svdb_set_uuid(svdb_engine *e, size_t index, const char *uuid);
+
 /* ---- compare ---- */
 /* out[i] = metric(row[index1[i]], row[index2[i]]); out-of-range pairs give -1.0f
  * (the reference's mismatch sentinel, vector_database.c:302-305). Host buffers. */
@@ -151,6 +165,8 @@ typedef struct svdb_stats {
     uint64_t exact_reruns;       /* queries that needed the exact fallback scan */
     uint64_t tree_reruns;        /* queries that needed the tree traversal as the last resort */
     uint64_t tree_rounds;        /* level-synchronous insertion rounds run so far (K5) */
+    uint64_t coalesced_calls;    /* single-query calls answered inside another caller's pass */
+    uint64_t coalesced_passes;   /* passes that carried more than one caller's query */
     uint64_t hbm_bytes_mapped;   /* physical HBM currently mapped by the arenas */
     uint64_t h2d_bytes, d2h_bytes;
 } svdb_stats;

@@ -57,6 +57,33 @@ void PinnedScratch::free_() {
     cap = 0;
 }
 
+// The reference's save file packs rows as { char uuid[37]; u64 dim; f64 data[D] }: 45 + 8D bytes per
+// record, so the doubles are never 8-byte aligned.  Unpack / pack them on the device, byte-wise.
+constexpr size_t REC_HDR = 37 + 8;
+__global__ void unpack_records_kernel(const unsigned char *__restrict__ raw, size_t rec_bytes, int D, size_t n,
+                                      double *__restrict__ rows) {
+    const size_t total = n * (size_t)D;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / D, c = i % D;
+        const unsigned char *src = raw + r * rec_bytes + REC_HDR + c * 8;
+        unsigned long long v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) v |= (unsigned long long)src[b] << (8 * b);
+        rows[i] = __longlong_as_double((long long)v);
+    }
+}
+__global__ void pack_records_kernel(const double *__restrict__ rows, int ldr, const unsigned long long *__restrict__ cur,
+                                    size_t first, int D, size_t n, size_t rec_bytes, unsigned char *__restrict__ raw) {
+    const size_t total = n * (size_t)D;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / D, c = i % D;
+        const unsigned long long v = (unsigned long long)__double_as_longlong(rows[cur[first + r] * (size_t)ldr + c]);
+        unsigned char *dst = raw + r * rec_bytes + REC_HDR + c * 8;
+#pragma unroll
+        for (int b = 0; b < 8; b++) dst[b] = (unsigned char)(v >> (8 * b));
+    }
+}
+
 __global__ void fill_f32_kernel(float *dst, float v, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
 }
@@ -439,7 +466,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
 }
 
 int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
-                              uint64_t *seq_out) {
+                              uint64_t *seq_out, svdb_candidate *cand_out) {
     if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
     if (nq == 0) return SVDB_OK;
     if (!Q || ldq < (size_t)K) return fail(SVDB_ERR_ARG, "bad query buffer");
@@ -492,7 +519,61 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         if (dist_out) dist_out[i] = res[i].dist;
         if (seq_out) seq_out[i] = res[i].seq;
     }
+    if (cand_out) memcpy(cand_out, res, nq * k * sizeof(svdb_candidate));
     return SVDB_OK;
+}
+
+// Concurrent single-query callers: whoever finds no pass in flight becomes the leader and
+// answers everything queued so far in ONE pass (queries of the same k share it); callers that
+// arrive meanwhile queue up for the next leader.  Nobody waits for a timer.
+int svdb_engine::nearest_one_coalesced(const double *q, size_t k, svdb_candidate *res) {
+    PendingQuery me;
+    me.q = q;
+    me.k = k;
+    me.res = res;
+    std::unique_lock<std::mutex> lk(bq_mu);
+    bq.push_back(&me);
+    while (!me.done) {
+        if (bq_leader) {
+            bq_cv.wait(lk);
+            continue;
+        }
+        bq_leader = true;
+        std::vector<PendingQuery *> batch;
+        for (auto it = bq.begin(); it != bq.end();) {
+            if ((*it)->k == k) {
+                batch.push_back(*it);
+                it = bq.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        const size_t nb = batch.size();
+        std::vector<double> Q(nb * (size_t)K);
+        for (size_t i = 0; i < nb; i++) memcpy(Q.data() + i * K, batch[i]->q, (size_t)K * 8);
+        std::vector<svdb_candidate> out(nb * k);
+        int rc;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            rc = nearest_host(Q.data(), nb, K, k, nullptr, nullptr, nullptr, out.data());
+            if (nb > 1) {
+                stats.coalesced_passes++;
+                stats.coalesced_calls += nb - 1;
+            }
+        }
+        const std::string err = rc ? get_last_error() : std::string();
+        lk.lock();
+        for (size_t i = 0; i < nb; i++) {
+            if (!rc) memcpy(batch[i]->res, out.data() + i * k, k * sizeof(svdb_candidate));
+            batch[i]->rc = rc;
+            batch[i]->done = true;
+        }
+        bq_leader = false;
+        bq_cv.notify_all();
+        if (rc) set_last_error(err);
+    }
+    return me.rc;
 }
 
 int svdb_engine::compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out) {
@@ -550,6 +631,64 @@ int svdb_engine::compare_host(int mode, const size_t *i1, const size_t *i2, size
     memcpy(out, hf.p, n * per * 4);
     return SVDB_OK;
 }
+
+int svdb_engine::ingest_device_rows(const double *d_rows, size_t n, size_t ld, size_t *first_index) {
+    svdb_engine *e = this;
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine: use svdb_append_kdpoints");
+    if (ld < (size_t)e->D) return e->fail(SVDB_ERR_ARG, "ld < dimension");
+    int rc = e->flush();
+    if (rc) return rc;
+    if (first_index) *first_index = e->cur_host.size();
+    if (n == 0) return SVDB_OK;
+    if (cudaSetDevice(e->device) != cudaSuccess) return e->fail_cuda("cudaSetDevice", cudaGetLastError());
+    const size_t n0 = e->n_versions, n1 = n0 + n;
+    if (n1 > e->max_versions) return e->fail(SVDB_ERR_OOM, "store exceeds the reserved address range");
+    std::string err;
+    bool ok = (e->no_log || e->log_idx.ensure(n1 * 8, e->stream, err)) &&
+              e->rows.ensure(n1 * (size_t)e->Dpad * 8, e->stream, err) && e->norms.ensure(n1 * 4, e->stream, err);
+    if (!e->alias && !e->no_log) ok = ok && e->kdpts.ensure(n1 * (size_t)e->kstride * 8, e->stream, err);
+    if (!ok) return e->fail(SVDB_ERR_OOM, err);
+    double *dst = e->rows.as<double>() + n0 * (size_t)e->Dpad;
+    cudaError_t ce;
+    if (e->Dpad != e->D) {
+        ce = cudaMemsetAsync(dst, 0, n * (size_t)e->Dpad * 8, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("cudaMemsetAsync", ce);
+    }
+    ce = cudaMemcpy2DAsync(dst, (size_t)e->Dpad * 8, d_rows, ld * 8, (size_t)e->D * 8, n, cudaMemcpyDeviceToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("cudaMemcpy2DAsync", ce);
+    const size_t base_index = e->cur_host.size();
+    if (!e->no_log) {
+        ce = launch_iota(e->log_idx.as<u64>() + n0, base_index, n, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("iota", ce);
+        e->stats.kernels_launched++;
+    }
+    if (!e->alias && !e->no_log) {
+        ce = launch_extract_prefix(dst, e->Dpad, e->kdpts.as<double>() + n0 * (size_t)e->kstride, e->kstride, e->K, n, e->stream);
+        if (ce != cudaSuccess) return e->fail_cuda("extract_prefix", ce);
+        e->stats.kernels_launched++;
+    }
+    CompareArgs ca{};
+    ca.rows = e->rows.as<double>();
+    ca.ldr = e->Dpad;
+    ca.D = e->D;
+    ca.first = n0;
+    ca.n = n;
+    ca.out = e->norms.as<float>() + n0;
+    ca.mode = 4;
+    ce = launch_compare(ca, e->tune.num_sms, e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("norm precompute", ce);
+    e->stats.kernels_launched++;
+    rc = e->tree_append(n0, n);
+    if (rc) return rc;
+    e->cur_host.reserve(base_index + n);
+    for (size_t i = 0; i < n; i++) e->cur_host.push_back(n0 + i);
+    e->uuids.resize(e->cur_host.size(), std::array<char, 37>{});
+    e->n_versions = n1;
+    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
+    return SVDB_OK;
+}
+
 
 // =====================================================================================
 // C-ABI
@@ -613,6 +752,7 @@ int svdb_insert_batch(svdb_engine *e, const double *rows, size_t n, size_t ld, s
         int rc = e->stage_one(rows + i * ld, e->D, e->cur_host.size());
         if (rc) return rc;
         e->cur_host.push_back(ver);
+        e->uuids.emplace_back();
     }
     return SVDB_OK;
 }
@@ -640,6 +780,7 @@ int svdb_delete_batch(svdb_engine *e, const size_t *index, size_t n) {
     for (size_t i = 0; i < n; i++) {
         if (index[i] >= e->cur_host.size()) continue;   // vector_database.c:187: silent no-op
         e->cur_host.erase(e->cur_host.begin() + index[i]);   // :189-191 shift; the log keeps its entries
+        if (index[i] < e->uuids.size()) e->uuids.erase(e->uuids.begin() + index[i]);
         e->cur_dirty_lo = std::min(e->cur_dirty_lo, index[i]);
     }
     return SVDB_OK;
@@ -660,58 +801,7 @@ int svdb_append_kdpoints(svdb_engine *e, const double *pts, const size_t *index,
 int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, size_t ld, size_t *first_index) {
     if (!e || (!d_rows && n)) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    if (e->log_only) return e->fail(SVDB_ERR_ARG, "log-only engine: use svdb_append_kdpoints");
-    if (ld < (size_t)e->D) return e->fail(SVDB_ERR_ARG, "ld < dimension");
-    int rc = e->flush();
-    if (rc) return rc;
-    if (first_index) *first_index = e->cur_host.size();
-    if (n == 0) return SVDB_OK;
-    if (cudaSetDevice(e->device) != cudaSuccess) return e->fail_cuda("cudaSetDevice", cudaGetLastError());
-    const size_t n0 = e->n_versions, n1 = n0 + n;
-    if (n1 > e->max_versions) return e->fail(SVDB_ERR_OOM, "store exceeds the reserved address range");
-    std::string err;
-    bool ok = (e->no_log || e->log_idx.ensure(n1 * 8, e->stream, err)) &&
-              e->rows.ensure(n1 * (size_t)e->Dpad * 8, e->stream, err) && e->norms.ensure(n1 * 4, e->stream, err);
-    if (!e->alias && !e->no_log) ok = ok && e->kdpts.ensure(n1 * (size_t)e->kstride * 8, e->stream, err);
-    if (!ok) return e->fail(SVDB_ERR_OOM, err);
-    double *dst = e->rows.as<double>() + n0 * (size_t)e->Dpad;
-    cudaError_t ce;
-    if (e->Dpad != e->D) {
-        ce = cudaMemsetAsync(dst, 0, n * (size_t)e->Dpad * 8, e->stream);
-        if (ce != cudaSuccess) return e->fail_cuda("cudaMemsetAsync", ce);
-    }
-    ce = cudaMemcpy2DAsync(dst, (size_t)e->Dpad * 8, d_rows, ld * 8, (size_t)e->D * 8, n, cudaMemcpyDeviceToDevice, e->stream);
-    if (ce != cudaSuccess) return e->fail_cuda("cudaMemcpy2DAsync", ce);
-    const size_t base_index = e->cur_host.size();
-    if (!e->no_log) {
-        ce = launch_iota(e->log_idx.as<u64>() + n0, base_index, n, e->stream);
-        if (ce != cudaSuccess) return e->fail_cuda("iota", ce);
-        e->stats.kernels_launched++;
-    }
-    if (!e->alias && !e->no_log) {
-        ce = launch_extract_prefix(dst, e->Dpad, e->kdpts.as<double>() + n0 * (size_t)e->kstride, e->kstride, e->K, n, e->stream);
-        if (ce != cudaSuccess) return e->fail_cuda("extract_prefix", ce);
-        e->stats.kernels_launched++;
-    }
-    CompareArgs ca{};
-    ca.rows = e->rows.as<double>();
-    ca.ldr = e->Dpad;
-    ca.D = e->D;
-    ca.first = n0;
-    ca.n = n;
-    ca.out = e->norms.as<float>() + n0;
-    ca.mode = 4;
-    ce = launch_compare(ca, e->tune.num_sms, e->stream);
-    if (ce != cudaSuccess) return e->fail_cuda("norm precompute", ce);
-    e->stats.kernels_launched++;
-    rc = e->tree_append(n0, n);
-    if (rc) return rc;
-    e->cur_host.reserve(base_index + n);
-    for (size_t i = 0; i < n; i++) e->cur_host.push_back(n0 + i);
-    e->n_versions = n1;
-    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
-    return SVDB_OK;
+    return e->ingest_device_rows(d_rows, n, ld, first_index);
 }
 
 int svdb_flush(svdb_engine *e) {
@@ -747,6 +837,17 @@ int svdb_read_row(svdb_engine *e, size_t index, double *out) {
 int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out,
                        double *dist_out, uint64_t *seq_out) {
     if (!e) return SVDB_ERR_ARG;
+    if (nq == 1 && Q && k >= 1 && k <= SVDB_MAX_K && ldq >= (size_t)e->K) {
+        svdb_candidate res[SVDB_MAX_K];
+        int rc = e->nearest_one_coalesced(Q, k, res);
+        if (rc) return rc;
+        for (size_t i = 0; i < k; i++) {
+            if (index_out) index_out[i] = (size_t)res[i].index;
+            if (dist_out) dist_out[i] = res[i].dist;
+            if (seq_out) seq_out[i] = res[i].seq;
+        }
+        return SVDB_OK;
+    }
     std::lock_guard<std::mutex> g(e->mu);
     return e->nearest_host(Q, nq, ldq, k, index_out, dist_out, seq_out);
 }
@@ -867,6 +968,182 @@ int svdb_compare_vectors(int device, int metric, const double *a, const double *
         return SVDB_ERR_CUDA;
     }
     memcpy(out, h + 2 * row_bytes + 32, 4);
+    return SVDB_OK;
+}
+
+// Stream `count` records of `rec` bytes from f into e (caller owns f and e).
+static int load_records(svdb_engine *e, FILE *f, uint64_t count, uint64_t dim) {
+    std::lock_guard<std::mutex> g(e->mu);
+    const size_t rec = REC_HDR + (size_t)dim * 8;
+    const size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / rec);
+    PinnedScratch hraw;
+    Scratch draw, drows;
+    std::string err;
+    int rc = SVDB_OK;
+    if (!hraw.ensure(chunk_rows * rec, err) || !draw.ensure(chunk_rows * rec, err) ||
+        !drows.ensure(chunk_rows * (size_t)dim * 8, err))
+        rc = e->fail(SVDB_ERR_OOM, err);
+    cudaSetDevice(e->device);
+    size_t done = 0;
+    while (done < count && rc == SVDB_OK) {
+        const size_t m = std::min<size_t>(chunk_rows, count - done);
+        const size_t got = fread(hraw.p, rec, m, f);
+        if (got == 0) break;   // short file: keep what was read (the reference does not check fread at all)
+        const unsigned char *h = hraw.as<unsigned char>();
+        for (size_t i = 0; i < got && rc == SVDB_OK; i++) {
+            uint64_t d;
+            memcpy(&d, h + i * rec + 37, 8);
+            if (d != dim) rc = e->fail(SVDB_ERR_ARG, "rows of different dimensions in one file: not supported by the bulk loader");
+        }
+        if (rc) break;
+        cudaError_t ce = cudaMemcpyAsync(draw.p, hraw.p, got * rec, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) {
+            const size_t total = got * (size_t)dim;
+            unpack_records_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->tune.num_sms * 16), 256, 0, e->stream>>>(
+                draw.as<unsigned char>(), rec, (int)dim, got, drows.as<double>());
+            ce = cudaGetLastError();
+        }
+        if (ce != cudaSuccess) {
+            rc = e->fail_cuda("bulk load", ce);
+            break;
+        }
+        e->stats.kernels_launched++;
+        e->stats.h2d_bytes += got * rec;
+        const size_t base = e->cur_host.size();
+        rc = e->ingest_device_rows(drows.as<double>(), got, (size_t)dim, nullptr);
+        if (rc) break;
+        ce = cudaStreamSynchronize(e->stream);   // hraw / draw / drows are reused by the next chunk
+        if (ce != cudaSuccess) {
+            rc = e->fail_cuda("bulk load", ce);
+            break;
+        }
+        for (size_t i = 0; i < got; i++) {
+            memcpy(e->uuids[base + i].data(), h + i * rec, 37);
+            e->uuids[base + i][36] = 0;
+        }
+        done += got;
+        if (got < m) break;
+    }
+    hraw.free_();
+    draw.free_();
+    drows.free_();
+    return rc;
+}
+
+int svdb_engine_load_file(const char *path, size_t kd_dim, int device, uint32_t flags, svdb_engine **out) {
+    if (!path || !out) {
+        set_last_error("NULL argument");
+        return SVDB_ERR_ARG;
+    }
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_last_error(std::string("cannot open ") + path);
+        return SVDB_ERR_ARG;
+    }
+    uint64_t count = 0, dim = 0;
+    char uuid0[37];
+    if (fread(&count, 8, 1, f) != 1) count = 0;
+    const long data0 = ftell(f);
+    if (count && (fread(uuid0, 1, 37, f) != 37 || fread(&dim, 8, 1, f) != 1 || dim == 0)) {
+        fclose(f);
+        set_last_error("truncated or empty first record");
+        return SVDB_ERR_ARG;
+    }
+    if (count == 0) dim = kd_dim;   // nothing to learn the row dimension from
+    svdb_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.dimension = (size_t)dim;
+    cfg.kd_dim = kd_dim;
+    cfg.device = device;
+    cfg.flags = flags;
+    cfg.reserve_rows = (size_t)count;
+    svdb_engine *e = nullptr;
+    int rc = svdb_engine_create(&cfg, &e);
+    if (rc == SVDB_OK && count) {
+        fseek(f, data0, SEEK_SET);
+        rc = load_records(e, f, count, dim);
+        if (rc) {
+            const std::string keep = get_last_error();
+            svdb_engine_destroy(e);
+            e = nullptr;
+            set_last_error(keep);
+        }
+    }
+    fclose(f);
+    if (rc) return rc;
+    *out = e;
+    return SVDB_OK;
+}
+
+int svdb_save_file(svdb_engine *e, const char *path) {
+    if (!e || !path) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->log_only) return e->fail(SVDB_ERR_ARG, "a log-only engine stores no rows");
+    int rc = e->flush();
+    if (rc) return rc;
+    rc = e->upload_cur();
+    if (rc) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return e->fail(SVDB_ERR_ARG, std::string("cannot open ") + path + " for writing");
+    const uint64_t count = e->cur_host.size(), dim = (uint64_t)e->D;
+    fwrite(&count, 8, 1, f);
+    const size_t rec = REC_HDR + (size_t)dim * 8;
+    const size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / rec);
+    PinnedScratch hraw;
+    Scratch draw;
+    std::string err;
+    if (count && (!hraw.ensure(chunk_rows * rec, err) || !draw.ensure(chunk_rows * rec, err))) {
+        fclose(f);
+        return e->fail(SVDB_ERR_OOM, err);
+    }
+    cudaSetDevice(e->device);
+    rc = SVDB_OK;
+    for (size_t done = 0; done < count; done += chunk_rows) {
+        const size_t m = std::min<size_t>(chunk_rows, count - done);
+        const size_t total = m * (size_t)dim;
+        pack_records_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->tune.num_sms * 16), 256, 0, e->stream>>>(
+            e->rows.as<double>(), e->Dpad, e->cur.as<unsigned long long>(), done, (int)dim, m, rec, draw.as<unsigned char>());
+        cudaError_t ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(hraw.p, draw.p, m * rec, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) {
+            rc = e->fail_cuda("save", ce);
+            break;
+        }
+        e->stats.kernels_launched++;
+        e->stats.d2h_bytes += m * rec;
+        unsigned char *h = hraw.as<unsigned char>();
+        for (size_t i = 0; i < m; i++) {
+            memcpy(h + i * rec, e->uuids[done + i].data(), 37);
+            memcpy(h + i * rec + 37, &dim, 8);
+        }
+        if (fwrite(h, rec, m, f) != m) {
+            rc = e->fail(SVDB_ERR_ARG, "short write");
+            break;
+        }
+    }
+    fclose(f);
+    hraw.free_();
+    draw.free_();
+    return rc;
+}
+
+int svdb_get_uuid(svdb_engine *e, size_t index, char out[37]) {
+    if (!e || !out) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (index >= e->cur_host.size()) return e->fail(SVDB_ERR_RANGE, "index out of range");
+    memcpy(out, e->uuids[index].data(), 37);
+    out[36] = 0;
+    return SVDB_OK;
+}
+
+int svdb_set_uuid(svdb_engine *e, size_t index, const char *uuid) {
+    if (!e || !uuid) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (index >= e->cur_host.size()) return e->fail(SVDB_ERR_RANGE, "index out of range");
+    memset(e->uuids[index].data(), 0, 37);
+    strncpy(e->uuids[index].data(), uuid, 36);
     return SVDB_OK;
 }
 

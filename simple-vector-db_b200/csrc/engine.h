@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -67,6 +69,23 @@ struct svdb_engine {
     svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag, qnorm, xnmax;
     svdb::PinnedScratch hq, hout, hidx, hf, tree_hflag;
 
+    // host-side uuid of each index (file round trip); shifts with deletes like the reference's structs
+    std::vector<std::array<char, 37>> uuids;
+
+    // coalescing of concurrent single-query callers
+    struct PendingQuery {
+        const double *q;
+        size_t k;
+        svdb_candidate *res;     // k results
+        int rc = 0;
+        bool done = false;
+    };
+    std::mutex bq_mu;
+    std::condition_variable bq_cv;
+    std::vector<PendingQuery *> bq;
+    bool bq_leader = false;
+    int nearest_one_coalesced(const double *q, size_t k, svdb_candidate *res);
+
     svdb::ScanTuning tune;
     bool force_exact = false;
     bool profile_scan = false;
@@ -86,7 +105,8 @@ struct svdb_engine {
     int tree_append(size_t n0, size_t m);
     int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode);
     int nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
-                     uint64_t *seq_out);
+                     uint64_t *seq_out, svdb_candidate *cand_out = nullptr);
+    int ingest_device_rows(const double *d_rows, size_t n, size_t ld, size_t *first_index);
     int compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out);
     int compare_host(int mode, const size_t *i1, const size_t *i2, size_t n, float *out);
     int fail_cuda(const char *what, cudaError_t e);

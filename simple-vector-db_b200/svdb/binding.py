@@ -35,7 +35,7 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernels_launched", C.c_uint64), ("exact_reruns", C.c_uint64), ("tree_reruns", C.c_uint64),
-                ("tree_rounds", C.c_uint64),
+                ("tree_rounds", C.c_uint64), ("coalesced_calls", C.c_uint64), ("coalesced_passes", C.c_uint64),
                 ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -53,6 +53,7 @@ NATIVE_SYMBOLS = [
     "svdb_read_row", "svdb_nearest_batch", "svdb_nearest_batch_device", "svdb_merge_candidates_device",
     "svdb_compare_batch", "svdb_compare_batch_all", "svdb_compare_batch_device", "svdb_compare_vectors",
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
+    "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -99,6 +100,10 @@ def lib() -> C.CDLL:
     L.svdb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
     L.svdb_time_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _fp]
     L.svdb_take_scan_time.argtypes = [C.c_void_p, _fp, _u64p]
+    L.svdb_engine_load_file.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.svdb_save_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.svdb_get_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
+    L.svdb_set_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     _lib = L
     return L
 
@@ -127,6 +132,28 @@ class Engine:
         _check(self.L.svdb_engine_create(C.byref(cfg), C.byref(h)), "svdb_engine_create")
         self.h = h
         self.D, self.K, self.device = dimension, cfg.kd_dim, device
+
+    @classmethod
+    def load_file(cls, path: str, kd_dim: int, device: int = 0, flags: int = 0) -> "Engine":
+        """Bulk load of the reference's save file straight into HBM (svdb_engine_load_file)."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.svdb_engine_load_file(path.encode(), kd_dim, device, flags, C.byref(h)), "svdb_engine_load_file")
+        self.h = h
+        self.D, self.K, self.device = self.L.svdb_dimension(h), self.L.svdb_kd_dim(h), device
+        return self
+
+    def save_file(self, path: str) -> None:
+        _check(self.L.svdb_save_file(self.h, path.encode()), "svdb_save_file")
+
+    def get_uuid(self, index: int) -> str:
+        buf = C.create_string_buffer(37)
+        _check(self.L.svdb_get_uuid(self.h, index, buf), "svdb_get_uuid")
+        return buf.value.decode()
+
+    def set_uuid(self, index: int, uuid: str) -> None:
+        _check(self.L.svdb_set_uuid(self.h, index, uuid.encode()), "svdb_set_uuid")
 
     def close(self) -> None:
         if getattr(self, "h", None):

@@ -515,3 +515,78 @@ def test_one_million_rows_config2(port):
         for m in range(3):
             want = np.array([port.metric(m, rows[a], rows[b]) for a, b in zip(i1[:300], i2[:300])], dtype=np.float32)
             np.testing.assert_array_equal(got[:300, m].view(np.uint32), want.view(np.uint32))
+
+
+# ---- "next" rows of the scope table: bulk load/save, coalescing of concurrent callers ---------
+
+def _write_reference_file(path, rows, uuids):
+    """The reference's save format (vector_database.c:213-222), written by numpy."""
+    with open(path, "wb") as f:
+        np.array([len(rows)], dtype=np.uint64).tofile(f)
+        for r, u in zip(rows, uuids):
+            f.write(u.encode().ljust(37, b"\0"))
+            np.array([len(r)], dtype=np.uint64).tofile(f)
+            np.asarray(r, dtype=np.float64).tofile(f)
+
+
+def test_bulk_load_save_reference_file_format(tmp_path, port):
+    n, D, K = 5000, 24, 3
+    rows = synth.script_values(5, (n, D))
+    uuids = [f"uuid-{i:06d}" for i in range(n)]
+    src = str(tmp_path / "ref.db")
+    if OB.have_ref():                       # let the reference itself write the file when it is here
+        ref = OB.load_ref()
+        db = ref.lib.vector_db_init(0, K)
+        for r, u in zip(rows, uuids):
+            ref.lib.vector_db_insert(db, ref.make_vector(r, uuid=u))
+        ref.lib.vector_db_save(db, src.encode())
+        ref.lib.vector_db_free(db)
+    else:
+        _write_reference_file(src, rows, uuids)
+    Q = synth.script_values(6, (200, D))
+    want = oracle_tree_ids(port, rows, K, Q)
+    with B.Engine.load_file(src, K) as e:
+        assert e.size == n and e.D == D and e.K == K
+        np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], want)
+        assert e.get_uuid(0) == uuids[0] and e.get_uuid(n - 1) == uuids[-1]
+        np.testing.assert_array_equal(e.read_row(1234), rows[1234])
+        out = str(tmp_path / "ours.db")
+        e.save_file(out)
+        assert open(out, "rb").read() == open(src, "rb").read()
+        # delete + update, save, reload through the reference-compatible drop-in loader
+        e.delete(10)
+        e.update(20, rows[0])
+        e.save_file(out)
+    api = OB.RefApi(B.LIB_PATH)
+    db = api.lib.vector_db_load(out.encode(), K)
+    assert db.contents.size == n - 1
+    assert api.lib.vector_db_read(db, 10).contents.uuid == uuids[11].encode()
+    np.testing.assert_array_equal(np.ctypeslib.as_array(api.lib.vector_db_read(db, 20).contents.data, shape=(D,)), rows[0])
+    api.lib.vector_db_free(db)
+
+
+def test_concurrent_single_queries_are_coalesced(port):
+    """Thread-per-connection callers (main.c:382) each issue single queries; calls that arrive
+    during a pass share the next one.  Answers are the same as when issued one by one."""
+    import threading
+    n, D = 60000, 64
+    rows = synth.uniform_rows(3, n, D)
+    Q = synth.uniform_rows(4, 256, D)
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        serial = e.nearest(Q, 1)[0][:, 0]
+        got = np.zeros(len(Q), dtype=np.uint64)
+        nthreads = 16
+
+        def worker(t):
+            for i in range(t, len(Q), nthreads):
+                got[i] = e.nearest(Q[i], 1)[0][0, 0]
+
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        np.testing.assert_array_equal(got, serial)
+        st = e.stats()
+        assert st["coalesced_calls"] > 0 and st["coalesced_passes"] > 0
