@@ -189,7 +189,7 @@ def workload_config(args):
     return {"workload": f"config3: {args.rows}x{args.dim} fp64 store, kd_dim={args.kd_dim}, single-query nearest top-1 "
                         f"per step, row-sharded over n_gpus",
             "rows": args.rows, "dim": args.dim, "kd_dim": args.kd_dim, "k": 1, "queries_per_step": 1,
-            "parallelism": f"row-shards x{args.gpus}",
+            "parallelism": f"row-shards x{args.gpus}", "exchange": os.environ.get("SVDB_EXCHANGE", "p2p") if args.gpus > 1 else None,
             "l2": "store per GPU >> 126 MB L2 (no flush needed)" if args.rows * args.dim * 8 // max(1, args.gpus) > 4 * L2_BYTES
                   else "store fits L2: flushed between steps"}
 
@@ -218,7 +218,7 @@ def ours(args):
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     D, K, N = args.dim, args.kd_dim, args.rows
-    idx = ShardedIndex(D, K, N, rank, world, local)
+    idx = ShardedIndex(D, K, N, rank, world, local, exchange=os.environ.get("SVDB_EXCHANGE", "p2p"))
     idx.bind_current_stream()
     e = idx.engine
     for name, val in (kv.split("=") for kv in args.opt):

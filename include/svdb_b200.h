@@ -132,6 +132,20 @@ int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards,
                                  size_t nq, size_t k, svdb_candidate *d_out);
 
+/* ---- cross-shard exchange over NVLink peer memory (one process per GPU) ----
+ * Every rank creates an exchange, the 64-byte handles are all-gathered by the host (any transport),
+ * every rank connects.  svdb_exchange_merge is then the whole "all-gather + merge" step: the rank
+ * stores its candidates into every peer's buffer, publishes an epoch flag, waits for the peers'
+ * flags and merges -- two small launches on `stream`, no NCCL call.  Collective: all ranks call it
+ * in the same order.  max_records bounds nq * k of one call. */
+typedef struct svdb_exchange svdb_exchange;
+int  svdb_exchange_create(int device, int rank, int world, size_t max_records, svdb_exchange **out,
+                          unsigned char handle_out[64]);
+int  svdb_exchange_connect(svdb_exchange *x, const unsigned char *all_handles /* world x 64 bytes */);
+void svdb_exchange_destroy(svdb_exchange *x);
+int  svdb_exchange_merge(svdb_exchange *x, void *stream, const svdb_candidate *d_local, size_t nq, size_t k,
+                         svdb_candidate *d_out);
+
 /* Concurrent single-query callers (the server is thread-per-connection, main.c:382, and
  * kdtree_nearest is called with no lock held, compare_handler.c:403): calls with nq == 1 that
  * arrive while a pass is running are coalesced into the next pass (no added wait). Same results. */

@@ -40,7 +40,7 @@ def main():
         g = torch.Generator().manual_seed(n)
         rows = torch.rand((n, D), dtype=torch.float64, generator=g)       # same on every rank
         Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()
-        idx = ShardedIndex(D, K, n, rank, world, local)
+        idx = ShardedIndex(D, K, n, rank, world, local, exchange=os.environ.get("SVDB_EXCHANGE", "p2p"))
         idx.bind_current_stream()
         idx.ingest_device(rows[idx.lo:idx.hi].to(dev).contiguous())
         for k in (1, 10):

@@ -110,11 +110,12 @@ struct WarpList {
         kd = __shfl_sync(FULL, d, pos);
         ks = __shfl_sync(FULL, seq, pos);
     }
-    // Offer one candidate per lane (has = this lane holds one). tau = current key at lane 31.
-    __device__ __forceinline__ void offer(bool has, double cd, u64 cs, int lane) {
+    // Offer one candidate per lane (has = this lane holds one).  Only the best `lim` keys are
+    // maintained (tau = key at lane lim-1); lanes beyond hold sorted leftovers nobody reads.
+    __device__ __forceinline__ void offer(bool has, double cd, u64 cs, int lane, int lim = 32) {
         double td;
         u64 ts;
-        key_at(31, td, ts);
+        key_at(lim - 1, td, ts);
         unsigned m = __ballot_sync(FULL, has && cd < CUDART_INF && key_less(cd, cs, td, ts));
         while (m) {
             const int src = __ffs(m) - 1;

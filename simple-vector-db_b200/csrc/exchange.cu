@@ -1,0 +1,203 @@
+// exchange.cu -- the cross-shard candidate exchange over NVLink peer memory, fused with K7.
+//
+// One process per GPU.  Every rank owns a small gather buffer in its own HBM and maps all the
+// peers' buffers (CUDA IPC).  After finalize, a rank STORES its k x 32-byte answers straight
+// into every peer's buffer (NVLink/NVSwitch writes), fences, and publishes an epoch flag there;
+// the merge kernel on each rank spins on its LOCAL flags until every shard of this epoch has
+// landed and merges (K7) in the same launch.  No NCCL call, no host round trip: the exchange is
+// two tiny launches behind the scan on the same stream.  (The payload is 32..8192 bytes per
+// rank, so this is purely about latency.)
+//
+// Buffer layout (per rank, cudaMalloc'ed so that it can be exported):
+//   [ flags: 32 x u64 ]  flags[src] = last epoch whose data from `src` is complete
+//   [ parity 0: world x max_rec candidates ][ parity 1: ... ]   double-buffered by epoch parity
+#include <string>
+
+#include "common.cuh"
+#include "engine.h"
+#include "kernels.h"
+
+namespace svdb {
+
+constexpr int XCH_MAX_WORLD = 16;
+constexpr size_t XCH_FLAG_BYTES = 32 * 8;
+
+struct PeerPtrs {
+    unsigned char *p[XCH_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_release_sys_u64(u64 *p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_acquire_sys_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// local results (nrec candidates) -> slot `rank` of every peer's gather buffer, then the flags
+__global__ void __launch_bounds__(256) exchange_push_kernel(const svdb_candidate *__restrict__ local, int nrec, PeerPtrs peers,
+                                                            int rank, int world, size_t max_rec, u64 epoch) {
+    const size_t parity_off = XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate);
+    const int words = nrec * 4;                                    // 8-byte words
+    const u64 *src = reinterpret_cast<const u64 *>(local);
+    for (int r = 0; r < world; r++) {
+        u64 *dst = reinterpret_cast<u64 *>(peers.p[r] + parity_off + (size_t)rank * max_rec * sizeof(svdb_candidate));
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) st_release_sys_u64(reinterpret_cast<u64 *>(peers.p[threadIdx.x]) + rank, epoch);
+}
+
+// wait until every shard's data of `epoch` has landed locally, then K7 (one warp per query)
+__global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char *__restrict__ mine, int world, size_t max_rec, u64 epoch,
+                                                            int nq, int k, svdb_candidate *out) {
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    const u64 *flags = reinterpret_cast<const u64 *>(mine);
+    if (lane < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(flags + lane) < epoch) {
+            if (clock64() - t0 > 20000000000ll) __trap();          // a peer died: do not hang the GPU
+        }
+    }
+    __syncwarp();
+    const svdb_candidate *in = reinterpret_cast<const svdb_candidate *>(
+        mine + XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate));
+    WarpList wl;
+    wl.reset();
+    u64 fl = 0;
+    const int total = world * k;
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        double d = CUDART_INF;
+        u64 s = SEQ_NONE;
+        if (i < total) {
+            const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+            d = __ldcg(&c->dist);
+            s = __ldcg(&c->seq);
+            fl |= __ldcg(&c->flags);
+        }
+        wl.offer(s != SEQ_NONE, d, s, lane);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) fl |= __shfl_xor_sync(FULL, fl, m);
+    if (lane < k) {
+        svdb_candidate c;
+        c.dist = wl.d;
+        c.seq = wl.seq;
+        c.index = (u64)SVDB_NONE;
+        c.flags = fl;
+        if (wl.seq != SEQ_NONE) {
+            for (int i = 0; i < total; i++) {
+                const svdb_candidate *src = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+                if (__ldcg(&src->seq) == wl.seq) {
+                    c.index = __ldcg(&src->index);
+                    break;
+                }
+            }
+        }
+        out[(size_t)qi * k + lane] = c;
+    }
+}
+
+}  // namespace svdb
+
+using namespace svdb;
+
+struct svdb_exchange {
+    int device = 0, rank = 0, world = 1;
+    size_t max_rec = 0, bytes = 0;
+    unsigned char *mine = nullptr;
+    PeerPtrs peers{};
+    bool opened[XCH_MAX_WORLD] = {};
+    uint64_t epoch = 0;
+};
+
+extern "C" {
+
+int svdb_exchange_create(int device, int rank, int world, size_t max_records, svdb_exchange **out, unsigned char handle_out[64]) {
+    if (!out || !handle_out || world < 1 || world > XCH_MAX_WORLD || rank < 0 || rank >= world || max_records == 0) {
+        set_last_error("bad argument to svdb_exchange_create");
+        return SVDB_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    *out = nullptr;
+    svdb_exchange *x = new (std::nothrow) svdb_exchange();
+    if (!x) return SVDB_ERR_OOM;
+    x->device = device;
+    x->rank = rank;
+    x->world = world;
+    x->max_rec = max_records;
+    x->bytes = XCH_FLAG_BYTES + 2 * (size_t)world * max_records * sizeof(svdb_candidate);
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaMalloc(&x->mine, x->bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(x->mine, 0, x->bytes);
+    cudaIpcMemHandle_t h;
+    if (ce == cudaSuccess) ce = cudaIpcGetMemHandle(&h, x->mine);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("svdb_exchange_create: ") + cudaGetErrorString(ce));
+        cudaGetLastError();
+        if (x->mine) cudaFree(x->mine);
+        delete x;
+        return SVDB_ERR_CUDA;
+    }
+    memcpy(handle_out, &h, 64);
+    x->peers.p[rank] = x->mine;
+    *out = x;
+    return SVDB_OK;
+}
+
+int svdb_exchange_connect(svdb_exchange *x, const unsigned char *all_handles) {
+    if (!x || !all_handles) return SVDB_ERR_ARG;
+    cudaSetDevice(x->device);
+    for (int r = 0; r < x->world; r++) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {
+            set_last_error(std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(ce));
+            cudaGetLastError();
+            return SVDB_ERR_CUDA;
+        }
+        x->peers.p[r] = static_cast<unsigned char *>(p);
+        x->opened[r] = true;
+    }
+    return SVDB_OK;
+}
+
+void svdb_exchange_destroy(svdb_exchange *x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; r++)
+        if (x->opened[r]) cudaIpcCloseMemHandle(x->peers.p[r]);
+    if (x->mine) cudaFree(x->mine);
+    delete x;
+}
+
+// d_local: this shard's nq x k candidates (e.g. from svdb_nearest_batch_device) -> d_out: merged nq x k.
+// Collective: every rank must call it the same number of times. Asynchronous on `stream`.
+int svdb_exchange_merge(svdb_exchange *x, void *stream, const svdb_candidate *d_local, size_t nq, size_t k, svdb_candidate *d_out) {
+    if (!x || !d_local || !d_out || k < 1 || k > SVDB_MAX_K || nq * k > x->max_rec) {
+        set_last_error("bad argument to svdb_exchange_merge (nq*k exceeds the exchange capacity?)");
+        return SVDB_ERR_ARG;
+    }
+    if (nq == 0) return SVDB_OK;
+    cudaSetDevice(x->device);
+    const uint64_t epoch = ++x->epoch;
+    cudaStream_t st = (cudaStream_t)stream;
+    exchange_push_kernel<<<1, 256, 0, st>>>(d_local, (int)(nq * k), x->peers, x->rank, x->world, x->max_rec, epoch);
+    exchange_merge_kernel<<<(unsigned)nq, 32, 0, st>>>(x->mine, x->world, x->max_rec, epoch, (int)nq, (int)k, d_out);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("svdb_exchange_merge: ") + cudaGetErrorString(ce));
+        return SVDB_ERR_CUDA;
+    }
+    return SVDB_OK;
+}
+
+}  // extern "C"

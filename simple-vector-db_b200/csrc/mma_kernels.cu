@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
 #pragma unroll
             for (int it = 0; it < MM_ROWS / 32; it++) {
                 const int r = it * 32 + lane;
-                wl[j].offer(row0 + r < p.n, col[r], row0 + r, lane);
+                wl[j].offer(row0 + r < p.n, col[r], row0 + r, lane, p.cap);
             }
         }
         // the next tile's first __syncthreads (inside its K loop) orders these reads before dt is rewritten,

@@ -35,7 +35,7 @@ __device__ __forceinline__ void cta_merge_emit(WarpList &mine, Cand *mrg, int W,
     if (warp == 0) {
         for (int w = 1; w < W; w++) {
             const Cand c = mrg[w * 32 + lane];
-            mine.offer(c.seq != SEQ_NONE, c.d, c.seq, lane);
+            mine.offer(c.seq != SEQ_NONE, c.d, c.seq, lane, cap);
         }
         if (lane < cap) out[lane] = Cand{mine.d, mine.seq};
     }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
         const u64 row0 = t * TR;
         const bool has = lane < TR && row0 + lane < p.n;
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane);
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) scan_ldg_kernel(ScanArgs p) {
             }
         const bool has = lane < rows;
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane);
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(ScanArgs p) {
             }
         }
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, d[qi], row, lane);
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, d[qi], row, lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
             if (i < hi) c = L[i];
             const bool has = c.seq != SEQ_NONE;
             if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);   // that list was full
-            wl.offer(has, c.d, c.seq, lane);
+            wl.offer(has, c.d, c.seq, lane, p.cap);
         }
     }
 #pragma unroll
@@ -355,16 +355,16 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         for (int w = 1; w < FIN_WARPS; w++) {
             const Cand c = mrg[w * 32 + lane];
             // a slice list that is full may itself have dropped keys >= its last one
-            if (lane == 31 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
-            wl.offer(c.seq != SEQ_NONE, c.d, c.seq, lane);
+            if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
+            wl.offer(c.seq != SEQ_NONE && lane < p.cap, c.d, c.seq, lane, p.cap);
             bound = fmin(bound, wbound[w]);
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-        double d31;
-        u64 s31;
-        wl.key_at(31, d31, s31);
-        if (s31 != SEQ_NONE) bound = fmin(bound, d31);   // the final list is full too
+        double dl;
+        u64 sl;
+        wl.key_at(p.cap - 1, dl, sl);
+        if (sl != SEQ_NONE) bound = fmin(bound, dl);     // the final list is full too
     }
 
     // ---- 2. which candidates can still belong to the exact top-k ----
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     if (p.eabs_coef > 0.0) eabs = p.eabs_coef * (__longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi]);
     int nneed = 0;
     if (warp == 0) {
-        const bool valid = wl.seq != SEQ_NONE;
+        const bool valid = wl.seq != SEQ_NONE && lane < p.cap;
         bool need = valid;
         if (p.eps >= 0.0) {
             double dk;
@@ -394,11 +394,15 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     } else {
         dex = 0.0;
         const double *qv = p.q + (size_t)qi * p.ldq;
-        for (int c0 = 0; c0 < p.K; c0 += FIN_CH) {
-            const int len = min(FIN_CH, p.K - c0);
+        // as many coordinates per round as the buffer holds for `nneed` candidates (usually all K)
+        int ch = nneed > 0 ? ((32 * FIN_LD) / nneed - 1) & ~31 : FIN_CH;
+        if (ch > p.K) ch = (p.K + 31) & ~31;
+        const int ld = ch + 1;
+        for (int c0 = 0; c0 < p.K; c0 += ch) {
+            const int len = min(ch, p.K - c0);
             for (int j = warp; j < nneed; j += FIN_WARPS) {
                 const double *row = p.pts + cseq[j] * (u64)p.stride + c0;
-                double *t = tbuf + j * FIN_LD;
+                double *t = tbuf + j * ld;
                 for (int i = lane; i < len; i += 32) {
                     const double df = __dsub_rn(__ldg(row + i), __ldg(qv + c0 + i));
                     t[i] = __dmul_rn(df, df);
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
             }
             __syncthreads();
             if (warp == 0 && lane < nneed) {
-                const double *t = tbuf + lane * FIN_LD;
+                const double *t = tbuf + lane * ld;
 #pragma unroll 8
                 for (int i = 0; i < len; i++) dex = __dadd_rn(dex, t[i]);   // kdtree.c:136, in index order
             }

@@ -54,6 +54,7 @@ NATIVE_SYMBOLS = [
     "svdb_compare_batch", "svdb_compare_batch_all", "svdb_compare_batch_device", "svdb_compare_vectors",
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
+    "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -102,6 +103,10 @@ def lib() -> C.CDLL:
     L.svdb_take_scan_time.argtypes = [C.c_void_p, _fp, _u64p]
     L.svdb_engine_load_file.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
     L.svdb_save_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.svdb_exchange_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    L.svdb_exchange_connect.argtypes = [C.c_void_p, C.c_char_p]
+    L.svdb_exchange_destroy.argtypes = [C.c_void_p]
+    L.svdb_exchange_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
     L.svdb_get_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     L.svdb_set_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     _lib = L
@@ -292,3 +297,27 @@ def merge_candidates_device(device: int, stream: int | None, in_ptr: int, nshard
                             out_ptr: int) -> None:
     _check(lib().svdb_merge_candidates_device(device, C.c_void_p(stream or 0), C.c_void_p(in_ptr), nshards, nq, k,
                                               C.c_void_p(out_ptr)), "svdb_merge_candidates_device")
+
+
+class Exchange:
+    """Peer-memory candidate exchange (svdb_exchange): create -> all-gather handles -> connect."""
+
+    def __init__(self, device: int, rank: int, world: int, max_records: int):
+        self.L = lib()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        _check(self.L.svdb_exchange_create(device, rank, world, max_records, C.byref(h), buf), "svdb_exchange_create")
+        self.h, self.handle, self.world = h, buf.raw, world
+
+    def connect(self, all_handles: bytes) -> None:
+        assert len(all_handles) == 64 * self.world
+        _check(self.L.svdb_exchange_connect(self.h, all_handles), "svdb_exchange_connect")
+
+    def merge(self, stream: int, local_ptr: int, nq: int, k: int, out_ptr: int) -> None:
+        _check(self.L.svdb_exchange_merge(self.h, C.c_void_p(stream), C.c_void_p(local_ptr), nq, k, C.c_void_p(out_ptr)),
+               "svdb_exchange_merge")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.svdb_exchange_destroy(self.h)
+            self.h = None

@@ -41,7 +41,7 @@ class ShardedIndex:
     """One rank's shard plus the exchange.  world == 1 needs no process group."""
 
     def __init__(self, dimension: int, kd_dim: int, n_rows_total: int, rank: int = 0, world: int = 1,
-                 device: int = 0, group=None):
+                 device: int = 0, group=None, exchange: str = "p2p", max_records: int = 32768):
         import torch
         self.torch = torch
         self.rank, self.world, self.device, self.group = rank, world, device, group
@@ -52,8 +52,25 @@ class ShardedIndex:
                                flags=B.FLAG_SHARD if world > 1 else 0)
         self.merge_launches = 0
         self._bufs = {}
+        # "p2p": candidates are stored into the peers' HBM over NVLink and merged in the same launch
+        # (svdb_exchange); "nccl": all_gather_into_tensor + svdb_merge_candidates_device
+        self.xch = None
+        self.max_records = max_records
+        if world > 1 and exchange == "p2p":
+            self.xch = B.Exchange(device, rank, world, max_records)
+            mine = torch.frombuffer(bytearray(self.xch.handle), dtype=torch.uint8).to(torch.device("cuda", device))
+            allh = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
+            torch.distributed.all_gather_into_tensor(allh, mine, group=group)
+            self.xch.connect(bytes(allh.cpu().numpy().tobytes()))
+            torch.distributed.barrier(group=group)
 
     def close(self):
+        if self.xch is not None:
+            self.torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                self.torch.distributed.barrier(group=self.group)   # nobody unmaps while a peer may still store
+            self.xch.close()
+            self.xch = None
         self.engine.close()
 
     def bind_current_stream(self):
@@ -83,10 +100,14 @@ class ShardedIndex:
         local, gathered, merged, _ = self._buffers(nq, k)
         self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), mode)
         if self.world > 1:
-            self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
-            B.merge_candidates_device(self.device, self.torch.cuda.current_stream(self.device).cuda_stream,
-                                      gathered.data_ptr(), self.world, nq, k, merged.data_ptr())
-            self.merge_launches += 1
+            stream = self.torch.cuda.current_stream(self.device).cuda_stream
+            if self.xch is not None and nq * k <= self.max_records:
+                self.xch.merge(stream, local.data_ptr(), nq, k, merged.data_ptr())
+                self.merge_launches += 2
+            else:
+                self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
+                B.merge_candidates_device(self.device, stream, gathered.data_ptr(), self.world, nq, k, merged.data_ptr())
+                self.merge_launches += 1
         return merged
 
     def nearest(self, q_host, k: int):
