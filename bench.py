@@ -213,6 +213,7 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SVDB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     # one explicit stream carries everything: our kernels, the NCCL exchange, the timing events
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))

@@ -337,13 +337,21 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     {
         const int per = ((total + FIN_WARPS - 1) / FIN_WARPS + 31) & ~31;
         const int lo = warp * per, hi = min(total, lo + per);
-        for (int base = lo; base < hi; base += 32) {
-            const int i = base + lane;
-            Cand c = Cand{CUDART_INF, SEQ_NONE};
-            if (i < hi) c = L[i];
-            const bool has = c.seq != SEQ_NONE;
-            if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);   // that list was full
-            wl.offer(has, c.d, c.seq, lane, p.cap);
+        for (int base = lo; base < hi; base += 128) {
+            Cand c[4];                                   // four independent loads in flight per lane
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                c[u] = Cand{CUDART_INF, SEQ_NONE};
+                if (i < hi) c[u] = L[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                const bool has = c[u].seq != SEQ_NONE;
+                if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c[u].d);   // that list was full
+                wl.offer(has, c[u].d, c[u].seq, lane, p.cap);
+            }
         }
     }
 #pragma unroll
@@ -400,12 +408,27 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         const int ld = ch + 1;
         for (int c0 = 0; c0 < p.K; c0 += ch) {
             const int len = min(ch, p.K - c0);
-            for (int j = warp; j < nneed; j += FIN_WARPS) {
-                const double *row = p.pts + cseq[j] * (u64)p.stride + c0;
-                double *t = tbuf + j * ld;
-                for (int i = lane; i < len; i += 32) {
-                    const double df = __dsub_rn(__ldg(row + i), __ldg(qv + c0 + i));
-                    t[i] = __dmul_rn(df, df);
+            // work items = (candidate, 256-coordinate segment), dealt round-robin to the warps; every
+            // lane keeps 8 row loads and 8 query loads in flight
+            const int nseg = (len + 255) >> 8;
+            for (int w = warp; w < nneed * nseg; w += FIN_WARPS) {
+                const int j = w / nseg, s0 = (w % nseg) << 8;
+                const double *row = p.pts + cseq[j] * (u64)p.stride + c0 + s0;
+                const double *qq = qv + c0 + s0;
+                double *t = tbuf + j * ld + s0;
+                const int slen = min(256, len - s0);
+                double x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = u * 32 + lane;
+                    x[u] = i < slen ? __ldg(row + i) : 0.0;
+                    y[u] = i < slen ? __ldg(qq + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = u * 32 + lane;
+                    const double df = __dsub_rn(x[u], y[u]);
+                    if (i < slen) t[i] = __dmul_rn(df, df);
                 }
             }
             __syncthreads();
