@@ -182,7 +182,7 @@ def reference_arm(args):
         "e2e": {"value": r["qps_full"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -213,7 +213,6 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SVDB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     # one explicit stream carries everything: our kernels, the NCCL exchange, the timing events
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
@@ -395,7 +394,7 @@ def ours(args):
         "store": {"rows_per_rank": rows_per_rank, "build_s": build_s, "hbm_gib_mapped": e.stats()["hbm_bytes_mapped"] / 2**30,
                   "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0])},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -408,7 +407,21 @@ def e_variant(args):
     return int(os.environ.get("SVDB_SCAN_VARIANT", "0"))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1
+    (e.g. NCCL's version banner) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
