@@ -128,6 +128,11 @@ def main():
         res += nearest_case("latency_4k_x768", 4096, 768, 768, 1, (1,), iters=200)
         res += nearest_case("latency_4k_x768_top10", 4096, 768, 768, 10, (1,), iters=200)
         res += nearest_case("latency_4k_x128", 4096, 128, 128, 1, (1,), iters=200)
+    if "thin" in which:  # the exact thread-per-entry scan (K1'), tree traversal switched off
+        res += nearest_case("thin_20M_x16_k3_scan", 20_000_000, 16, 3, 10, (1, 8), iters=10,
+                            extra_opts=(("nearest.tree_max_k", 0),))
+        res += nearest_case("thin_20M_x16_k16_scan", 20_000_000, 16, 16, 1, (1,), iters=10,
+                            extra_opts=(("nearest.tree_max_k", 0),))
     if "c2" in which:
         res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50)
         res += compare_case("c2_compare_1M_x128", 1_000_000, 128, 100_000)

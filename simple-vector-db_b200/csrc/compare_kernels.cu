@@ -13,14 +13,16 @@
 // filled with 16-byte cp.async copies in which 8 consecutive lanes fetch one contiguous
 // 128-byte row segment (full-sector, coalesced), and XOR-swizzled so that each lane can then
 // read ITS pair's chunk with conflict-free 128-bit shared loads.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace svdb {
 
-constexpr int CMP_WARPS = 4;
 constexpr int CMP_STAGES = 3;
-constexpr int CMP_STAGE_BYTES = 32 * 2 * 128;  // 32 pairs x (a, b) x 128 B
+// CH = coordinates of each row fetched per stage (16 / 32 / 64 -> 128 / 256 / 512-byte bursts per row);
+// a warp-stage holds 32 pairs x (a, b) x CH doubles
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -51,12 +53,15 @@ __device__ __forceinline__ float finish_cosine(float dot, float na, float nb) {
 __device__ __forceinline__ float finish_euclid(float sum) { return __double2float_rn(__dsqrt_rn((double)sum)); }
 
 // MODE 0 cosine, 1 euclidean, 2 dot, 3 all three, 4 self-dot of one row (K4)
-template <int MODE>
+template <int MODE, int CH, int CMP_WARPS>
 __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int ROWB = CH * 8;                       // bytes of one row segment
+    constexpr int CMP_STAGE_BYTES = 32 * 2 * ROWB;
+    constexpr int PIECES = CH / 2;                     // 16-byte pieces per row segment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ring = smem_u32(smem) + warp * (CMP_STAGES * CMP_STAGE_BYTES);
-    const int nchunks = (p.D + 15) >> 4;
+    const int nchunks = (p.D + CH - 1) / CH;
     const u64 ngroups = (p.n + 31) >> 5;
     const u64 gw = (u64)blockIdx.x * CMP_WARPS + warp, GW = (u64)gridDim.x * CMP_WARPS;
     const int sub = lane >> 3, piece = lane & 7;
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
         const double *pa = p.rows + ra * (u64)p.ldr;
         const double *pb = p.rows + rb * (u64)p.ldr;
 
+        // rows are padded to 16 doubles; a CH > 16 segment may reach past the padded row end: clamp
         auto issue = [&](int c) {
             const uint32_t st = ring + (c % CMP_STAGES) * CMP_STAGE_BYTES;
 #pragma unroll
@@ -87,12 +93,16 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
                 const int pr = i * 4 + sub;  // pair whose segment this lane helps to fetch
                 const double *sa = reinterpret_cast<const double *>(
                     __shfl_sync(FULL, reinterpret_cast<unsigned long long>(pa), pr));
-                const uint32_t col = (uint32_t)((piece ^ (pr & 7)) * 16);
-                cp_async16(st + (pr * 2 + 0) * 128 + col, sa + c * 16 + piece * 2);
-                if (MODE != 4) {
-                    const double *sb = reinterpret_cast<const double *>(
-                        __shfl_sync(FULL, reinterpret_cast<unsigned long long>(pb), pr));
-                    cp_async16(st + (pr * 2 + 1) * 128 + col, sb + c * 16 + piece * 2);
+                const double *sb = reinterpret_cast<const double *>(
+                    __shfl_sync(FULL, reinterpret_cast<unsigned long long>(pb), pr));
+#pragma unroll
+                for (int l = 0; l < PIECES / 8; l++) {     // 128-byte lines of the segment
+                    const int e = c * CH + l * 16 + piece * 2;
+                    if (e < p.ldr) {
+                        const uint32_t col = (uint32_t)(l * 128 + ((piece ^ (pr & 7)) << 4));
+                        cp_async16(st + (pr * 2 + 0) * ROWB + col, sa + e);
+                        if (MODE != 4) cp_async16(st + (pr * 2 + 1) * ROWB + col, sb + e);
+                    }
                 }
             }
         };
@@ -109,23 +119,23 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
             cp_async_commit();
             cp_async_wait<CMP_STAGES - 1>();
             __syncwarp();
-            const uint32_t st = ring + (c % CMP_STAGES) * CMP_STAGE_BYTES + lane * 256;
-            const int e0 = c * 16;
-            if (e0 + 16 <= p.D) {
+            const uint32_t st = ring + (c % CMP_STAGES) * CMP_STAGE_BYTES + lane * (2 * ROWB);
+            const int e0 = c * CH;
+            if (e0 + CH <= p.D) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t col = (uint32_t)((j ^ (lane & 7)) * 16);
+                for (int j = 0; j < PIECES; j++) {
+                    const uint32_t col = (uint32_t)((j >> 3) * 128 + (((j & 7) ^ (lane & 7)) << 4));
                     const double2 a = lds128(st + col);
-                    const double2 b = MODE == 4 ? a : lds128(st + 128 + col);
+                    const double2 b = MODE == 4 ? a : lds128(st + ROWB + col);
                     acc.step<MODE>(a.x, b.x);
                     acc.step<MODE>(a.y, b.y);
                 }
             } else {
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t col = (uint32_t)((j ^ (lane & 7)) * 16);
+                for (int j = 0; j < PIECES && e0 + 2 * j < p.D; j++) {
+                    const uint32_t col = (uint32_t)((j >> 3) * 128 + (((j & 7) ^ (lane & 7)) << 4));
                     const double2 a = lds128(st + col);
-                    const double2 b = MODE == 4 ? a : lds128(st + 128 + col);
-                    if (e0 + 2 * j < p.D) acc.step<MODE>(a.x, b.x);
+                    const double2 b = MODE == 4 ? a : lds128(st + ROWB + col);
+                    acc.step<MODE>(a.x, b.x);
                     if (e0 + 2 * j + 1 < p.D) acc.step<MODE>(a.y, b.y);
                 }
             }
@@ -156,36 +166,47 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
     }
 }
 
+template <int MODE, int CH, int W>
+static cudaError_t launch_compare_inst(const CompareArgs &a, int num_sms, cudaStream_t st) {
+    constexpr size_t smem = (size_t)W * CMP_STAGES * 32 * 2 * CH * 8;   // 96 KB (two CTAs per SM) or 192 KB
+    const u64 ngroups = (a.n + 31) / 32;
+    u64 grid = (ngroups + W - 1) / W;
+    const u64 maxgrid = (u64)num_sms * (smem <= 100 * 1024 ? 2 : 1);
+    if (grid > maxgrid) grid = maxgrid;
+    cudaError_t e = cudaFuncSetAttribute(compare_kernel<MODE, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    compare_kernel<MODE, CH, W><<<(unsigned)grid, W * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_compare_mode(const CompareArgs &a, int num_sms, int chunk, cudaStream_t st) {
+    switch (chunk) {
+        case 64: return launch_compare_inst<MODE, 64, 2>(a, num_sms, st);
+        case 32: return launch_compare_inst<MODE, 32, 4>(a, num_sms, st);
+        default: return launch_compare_inst<MODE, 16, 4>(a, num_sms, st);
+    }
+}
+
 cudaError_t launch_compare(const CompareArgs &a, int num_sms, cudaStream_t st) {
     if (a.n == 0) return cudaSuccess;
     if (a.ldr % 16 != 0) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)CMP_WARPS * CMP_STAGES * CMP_STAGE_BYTES;  // 96 KB: two CTAs per SM
-    const u64 ngroups = (a.n + 31) / 32;
-    u64 grid = (ngroups + CMP_WARPS - 1) / CMP_WARPS;
-    const u64 maxgrid = (u64)num_sms * 2;
-    if (grid > maxgrid) grid = maxgrid;
-#define SVDB_CMP_LAUNCH(M)                                                                                     \
-    case M: {                                                                                                  \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            cudaError_t e = cudaFuncSetAttribute(compare_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                    \
-            configured = true;                                                                                 \
-        }                                                                                                      \
-        compare_kernel<M><<<(unsigned)grid, CMP_WARPS * 32, smem, st>>>(a);                                    \
-        break;                                                                                                 \
+    static int chunk = 0;
+    if (chunk == 0) {
+        const char *v = getenv("SVDB_CMP_CHUNK");
+        chunk = v ? atoi(v) : 16;
+        if (chunk != 16 && chunk != 32 && chunk != 64) chunk = 16;
     }
+    // short rows gain nothing from long bursts
+    const int ch = a.D >= 4 * chunk ? chunk : 16;
     switch (a.mode) {
-        SVDB_CMP_LAUNCH(0)
-        SVDB_CMP_LAUNCH(1)
-        SVDB_CMP_LAUNCH(2)
-        SVDB_CMP_LAUNCH(3)
-        SVDB_CMP_LAUNCH(4)
-        default:
-            return cudaErrorInvalidValue;
+        case 0: return launch_compare_mode<0>(a, num_sms, ch, st);
+        case 1: return launch_compare_mode<1>(a, num_sms, ch, st);
+        case 2: return launch_compare_mode<2>(a, num_sms, ch, st);
+        case 3: return launch_compare_mode<3>(a, num_sms, ch, st);
+        case 4: return launch_compare_mode<4>(a, num_sms, ch, st);
+        default: return cudaErrorInvalidValue;
     }
-#undef SVDB_CMP_LAUNCH
-    return cudaGetLastError();
 }
 
 }  // namespace svdb

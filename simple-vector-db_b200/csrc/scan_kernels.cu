@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) scan_ldg_kernel(ScanArgs p) {
 // Exact scan: one thread per log entry, reference operation order (kdtree.c:134-137).
 // =====================================================================================
 template <int NQ>
-__global__ void __launch_bounds__(256) scan_exact_kernel(ScanArgs p) {
+__global__ void __launch_bounds__(512, 1) scan_exact_kernel(ScanArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,26 +275,37 @@ __global__ void __launch_bounds__(256) scan_exact_kernel(ScanArgs p) {
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
 
+    // UNR rows per lane per step: UNR independent load streams in flight (the loop is latency-bound)
+    constexpr int UNR = NQ >= 4 ? 1 : (NQ == 2 ? 2 : 4);
     const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
-    for (u64 base = gw * 32; base < p.n; base += GW * 32) {
-        const u64 row = base + lane;
-        const bool has = row < p.n;
-        double d[NQ];
+    for (u64 base = gw * (32 * UNR); base < p.n; base += GW * (32 * UNR)) {
+        double d[UNR][NQ];
+        const double *r[UNR];
+        bool has[UNR];
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) d[qi] = 0.0;
-        if (has) {
-            const double *r = p.pts + row * (u64)p.stride;
-            for (int i = 0; i < K; i++) {
-                const double x = __ldg(r + i);
+        for (int u = 0; u < UNR; u++) {
+            const u64 row = base + u * 32 + lane;
+            has[u] = row < p.n;
+            r[u] = p.pts + (has[u] ? row : 0) * (u64)p.stride;
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) d[u][qi] = 0.0;
+        }
+        for (int i = 0; i < K; i++) {
+            double x[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) x[u] = __ldg(r[u] + i);
+#pragma unroll
+            for (int u = 0; u < UNR; u++)
 #pragma unroll
                 for (int qi = 0; qi < NQ; qi++) {
-                    const double t = __dsub_rn(x, qs[qi * K + i]);
-                    d[qi] = __dadd_rn(d[qi], __dmul_rn(t, t));
+                    const double t = __dsub_rn(x[u], qs[qi * K + i]);
+                    d[u][qi] = __dadd_rn(d[u][qi], __dmul_rn(t, t));
                 }
-            }
         }
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, d[qi], row, lane, p.cap);
+        for (int u = 0; u < UNR; u++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has[u], d[u][qi], base + u * 32 + lane, lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -670,7 +681,8 @@ cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_
 
 template <int NQ>
 static cudaError_t launch_exact_inst(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
-    const int W = 8;
+    // latency-bound gather-like loop: fill the SM with warps; small logs do not need them all
+    const int W = a.n >= (u64)t.num_sms * 32 * 16 ? 16 : 8;
     const int grid = scan_num_lists(t, false);
     const size_t smem = (((size_t)NQ * a.K * 8 + 15) & ~(size_t)15) + (size_t)W * 32 * sizeof(Cand);
     if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
