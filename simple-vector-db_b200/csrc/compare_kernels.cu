@@ -9,10 +9,11 @@
 // sequential chain over i.  Parallelism comes from the pairs: one pair per lane.
 //
 // Memory plan (HBM-bound, 2*D*8 bytes per pair): a warp owns 32 pairs and a ring of
-// shared-memory stages.  A stage holds one 128-byte chunk of both rows of every pair; it is
-// filled with 16-byte cp.async copies in which 8 consecutive lanes fetch one contiguous
-// 128-byte row segment (full-sector, coalesced), and XOR-swizzled so that each lane can then
-// read ITS pair's chunk with conflict-free 128-bit shared loads.
+// shared-memory stages.  A stage holds one CH-coordinate segment (default 32 = 256 bytes) of
+// both rows of every pair; it is filled with 16-byte cp.async copies in which 8 consecutive
+// lanes fetch one contiguous 128-byte line (full sectors) and the lines of a segment are
+// requested back to back (one DRAM burst per row instead of two), XOR-swizzled so that each
+// lane can then read ITS pair's segment with conflict-free 128-bit shared loads.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -194,8 +195,8 @@ cudaError_t launch_compare(const CompareArgs &a, int num_sms, cudaStream_t st) {
     static int chunk = 0;
     if (chunk == 0) {
         const char *v = getenv("SVDB_CMP_CHUNK");
-        chunk = v ? atoi(v) : 16;
-        if (chunk != 16 && chunk != 32 && chunk != 64) chunk = 16;
+        chunk = v ? atoi(v) : 32;   // 256-byte bursts: 1.03x the measured copy peak at D = 1536 (128-byte: 0.71x)
+        if (chunk != 16 && chunk != 32 && chunk != 64) chunk = 32;
     }
     // short rows gain nothing from long bursts
     const int ch = a.D >= 4 * chunk ? chunk : 16;
