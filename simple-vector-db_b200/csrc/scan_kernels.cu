@@ -603,8 +603,9 @@ __global__ void pad_queries_kernel(const double *src, int ldq, double *dst, int 
 static int pick_tile_rows(const ScanTuning &t, int row_bytes, int nq) {
     int tr = t.tile_rows;
     if (tr <= 0) {
+        // ~4 KB tiles measured best (profiles/r01_sweep_scan_*.jsonl): enough per bulk copy, more tiles in flight
         tr = 1;
-        while (tr < 8 && tr * 2 * row_bytes <= 8192) tr *= 2;
+        while (tr < 8 && tr * 2 * row_bytes <= 4096) tr *= 2;
     }
     while (tr > 1 && tr * nq > 16) tr >>= 1;
     if (tr >= 8) return 8;
