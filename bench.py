@@ -318,10 +318,13 @@ def ours(args):
         idx.nearest_device(qb_dev[:64], kb)           # warm-up of the DMMA path (K2)
         barrier()
         l0 = e.stats()["kernels_launched"]
+        bsampler = ClockSampler(local)
+        bsampler.start()
         ev0.record()
         idx.nearest_device(qb_dev, kb)
         ev1.record()
         barrier()
+        bsampler.stop()
         b_launches = e.stats()["kernels_launched"] - l0
         b_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         t0 = time.perf_counter()
@@ -339,7 +342,9 @@ def ours(args):
                  "roofline": {"bound": "fp64 tensor (DMMA)", "achieved": flops / (float(b_ms) / 1e3) / 1e12, "peak": 37.1,
                               "unit": "TFLOP/s", "frac": flops / (float(b_ms) / 1e3) / 1e12 / 37.1,
                               "peak_source": "profiles/r01_fp64_peak_dfma_vs_dmma.txt (DMMA.8x8x4 microbenchmark on this pool)",
-                              "note": "whole step incl. re-rank; per-GPU flops = 2*queries*rows_per_rank*K"},
+                              "note": "whole step incl. re-rank; per-GPU flops = 2*queries*rows_per_rank*K; the peak was "
+                                      "measured in a short burst at full clock, see clocks for the clock this step ran at"},
+                 "clocks": bsampler.summary(),
                  "unsafe_flags": int(np.count_nonzero(res_b["flags"] & B.CAND_UNSAFE))}
 
     if rank != 0:

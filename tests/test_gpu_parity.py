@@ -569,14 +569,15 @@ def test_concurrent_single_queries_are_coalesced(port):
     """Thread-per-connection callers (main.c:382) each issue single queries; calls that arrive
     during a pass share the next one.  Answers are the same as when issued one by one."""
     import threading
-    n, D = 60000, 64
-    rows = synth.uniform_rows(3, n, D)
-    Q = synth.uniform_rows(4, 256, D)
-    with B.Engine(D, D) as e:
-        e.insert(rows)
+    n, D = 1_000_000, 64          # a pass takes long enough (~100 us) for other callers to queue up behind it
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dev_rows = torch.rand((n, D), dtype=torch.float64, device="cuda", generator=g)
+    Q = synth.uniform_rows(4, 384, D)
+    with B.Engine(D, D, reserve_rows=n) as e:
+        e.insert_device(dev_rows.data_ptr(), n, D)
         serial = e.nearest(Q, 1)[0][:, 0]
         got = np.zeros(len(Q), dtype=np.uint64)
-        nthreads = 16
+        nthreads = 24
 
         def worker(t):
             for i in range(t, len(Q), nthreads):
@@ -590,3 +591,58 @@ def test_concurrent_single_queries_are_coalesced(port):
         np.testing.assert_array_equal(got, serial)
         st = e.stats()
         assert st["coalesced_calls"] > 0 and st["coalesced_passes"] > 0
+
+
+# ---- randomized differential runs against the store model -----------------------------------
+
+@pytest.mark.parametrize("D,K,seed,coarse", [(1, 1, 1, True), (5, 2, 2, True), (12, 12, 3, False), (40, 33, 4, False),
+                                             (20, 20, 5, True), (9, 8, 6, False)])
+def test_random_batched_deltas_vs_model(port, D, K, seed, coarse):
+    """Batched insert / update / delete calls (duplicates inside a batch, out-of-range indices,
+    empty batches) interleaved with top-k queries and compares; every answer equals the model's
+    (oracle/svdb_oracle.c, itself pinned against the reference)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gen = (lambda shape: np.round(rng.random(shape) * 6) / 2) if coarse else (lambda shape: rng.random(shape))
+    model = PortDB(port, D, K)
+    with B.Engine(D, K) as e:
+        for step in range(60):
+            r = rng.random()
+            if model.size < 8 or r < 0.5:
+                m = int(rng.integers(0, 40))
+                rows = gen((m, D))
+                first = e.insert(rows) if m else e.size
+                assert first == model.size
+                for row in rows:
+                    model.insert(row)
+            elif r < 0.75:
+                m = int(rng.integers(1, 12))
+                idx = rng.integers(0, model.size + 3, size=m).astype(np.uint64)     # repeats + out of range
+                rows = gen((m, D))
+                e.update(idx, rows)
+                for i, row in zip(idx, rows):
+                    model.update(int(i), row)
+            else:
+                m = int(rng.integers(1, 6))
+                idx = rng.integers(0, model.size + 2, size=m).astype(np.uint64)
+                e.delete(idx)
+                for i in idx:
+                    model.delete(int(i))
+            assert e.size == model.size and e.log_size == port.lib.orc_log_size(model.log)
+            Q = gen((3, D))
+            k = int(rng.integers(1, 8))
+            idx, dist, seq = e.nearest(Q, k)
+            for qi, q in enumerate(Q):
+                wseq, widx, wd = model.topk(q, k)
+                m = len(wd)
+                np.testing.assert_array_equal(dist[qi, :m].view(np.uint64), wd.view(np.uint64), err_msg=f"step {step}")
+                assert idx[qi, 0] == model.nearest(q), f"step {step}: nearest id"
+                assert set(zip(dist[qi, :m], seq[qi, :m])) <= {(d_, s_) for d_, s_ in zip(*[model.topk(q, min(m + 40, model.size + 400))[i] for i in (2, 0)])}
+            if model.size >= 2:
+                i1 = rng.integers(0, model.size, size=16).astype(np.uint64)
+                i2 = rng.integers(0, model.size, size=16).astype(np.uint64)
+                got = e.compare(B.ALL_METRICS, i1, i2)
+                for m_ in range(3):
+                    want = np.array([model.compare(m_, int(a), int(b)) for a, b in zip(i1, i2)], dtype=np.float32)
+                    ok = (got[:, m_].view(np.uint32) == want.view(np.uint32)) | (np.isnan(got[:, m_]) & np.isnan(want))
+                    assert ok.all(), f"step {step} metric {m_}"
+    model.close()
