@@ -27,7 +27,7 @@ constexpr int MM_Q_BYTES = MM_Q * MM_KC * 8;           // 16 KB
 constexpr int MM_STAGE_BYTES = MM_X_BYTES + MM_Q_BYTES;
 constexpr int MM_DT_LD = MM_ROWS + 2;                  // keys tile [64][130] doubles
 constexpr int MM_DT_BYTES = MM_Q * MM_DT_LD * 8;
-constexpr int MM_SMEM = MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES + (MM_ROWS + MM_Q) * 8;
+constexpr int MM_SMEM = MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES + MM_Q * 8;
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -60,13 +60,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
     const int group = blockIdx.x % p.ngroups, stream = blockIdx.x / p.ngroups;
     const uint32_t sbase = smem_u32(smem);
     double *dt = reinterpret_cast<double *>(smem + MM_STAGES * MM_STAGE_BYTES);
-    double *xn_s = reinterpret_cast<double *>(smem + MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES);
-    double *qn_s = xn_s + MM_ROWS;
+    double *qn_s = reinterpret_cast<double *>(smem + MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES);
 
     const int q0 = group * MM_Q;                       // first query of this CTA's group
     if (tid < MM_Q) qn_s[tid] = p.qnorm[q0 + tid];
     const int nchunks = (p.K + MM_KC - 1) / MM_KC;
     const u64 ntiles = (p.n + MM_ROWS - 1) / MM_ROWS;
+    const u64 my_tiles = ntiles > (u64)stream ? (ntiles - stream + p.nstreams - 1) / p.nstreams : 0;
+    const u64 total = my_tiles * nchunks;              // (tile, chunk) steps of this CTA, one continuous pipeline
 
     WarpList wl[8];                                    // this warp owns queries warp*8 .. warp*8+7 of the group
 #pragma unroll
@@ -75,97 +76,108 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
     const int wr = warp >> 1, wc = warp & 1;           // warp tile: rows wr*32.., queries wc*32..
     const int g = lane >> 2, t4 = lane & 3;
 
-    for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
-        const u64 row0 = tile * MM_ROWS;
-        auto issue = [&](int kc, int s) {
-            const uint32_t st = sbase + s * MM_STAGE_BYTES;
-            const int c0 = kc * MM_KC;
+    // producer cursor: which (tile, chunk) the next cp.async batch fetches, into which stage
+    u64 p_tile = stream;
+    int p_kc = 0, p_stage = 0;
+    auto issue_next = [&]() {
+        const uint32_t st = sbase + p_stage * MM_STAGE_BYTES;
+        const int c0 = p_kc * MM_KC;
+        const u64 row0 = p_tile * MM_ROWS;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {              // rows: 128 x 16 chunks of 16 bytes
-                const int idx = tid + i * MM_THREADS;
-                const int r = idx >> 4, ch = idx & 15;
-                const int col = c0 + ch * 2;
-                const u64 row = row0 + r;
-                const bool ok = row < p.n && col < p.stride;
-                const double *src = ok ? p.pts + row * (u64)p.stride + col : p.pts;
-                cp_async16_zfill(st + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {              // queries: 64 x 16 chunks
-                const int idx = tid + i * MM_THREADS;
-                const int r = idx >> 4, ch = idx & 15;
-                const int col = c0 + ch * 2;
-                const bool ok = col < p.ldq;
-                const double *src = ok ? p.q + (size_t)(q0 + r) * p.ldq + col : p.q;
-                cp_async16_zfill(st + MM_X_BYTES + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
-            }
-        };
-
-        double acc[4][4][2];
-#pragma unroll
-        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-#pragma unroll
-        for (int s = 0; s < MM_STAGES - 1; s++) {
-            if (s < nchunks) issue(s, s);
-            cp_commit();
+        for (int i = 0; i < 8; i++) {                  // rows: 128 x 16 chunks of 16 bytes
+            const int idx = tid + i * MM_THREADS;
+            const int r = idx >> 4, ch = idx & 15;
+            const int col = c0 + ch * 2;
+            const u64 row = row0 + r;
+            const bool ok = row < p.n && col < p.stride;
+            const double *src = ok ? p.pts + row * (u64)p.stride + col : p.pts;
+            cp_async16_zfill(st + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
-        if (tid < MM_ROWS) xn_s[tid] = row0 + tid < p.n ? p.xnorm[row0 + tid] : 0.0;
-
-        for (int kc = 0; kc < nchunks; kc++) {
-            cp_wait<MM_STAGES - 2>();
-            __syncthreads();                           // chunk kc landed; stage (kc-1)%S is free again
-            if (kc + MM_STAGES - 1 < nchunks) issue(kc + MM_STAGES - 1, (kc + MM_STAGES - 1) % MM_STAGES);
-            cp_commit();
-            const uint32_t xs = sbase + (kc % MM_STAGES) * MM_STAGE_BYTES;
-            const uint32_t qs = xs + MM_X_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < MM_KC / 4; ks++) {
-                const int c = ks * 4 + t4;
-                double a[4], b[4];
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++) a[mi] = lds64(xs + swz(wr * 32 + mi * 8 + g, c));
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) b[ni] = lds64(qs + swz(wc * 32 + ni * 8 + g, c));
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-            }
+        for (int i = 0; i < 4; i++) {                  // queries: 64 x 16 chunks
+            const int idx = tid + i * MM_THREADS;
+            const int r = idx >> 4, ch = idx & 15;
+            const int col = c0 + ch * 2;
+            const bool ok = col < p.ldq;
+            const double *src = ok ? p.q + (size_t)(q0 + r) * p.ldq + col : p.q;
+            cp_async16_zfill(st + MM_X_BYTES + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
-        cp_wait<0>();
+        if (++p_kc == nchunks) {
+            p_kc = 0;
+            p_tile += p.nstreams;
+        }
+        if (++p_stage == MM_STAGES) p_stage = 0;
+    };
 
-        // keys -> shared memory, transposed to [query][row]
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < MM_STAGES - 1; s++) {
+        if ((u64)s < total) issue_next();
+        cp_commit();
+    }
+
+    u64 c_tile = stream;                               // consumer cursor
+    int c_kc = 0, c_stage = 0;
+    for (u64 it = 0; it < total; it++) {
+        cp_wait<MM_STAGES - 2>();
+        __syncthreads();                               // step `it` landed; the stage consumed last step is free again
+        if (it + MM_STAGES - 1 < total) issue_next();  // next tile's first chunks are prefetched under this tile's last MMAs
+        cp_commit();
+        const uint32_t xs = sbase + c_stage * MM_STAGE_BYTES;
+        const uint32_t qs = xs + MM_X_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < MM_KC / 4; ks++) {
+            const int c = ks * 4 + t4;
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = lds64(xs + swz(wr * 32 + mi * 8 + g, c));
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = lds64(qs + swz(wc * 32 + ni * 8 + g, c));
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        if (++c_stage == MM_STAGES) c_stage = 0;
+        if (++c_kc < nchunks) continue;
+
+        // ---- tile finished: keys -> shared memory, transposed to [query][row] ----
+        const u64 row0 = c_tile * MM_ROWS;
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
             const int r = wr * 32 + mi * 8 + g;
-            const double xn = xn_s[r];
+            const double xn = row0 + r < p.n ? __ldg(p.xnorm + row0 + r) : 0.0;
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int qc = wc * 32 + ni * 8 + t4 * 2 + h;
                     dt[qc * MM_DT_LD + r] = fma(-2.0, acc[mi][ni][h], xn + qn_s[qc]);
+                    acc[mi][ni][h] = 0.0;
                 }
             }
         }
         __syncthreads();
-        // selection: each warp feeds the lists of its 8 queries
+        // selection: each warp feeds the lists of its 8 queries; the loop-top barrier of the next step
+        // orders these reads before the next tile's keys overwrite dt
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const double *col = dt + (warp * 8 + j) * MM_DT_LD;
 #pragma unroll
-            for (int it = 0; it < MM_ROWS / 32; it++) {
-                const int r = it * 32 + lane;
+            for (int it2 = 0; it2 < MM_ROWS / 32; it2++) {
+                const int r = it2 * 32 + lane;
                 wl[j].offer(row0 + r < p.n, col[r], row0 + r, lane, p.cap);
             }
         }
-        // the next tile's first __syncthreads (inside its K loop) orders these reads before dt is rewritten,
-        // but xn_s / stage buffers are rewritten right away:
-        __syncthreads();
+        c_kc = 0;
+        c_tile += p.nstreams;
     }
+    cp_wait<0>();
 
 #pragma unroll
     for (int j = 0; j < 8; j++) {
