@@ -48,10 +48,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// byte offset of element (r, c) in a [rows][32 doubles] tile: two 128-byte lines per row, the
-// eight 16-byte chunks of each line XOR-permuted with the row number
-__device__ __forceinline__ uint32_t swz(int r, int c) {
-    return (uint32_t)(r * 256 + (c >> 4) * 128 + ((((c & 15) >> 1) ^ (r & 7)) << 4) + (c & 1) * 8);
+// A [rows][32 doubles] tile is two 128-byte lines per row; the eight 16-byte chunks of a line are
+// XOR-permuted with a per-row mask chosen so that the fragment loads below -- 128-bit loads in
+// which a quarter-warp touches rows r, r+1 and four consecutive chunks each -- are conflict-free:
+// the masks of rows r and r^1 differ in bit 2.
+__device__ __forceinline__ int row_mask(int r) { return ((r & 1) << 2) | ((r >> 1) & 3); }
+__device__ __forceinline__ uint32_t chunk_off(int r, int ch /* 16-byte chunk 0..15 of the 256-byte row */) {
+    return (uint32_t)(r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ row_mask(r)) << 4));
 }
 
 __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
             const u64 row = row0 + r;
             const bool ok = row < p.n && col < p.stride;
             const double *src = ok ? p.pts + row * (u64)p.stride + col : p.pts;
-            cp_async16_zfill(st + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            cp_async16_zfill(st + chunk_off(r, ch), src, ok ? 16u : 0u);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {                  // queries: 64 x 16 chunks
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
             const int col = c0 + ch * 2;
             const bool ok = col < p.ldq;
             const double *src = ok ? p.q + (size_t)(q0 + r) * p.ldq + col : p.q;
-            cp_async16_zfill(st + MM_X_BYTES + r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            cp_async16_zfill(st + MM_X_BYTES + chunk_off(r, ch), src, ok ? 16u : 0u);
         }
         if (++p_kc == nchunks) {
             p_kc = 0;
@@ -130,18 +133,24 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
         cp_commit();
         const uint32_t xs = sbase + c_stage * MM_STAGE_BYTES;
         const uint32_t qs = xs + MM_X_BYTES;
+        // Eight coordinates per step: lane t4 fetches coordinates {2*t4, 2*t4+1} of the step with ONE
+        // 128-bit load per fragment row and feeds .x to one m8n8k4 and .y to the next (the k slots of an
+        // MMA may hold any 4 coordinates as long as A and B agree).
 #pragma unroll
-        for (int ks = 0; ks < MM_KC / 4; ks++) {
-            const int c = ks * 4 + t4;
-            double a[4], b[4];
+        for (int j = 0; j < MM_KC / 8; j++) {
+            double2 a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = lds64(xs + swz(wr * 32 + mi * 8 + g, c));
+            for (int mi = 0; mi < 4; mi++) a[mi] = lds128(xs + chunk_off(wr * 32 + mi * 8 + g, j * 4 + t4));
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = lds64(qs + swz(wc * 32 + ni * 8 + g, c));
+            for (int ni = 0; ni < 4; ni++) b[ni] = lds128(qs + chunk_off(wc * 32 + ni * 8 + g, j * 4 + t4));
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
         }
         if (++c_stage == MM_STAGES) c_stage = 0;
         if (++c_kc < nchunks) continue;
