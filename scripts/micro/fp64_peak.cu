@@ -69,7 +69,7 @@ int main() {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     double *out; cudaMalloc(&out, sizeof(double) * sms * 8 * 1024);
     const int iters = 20000;
-    for (int warps : {4, 8, 16, 32}) {
+    for (int warps : {4, 8, 16}) {
         const int threads = warps * 32, grid = sms * 2;
         float ms = time_ms([&] { dfma_kernel<<<grid, threads>>>(out, iters); });
         double fl = 2.0 * 8 * iters * (double)threads * grid;
@@ -80,6 +80,26 @@ int main() {
         ms = time_ms([&] { dmma16816_kernel<<<grid, threads>>>(out, iters); });
         fl = 2.0 * 16 * 8 * 16 * 4 * iters * (double)warps * grid;
         printf("DMMA16816 warps/CTA=%2d (2 CTA/SM): %8.3f ms  %7.2f TFLOP/s\n", warps, ms, fl / ms / 1e9);
+    }
+    // sustained: ~1 s of back-to-back DMMA / DFMA (the power cap, not the pipe, may set the ceiling)
+    {
+        const int threads = 256, grid = sms * 2, reps = 60;
+        for (int which = 0; which < 2; which++) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaDeviceSynchronize();
+            cudaEventRecord(a);
+            for (int r = 0; r < reps; r++) {
+                if (which == 0) dmma884_kernel<<<grid, threads>>>(out, iters * 4);
+                else dfma_kernel<<<grid, threads>>>(out, iters * 32);
+            }
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms; cudaEventElapsedTime(&ms, a, b);
+            const double fl = which == 0 ? 2.0 * 8 * 8 * 4 * 8 * (iters * 4.0) * 8 * grid * reps
+                                         : 2.0 * 8 * (iters * 32.0) * threads * grid * reps;
+            printf("%s sustained over %.0f ms: %7.2f TFLOP/s\n", which == 0 ? "DMMA 884" : "DFMA    ", ms, fl / ms / 1e9);
+        }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
