@@ -425,6 +425,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
             sa.nq = nqp;
             sa.cap = cap;
             sa.lists = lists.as<Cand>();
+            sa.assign = tune.assign;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profile_scan) {
                 if (scan_events_used == scan_events.size()) {
@@ -1162,6 +1163,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.stages") e->tune.stages = (int)value;
     else if (n == "scan.tile_rows") e->tune.tile_rows = (int)value;
     else if (n == "scan.ctas_per_sm") e->tune.ctas_per_sm = (int)value;
+    else if (n == "scan.assign") e->tune.assign = (int)value;
     else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
@@ -1203,6 +1205,7 @@ int svdb_time_scan(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, siz
     sa.nq = nqp;
     sa.cap = cap;
     sa.lists = e->lists.as<Cand>();
+    sa.assign = e->tune.assign;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);

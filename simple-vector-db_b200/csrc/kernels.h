@@ -14,10 +14,11 @@ struct Cand;  // 16-byte (d, seq) record, see common.cuh
 // Tunables of the scan launch (engine options "scan.*").
 struct ScanTuning {
     int variant = 0;        // 0: TMA bulk-copy ring per warp; 1: direct LDG.128 streaming
-    int warps = 8;          // warps per CTA
-    int stages = 3;         // ring depth per warp (variant 0); 3 beats 4 by 3 % in bench A/B on one box
+    int warps = 4;          // warps per CTA (bench A/B: 2 CTAs/SM x 4 warps x 2 stages beats 1 x 8 x 3 by 1.3 %)
+    int stages = 2;         // ring depth per warp (variant 0)
     int tile_rows = 0;      // rows per tile, 0 = choose from the row size
-    int ctas_per_sm = 1;
+    int ctas_per_sm = 2;
+    int assign = 0;         // 0: tiles dealt round-robin over all warps; 1: every CTA streams one contiguous slab
     int nq_per_pass = 4;    // queries sharing one pass over the log (1, 2, 4, 8)
     int thin_max_k = 16;    // K <= this: thread-per-row exact kernel is the primary path
     int num_sms = 148;
@@ -33,6 +34,7 @@ struct ScanArgs {
     int nq;                 // queries in this pass (<= 8)
     int cap;                // candidates each CTA emits per query
     Cand *lists;            // [nq][nlists][cap]
+    int assign;             // ScanTuning::assign
 };
 
 // Number of per-CTA lists a scan with this tuning writes per query.

@@ -73,8 +73,22 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
             bulk_g2s(smem_u32(qs) + qi * row_bytes, p.q + (size_t)qi * p.ldq, row_bytes, qbar);
     }
 
-    const u64 ntiles = (p.n + TR - 1) / TR;
-    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const u64 ntiles_all = (p.n + TR - 1) / TR;
+    // tile assignment: round-robin over all warps of the grid, or one contiguous slab per CTA
+    // (then round-robin over the CTA's warps inside the slab)
+    u64 gw, GW, ntiles;
+    if (p.assign == 1) {
+        const u64 per = (ntiles_all + gridDim.x - 1) / gridDim.x;
+        const u64 lo = (u64)blockIdx.x * per;
+        const u64 hi = lo + per < ntiles_all ? lo + per : ntiles_all;
+        gw = lo + warp;
+        GW = W;
+        ntiles = lo < ntiles_all ? hi : 0;
+    } else {
+        gw = (u64)blockIdx.x * W + warp;
+        GW = (u64)gridDim.x * W;
+        ntiles = ntiles_all;
+    }
     const uint32_t my_stage = smem_u32(stage_base) + (uint32_t)warp * nstages * tile_bytes;
     const uint32_t my_bar = smem_u32(bars + warp * nstages);
 
@@ -639,10 +653,20 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
     auto need = [&](int w, int ns) {
         return (size_t)w * ns * TR * row_bytes + (size_t)NQ * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)(w * ns + 1) * 8;
     };
-    const size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    const int W0 = W, NS0 = NS;
     while (need(W, NS) > budget && NS > 2) NS--;
-    while (need(W, NS) > budget && W > 1) W--;
-    if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    while (need(W, NS) > budget && W > 2) W--;
+    if (need(W, NS) > budget) {
+        // too big to co-reside cps CTAs per SM (long rows x many queries): keep the grid (the list
+        // layout depends on it) and let the CTAs run in waves with the whole SM's shared memory each
+        budget = (size_t)MAX_SMEM;
+        W = W0;
+        NS = NS0;
+        while (need(W, NS) > budget && NS > 2) NS--;
+        while (need(W, NS) > budget && W > 1) W--;
+        if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    }
     const size_t smem = need(W, NS);
     static size_t configured = 0;
     if (smem > configured) {
