@@ -116,11 +116,48 @@ def compare_case(name, n, D, npairs, iters=5):
     return out
 
 
+def cpu_case(name, n, D, K, nq, npairs=0, script=False):
+    """The reference's own CPU path (oracle/_ref, else the port) on this box's cores, same shapes."""
+    from oracle import binding as OB
+    from svdb import synth
+    drv = OB.load_cpu_driver()
+    cores = os.cpu_count() or 1
+    rows = synth.script_values(1, (n, D)) if script else synth.uniform_rows(1, n, D)
+    Q = synth.script_values(2, (nq, D)) if script else synth.uniform_rows(2, nq, D)
+    t0 = time.perf_counter()
+    h = drv.build(rows, K)
+    build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    drv.nearest_batch(h, Q[: max(1, nq // cores)], 1)
+    one_core = (time.perf_counter() - t0) / max(1, nq // cores)
+    t0 = time.perf_counter()
+    drv.nearest_batch(h, Q, cores)
+    all_cores = time.perf_counter() - t0
+    out = {"config": name, "impl": drv.kind, "rows": n, "dim": D, "kd_dim": K, "queries": nq, "cores": cores,
+           "build_s": build_s, "one_core_s_per_query": one_core, "one_core_queries_per_s": 1.0 / one_core,
+           "all_cores_queries_per_s": nq / all_cores}
+    if npairs:
+        i1 = np.random.default_rng(3).integers(0, n, npairs).astype(np.uint64)
+        i2 = np.random.default_rng(4).integers(0, n, npairs).astype(np.uint64)
+        for m, label in ((0, "cosine"), (1, "euclidean"), (2, "dot")):
+            t0 = time.perf_counter()
+            drv.compare_batch(h, m, i1, i2, cores)
+            out[f"compare_{label}_pairs_per_s_all_cores"] = npairs / (time.perf_counter() - t0)
+    drv.free(h)
+    print(json.dumps(out), flush=True)
+    return [out]
+
+
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c2", "c4"]
     torch.cuda.set_device(0)
     torch.cuda.set_stream(torch.cuda.Stream(device=DEV))
     res = []
+    if "cpu" in which:  # CPU reference on the same shapes (configs 1, 2, 4); bounded so it ends in ~2 min
+        res += cpu_case("cpu_c1_10k_x128_k3", 10_000, 128, 3, 10_000, script=True)
+        res += cpu_case("cpu_c1b_100k_x128_k3", 100_000, 128, 3, 10_000, script=True)
+        res += cpu_case("cpu_c2_1M_x128", 1_000_000, 128, 128, 64, npairs=100_000)
+        res += cpu_case("cpu_c4_100k_x1536_compare", 100_000, 1536, 3, 16, npairs=100_000)
     if "c1" in which:   # the reference's own CPU-runnable case: kd_dim 3 prefix of 128-dim rows
         res += nearest_case("c1_10k_x128_k3", 10_000, 128, 3, 1, (1, 1024), iters=50)
         res += nearest_case("c1b_100k_x128_k3", 100_000, 128, 3, 1, (1, 1024), iters=50)

@@ -20,13 +20,13 @@ def script_values(seed: int, shape) -> np.ndarray:
     ip = rng.integers(1, 10, size=n)
     places = rng.integers(0, 7, size=n)
     digits = rng.integers(0, 10, size=(n, 6))
-    out = np.empty(n, dtype=np.float64)
-    for i in range(n):
-        p = int(places[i])
-        if p:
-            out[i] = float(f"{ip[i]}." + "".join(str(int(d)) for d in digits[i, :p]))
-        else:
-            out[i] = float(ip[i])
+    # "i.d1..dp" parsed by strtod == correctly rounded (i*10^p + d1..dp) / 10^p: both operands are
+    # exact doubles and IEEE division rounds correctly, so this equals float(text) bit for bit
+    frac = np.zeros(n, dtype=np.int64)
+    for j in range(6):
+        frac = np.where(j < places, frac * 10 + digits[:, j], frac)
+    scale = 10.0 ** places
+    out = (ip * scale + frac) / scale
     return out.reshape(shape)
 
 
