@@ -159,8 +159,8 @@ def main():
         res += cpu_case("cpu_c2_1M_x128", 1_000_000, 128, 128, 64, npairs=100_000)
         res += cpu_case("cpu_c4_100k_x1536_compare", 100_000, 1536, 3, 16, npairs=100_000)
     if "c1" in which:   # the reference's own CPU-runnable case: kd_dim 3 prefix of 128-dim rows
-        res += nearest_case("c1_10k_x128_k3", 10_000, 128, 3, 1, (1, 1024), iters=50)
-        res += nearest_case("c1b_100k_x128_k3", 100_000, 128, 3, 1, (1, 1024), iters=50)
+        res += nearest_case("c1_10k_x128_k3", 10_000, 128, 3, 1, (1, 1024, 65536), iters=50)
+        res += nearest_case("c1b_100k_x128_k3", 100_000, 128, 3, 1, (1, 1024, 65536), iters=50)
     if "lat" in which:  # fixed per-query cost: a store so small that the scan itself is ~free
         res += nearest_case("latency_4k_x768", 4096, 768, 768, 1, (1,), iters=200)
         res += nearest_case("latency_4k_x768_top10", 4096, 768, 768, 10, (1,), iters=200)
