@@ -32,6 +32,9 @@ def build(ref_root: str = "/root/reference") -> None:
     """Compile the checkers (port always; _ref when the reference tree is present)."""
     subprocess.run(["make", "-s", "-C", HERE, "all", f"REF={ref_root}"], check=True,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # the reference's handlers driven in-process (needs the CUDA library to link the second binary)
+    subprocess.run(["make", "-s", "-C", HERE, "handlers", f"REF={ref_root}"], check=False,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def _as_f64(a) -> np.ndarray:
