@@ -234,7 +234,16 @@ int svdb_engine::tree_append(size_t n0, size_t m) {
         return fail(SVDB_ERR_OOM, err);
     int rounds = 0;
     CK(launch_tree_insert(kd_ptr(), kstride, K, child.as<uint32_t>(), n0, m, tree_pn.as<uint32_t>(), tree_pds.as<uint32_t>(),
-                          tree_flag.as<unsigned>(), tree_hflag.as<unsigned>(), tune.num_sms, stream, &rounds));
+                          tree_flag.as<unsigned>(), tree_hflag.as<unsigned>(), tune.num_sms, stream, tree_max_depth, &rounds));
+    if (rounds < 0) {
+        // The reference's tree for this insertion order is deeper than tree_max_depth (sorted input makes it
+        // a linked list: its own recursive insert/search would be O(N) deep).  Keep serving from the scan:
+        // exact nearest neighbours, exact-distance ties between distinct points fall back to the lowest seq.
+        fprintf(stderr, "svdb_b200: KD tree deeper than %d levels (degenerate insertion order); tree dropped, "
+                        "nearest is answered by the scan from now on\n", tree_max_depth);
+        use_tree = false;
+        rounds = -rounds;
+    }
     stats.tree_rounds += rounds;
     stats.kernels_launched += rounds + 1;
     return SVDB_OK;
@@ -1167,6 +1176,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
+    else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);

@@ -87,9 +87,11 @@ cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int n
 
 // K5: insert log entries [n0, n0+m) into the reference-shaped tree (level-synchronous; see tree_kernels.cu).
 // pn/pds: m-entry u32 scratch; d_flag: device word; h_flag_pinned: pinned host word. Synchronizes the stream.
+// Gives up after max_rounds rounds (tree deeper than that: degenerate insertion order) and reports a
+// NEGATIVE round count; the tree is then incomplete and must not be used.
 cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *child, u64 n0, u64 m, uint32_t *pn,
                                uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
-                               int *rounds_out);
+                               int max_rounds, int *rounds_out);
 // K6: the reference's traversal, one thread per query, k = 1.
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, const u64 *log_index, u64 seq_base, svdb_candidate *out, cudaStream_t st);

@@ -69,7 +69,7 @@ __global__ void tree_init_kernel(uint32_t *child, uint32_t n0, uint32_t m, uint3
 
 cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *child, u64 n0, u64 m, uint32_t *pn,
                                uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
-                               int *rounds_out) {
+                               int max_rounds, int *rounds_out) {
     if (m == 0) return cudaSuccess;
     const uint32_t M = (uint32_t)m, N0 = (uint32_t)n0;
     const int grid_all = (int)((m + 255) / 256 > (u64)num_sms * 8 ? (u64)num_sms * 8 : (m + 255) / 256);
@@ -110,7 +110,10 @@ cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *c
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return e;
         if (*h_flag_pinned == 0) break;
-        if (total_rounds > (1 << 22)) return cudaErrorLaunchTimeout;   // degenerate (sorted) input: depth ~ N
+        if (total_rounds > max_rounds) {   // degenerate (e.g. sorted) insertion order: depth ~ N
+            if (rounds_out) *rounds_out = -total_rounds;
+            return cudaSuccess;
+        }
     }
     if (rounds_out) *rounds_out = total_rounds;
     return cudaSuccess;

@@ -646,3 +646,21 @@ def test_random_batched_deltas_vs_model(port, D, K, seed, coarse):
                     ok = (got[:, m_].view(np.uint32) == want.view(np.uint32)) | (np.isnan(got[:, m_]) & np.isnan(want))
                     assert ok.all(), f"step {step} metric {m_}"
     model.close()
+
+
+def test_degenerate_insertion_order_drops_the_tree_but_keeps_answers(port, capfd):
+    """Sorted input turns the reference's tree into a list (depth ~ N).  The level-synchronous
+    build gives up beyond tree.max_depth, the engine keeps answering from the scan."""
+    n, D = 6000, 4
+    rows = np.cumsum(np.ones((n, D)), axis=0) + synth.uniform_rows(1, n, D) * 0.1     # increasing in every coordinate
+    Q = rows[[5, 999, 4321]] + 0.01
+    want = oracle_topk(port, rows, 2, Q, 3)
+    with B.Engine(D, 2) as e:
+        e.set_option("tree.max_depth", 512)
+        e.insert(rows)
+        assert_topk_equal(e.nearest(Q, 3), want, 3)
+        np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], [w[1][0] for w in want])
+        e.insert(rows[:10] + 0.5)                      # later inserts keep working without a tree
+        assert e.log_size == n + 10
+        assert e.nearest(rows[3] + 0.5, 1)[0][0, 0] == n + 3
+    assert "tree dropped" in capfd.readouterr().err
