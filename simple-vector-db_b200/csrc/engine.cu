@@ -334,7 +334,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     const int cap = (int)std::min<size_t>(32, k + 8);
     // K2: a batch large enough to be compute-bound goes to the FP64 tensor cores
     if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
-        const int G = mma_queries_per_group();
+        const int G = mma_group_size(nq);
         std::string err;
         const int ldp = kstride;
         size_t done = 0;
@@ -358,6 +358,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
             ma.qnorm = qnorm.as<double>();
             ma.ldq = ldp;
             ma.nq = (int)nqp;
+            ma.group = G;
             ma.ngroups = ngroups;
             ma.nstreams = nstreams;
             ma.cap = cap;

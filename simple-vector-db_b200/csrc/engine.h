@@ -49,7 +49,7 @@ struct svdb_engine {
     svdb_config cfg;
     int D = 0, K = 0, Dpad = 0, kstride = 0;
     bool log_only = false, no_log = false, alias = false, wide = false, use_tree = false;
-    int mma_min_q = 16;                  // AUTO: batches of at least this many queries take the DMMA path (K2)
+    int mma_min_q = 4;                   // AUTO: batches of at least this many queries take the DMMA path (K2)
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
     int device = 0;

@@ -71,15 +71,16 @@ struct MmaArgs {
     u64 n;
     int K, stride;
     const double *xnorm;    // |x_r|^2 per log entry
-    const double *q;        // padded queries [ngroups*64][ldq], zeros beyond K and beyond nq
+    const double *q;        // padded queries [ngroups*group][ldq], zeros beyond K and beyond nq
     const double *qnorm;    // |q|^2 per padded query
     int ldq, nq;            // nq real queries
-    int ngroups, nstreams;  // grid = ngroups * nstreams CTAs; a group = 64 queries
+    int group;              // queries per CTA group: 64, 32 or 16 (mma_group_size)
+    int ngroups, nstreams;  // grid = ngroups * nstreams CTAs
     int cap;
-    Cand *lists;            // [ngroups*64][nstreams][cap]
+    Cand *lists;            // [ngroups*group][nstreams][cap]
 };
 cudaError_t launch_scan_mma(const MmaArgs &a, cudaStream_t st);
-int mma_queries_per_group();
+int mma_group_size(size_t nq);
 cudaError_t launch_rownorm(const double *pts, int stride, int K, u64 first, u64 n, double *out, unsigned long long *max_bits,
                            int num_sms, cudaStream_t st);
 cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int nq_pad, double *dst, int ldp, double *qnorm,

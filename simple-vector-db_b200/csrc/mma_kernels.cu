@@ -21,13 +21,24 @@
 
 namespace svdb {
 
-constexpr int MM_ROWS = 128, MM_Q = 64, MM_KC = 32, MM_STAGES = 3, MM_THREADS = 256;
+constexpr int MM_ROWS = 128, MM_KC = 32, MM_STAGES = 3, MM_THREADS = 256;
 constexpr int MM_X_BYTES = MM_ROWS * MM_KC * 8;        // 32 KB
-constexpr int MM_Q_BYTES = MM_Q * MM_KC * 8;           // 16 KB
-constexpr int MM_STAGE_BYTES = MM_X_BYTES + MM_Q_BYTES;
-constexpr int MM_DT_LD = MM_ROWS + 2;                  // keys tile [64][130] doubles
-constexpr int MM_DT_BYTES = MM_Q * MM_DT_LD * 8;
-constexpr int MM_SMEM = MM_STAGES * MM_STAGE_BYTES + MM_DT_BYTES + MM_Q * 8;
+constexpr int MM_DT_LD = MM_ROWS + 2;                  // keys tile [NQT][130] doubles
+
+// Shape of one CTA for a query group of NQT queries (64 / 32 / 16): 8 warps, WR x WC of them,
+// each owning MI x NI accumulator fragments of 8 rows x 8 queries.
+template <int NQT>
+struct MmaShape {
+    static constexpr int WC = NQT == 64 ? 2 : 1;
+    static constexpr int WR = 8 / WC;
+    static constexpr int MI = MM_ROWS / (8 * WR);      // 4 (NQT=64) or 2
+    static constexpr int NI = NQT / (8 * WC);          // 4, 4, 2
+    static constexpr int QPW = NQT / 8;                // queries whose lists one warp owns
+    static constexpr int Q_BYTES = NQT * MM_KC * 8;
+    static constexpr int STAGE_BYTES = MM_X_BYTES + Q_BYTES;
+    static constexpr int DT_BYTES = NQT * MM_DT_LD * 8;
+    static constexpr int SMEM = MM_STAGES * STAGE_BYTES + DT_BYTES + NQT * 8;
+};
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -57,7 +68,11 @@ __device__ __forceinline__ uint32_t chunk_off(int r, int ch /* 16-byte chunk 0..
     return (uint32_t)(r * 256 + (ch >> 3) * 128 + (((ch & 7) ^ row_mask(r)) << 4));
 }
 
+template <int NQT>
 __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
+    using S = MmaShape<NQT>;
+    constexpr int MM_Q = NQT, MM_STAGE_BYTES = S::STAGE_BYTES, MM_DT_BYTES = S::DT_BYTES;
+    constexpr int MI = S::MI, NI = S::NI, QPW = S::QPW;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = blockIdx.x % p.ngroups, stream = blockIdx.x / p.ngroups;
@@ -72,11 +87,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
     const u64 my_tiles = ntiles > (u64)stream ? (ntiles - stream + p.nstreams - 1) / p.nstreams : 0;
     const u64 total = my_tiles * nchunks;              // (tile, chunk) steps of this CTA, one continuous pipeline
 
-    WarpList wl[8];                                    // this warp owns queries warp*8 .. warp*8+7 of the group
+    WarpList wl[QPW];                                  // this warp owns queries warp*QPW .. of the group
 #pragma unroll
-    for (int j = 0; j < 8; j++) wl[j].reset();
+    for (int j = 0; j < QPW; j++) wl[j].reset();
 
-    const int wr = warp >> 1, wc = warp & 1;           // warp tile: rows wr*32.., queries wc*32..
+    const int wr = warp / S::WC, wc = warp % S::WC;    // warp tile: rows wr*MI*8.., queries wc*NI*8..
     const int g = lane >> 2, t4 = lane & 3;
 
     // producer cursor: which (tile, chunk) the next cp.async batch fetches, into which stage
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
             cp_async16_zfill(st + chunk_off(r, ch), src, ok ? 16u : 0u);
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {                  // queries: 64 x 16 chunks
+        for (int i = 0; i < MM_Q * 16 / MM_THREADS; i++) {   // queries: NQT x 16 chunks
             const int idx = tid + i * MM_THREADS;
             const int r = idx >> 4, ch = idx & 15;
             const int col = c0 + ch * 2;
@@ -112,11 +127,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
         if (++p_stage == MM_STAGES) p_stage = 0;
     };
 
-    double acc[4][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < MM_STAGES - 1; s++) {
@@ -138,19 +153,19 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
         // MMA may hold any 4 coordinates as long as A and B agree).
 #pragma unroll
         for (int j = 0; j < MM_KC / 8; j++) {
-            double2 a[4], b[4];
+            double2 a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = lds128(xs + chunk_off(wr * 32 + mi * 8 + g, j * 4 + t4));
+            for (int mi = 0; mi < MI; mi++) a[mi] = lds128(xs + chunk_off(wr * (MI * 8) + mi * 8 + g, j * 4 + t4));
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = lds128(qs + chunk_off(wc * 32 + ni * 8 + g, j * 4 + t4));
+            for (int ni = 0; ni < NI; ni++) b[ni] = lds128(qs + chunk_off(wc * (NI * 8) + ni * 8 + g, j * 4 + t4));
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
         }
         if (++c_stage == MM_STAGES) c_stage = 0;
         if (++c_kc < nchunks) continue;
@@ -158,14 +173,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
         // ---- tile finished: keys -> shared memory, transposed to [query][row] ----
         const u64 row0 = c_tile * MM_ROWS;
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) {
-            const int r = wr * 32 + mi * 8 + g;
+        for (int mi = 0; mi < MI; mi++) {
+            const int r = wr * (MI * 8) + mi * 8 + g;
             const double xn = row0 + r < p.n ? __ldg(p.xnorm + row0 + r) : 0.0;
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
+            for (int ni = 0; ni < NI; ni++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int qc = wc * 32 + ni * 8 + t4 * 2 + h;
+                    const int qc = wc * (NI * 8) + ni * 8 + t4 * 2 + h;
                     dt[qc * MM_DT_LD + r] = fma(-2.0, acc[mi][ni][h], xn + qn_s[qc]);
                     acc[mi][ni][h] = 0.0;
                 }
@@ -175,8 +190,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
         // selection: each warp feeds the lists of its 8 queries; the loop-top barrier of the next step
         // orders these reads before the next tile's keys overwrite dt
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double *col = dt + (warp * 8 + j) * MM_DT_LD;
+        for (int j = 0; j < QPW; j++) {
+            const double *col = dt + (warp * QPW + j) * MM_DT_LD;
 #pragma unroll
             for (int it2 = 0; it2 < MM_ROWS / 32; it2++) {
                 const int r = it2 * 32 + lane;
@@ -189,22 +204,33 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
     cp_wait<0>();
 
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int q = q0 + warp * 8 + j;
+    for (int j = 0; j < QPW; j++) {
+        const int q = q0 + warp * QPW + j;
         if (q < p.nq && lane < p.cap)
             p.lists[((size_t)q * p.nstreams + stream) * p.cap + lane] = Cand{wl[j].d, wl[j].seq};
     }
 }
 
-cudaError_t launch_scan_mma(const MmaArgs &a, cudaStream_t st) {
-    if (a.ngroups < 1 || a.nstreams < 1 || (a.stride & 1) || (a.ldq & 1)) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+template <int NQT>
+static cudaError_t launch_scan_mma_inst(const MmaArgs &a, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaShape<NQT>::SMEM);
     if (e != cudaSuccess) return e;
-    scan_mma_kernel<<<a.ngroups * a.nstreams, MM_THREADS, MM_SMEM, st>>>(a);
+    scan_mma_kernel<NQT><<<a.ngroups * a.nstreams, MM_THREADS, MmaShape<NQT>::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
-int mma_queries_per_group() { return MM_Q; }
+cudaError_t launch_scan_mma(const MmaArgs &a, cudaStream_t st) {
+    if (a.ngroups < 1 || a.nstreams < 1 || (a.stride & 1) || (a.ldq & 1)) return cudaErrorInvalidValue;
+    switch (a.group) {
+        case 64: return launch_scan_mma_inst<64>(a, st);
+        case 32: return launch_scan_mma_inst<32>(a, st);
+        case 16: return launch_scan_mma_inst<16>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// queries per CTA group for a batch of nq: small batches get small groups (less padding)
+int mma_group_size(size_t nq) { return nq <= 16 ? 16 : (nq <= 32 ? 32 : 64); }
 
 // ---- |x_r|^2 at insert: one warp per row, any summation order (these feed approximate keys only) ----
 __global__ void __launch_bounds__(256) rownorm_kernel(const double *__restrict__ pts, int stride, int K, u64 first, u64 n,

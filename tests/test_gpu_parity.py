@@ -293,6 +293,8 @@ def test_topk_vs_oracle(port, n, D, K, k, seed):
         st = e.stats()
         assert st["kernels_launched"] > 0 and st["exact_reruns"] == 0
         if K > 16:
+            e.set_option("nearest.mma_min_queries", 0)      # 13 queries: K1 in passes of 8 + 4 + 1 from here on
+            assert_topk_equal(e.nearest(Q, k), want, k)
             for opts in ({"scan.variant": 1}, {"scan.variant": 0, "scan.nq_per_pass": 1},
                          {"scan.nq_per_pass": 8, "scan.warps": 4, "scan.stages": 2},
                          {"scan.tile_rows": 1, "scan.ctas_per_sm": 2}, {"scan.force_exact": 1}):
@@ -306,10 +308,12 @@ def test_topk_vs_oracle(port, n, D, K, k, seed):
     (9000, 768, 768, 64, 10, 2),       # config-3 rows, exactly one group
     (6000, 100, 100, 40, 5, 3),        # K not a multiple of the 32-coordinate chunk (zero-filled tail)
     (5000, 200, 50, 33, 24, 4),        # compact kd array (K < D), k = SVDB_MAX_K
-    (300, 40, 40, 16, 3, 5),           # fewer rows than one 128-row tile per stream
+    (300, 40, 40, 16, 3, 5),           # fewer rows than one 128-row tile per stream; group of 16
+    (7000, 96, 96, 24, 10, 6),         # group of 32
+    (7000, 64, 64, 5, 1, 7),           # smallest batch that takes the tensor-core path (group of 16, 11 padded)
 ])
 def test_batched_dmma_path_vs_oracle(port, n, D, K, nq, k, seed):
-    """K2: >= 16 queries per call go through the FP64 tensor-core GEMM-form scan; after the
+    """K2: >= 4 queries per call go through the FP64 tensor-core GEMM-form scan; after the
     reference-order re-rank the answers are bit-identical to the oracle's."""
     rows = synth.uniform_rows(seed, n, D)
     Q = synth.uniform_rows(seed + 70, nq, D)
