@@ -259,9 +259,17 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    q_np = q_host.numpy()        # the same pinned host buffers, seen as plain host memory by the C-ABI
+
     def step_e2e(i):
+        """The call a user makes.  1 GPU: the C-ABI host entry point svdb_nearest_batch (host query in,
+        host result out; H2D, kernels, D2H and the sync all inside).  N GPUs: ShardedIndex.nearest
+        (H2D of the query, scan, peer-memory exchange + merge, D2H of the merged result)."""
         if flush_buf is not None:
             flush_buf.zero_()
+        if world == 1:
+            ix, ds, sq = e.nearest(q_np[i % pool], k)
+            return {"seq": sq, "dist": ds, "index": ix}
         return idx.nearest(q_host[i % pool], k)
 
     def step_dev(i):
@@ -397,7 +405,8 @@ def ours(args):
         "clocks": sampler.summary(),
         "batch": batch,
         "store": {"rows_per_rank": rows_per_rank, "build_s": build_s, "hbm_gib_mapped": e.stats()["hbm_bytes_mapped"] / 2**30,
-                  "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0])},
+                  "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0]),
+                  "e2e_entry_point": "svdb_nearest_batch (C-ABI, host buffers)" if world == 1 else "svdb.sharded.ShardedIndex.nearest"},
     }
     emit(line)
     if world > 1:
