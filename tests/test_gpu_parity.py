@@ -668,3 +668,27 @@ def test_degenerate_insertion_order_drops_the_tree_but_keeps_answers(port, capfd
         assert e.log_size == n + 10
         assert e.nearest(rows[3] + 0.5, 1)[0][0, 0] == n + 3
     assert "tree dropped" in capfd.readouterr().err
+
+
+def test_large_dimension_and_empty_calls(port, cpu):
+    """D = 4100 (32.8 KB rows, not a multiple of anything convenient): scan tiles larger than the
+    co-residency budget, several re-rank rounds, zero-padded tails; plus zero-sized calls."""
+    n, D = 400, 4100
+    rows = synth.normal_rows(1, n, D)
+    Q = synth.normal_rows(2, 6, D)
+    want = oracle_topk(port, rows, D, Q, 24)
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        assert_topk_equal(e.nearest(Q, 24), want, 24)                       # K2 (6 queries -> group of 16)
+        assert_topk_equal(e.nearest(Q[:1], 24), want[:1], 24)               # K1 single query
+        e.set_option("nearest.mma_min_queries", 0)
+        assert_topk_equal(e.nearest(Q, 24), want, 24)                       # K1, passes of 4 + 2
+        i1, i2 = synth.index_pairs(1, 300, n)
+        h = cpu.build(rows, 1)
+        for m in range(3):
+            np.testing.assert_array_equal(e.compare(m, i1, i2).view(np.uint32), cpu.compare_batch(h, m, i1, i2).view(np.uint32))
+        cpu.free(h)
+        idx, dist, seq = e.nearest(np.zeros((0, D)), 3)
+        assert idx.shape == (0, 3)
+        assert e.compare(B.DOT, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)).shape == (0,)
+        assert e.insert(np.zeros((0, D))) == n and e.size == n
