@@ -25,7 +25,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from svdb import binding as B  # noqa: E402
-from svdb.sharded import ShardedIndex  # noqa: E402
+from svdb.sharded import ReplicatedCompare, ShardedIndex  # noqa: E402
 
 
 def main():
@@ -53,6 +53,25 @@ def main():
                 ok &= bool(same)
                 report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "identical_to_single_gpu": bool(same)})
         idx.close()
+    # /compare: replicas, pairs split over the ranks, results all-gathered
+    n, D = 20_000, 256
+    g = torch.Generator().manual_seed(7)
+    rows = torch.rand((n, D), dtype=torch.float64, generator=g).to(dev)
+    i1 = torch.randint(0, n, (5001,), generator=g).to(dev)
+    i2 = torch.randint(0, n, (5001,), generator=g).to(dev)
+    with B.Engine(D, 1, device=local, flags=B.FLAG_NO_LOG) as e:
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        e.insert_device(rows.data_ptr(), n, D)
+        rc = ReplicatedCompare(e, rank, world)
+        for metric in (0, 1, 2, 3):
+            got = rc.compare(metric, i1, i2)
+            full = torch.empty_like(got)
+            e.compare_device(metric, i1.data_ptr(), i2.data_ptr(), i1.numel(), full.data_ptr())
+            torch.cuda.synchronize()
+            same = bool(torch.equal(got.view(torch.int32), full.view(torch.int32)))
+            ok &= same
+            if rank == 0:
+                report.append({"compare_metric": metric, "pairs": i1.numel(), "identical_to_single_gpu": same})
     dist.barrier()
     if rank == 0:
         print(json.dumps({"check": "sharded_vs_single", "world": world, "ok": ok, "cases": report}), flush=True)

@@ -128,3 +128,33 @@ class ShardedIndex:
             t.cuda.current_stream(self.device).synchronize()
             res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
         return res.copy()
+
+
+class ReplicatedCompare:
+    """/compare over N GPUs: pairs are independent, so every rank holds a replica of
+    the rows and answers a contiguous slice of the pairs; one all-gather returns the whole result.
+    No exchange inside the kernel -- this is the "replicas, no collective" case."""
+
+    def __init__(self, engine: "B.Engine", rank: int = 0, world: int = 1, group=None):
+        import torch
+        self.torch, self.e, self.rank, self.world, self.group = torch, engine, rank, world, group
+
+    def compare(self, metric: int, i1, i2):
+        """i1, i2: int64 CUDA tensors of n pair indices (same on every rank). Returns float32 [n] (or
+        [n, 3] for metric 3) on every rank."""
+        t = self.torch
+        n = i1.numel()
+        per = -(-n // self.world)
+        lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        width = 3 if metric == B.ALL_METRICS else 1
+        mine = t.full((per, width), -1.0, dtype=t.float32, device=i1.device)
+        if hi > lo:
+            a, b = i1[lo:hi].contiguous(), i2[lo:hi].contiguous()
+            self.e.compare_device(metric, a.data_ptr(), b.data_ptr(), hi - lo, mine.data_ptr())
+        if self.world == 1:
+            out = mine
+        else:
+            out = t.empty((self.world * per, width), dtype=t.float32, device=i1.device)
+            t.distributed.all_gather_into_tensor(out, mine, group=self.group)
+        out = out[:n]
+        return out if width == 3 else out[:, 0]

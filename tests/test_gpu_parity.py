@@ -692,3 +692,24 @@ def test_large_dimension_and_empty_calls(port, cpu):
         assert idx.shape == (0, 3)
         assert e.compare(B.DOT, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)).shape == (0,)
         assert e.insert(np.zeros((0, D))) == n and e.size == n
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 3), st.integers(1, 80), st.integers(0, 2 ** 32 - 1))
+def test_gpu_equals_oracle_on_small_grids(K, n, seed):
+    """Tie-heavy random instances (coordinates from {0, 0.5, .., 2}): the id must be the one the
+    reference's traversal reaches first, through the tree traversal AND through scan + resolver."""
+    port = OB.load_port()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = rng.integers(0, 5, size=(n, K + 1)) / 2.0
+    Q = rng.integers(0, 5, size=(8, K + 1)) / 2.0
+    want = oracle_tree_ids(port, rows, K, Q)
+    with B.Engine(K + 1, K) as e:
+        e.insert(rows)
+        np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], want)
+        e.set_option("nearest.tree_max_k", 0)
+        np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], want)
+        np.testing.assert_array_equal(e.nearest(Q, min(3, n))[0][:, 0], want)

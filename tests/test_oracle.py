@@ -160,3 +160,27 @@ def test_reference_save_load_roundtrip(ref, tmp_path):
     np.testing.assert_array_equal(np.ctypeslib.as_array(v.data, shape=(4,)), rows[3])
     L.vector_db_free(db)
     L.vector_db_free(db2)
+
+
+# ---- property test: tie-heavy random instances, port == reference -----------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(1, 3), st.integers(1, 60), st.integers(0, 2 ** 32 - 1))
+def test_port_equals_reference_on_small_grids(K, n, seed):
+    """Coordinates from {0, 0.5, .., 2}: duplicates and distinct equidistant points everywhere, so
+    this pins the traversal ORDER (which tied entry is reached first), not just the distances."""
+    from oracle import binding as OB
+    if not OB.have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref, port = OB.load_ref(), OB.load_port()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = rng.integers(0, 5, size=(n, K + 1)) / 2.0
+    Q = rng.integers(0, 5, size=(8, K + 1)) / 2.0
+    hr, hp = ref.build(rows, K), port.build(rows, K)
+    try:
+        np.testing.assert_array_equal(ref.nearest_batch(hr, Q), port.nearest_batch(hp, Q))
+    finally:
+        ref.free(hr)
+        port.free(hp)
