@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -16,8 +17,12 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string &s) { g_last_error = s; }
 const std::string &get_last_error() { return g_last_error; }
 
+static std::atomic<unsigned long long> g_scratch_gen{0};
+unsigned long long scratch_generation() { return g_scratch_gen.load(); }
+
 bool Scratch::ensure(size_t bytes, std::string &err) {
     if (bytes <= cap) return true;
+    g_scratch_gen++;
     size_t want = std::max(bytes, cap + cap / 2);
     void *np = nullptr;
     if (cudaMalloc(&np, want) != cudaSuccess) {
@@ -40,6 +45,7 @@ void Scratch::free_() {
 }
 bool PinnedScratch::ensure(size_t bytes, std::string &err) {
     if (bytes <= cap) return true;
+    g_scratch_gen++;
     const size_t want = std::max(bytes, cap + cap / 2);
     void *np = nullptr;
     if (cudaMallocHost(&np, want) != cudaSuccess) {
@@ -145,6 +151,7 @@ int svdb_engine::init(const svdb_config &c) {
     const size_t main_row_bytes = (size_t)(log_only ? kstride : Dpad) * 8;
     max_versions = std::min<size_t>(va / main_row_bytes, 0xfffffffeull);   // tree links are u32
     use_tree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !getenv("SVDB_NO_TREE");
+    graphs_enabled = !getenv("SVDB_NO_GRAPH");
     std::string err;
     if (!log_only) {
         if (!rows.init(device, max_versions * (size_t)Dpad * 8, err)) return fail(SVDB_ERR_CUDA, err);
@@ -185,9 +192,15 @@ int svdb_engine::init(const svdb_config &c) {
     return SVDB_OK;
 }
 
+void svdb_engine::drop_graphs() {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+}
+
 void svdb_engine::destroy() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
+    drop_graphs();
     for (auto &ev : scan_events) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -487,13 +500,59 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         !outc.ensure((nq * k + 1) * sizeof(svdb_candidate), err) || !hout.ensure(nq * k * sizeof(svdb_candidate), err))
         return fail(SVDB_ERR_OOM, err);
     for (size_t i = 0; i < nq; i++) memcpy(hq.as<double>() + i * K, Q + i * ldq, (size_t)K * 8);
-    CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += nq * (size_t)K * 8;
-    int rc = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), SVDB_MODE_AUTO);
+    int rc = flush();
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hout.p, outc.p, nq * k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
+    stats.h2d_bytes += nq * (size_t)K * 8;
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
+
+    // the enqueue sequence of one call: H2D of the queries, the kernels, D2H of the candidates
+    auto enqueue = [&]() -> int {
+        CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+        int r = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), SVDB_MODE_AUTO);
+        if (r) return r;
+        CK(cudaMemcpyAsync(hout.p, outc.p, nq * k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
+        return SVDB_OK;
+    };
+    const unsigned long long gen = scratch_generation() + opt_gen;
+    bool done = false;
+    if (graphs_enabled && !profile_scan && nq <= 64 && n_versions > 0) {
+        for (auto &g : graphs) {
+            if (g.nq == nq && g.k == k && g.n_versions == n_versions && g.gen == gen && g.stream == stream) {
+                CK(cudaGraphLaunch(g.exec, stream));
+                stats.kernels_launched += g.launches;
+                done = true;
+                break;
+            }
+        }
+        if (!done && last_nq == nq && last_k == k) {
+            // second call of this shape in a row (buffers are warm, nothing will allocate): capture it
+            if (graphs.size() >= 8 || (!graphs.empty() && (graphs[0].n_versions != n_versions || graphs[0].gen != gen))) drop_graphs();
+            const uint64_t l0 = stats.kernels_launched;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+            int r = ce == cudaSuccess ? enqueue() : SVDB_ERR_CUDA;
+            cudaError_t ce2 = ce == cudaSuccess ? cudaStreamEndCapture(stream, &graph) : ce;
+            if (r == SVDB_OK && ce2 == cudaSuccess && graph && scratch_generation() + opt_gen == gen &&
+                cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                graphs.push_back(HostGraph{nq, k, n_versions, gen, stream, exec, stats.kernels_launched - l0});
+                CK(cudaGraphLaunch(exec, stream));
+                done = true;
+            } else {
+                cudaGetLastError();
+                graphs_enabled = false;      // something in the sequence is not capturable here: plain launches from now on
+                stats.kernels_launched = l0;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        last_nq = nq;
+        last_k = k;
+    }
+    if (!done) {
+        rc = enqueue();
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(stream));
     svdb_candidate *res = hout.as<svdb_candidate>();
     // Escalation for queries whose answer could not be proven complete:
     //   AUTO -> EXACT (mass near-ties defeated the approximate candidate set, or the traversal
@@ -748,6 +807,7 @@ int svdb_set_stream(svdb_engine *e, void *stream) {
     if (!e) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     e->stream = stream == SVDB_STREAM_OWN ? e->own_stream : (cudaStream_t)stream;
+    e->opt_gen++;
     return SVDB_OK;
 }
 
@@ -1168,6 +1228,8 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     if (!e || !name) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     const std::string n(name);
+    e->opt_gen++;
+    if (n == "host.graphs") { e->graphs_enabled = value != 0; return SVDB_OK; }
     if (n == "scan.variant") e->tune.variant = (int)value;
     else if (n == "scan.warps") e->tune.warps = (int)value;
     else if (n == "scan.stages") e->tune.stages = (int)value;

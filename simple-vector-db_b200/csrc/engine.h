@@ -14,6 +14,10 @@
 
 namespace svdb {
 
+// bumped whenever any Scratch / PinnedScratch block is reallocated: captured CUDA graphs that baked the
+// old pointers in must not be replayed
+unsigned long long scratch_generation();
+
 void set_last_error(const std::string &s);
 const std::string &get_last_error();
 
@@ -86,6 +90,22 @@ struct svdb_engine {
     std::vector<PendingQuery *> bq;
     bool bq_leader = false;
     int nearest_one_coalesced(const double *q, size_t k, svdb_candidate *res);
+
+    // CUDA graphs of the host single/small-batch query path (H2D, kernels, D2H): one launch instead of
+    // five driver calls.  Valid for one (nq, k) shape while the log, the scratch blocks, the options
+    // and the stream stay the same.
+    struct HostGraph {
+        size_t nq, k, n_versions;
+        unsigned long long gen;
+        cudaStream_t stream;
+        cudaGraphExec_t exec;
+        uint64_t launches;
+    };
+    std::vector<HostGraph> graphs;
+    bool graphs_enabled = true;
+    unsigned long long opt_gen = 0;          // bumped by svdb_set_option / svdb_set_stream
+    size_t last_nq = 0, last_k = 0;          // a shape is captured the second time it shows up in a row
+    void drop_graphs();
 
     svdb::ScanTuning tune;
     bool force_exact = false;

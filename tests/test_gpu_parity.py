@@ -713,3 +713,41 @@ def test_gpu_equals_oracle_on_small_grids(K, n, seed):
         e.set_option("nearest.tree_max_k", 0)
         np.testing.assert_array_equal(e.nearest(Q, 1)[0][:, 0], want)
         np.testing.assert_array_equal(e.nearest(Q, min(3, n))[0][:, 0], want)
+
+
+def test_host_path_graph_replay_tracks_store_and_options(port):
+    """The host query path replays a captured CUDA graph from the second call of a shape on; the
+    graph must be dropped whenever the log, the options or the scratch blocks change."""
+    n, D = 5000, 48
+    rows = synth.uniform_rows(3, n, D)
+    Q = synth.uniform_rows(4, 3, D)
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        want = oracle_topk(port, rows, D, Q, 5)
+        for _ in range(4):                                    # plain, capture, replay, replay
+            assert_topk_equal(e.nearest(Q, 5), want, 5)
+        assert_topk_equal(e.nearest(Q[:1], 5), want[:1], 5)     # another shape in between
+        assert_topk_equal(e.nearest(Q, 5), want, 5)
+        # the store changes: a new row equal to query 0 must win immediately
+        e.insert(Q[0])
+        for _ in range(3):
+            idx, dist, _ = e.nearest(Q, 5)
+            assert idx[0, 0] == n and dist[0, 0] == 0.0
+        e.update(n, rows[0])                                     # stale point stays searchable, as in the reference
+        assert e.nearest(Q, 5)[0][0, 0] == n
+        e.set_option("scan.force_exact", 1)
+        for _ in range(3):
+            assert e.nearest(Q, 5)[0][0, 0] == n
+        big = synth.uniform_rows(5, 40, D)                        # larger batch: scratch blocks grow
+        e.nearest(big, 5)
+        for _ in range(3):
+            assert e.nearest(Q, 5)[0][0, 0] == n
+    with B.Engine(8, 3) as e:                                     # tree path (one kernel) through the graph as well
+        pts = synth.uniform_rows(6, 3000, 8)
+        e.insert(pts)
+        h = port.build(pts, 3)
+        q = synth.uniform_rows(7, 1, 8)
+        want1 = port.nearest_batch(h, q)[0]
+        port.free(h)
+        for _ in range(5):
+            assert e.nearest(q, 1)[0][0, 0] == want1
