@@ -506,12 +506,14 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
 
     // the enqueue sequence of one call: H2D of the queries, the kernels, D2H of the candidates
+    // Small transfers are latency, not bandwidth: the kernels write the candidates straight into the
+    // pinned host block (posted PCIe writes, no separate D2H op), and a thin query batch (a few hundred
+    // bytes, read once per CTA) is read straight from pinned memory instead of being copied first.
+    const bool q_zero_copy = !wide && nq * (size_t)K * 8 <= 2048;
+    const double *d_q = q_zero_copy ? hq.as<double>() : qraw.as<double>();
     auto enqueue = [&]() -> int {
-        CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
-        int r = nearest_device(qraw.as<double>(), nq, K, k, outc.as<svdb_candidate>(), SVDB_MODE_AUTO);
-        if (r) return r;
-        CK(cudaMemcpyAsync(hout.p, outc.p, nq * k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
-        return SVDB_OK;
+        if (!q_zero_copy) CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
+        return nearest_device(d_q, nq, K, k, hout.as<svdb_candidate>(), SVDB_MODE_AUTO);
     };
     const unsigned long long gen = scratch_generation() + opt_gen;
     bool done = false;
@@ -561,9 +563,8 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         svdb_candidate *r = res + i * k;
         if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
         stats.exact_reruns++;
-        rc = nearest_device(qraw.as<double>() + i * K, 1, K, k, outc.as<svdb_candidate>() + i * k, SVDB_MODE_EXACT);
+        rc = nearest_device(d_q + i * K, 1, K, k, r, SVDB_MODE_EXACT);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(r, outc.as<svdb_candidate>() + i * k, k * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         if (!(r[0].flags & SVDB_CAND_UNSAFE) || !use_tree) continue;
         // more exactly-tied entries than a list holds: ask the tree which one the reference reaches first
@@ -571,7 +572,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         if (!outc.ensure((nq * k + 1) * sizeof(svdb_candidate), err)) return fail(SVDB_ERR_OOM, err);
         svdb_candidate *d_one = outc.as<svdb_candidate>() + nq * k;
         svdb_candidate w;
-        rc = nearest_device(qraw.as<double>() + i * K, 1, K, 1, d_one, SVDB_MODE_TREE);
+        rc = nearest_device(d_q + i * K, 1, K, 1, d_one, SVDB_MODE_TREE);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&w, d_one, sizeof w, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
