@@ -129,7 +129,14 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
                                                            svdb_candidate *out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
-    const double *__restrict__ q = Q + (size_t)qi * ldq;   // K doubles, L1-resident after the first node
+    // thin queries are copied once into thread-local storage (the host path hands them over in pinned
+    // host memory, zero-copy); longer ones are read in place (L1-resident after the first node)
+    double ql[16];
+    const double *__restrict__ q = Q + (size_t)qi * ldq;
+    if (K <= 16) {
+        for (int i = 0; i < K; i++) ql[i] = q[i];
+        q = ql;
+    }
     struct Frame {
         uint32_t node, depth;
         double plane;
