@@ -145,6 +145,11 @@ int  svdb_exchange_connect(svdb_exchange *x, const unsigned char *all_handles /*
 void svdb_exchange_destroy(svdb_exchange *x);
 int  svdb_exchange_merge(svdb_exchange *x, void *stream, const svdb_candidate *d_local, size_t nq, size_t k,
                          svdb_candidate *d_out);
+/* The whole sharded query as one host call (host buffers in, MERGED answers out): this shard's scan,
+ * the exchange and the merge, replayed as one CUDA graph from the second call of a shape on.
+ * Collective: every rank calls it with the same queries, nq and k. */
+int  svdb_nearest_batch_sharded(svdb_engine *e, svdb_exchange *x, const double *Q, size_t nq, size_t ldq, size_t k,
+                                size_t *index_out, double *dist_out, uint64_t *seq_out);
 
 /* Concurrent single-query callers (the server is thread-per-connection, main.c:382, and
  * kdtree_nearest is called with no lock held, compare_handler.c:403): calls with nq == 1 that

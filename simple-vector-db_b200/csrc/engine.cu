@@ -490,7 +490,8 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
 }
 
 int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
-                              uint64_t *seq_out, svdb_candidate *cand_out) {
+                              uint64_t *seq_out, svdb_candidate *cand_out, svdb_exchange *x) {
+    if (x && !exchange_fits(x, nq, k)) return fail(SVDB_ERR_ARG, "nq * k exceeds the exchange capacity");
     if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
     if (nq == 0) return SVDB_OK;
     if (!Q || ldq < (size_t)K) return fail(SVDB_ERR_ARG, "bad query buffer");
@@ -511,15 +512,24 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     // bytes, read once per CTA) is read straight from pinned memory instead of being copied first.
     const bool q_zero_copy = !wide && nq * (size_t)K * 8 <= 2048;
     const double *d_q = q_zero_copy ? hq.as<double>() : qraw.as<double>();
+    auto enqueue_mode = [&](int mode) -> int {
+        if (!x) return nearest_device(d_q, nq, K, k, hout.as<svdb_candidate>(), mode);
+        // sharded: local candidates stay in HBM, the exchange stores them to the peers and writes the merge
+        int r = nearest_device(d_q, nq, K, k, outc.as<svdb_candidate>(), mode);
+        if (r) return r;
+        CK(exchange_enqueue(x, stream, outc.as<svdb_candidate>(), nq, k, hout.as<svdb_candidate>()));
+        stats.kernels_launched += 2;
+        return SVDB_OK;
+    };
     auto enqueue = [&]() -> int {
         if (!q_zero_copy) CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
-        return nearest_device(d_q, nq, K, k, hout.as<svdb_candidate>(), SVDB_MODE_AUTO);
+        return enqueue_mode(SVDB_MODE_AUTO);
     };
     const unsigned long long gen = scratch_generation() + opt_gen;
     bool done = false;
-    if (graphs_enabled && !profile_scan && nq <= 64 && n_versions > 0) {
+    if (graphs_enabled && !profile_scan && nq <= 64 && (n_versions > 0 || x)) {
         for (auto &g : graphs) {
-            if (g.nq == nq && g.k == k && g.n_versions == n_versions && g.gen == gen && g.stream == stream) {
+            if (g.nq == nq && g.k == k && g.x == x && g.n_versions == n_versions && g.gen == gen && g.stream == stream) {
                 CK(cudaGraphLaunch(g.exec, stream));
                 stats.kernels_launched += g.launches;
                 done = true;
@@ -537,7 +547,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
             cudaError_t ce2 = ce == cudaSuccess ? cudaStreamEndCapture(stream, &graph) : ce;
             if (r == SVDB_OK && ce2 == cudaSuccess && graph && scratch_generation() + opt_gen == gen &&
                 cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-                graphs.push_back(HostGraph{nq, k, n_versions, gen, stream, exec, stats.kernels_launched - l0});
+                graphs.push_back(HostGraph{nq, k, n_versions, x, gen, stream, exec, stats.kernels_launched - l0});
                 CK(cudaGraphLaunch(exec, stream));
                 done = true;
             } else {
@@ -559,7 +569,18 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     // Escalation for queries whose answer could not be proven complete:
     //   AUTO -> EXACT (mass near-ties defeated the approximate candidate set, or the traversal
     //   stack overflowed) -> TREE (more exactly-tied entries than a candidate list holds; k = 1).
-    for (size_t i = 0; i < nq; i++) {
+    if (x) {
+        // merged flags are identical on every rank, so every rank takes (or skips) this branch together
+        bool any = false;
+        for (size_t i = 0; i < nq; i++) any = any || (res[i * k].flags & SVDB_CAND_UNSAFE);
+        if (any) {
+            stats.exact_reruns += nq;
+            rc = enqueue_mode(SVDB_MODE_EXACT);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(stream));
+        }
+    }
+    for (size_t i = 0; i < nq && !x; i++) {
         svdb_candidate *r = res + i * k;
         if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
         stats.exact_reruns++;
@@ -922,6 +943,15 @@ int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, s
     }
     std::lock_guard<std::mutex> g(e->mu);
     return e->nearest_host(Q, nq, ldq, k, index_out, dist_out, seq_out);
+}
+
+/* One shard's part of a sharded query, host buffers in and out: local scan, peer-memory exchange, merge.
+ * Collective -- every rank calls it with the same nq and k.  Outputs are the MERGED answers. */
+int svdb_nearest_batch_sharded(svdb_engine *e, svdb_exchange *x, const double *Q, size_t nq, size_t ldq, size_t k,
+                               size_t *index_out, double *dist_out, uint64_t *seq_out) {
+    if (!e || !x) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->nearest_host(Q, nq, ldq, k, index_out, dist_out, seq_out, nullptr, x);
 }
 
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out,

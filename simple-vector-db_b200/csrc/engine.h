@@ -41,6 +41,13 @@ struct PinnedScratch {
 
 }  // namespace svdb
 
+struct svdb_exchange;
+namespace svdb {
+cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candidate *d_local, size_t nq, size_t k,
+                             svdb_candidate *out);
+bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k);
+}  // namespace svdb
+
 // Layout in HBM (all fp64, row-major, one entry per VERSION = per insert/update/log append):
 //   rows     [versions][Dpad]   Dpad = D rounded up to 16 doubles (128-byte rows), zero padded
 //   kdpts    [versions][kstride] first K coordinates; aliases rows when K == D on the wide path
@@ -96,6 +103,7 @@ struct svdb_engine {
     // and the stream stay the same.
     struct HostGraph {
         size_t nq, k, n_versions;
+        svdb_exchange *x;
         unsigned long long gen;
         cudaStream_t stream;
         cudaGraphExec_t exec;
@@ -125,8 +133,10 @@ struct svdb_engine {
     int upload_cur();
     int tree_append(size_t n0, size_t m);
     int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode);
+    // x != NULL: this engine is one shard; the local candidates go through the peer-memory exchange and the
+    // outputs are the merged answers (collective: every rank calls with the same nq and k)
     int nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,
-                     uint64_t *seq_out, svdb_candidate *cand_out = nullptr);
+                     uint64_t *seq_out, svdb_candidate *cand_out = nullptr, svdb_exchange *x = nullptr);
     int ingest_device_rows(const double *d_rows, size_t n, size_t ld, size_t *first_index);
     int compare_device(int mode, const uint64_t *d_i1, const uint64_t *d_i2, size_t n, float *d_out);
     int compare_host(int mode, const size_t *i1, const size_t *i2, size_t n, float *out);

@@ -9,7 +9,9 @@
 // rank, so this is purely about latency.)
 //
 // Buffer layout (per rank, cudaMalloc'ed so that it can be exported):
-//   [ flags: 32 x u64 ]  flags[src] = last epoch whose data from `src` is complete
+//   [ flags: 32 x u64 ]  flags[src] = last epoch whose data from `src` is complete;
+//                        flags[31]  = this rank's own epoch counter, advanced ON THE DEVICE by the push
+//                        kernel, so that the exchange can sit inside a replayed CUDA graph
 //   [ parity 0: world x max_rec candidates ][ parity 1: ... ]   double-buffered by epoch parity
 #include <string>
 
@@ -21,6 +23,7 @@ namespace svdb {
 
 constexpr int XCH_MAX_WORLD = 16;
 constexpr size_t XCH_FLAG_BYTES = 32 * 8;
+constexpr int XCH_EPOCH_SLOT = 31;
 
 struct PeerPtrs {
     unsigned char *p[XCH_MAX_WORLD];
@@ -37,7 +40,15 @@ __device__ __forceinline__ u64 ld_acquire_sys_u64(const u64 *p) {
 
 // local results (nrec candidates) -> slot `rank` of every peer's gather buffer, then the flags
 __global__ void __launch_bounds__(256) exchange_push_kernel(const svdb_candidate *__restrict__ local, int nrec, PeerPtrs peers,
-                                                            int rank, int world, size_t max_rec, u64 epoch) {
+                                                            int rank, int world, size_t max_rec) {
+    __shared__ u64 s_epoch;
+    if (threadIdx.x == 0) {
+        u64 *mine = reinterpret_cast<u64 *>(peers.p[rank]);
+        s_epoch = mine[XCH_EPOCH_SLOT] + 1;
+        mine[XCH_EPOCH_SLOT] = s_epoch;               // read back by the merge kernel that follows in the stream
+    }
+    __syncthreads();
+    const u64 epoch = s_epoch;
     const size_t parity_off = XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate);
     const int words = nrec * 4;                                    // 8-byte words
     const u64 *src = reinterpret_cast<const u64 *>(local);
@@ -51,10 +62,11 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const svdb_candidate
 }
 
 // wait until every shard's data of `epoch` has landed locally, then K7 (one warp per query)
-__global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char *__restrict__ mine, int world, size_t max_rec, u64 epoch,
+__global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char *mine, int world, size_t max_rec,
                                                             int nq, int k, svdb_candidate *out) {
     const int qi = blockIdx.x, lane = threadIdx.x;
     const u64 *flags = reinterpret_cast<const u64 *>(mine);
+    const u64 epoch = __ldcg(flags + XCH_EPOCH_SLOT);
     if (lane < world) {
         const long long t0 = clock64();
         while (ld_acquire_sys_u64(flags + lane) < epoch) {
@@ -111,8 +123,18 @@ struct svdb_exchange {
     unsigned char *mine = nullptr;
     PeerPtrs peers{};
     bool opened[XCH_MAX_WORLD] = {};
-    uint64_t epoch = 0;
 };
+
+namespace svdb {
+// enqueue "store to every peer + wait for every peer + merge" on st (collective; see svdb_exchange_merge)
+cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candidate *d_local, size_t nq, size_t k,
+                             svdb_candidate *out) {
+    exchange_push_kernel<<<1, 256, 0, st>>>(d_local, (int)(nq * k), x->peers, x->rank, x->world, x->max_rec);
+    exchange_merge_kernel<<<(unsigned)nq, 32, 0, st>>>(x->mine, x->world, x->max_rec, (int)nq, (int)k, out);
+    return cudaGetLastError();
+}
+bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k) { return x && nq * k <= x->max_rec; }
+}  // namespace svdb
 
 extern "C" {
 
@@ -188,11 +210,7 @@ int svdb_exchange_merge(svdb_exchange *x, void *stream, const svdb_candidate *d_
     }
     if (nq == 0) return SVDB_OK;
     cudaSetDevice(x->device);
-    const uint64_t epoch = ++x->epoch;
-    cudaStream_t st = (cudaStream_t)stream;
-    exchange_push_kernel<<<1, 256, 0, st>>>(d_local, (int)(nq * k), x->peers, x->rank, x->world, x->max_rec, epoch);
-    exchange_merge_kernel<<<(unsigned)nq, 32, 0, st>>>(x->mine, x->world, x->max_rec, epoch, (int)nq, (int)k, d_out);
-    cudaError_t ce = cudaGetLastError();
+    cudaError_t ce = exchange_enqueue(x, (cudaStream_t)stream, d_local, nq, k, d_out);
     if (ce != cudaSuccess) {
         set_last_error(std::string("svdb_exchange_merge: ") + cudaGetErrorString(ce));
         return SVDB_ERR_CUDA;

@@ -55,6 +55,7 @@ NATIVE_SYMBOLS = [
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
     "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
+    "svdb_nearest_batch_sharded",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -107,6 +108,7 @@ def lib() -> C.CDLL:
     L.svdb_exchange_connect.argtypes = [C.c_void_p, C.c_char_p]
     L.svdb_exchange_destroy.argtypes = [C.c_void_p]
     L.svdb_exchange_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.svdb_nearest_batch_sharded.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _zp, _dp, _u64p]
     L.svdb_get_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     L.svdb_set_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     _lib = L
@@ -235,6 +237,19 @@ class Engine:
         seq = np.empty((nq, k), dtype=np.uint64)
         _check(self.L.svdb_nearest_batch(self.h, Q.ctypes.data_as(_dp), nq, Q.shape[1], k, idx.ctypes.data_as(_zp),
                                          dist.ctypes.data_as(_dp), seq.ctypes.data_as(_u64p)), "svdb_nearest_batch")
+        return idx, dist, seq
+
+    def nearest_sharded(self, xch: "Exchange", Q, k: int = 1):
+        """This shard's part of a sharded query (svdb_nearest_batch_sharded): merged (index, dist, seq)."""
+        Q = _f64(Q)
+        Q = Q.reshape(-1, Q.shape[-1])
+        nq = len(Q)
+        idx = np.empty((nq, k), dtype=np.uint64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        seq = np.empty((nq, k), dtype=np.uint64)
+        _check(self.L.svdb_nearest_batch_sharded(self.h, xch.h, Q.ctypes.data_as(_dp), nq, Q.shape[1], k,
+                                                 idx.ctypes.data_as(_zp), dist.ctypes.data_as(_dp),
+                                                 seq.ctypes.data_as(_u64p)), "svdb_nearest_batch_sharded")
         return idx, dist, seq
 
     def nearest_device(self, q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, mode: int = 0) -> None:
