@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU box, one call: parity suite, smoke, both bench arms, the other configs, and the ncu captures
+# that profiles/ keeps.   gpurun --timeout 2400 -- 'bash scripts/gpu_round.sh'
+set -u
+mkdir -p gpurun_out
+echo "== pytest -m gpu";  timeout 1200 python -m pytest tests -m gpu -q --timeout=900 -p no:cacheprovider 2>&1 | tail -6
+echo "== smoke";          timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench (ours)";   timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; cat gpurun_out/bench_full.json
+echo "== bench (reference arm)"; timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cut -c1-300 gpurun_out/bench_reference.json
+echo "== other configs";  rm -f gpurun_out/extra.jsonl; timeout 900 python scripts/bench_extra.py c1 c2 c4 lat > gpurun_out/extra.log 2>&1; tail -30 gpurun_out/extra.log | cut -c1-260
+echo "== host call latency"; timeout 300 python scripts/host_call_latency.py 2>&1 | tail -20
+echo "== ncu: launch list of bench.py"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_full.csv \
+    python bench.py --steps 3 --warmup 3 --batch-queries 64 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1; echo "exit $?"
+echo "== ncu: full capture of the scan kernel (one launch at full size)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:scan_wide_kernel -s 4 -c 1 -o gpurun_out/prof_scan_full \
+    python bench.py --steps 3 --warmup 3 --batch-queries 0 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1; echo "exit $?"
+echo "== ncu: K2 and compare kernels"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_mma_kernel -c 1 -o gpurun_out/prof_mma \
+    python bench.py --rows 1000000 --steps 3 --warmup 3 --batch-queries 1024 --no-cpu-baseline > gpurun_out/ncu_mma.log 2>&1; echo "exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:compare_kernel -s 12 -c 1 -o gpurun_out/prof_compare \
+    python scripts/bench_extra.py c4 --out=gpurun_out/tmp.jsonl > gpurun_out/ncu_compare.log 2>&1; echo "exit $?"
+ls -la gpurun_out
