@@ -6,6 +6,8 @@
 //   KDTree          -> a LOG_ONLY engine: the append-only (kd-point, index) log
 //   VectorDatabase  -> host array of Vector (callers index into it) + a NO_LOG engine
 //                      holding the rows for the /compare kernels
+// When the store's tree measures whole rows (kd_dim == row dimension, i.e. the server was started
+// with -d D) the two share ONE engine whose log aliases its rows: no second copy in HBM.
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,13 +29,16 @@ int env_device() {
 struct TreeImpl {
     KDTree pub;              // must be first: callers hold KDTree*
     svdb_engine *eng;        // created on first insert
+    bool shared;             // eng belongs to the VectorDatabase this tree was created for
+    bool attached;           // created by vector_db_init (may still become shared)
     KDTreeNode root_node;    // what pub.root points to once the log is non-empty
     std::vector<double> root_point;
 };
 
 struct DbImpl {
     VectorDatabase pub;      // must be first
-    svdb_engine *rows;       // NO_LOG engine, created on first insert (needs the row dimension)
+    svdb_engine *rows;       // created on first insert (needs the row dimension): NO_LOG, or rows + log when unified
+    bool unified;            // rows engine also carries the tree's log (kd_dim == row dimension)
     size_t row_dim;
     std::vector<unsigned char> dim_ok;   // per index: row has the engine's dimension
 };
@@ -57,19 +62,36 @@ bool tree_engine(TreeImpl *t) {
 
 bool db_engine(DbImpl *d, size_t dim) {
     if (d->rows) return true;
+    TreeImpl *t = reinterpret_cast<TreeImpl *>(d->pub.kdtree);
+    // one engine for rows and log when the tree measures whole rows and nothing went into it yet
+    const bool unify = t && t->attached && !t->eng && t->pub.dimension == dim;
     svdb_config c;
     memset(&c, 0, sizeof c);
     c.dimension = dim;
-    c.kd_dim = 1;
+    c.kd_dim = unify ? dim : 1;
     c.device = env_device();
-    c.flags = SVDB_FLAG_NO_LOG;
+    c.flags = unify ? 0u : SVDB_FLAG_NO_LOG;
     if (svdb_engine_create(&c, &d->rows) != SVDB_OK) {
         complain("vector_db: engine");
         d->rows = nullptr;
         return false;
     }
     d->row_dim = dim;
+    d->unified = unify;
+    if (unify) {
+        t->eng = d->rows;
+        t->shared = true;
+    }
     return true;
+}
+
+void tree_note_root(TreeImpl *t, const double *point, size_t index) {
+    if (t->pub.root) return;
+    t->root_point.assign(point, point + t->pub.dimension);
+    t->root_node.point = t->root_point.data();
+    t->root_node.index = index;
+    t->root_node.left = t->root_node.right = NULL;
+    t->pub.root = &t->root_node;
 }
 
 // Double the slot array of the host-visible Vector table; false (and a line on stderr) when
@@ -118,6 +140,7 @@ KDTree *kdtree_create(size_t dimension) {
     t->pub.root = NULL;
     t->pub.dimension = dimension;
     t->eng = nullptr;
+    t->shared = t->attached = false;
     return &t->pub;
 }
 
@@ -130,20 +153,14 @@ void kdtree_insert(KDTree *tree, const double *point, size_t index) {
         complain("kdtree_insert");
         return;
     }
-    if (!tree->root) {
-        t->root_point.assign(point, point + tree->dimension);
-        t->root_node.point = t->root_point.data();
-        t->root_node.index = index;
-        t->root_node.left = t->root_node.right = NULL;
-        tree->root = &t->root_node;
-    }
+    tree_note_root(t, point, index);
 }
 
 // ---- kdtree.c:112-118 ----
 void kdtree_free(KDTree *tree) {
     if (!tree) return;
     TreeImpl *t = reinterpret_cast<TreeImpl *>(tree);
-    if (t->eng) svdb_engine_destroy(t->eng);
+    if (t->eng && !t->shared) svdb_engine_destroy(t->eng);
     tree->root = NULL;
     delete t;
 }
@@ -184,6 +201,7 @@ VectorDatabase *vector_db_init(size_t initial_capacity, size_t dimension) {
         return NULL;
     }
     d->rows = nullptr;
+    d->unified = false;
     d->row_dim = 0;
     d->pub.size = 0;
     d->pub.capacity = initial_capacity > 0 ? initial_capacity : 10;
@@ -200,6 +218,7 @@ VectorDatabase *vector_db_init(size_t initial_capacity, size_t dimension) {
         delete d;
         return NULL;
     }
+    reinterpret_cast<TreeImpl *>(d->pub.kdtree)->attached = true;
     if (pthread_mutex_init(&d->pub.mutex, NULL) != 0) {
         fprintf(stderr, "Failed to initialize mutex\n");
         kdtree_free(d->pub.kdtree);
@@ -242,10 +261,12 @@ size_t vector_db_insert(VectorDatabase *db, Vector vec) {
         pthread_mutex_unlock(&db->mutex);
         return (size_t)-1;
     }
-    // HBM copy of the row for /compare; a row of another dimension gets a zero placeholder
+    // HBM copy of the row for /compare.  A row of another dimension keeps its slot: unified stores take
+    // its first row_dim (= kd_dim) coordinates -- exactly what the tree measures -- others a zero row;
+    // either way /compare on it answers the mismatch sentinel (dim_ok).
     const bool same = vec.dimension == d->row_dim;
     int rc;
-    if (same) {
+    if (same || d->unified) {
         rc = svdb_insert_batch(d->rows, vec.data, 1, vec.dimension, NULL);
     } else {
         std::vector<double> z(d->row_dim, 0.0);
@@ -259,7 +280,8 @@ size_t vector_db_insert(VectorDatabase *db, Vector vec) {
     d->dim_ok.push_back(same ? 1 : 0);
     vec.uuid[UUID_SIZE - 1] = '\0';
     db->vectors[db->size] = vec;                      // takes ownership of vec.data (:113)
-    kdtree_insert(db->kdtree, vec.data, db->size);    // :114
+    if (d->unified) tree_note_root(reinterpret_cast<TreeImpl *>(db->kdtree), vec.data, db->size);   // the insert above logged it
+    else kdtree_insert(db->kdtree, vec.data, db->size);                                              // :114
     const size_t index = db->size++;
     pthread_mutex_unlock(&db->mutex);
     return index;
@@ -300,12 +322,12 @@ void vector_db_update(VectorDatabase *db, size_t index, Vector vec) {
         }
         free(db->vectors[index].data);
         db->vectors[index] = vec;
-            kdtree_insert(db->kdtree, vec.data, index);
+        if (!d->unified) kdtree_insert(db->kdtree, vec.data, index);   // :174; unified: the update below re-appends
         const bool same = d->rows && vec.dimension == d->row_dim;
         if (d->rows) {
             std::vector<double> z;
             const double *src = vec.data;
-            if (!same) {
+            if (!same && !d->unified) {
                 z.assign(d->row_dim, 0.0);
                 src = z.data();
             }
