@@ -132,11 +132,10 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
     // thin queries are copied once into thread-local storage (the host path hands them over in pinned
     // host memory, zero-copy); longer ones are read in place (L1-resident after the first node)
     double ql[16];
-    const double *__restrict__ q = Q + (size_t)qi * ldq;
-    if (K <= 16) {
-        for (int i = 0; i < K; i++) ql[i] = q[i];
-        q = ql;
-    }
+    const double *qg = Q + (size_t)qi * ldq;
+    if (K <= 16)
+        for (int i = 0; i < K; i++) ql[i] = qg[i];
+    const double *q = K <= 16 ? ql : qg;       // (no __restrict__: q may point at ql)
     struct Frame {
         uint32_t node, depth;
         double plane;
