@@ -117,9 +117,10 @@ int svdb_read_row(svdb_engine *e, size_t index, double *out /* dimension doubles
 int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k,
                        size_t *index_out, double *dist_out, uint64_t *seq_out);
 /* Device buffers, asynchronous on the engine's stream: d_out receives nq x k candidates.
- * mode: SVDB_MODE_AUTO   tree traversal for thin kd-points and k = 1, else scan + exact re-rank;
+ * mode: SVDB_MODE_AUTO   tree traversal for thin kd-points (kd_dim <= 8), else scan + exact re-rank;
  *       SVDB_MODE_EXACT  reference-order scan of every entry (no approximation to prove complete);
- *       SVDB_MODE_TREE   the reference's own traversal on the GPU tree (k = 1 only).
+ *       SVDB_MODE_TREE   the reference's own traversal on the GPU tree (k > 1: its k-smallest generalisation,
+ *                        position 0 is still the reference's answer).
  * The caller must look at flags (SVDB_CAND_UNSAFE) once the results are on the host and escalate
  * AUTO -> EXACT -> TREE for those queries (svdb_nearest_batch does exactly that). */
 #define SVDB_MODE_AUTO  0

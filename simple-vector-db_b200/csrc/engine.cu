@@ -334,11 +334,11 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     int rc = flush();
     if (rc) return rc;
     CK(cudaSetDevice(device));
-    if (mode == SVDB_MODE_TREE && (!use_tree || k != 1))
-        return fail(SVDB_ERR_ARG, "tree traversal needs k == 1 and an engine that keeps the tree");
+    if (mode == SVDB_MODE_TREE && !use_tree)
+        return fail(SVDB_ERR_ARG, "tree traversal needs an engine that keeps the tree");
     // K6: thin kd-points prune well, and the traversal IS the reference's algorithm
-    if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && k == 1 && !force_exact && K <= tree_max_k)) {
-        CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq,
+    if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && !force_exact && K <= tree_max_k)) {
+        CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
                                log_idx.as<u64>(), cfg.seq_base, d_out, stream));
         stats.kernels_launched++;
         return SVDB_OK;

@@ -93,9 +93,10 @@ cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int n
 cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *child, u64 n0, u64 m, uint32_t *pn,
                                uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
                                int max_rounds, int *rounds_out);
-// K6: the reference's traversal, one thread per query, k = 1.
+// K6: the reference's traversal, one thread per query (k = 1), or its k-smallest generalisation (k > 1).
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
-                                int ldq, int nq, const u64 *log_index, u64 seq_base, svdb_candidate *out, cudaStream_t st);
+                                int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
+                                cudaStream_t st);
 
 struct CompareArgs {
     const double *rows;     // version rows, row s at rows + s * ldr; ldr % 16 == 0, zero padded

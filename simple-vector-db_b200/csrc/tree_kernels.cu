@@ -206,10 +206,128 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
     out[qi] = c;
 }
 
+// ---- K6 for k > 1: the same traversal keeping the k smallest (distance, seq) keys ----------------
+// The reference defines only k = 1.  Position 0 is still ITS answer (first minimum in near-first
+// order, strict '<'); the far side is visited whenever the plane is not beyond the current k-th key,
+// a superset of what the reference visits, in the same order -- so the first minimum is the same node.
+constexpr int KNN_MAX = SVDB_MAX_K;
+
+__global__ void __launch_bounds__(128) tree_knn_kernel(const double *__restrict__ pts, int stride, int K,
+                                                       const uint32_t *__restrict__ child, u64 n,
+                                                       const double *__restrict__ Q, int ldq, int nq, int k,
+                                                       const u64 *__restrict__ log_index, u64 seq_base,
+                                                       svdb_candidate *out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    double ql[16];
+    const double *qg = Q + (size_t)qi * ldq;
+    if (K <= 16)
+        for (int i = 0; i < K; i++) ql[i] = qg[i];
+    const double *q = K <= 16 ? ql : qg;
+    struct Frame {
+        uint32_t node, depth;
+        double plane;
+    };
+    Frame st[TREE_STACK];
+    double kd[KNN_MAX];
+    uint32_t ks[KNN_MAX];
+    int m = 0, sp = 0;
+    bool overflow = false;
+    double best = CUDART_INF;
+    uint32_t best_node = NODE_NONE;
+    uint32_t cur = n ? 0u : NODE_NONE;
+    uint32_t depth = 0;
+    for (;;) {
+        while (cur != NODE_NONE) {
+            const double *p = pts + (size_t)cur * stride;
+            double d = 0.0, pcd = 0.0;
+            const int cd = depth % K;
+            for (int i = 0; i < K; i++) {
+                const double x = __ldg(p + i);
+                if (i == cd) pcd = x;
+                const double t = __dsub_rn(x, q[i]);
+                d = __dadd_rn(d, __dmul_rn(t, t));
+            }
+            if (d < best) {
+                best = d;
+                best_node = cur;
+            }
+            if (d < CUDART_INF && (m < k || d < kd[m - 1] || (d == kd[m - 1] && cur < ks[m - 1]))) {
+                int pos = m < k ? m : k - 1;
+                while (pos > 0 && (d < kd[pos - 1] || (d == kd[pos - 1] && cur < ks[pos - 1]))) {
+                    kd[pos] = kd[pos - 1];
+                    ks[pos] = ks[pos - 1];
+                    pos--;
+                }
+                kd[pos] = d;
+                ks[pos] = cur;
+                if (m < k) m++;
+            }
+            const bool left_near = q[cd] < pcd;
+            const uint32_t lo = child[2 * (size_t)cur], hi = child[2 * (size_t)cur + 1];
+            const uint32_t near_c = left_near ? lo : hi, far_c = left_near ? hi : lo;
+            if (far_c != NODE_NONE) {
+                if (sp < TREE_STACK) {
+                    const double t = __dsub_rn(q[cd], pcd);
+                    st[sp].node = far_c;
+                    st[sp].depth = depth + 1;
+                    st[sp].plane = __dmul_rn(t, t);
+                    sp++;
+                } else {
+                    overflow = true;
+                }
+            }
+            cur = near_c;
+            depth++;
+        }
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            const double bound = m == k ? kd[k - 1] : CUDART_INF;
+            if (st[sp].plane <= bound) {
+                cur = st[sp].node;
+                depth = st[sp].depth;
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+    // winner first, the rest in (distance, seq) order
+    svdb_candidate *o = out + (size_t)qi * k;
+    const u64 fl = overflow ? SVDB_CAND_UNSAFE : 0ull;
+    int w = 0;
+    if (best_node != NODE_NONE) {
+        o[w].dist = best;
+        o[w].seq = (u64)best_node + seq_base;
+        o[w].index = log_index[best_node];
+        o[w].flags = fl;
+        w++;
+    }
+    for (int i = 0; i < m && w < k; i++) {
+        if (ks[i] == best_node) continue;
+        o[w].dist = kd[i];
+        o[w].seq = (u64)ks[i] + seq_base;
+        o[w].index = log_index[ks[i]];
+        o[w].flags = fl;
+        w++;
+    }
+    for (; w < k; w++) {
+        o[w].dist = CUDART_INF;
+        o[w].seq = SEQ_NONE;
+        o[w].index = (u64)SVDB_NONE;
+        o[w].flags = fl;
+    }
+}
+
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
-                                int ldq, int nq, const u64 *log_index, u64 seq_base, svdb_candidate *out, cudaStream_t st) {
+                                int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
+                                cudaStream_t st) {
     if (nq == 0) return cudaSuccess;
-    tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out);
+    if (k == 1)
+        tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out);
+    else
+        tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out);
     return cudaGetLastError();
 }
 

@@ -165,6 +165,10 @@ def test_many_distinct_points_at_equal_distance(port, K, n_far):
     with B.Engine(K, K) as e:
         e.insert(rows)
         np.testing.assert_array_equal(e.nearest(Q2, 1)[0][:, 0], want)
+        if K <= 8:                                                     # k-smallest traversal (K6 for k > 1)
+            idx, dist, _ = e.nearest(Q2, 4)
+            np.testing.assert_array_equal(idx[:, 0], want)
+            assert np.all(dist[0] == 25.0)
         e.set_option("nearest.tree_max_k", 0)                          # k = 1 through the scan
         np.testing.assert_array_equal(e.nearest(Q2, 1)[0][:, 0], want)
         st = e.stats()
@@ -181,10 +185,14 @@ def test_tree_traversal_equals_scan_on_random_data(port):
     with B.Engine(D, K) as e:
         e.insert(rows)
         a = e.nearest(Q, 1)
+        a10 = e.nearest(Q, 10)                       # k-smallest traversal
+        a24 = e.nearest(Q[:50], 24)
         e.set_option("nearest.tree_max_k", 0)
         b = e.nearest(Q, 1)
+        b10 = e.nearest(Q, 10)                       # exact scan + finalize
+        b24 = e.nearest(Q[:50], 24)
         assert e.stats()["tree_rounds"] > 0
-    for x, y in zip(a, b):
+    for x, y in list(zip(a, b)) + list(zip(a10, b10)) + list(zip(a24, b24)):
         np.testing.assert_array_equal(x, y)
     np.testing.assert_array_equal(a[0][:, 0], oracle_tree_ids(port, rows, K, Q))
 
