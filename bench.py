@@ -300,11 +300,13 @@ def ours(args):
     m0 = idx.merge_launches
     st0 = e.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()           # `ncu --profile-from-start off` lists the timed region only
     ev0.record()
     for i in range(args.steps):
         step_dev(args.warmup + i)
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     scan_ms, scan_launches = e.take_scan_time()

@@ -9,9 +9,9 @@ echo "== bench (ours)";   timeout 900 python bench.py > gpurun_out/bench_full.js
 echo "== bench (reference arm)"; timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cut -c1-300 gpurun_out/bench_reference.json
 echo "== other configs";  rm -f gpurun_out/extra.jsonl; timeout 900 python scripts/bench_extra.py c1 c2 c4 lat > gpurun_out/extra.log 2>&1; tail -30 gpurun_out/extra.log | cut -c1-260
 echo "== host call latency"; timeout 300 python scripts/host_call_latency.py 2>&1 | tail -20
-echo "== ncu: launch list of bench.py"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_full.csv \
-    python bench.py --steps 3 --warmup 3 --batch-queries 64 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1; echo "exit $?"
+echo "== ncu: launch list of bench.py (the timed region: bench.py brackets it with cudaProfilerStart/Stop)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches_full.csv \
+    python bench.py --steps 20 --warmup 3 --batch-queries 0 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1; echo "exit $?"
 echo "== ncu: full capture of the scan kernel (one launch at full size)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:scan_wide_kernel -s 4 -c 1 -o gpurun_out/prof_scan_full \
     python bench.py --steps 3 --warmup 3 --batch-queries 0 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1; echo "exit $?"
