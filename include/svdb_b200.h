@@ -47,7 +47,8 @@ typedef enum svdb_status {
     SVDB_ERR_ARG = -1,           /* bad argument (NULL, kd_dim > dimension, k > SVDB_MAX_K ...) */
     SVDB_ERR_CUDA = -2,          /* a CUDA call failed; text in svdb_last_error() */
     SVDB_ERR_OOM = -3,           /* device or host allocation failed */
-    SVDB_ERR_RANGE = -4          /* index out of range where the call cannot be a silent no-op */
+    SVDB_ERR_RANGE = -4,         /* index out of range where the call cannot be a silent no-op */
+    SVDB_ERR_STATE = -5          /* the shards of a collective call disagree (different inputs on different ranks) */
 } svdb_status;
 
 typedef enum svdb_metric {
@@ -69,18 +70,22 @@ typedef struct svdb_config {
 
 #define SVDB_FLAG_LOG_ONLY   1u  /* rows ARE kd-points (dimension == kd_dim), no index map: a bare KDTree */
 #define SVDB_FLAG_NO_LOG     2u  /* rows only (compare / read); nearest is not available */
-#define SVDB_FLAG_SHARD      4u  /* this engine holds a slice of a larger log: no reference-shaped tree
-                                    (exact distance ties resolve to the lowest sequence number) */
+#define SVDB_FLAG_SHARD      4u  /* this engine holds a slice of a larger log: results come in plain (dist, seq)
+                                    order and exact ties at the minimum are FLAGGED (SVDB_CAND_TIE); which tied
+                                    entry the reference's tree reaches first is decided across the shards
+                                    (svdb_resolve_ties_sharded; svdb_nearest_batch_sharded does it itself) */
 
 /* One result of a nearest query; also the unit exchanged between shards. 32 bytes. */
 typedef struct svdb_candidate {
     double   dist;               /* reference-order squared distance over kd_dim coords; +inf if none */
     uint64_t seq;                /* global log sequence number (tie-break key); UINT64_MAX if none */
     uint64_t index;              /* index carried by the log entry; SVDB_NONE if none */
-    uint64_t flags;              /* bit 0: SVDB_CAND_UNSAFE */
+    uint64_t flags;              /* SVDB_CAND_* */
 } svdb_candidate;
 
 #define SVDB_CAND_UNSAFE 1ull    /* candidate set could not be proven complete: rerun exact */
+#define SVDB_CAND_TIE    2ull    /* sharded stores: two or more entries may sit at exactly the minimal distance;
+                                    position 0 is the lowest seq until the tie is resolved across the shards */
 
 const char *svdb_last_error(void);
 const char *svdb_version(void);
@@ -152,6 +157,61 @@ int  svdb_exchange_merge(svdb_exchange *x, void *stream, const svdb_candidate *d
 int  svdb_nearest_batch_sharded(svdb_engine *e, svdb_exchange *x, const double *Q, size_t nq, size_t ldq, size_t k,
                                 size_t *index_out, double *dist_out, uint64_t *seq_out);
 
+/* ---- exact ties on a sharded store ----
+ * The reference returns, among DISTINCT kd-points at exactly the same minimal distance, whichever its
+ * insertion-order tree (kdtree.c:47-62) reaches first in the near-side-first traversal (:131-162).
+ * A sharded store has no such tree in one place, so the shards walk the path of the GLOBAL tree together:
+ * the node below the current one is the first log entry (lowest global seq) inside the current cell, found
+ * by every shard in its slice and min-reduced; the walk goes to the query's side if a tied entry lives
+ * there, else to the other side, and stops at the first tied entry it meets (or when one is left).  Two
+ * small all-gathers per tree level, levels ~ depth of the tied entries' common ancestor; only queries whose
+ * merged answer carries SVDB_CAND_TIE pay for it.
+ *
+ * svdb_tie_resolve is the walk itself, written against a backend (the shard's local primitives + an
+ * all-gather); svdb_resolve_ties_sharded runs it with the CUDA backend of an engine.  Collective: every
+ * rank calls it with the SAME queries and the SAME merged candidates (what the merge leaves on every rank).
+ * merged (host, nq x k) is updated in place: winner first, the rest in (dist, seq) order. */
+typedef struct svdb_tie_first {  /* a shard's first entry inside a cell */
+    uint64_t seq;                /* global seq; UINT64_MAX if the shard has none in the cell */
+    uint64_t index;
+    double   v;                  /* its coordinate on the axis its level splits on */
+    uint64_t tied;               /* 1 if it is itself one of the tied entries */
+} svdb_tie_first;
+typedef struct svdb_tie_split {  /* a shard's tied entries inside a cell, by side of a splitting value */
+    uint64_t n[2];               /* side 0: coordinate < v, side 1: >= v (kdtree.c:52) */
+    uint64_t min_seq[2];         /* lowest global seq on each side; UINT64_MAX if none */
+    uint64_t min_index[2];
+} svdb_tie_split;
+typedef int (*svdb_allgather_fn)(void *ctx, const void *send, void *recv, size_t bytes_per_rank);
+typedef struct svdb_tie_backend {
+    void *ctx;
+    int world, rank;
+    size_t kd_dim;
+    /* recv = world blocks of bytes_per_rank, in rank order (host memory) */
+    svdb_allgather_fn allgather;
+    void *allgather_ctx;
+    /* remember, for each of ne events (query i: queries + i*kd_dim, distance dstar[i]), the LOCAL entries at
+       exactly that reference distance.  n_local[i] = how many; same[i] = 1 iff they are all the same kd-point;
+       first[i*kd_dim ..] = coordinates of the one with the lowest seq (untouched if none). */
+    int (*collect)(void *ctx, size_t ne, const double *queries, const double *dstar, uint64_t *n_local,
+                   uint8_t *same, double *first);
+    /* For na active events (ev[i] = event id as passed to collect): the cell is the sequence of
+       depth[i] (value, side) pairs path_v/path_side[i*path_ld + j], level j splitting axis j % kd_dim.
+       out[i] = the first local entry with global seq > after[i] (UINT64_MAX: no lower bound) in the cell. */
+    int (*first_in_cell)(void *ctx, size_t na, const uint32_t *ev, const uint32_t *depth, const double *path_v,
+                         const uint8_t *path_side, size_t path_ld, const uint64_t *after, svdb_tie_first *out);
+    /* out[i] = the local tied entries of event ev[i] inside the cell, split by v[i] on axis depth[i] % kd_dim */
+    int (*split)(void *ctx, size_t na, const uint32_t *ev, const uint32_t *depth, const double *path_v,
+                 const uint8_t *path_side, size_t path_ld, const double *v, svdb_tie_split *out);
+} svdb_tie_backend;
+int svdb_tie_resolve(const svdb_tie_backend *b, const double *Q, size_t nq, size_t ldq, svdb_candidate *merged,
+                     size_t k, uint64_t *levels_walked /* may be NULL */);
+/* The same with this engine's CUDA backend; allgather moves host buffers between the ranks (any transport).
+ * x != NULL: use the peer-memory exchange instead (allgather may then be NULL). */
+int svdb_resolve_ties_sharded(svdb_engine *e, svdb_exchange *x, int rank, int world, svdb_allgather_fn allgather,
+                              void *allgather_ctx, const double *Q, size_t nq, size_t ldq, svdb_candidate *merged,
+                              size_t k);
+
 /* Concurrent single-query callers (the server is thread-per-connection, main.c:382, and
  * kdtree_nearest is called with no lock held, compare_handler.c:403): calls with nq == 1 that
  * arrive while a pass is running are coalesced into the next pass (no added wait). Same results. */
@@ -189,6 +249,8 @@ typedef struct svdb_stats {
     uint64_t coalesced_passes;   /* passes that carried more than one caller's query */
     uint64_t hbm_bytes_mapped;   /* physical HBM currently mapped by the arenas */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t tie_events;         /* sharded queries whose exact tie went through svdb_resolve_ties_sharded */
+    uint64_t tie_levels;         /* tree levels walked for them, summed */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm". */

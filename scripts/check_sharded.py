@@ -6,8 +6,9 @@
 
 Every rank owns a row-range shard; the merged answer of the sharded index (scan + NCCL
 all-gather + K7 merge) must be identical -- sequence numbers and distance bits -- to a
-single-engine scan of all rows (done on rank 0's GPU) for top-1 and top-10, host and device
-entry points.  Prints one JSON line from rank 0.
+single-engine scan of all rows (done on rank 0's GPU) for top-1 and top-10 -- including on lattice
+data where distinct points tie exactly and the winner is the one the reference's tree reaches first
+(the single engine keeps that tree; the shards walk its path together).  Prints one JSON line from rank 0.
 """
 from __future__ import annotations
 
@@ -36,10 +37,17 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     ok = True
     report = []
-    for (n, D, K) in ((400_003, 128, 128), (50_000, 768, 768), (300_000, 16, 3)):
-        g = torch.Generator().manual_seed(n)
-        rows = torch.rand((n, D), dtype=torch.float64, generator=g)       # same on every rank
-        Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()
+    # the last three are coarse lattices: distinct kd-points at exactly equal distance everywhere (and, with
+    # 0/1 coordinates, dozens of them per query), so the answer depends on the order of the reference's tree
+    for (n, D, K, levels) in ((400_003, 128, 128, 0), (50_000, 768, 768, 0), (300_000, 16, 3, 0),
+                              (200_000, 16, 3, 7), (100_000, 64, 64, 2), (60_000, 768, 768, 2)):
+        g = torch.Generator().manual_seed(n + levels)
+        if levels:
+            rows = torch.randint(0, levels, (n, D), generator=g).to(torch.float64) / 2      # same on every rank
+            Q = (torch.randint(0, levels, (16, D), generator=g).to(torch.float64) / 2).pin_memory()
+        else:
+            rows = torch.rand((n, D), dtype=torch.float64, generator=g)
+            Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()
         idx = ShardedIndex(D, K, n, rank, world, local, exchange=os.environ.get("SVDB_EXCHANGE", "p2p"))
         idx.bind_current_stream()
         idx.ingest_device(rows[idx.lo:idx.hi].to(dev).contiguous())
@@ -51,7 +59,9 @@ def main():
                     _, wdist, wseq = e.nearest(Q.numpy(), k)
                 same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
                 ok &= bool(same)
-                report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "identical_to_single_gpu": bool(same)})
+                report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels,
+                               "identical_to_single_gpu": bool(same), "tie_events": idx.engine.stats()["tie_events"],
+                               "tie_levels": idx.engine.stats()["tie_levels"]})
         idx.close()
     # /compare: replicas, pairs split over the ranks, results all-gathered
     n, D = 20_000, 256

@@ -409,6 +409,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
             fa.qnorm = qnorm.as<double>();
             fa.xn_max_bits = xnmax.as<unsigned long long>();
             fa.child = use_tree ? child.as<uint32_t>() : nullptr;
+            fa.mark_ties = (cfg.flags & SVDB_FLAG_SHARD) ? 1 : 0;
             fa.out = d_out + done * k;
             CK(launch_finalize(fa, stream));
             stats.kernels_launched += 3;
@@ -481,6 +482,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         fa.seq_base = cfg.seq_base;
         fa.eps = use_exact ? -1.0 : 4.0 * (double)(K + 2) * ldexp(1.0, -53);
         fa.child = use_tree ? child.as<uint32_t>() : nullptr;
+        fa.mark_ties = (cfg.flags & SVDB_FLAG_SHARD) ? 1 : 0;
         fa.out = d_out + done * k;
         CK(launch_finalize(fa, stream));
         stats.kernels_launched++;
@@ -578,6 +580,15 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
             rc = enqueue_mode(SVDB_MODE_EXACT);
             if (rc) return rc;
             CK(cudaStreamSynchronize(stream));
+        }
+        // distinct kd-points at exactly the minimal distance: which one does the reference's (global) tree reach
+        // first?  Decided by all shards together; again every rank sees the same flags.
+        any = false;
+        for (size_t i = 0; i < nq; i++) any = any || (res[i * k].flags & SVDB_CAND_TIE);
+        if (any) {
+            rc = resolve_ties_engine(this, x, exchange_rank(x), exchange_world(x), nullptr, nullptr, hq.as<double>(), nq,
+                                     (size_t)K, res, k);
+            if (rc) return rc;
         }
     }
     for (size_t i = 0; i < nq && !x; i++) {

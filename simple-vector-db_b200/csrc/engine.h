@@ -46,6 +46,13 @@ namespace svdb {
 cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candidate *d_local, size_t nq, size_t k,
                              svdb_candidate *out);
 bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k);
+int exchange_rank(const svdb_exchange *x);
+int exchange_world(const svdb_exchange *x);
+int exchange_allgather_host(svdb_exchange *x, cudaStream_t st, const void *send, void *recv, size_t bytes);
+// tie_protocol.cu: position 0 of TIE-flagged merged answers = the entry the reference's global tree reaches
+// first (collective over the shards; callers hold e->mu)
+int resolve_ties_engine(svdb_engine *e, svdb_exchange *x, int rank, int world, svdb_allgather_fn ag, void *ag_ctx,
+                        const double *Q, size_t nq, size_t ldq, svdb_candidate *merged, size_t k);
 }  // namespace svdb
 
 // Layout in HBM (all fp64, row-major, one entry per VERSION = per insert/update/log append):

@@ -13,6 +13,8 @@
 //                        flags[31]  = this rank's own epoch counter, advanced ON THE DEVICE by the push
 //                        kernel, so that the exchange can sit inside a replayed CUDA graph
 //   [ parity 0: world x max_rec candidates ][ parity 1: ... ]   double-buffered by epoch parity
+#include <algorithm>
+#include <cstring>
 #include <string>
 
 #include "common.cuh"
@@ -88,12 +90,30 @@ __global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char 
             const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
             d = __ldcg(&c->dist);
             s = __ldcg(&c->seq);
-            fl |= __ldcg(&c->flags);
+            fl |= __ldcg(&c->flags) & ~SVDB_CAND_TIE;
         }
         wl.offer(s != SEQ_NONE, d, s, lane);
     }
+    // SVDB_CAND_TIE of the merged answer: >= 2 entries at the merged minimum, or one that its shard flagged
+    double dmin;
+    u64 smin;
+    wl.key_at(0, dmin, smin);
+    int at_min = 0;
+    if (smin != SEQ_NONE) {
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            if (i < total) {
+                const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+                if (__ldcg(&c->seq) != SEQ_NONE && __ldcg(&c->dist) == dmin) at_min += (__ldcg(&c->flags) & SVDB_CAND_TIE) ? 2 : 1;
+            }
+        }
+    }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) fl |= __shfl_xor_sync(FULL, fl, m);
+    for (int m = 16; m >= 1; m >>= 1) {
+        fl |= __shfl_xor_sync(FULL, fl, m);
+        at_min += __shfl_xor_sync(FULL, at_min, m);
+    }
+    if (at_min >= 2) fl |= SVDB_CAND_TIE;
     if (lane < k) {
         svdb_candidate c;
         c.dist = wl.d;
@@ -113,6 +133,25 @@ __global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char 
     }
 }
 
+// generic all-gather on the same buffers: wait for every rank's `nrec` 32-byte records of this epoch and copy
+// them out in rank order (out: [world][nrec] records)
+__global__ void __launch_bounds__(256) exchange_wait_copy_kernel(const unsigned char *mine, int world, size_t max_rec, int nrec,
+                                                                 u64 *__restrict__ out) {
+    const u64 *flags = reinterpret_cast<const u64 *>(mine);
+    const u64 epoch = __ldcg(flags + XCH_EPOCH_SLOT);
+    if ((int)threadIdx.x < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) {
+            if (clock64() - t0 > 20000000000ll) __trap();
+        }
+    }
+    __syncthreads();
+    const u64 *in = reinterpret_cast<const u64 *>(mine + XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate));
+    const int words = nrec * 4;
+    for (int r = 0; r < world; r++)
+        for (int i = threadIdx.x; i < words; i += blockDim.x) out[(size_t)r * words + i] = __ldcg(in + (size_t)r * max_rec * 4 + i);
+}
+
 }  // namespace svdb
 
 using namespace svdb;
@@ -123,6 +162,8 @@ struct svdb_exchange {
     unsigned char *mine = nullptr;
     PeerPtrs peers{};
     bool opened[XCH_MAX_WORLD] = {};
+    // staging of the host-level all-gather (tie resolution): one chunk of max_rec records per rank
+    unsigned char *d_send = nullptr, *d_recv = nullptr, *h_send = nullptr, *h_recv = nullptr;
 };
 
 namespace svdb {
@@ -134,6 +175,47 @@ cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candi
     return cudaGetLastError();
 }
 bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k) { return x && nq * k <= x->max_rec; }
+int exchange_rank(const svdb_exchange *x) { return x->rank; }
+int exchange_world(const svdb_exchange *x) { return x->world; }
+
+// Host buffers in, host buffers out: recv = world blocks of `bytes`, in rank order.  Collective; synchronizes st.
+int exchange_allgather_host(svdb_exchange *x, cudaStream_t st, const void *send, void *recv, size_t bytes) {
+    if (!x || !send || !recv) return SVDB_ERR_ARG;
+    if (bytes == 0) return SVDB_OK;
+    cudaError_t ce = cudaSetDevice(x->device);
+    const size_t chunk = x->max_rec * sizeof(svdb_candidate);
+    if (ce == cudaSuccess && !x->d_send) {
+        ce = cudaMalloc(&x->d_send, chunk);
+        if (ce == cudaSuccess) ce = cudaMalloc(&x->d_recv, chunk * x->world);
+        if (ce == cudaSuccess) ce = cudaMallocHost(&x->h_send, chunk);
+        if (ce == cudaSuccess) ce = cudaMallocHost(&x->h_recv, chunk * x->world);
+    }
+    for (size_t off = 0; off < bytes && ce == cudaSuccess; off += chunk) {
+        const size_t len = std::min(chunk, bytes - off);
+        const int nrec = (int)((len + sizeof(svdb_candidate) - 1) / sizeof(svdb_candidate));
+        memset(x->h_send, 0, (size_t)nrec * sizeof(svdb_candidate));
+        memcpy(x->h_send, static_cast<const unsigned char *>(send) + off, len);
+        ce = cudaMemcpyAsync(x->d_send, x->h_send, (size_t)nrec * sizeof(svdb_candidate), cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) break;
+        exchange_push_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const svdb_candidate *>(x->d_send), nrec, x->peers, x->rank,
+                                                x->world, x->max_rec);
+        exchange_wait_copy_kernel<<<1, 256, 0, st>>>(x->mine, x->world, x->max_rec, nrec, reinterpret_cast<u64 *>(x->d_recv));
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(x->h_recv, x->d_recv, (size_t)x->world * nrec * sizeof(svdb_candidate), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) break;
+        for (int r = 0; r < x->world; r++)
+            memcpy(static_cast<unsigned char *>(recv) + (size_t)r * bytes + off,
+                   x->h_recv + (size_t)r * nrec * sizeof(svdb_candidate), len);
+    }
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("exchange all-gather: ") + cudaGetErrorString(ce));
+        cudaGetLastError();
+        return SVDB_ERR_CUDA;
+    }
+    return SVDB_OK;
+}
 }  // namespace svdb
 
 extern "C" {
@@ -198,6 +280,10 @@ void svdb_exchange_destroy(svdb_exchange *x) {
     for (int r = 0; r < x->world; r++)
         if (x->opened[r]) cudaIpcCloseMemHandle(x->peers.p[r]);
     if (x->mine) cudaFree(x->mine);
+    if (x->d_send) cudaFree(x->d_send);
+    if (x->d_recv) cudaFree(x->d_recv);
+    if (x->h_send) cudaFreeHost(x->h_send);
+    if (x->h_recv) cudaFreeHost(x->h_recv);
     delete x;
 }
 

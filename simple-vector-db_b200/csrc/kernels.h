@@ -58,6 +58,7 @@ struct FinalArgs {
     const double *qnorm;    // |q|^2 per query of this launch (K2), else NULL
     const unsigned long long *xn_max_bits;   // largest |x|^2 in the log, as double bits (K2), else NULL
     const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
+    int mark_ties;          // shards (child == NULL): flag SVDB_CAND_TIE when distinct kd-points may tie at the minimum
     svdb_candidate *out;    // [nq][k]
 };
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st);

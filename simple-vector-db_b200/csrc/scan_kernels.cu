@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     }
 
     // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----
-    if (p.child != nullptr && nvalid >= 2) {
+    bool tie_flag = false;
+    if ((p.child != nullptr || p.mark_ties) && nvalid >= 2) {
         const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
         const int l0 = __ffs(m0) - 1;
         const double e1 = __shfl_sync(FULL, dex, l0);
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         if (nt >= 2) {
             // a dropped entry could tie as well: exact keys -> bound <= e1; approximate keys are
             // already covered by the completeness proof above (e1 <= ek < bound(1-eps))
-            if (p.eps < 0.0 && bound <= e1) unsafe = true;
+            const bool more = p.eps < 0.0 && bound <= e1;
+            if (more && p.child != nullptr) unsafe = true;
             // identical kd-points? then the earliest insert is an ancestor of the others and wins
             bool differs = false;
             const double *r0 = p.pts + seq0 * (u64)p.stride;
@@ -514,7 +516,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
                 const double *rt = p.pts + st * (u64)p.stride;
                 for (int i = lane; i < p.K; i += 32) differs |= rt[i] != r0[i];
             }
-            if (__any_sync(FULL, differs)) {
+            differs = __any_sync(FULL, differs);
+            if (p.child == nullptr) {
+                // one shard of a larger log: the order of the GLOBAL tree decides (tie_protocol.cu); say so
+                tie_flag = differs || more;
+            } else if (differs) {
                 if (tied) cseq[rank] = seq;            // tied entries hold ranks 0..nt-1
                 __syncwarp();
                 u64 w = 0;
@@ -529,13 +535,14 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
             }
         }
     }
+    const u64 oflags = (unsafe ? SVDB_CAND_UNSAFE : 0ull) | (tie_flag ? SVDB_CAND_TIE : 0ull);
     svdb_candidate *out = p.out + (size_t)qi * p.k;
     if (valid && rank < p.k) {
         svdb_candidate c;
         c.dist = dex;
         c.seq = seq + p.seq_base;
         c.index = p.log_index[seq];
-        c.flags = unsafe ? SVDB_CAND_UNSAFE : 0ull;
+        c.flags = oflags;
         out[rank] = c;
     }
     if (lane < p.k && lane >= nvalid) {
@@ -543,7 +550,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         c.dist = CUDART_INF;
         c.seq = SEQ_NONE;
         c.index = (u64)SVDB_NONE;
-        c.flags = unsafe ? SVDB_CAND_UNSAFE : 0ull;
+        c.flags = oflags;
         out[lane] = c;
     }
 }
@@ -566,12 +573,30 @@ __global__ void __launch_bounds__(32) merge_candidates_kernel(const svdb_candida
             const svdb_candidate c = in[((size_t)(i / k) * nq + qi) * k + (i % k)];
             d = c.dist;
             s = c.seq;
-            flags |= c.flags;
+            flags |= c.flags & ~SVDB_CAND_TIE;
         }
         wl.offer(s != SEQ_NONE, d, s, lane);
     }
+    // SVDB_CAND_TIE of the merged answer: >= 2 entries at the merged minimum, or one that was flagged by its shard
+    double dmin;
+    u64 smin;
+    wl.key_at(0, dmin, smin);
+    int at_min = 0;
+    if (smin != SEQ_NONE) {
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            if (i < total) {
+                const svdb_candidate c = in[((size_t)(i / k) * nq + qi) * k + (i % k)];
+                if (c.seq != SEQ_NONE && c.dist == dmin) at_min += (c.flags & SVDB_CAND_TIE) ? 2 : 1;
+            }
+        }
+    }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) flags |= __shfl_xor_sync(FULL, flags, m);
+    for (int m = 16; m >= 1; m >>= 1) {
+        flags |= __shfl_xor_sync(FULL, flags, m);
+        at_min += __shfl_xor_sync(FULL, at_min, m);
+    }
+    if (at_min >= 2) flags |= SVDB_CAND_TIE;
     if (lane < k) {
         svdb_candidate c;
         c.dist = wl.d;

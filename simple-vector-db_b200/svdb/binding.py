@@ -18,7 +18,7 @@ MAX_K = 24
 COSINE, EUCLIDEAN, DOT, ALL_METRICS = 0, 1, 2, 3
 FLAG_LOG_ONLY, FLAG_NO_LOG, FLAG_SHARD = 1, 2, 4
 MODE_AUTO, MODE_EXACT, MODE_TREE = 0, 1, 2
-CAND_UNSAFE = 1
+CAND_UNSAFE, CAND_TIE = 1, 2
 
 _dp = C.POINTER(C.c_double)
 _zp = C.POINTER(C.c_size_t)
@@ -36,7 +36,25 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernels_launched", C.c_uint64), ("exact_reruns", C.c_uint64), ("tree_reruns", C.c_uint64),
                 ("tree_rounds", C.c_uint64), ("coalesced_calls", C.c_uint64), ("coalesced_passes", C.c_uint64),
-                ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("tie_events", C.c_uint64), ("tie_levels", C.c_uint64)]
+
+
+# ---- exact ties on a sharded store (svdb_tie_resolve / svdb_resolve_ties_sharded) ----
+tie_first_dtype = np.dtype([("seq", "<u8"), ("index", "<u8"), ("v", "<f8"), ("tied", "<u8")])
+tie_split_dtype = np.dtype([("n", "<u8", (2,)), ("min_seq", "<u8", (2,)), ("min_index", "<u8", (2,))])
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+TIE_COLLECT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+TIE_FIRST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                           C.c_void_p, C.c_void_p)
+TIE_SPLIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                           C.c_void_p, C.c_void_p)
+
+
+class TieBackend(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("world", C.c_int), ("rank", C.c_int), ("kd_dim", C.c_size_t),
+                ("allgather", ALLGATHER_FN), ("allgather_ctx", C.c_void_p), ("collect", TIE_COLLECT_FN),
+                ("first_in_cell", TIE_FIRST_FN), ("split", TIE_SPLIT_FN)]
 
 
 class SvdbError(RuntimeError):
@@ -55,7 +73,7 @@ NATIVE_SYMBOLS = [
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
     "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
-    "svdb_nearest_batch_sharded",
+    "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -109,6 +127,9 @@ def lib() -> C.CDLL:
     L.svdb_exchange_destroy.argtypes = [C.c_void_p]
     L.svdb_exchange_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
     L.svdb_nearest_batch_sharded.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _zp, _dp, _u64p]
+    L.svdb_tie_resolve.argtypes = [C.POINTER(TieBackend), C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, _u64p]
+    L.svdb_resolve_ties_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, C.c_void_p,
+                                            C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
     L.svdb_get_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     L.svdb_set_uuid.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
     _lib = L
@@ -252,6 +273,20 @@ class Engine:
                                                  seq.ctypes.data_as(_u64p)), "svdb_nearest_batch_sharded")
         return idx, dist, seq
 
+    def resolve_ties_sharded(self, rank: int, world: int, Q, merged: np.ndarray, allgather=None, xch: "Exchange" = None):
+        """Position 0 of every SVDB_CAND_TIE-flagged row of `merged` (nq x k candidates, the same on every rank)
+        becomes the entry the reference's global tree reaches first; in place.  Collective.  allgather(send, recv):
+        numpy uint8 arrays, recv = world blocks of len(send) in rank order; or pass the peer-memory exchange."""
+        Q = _f64(Q)
+        Q = Q.reshape(-1, Q.shape[-1])
+        assert merged.dtype == candidate_dtype and merged.flags["C_CONTIGUOUS"] and merged.shape[0] == len(Q)
+        cb = make_allgather_cb(allgather, world) if allgather is not None else C.cast(None, ALLGATHER_FN)
+        _check(self.L.svdb_resolve_ties_sharded(self.h, xch.h if xch is not None else None, rank, world, cb, None,
+                                                C.c_void_p(Q.ctypes.data), len(Q), Q.shape[1],
+                                                C.c_void_p(merged.ctypes.data), merged.shape[1]),
+               "svdb_resolve_ties_sharded")
+        return merged
+
     def nearest_device(self, q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, mode: int = 0) -> None:
         _check(self.L.svdb_nearest_batch_device(self.h, C.c_void_p(q_ptr), nq, ldq, k, C.c_void_p(out_ptr), int(mode)),
                "svdb_nearest_batch_device")
@@ -306,6 +341,38 @@ def compare_vectors(metric: int, a, b, device: int = 0) -> np.float32:
     _check(lib().svdb_compare_vectors(device, metric, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), len(a), C.byref(out)),
            "svdb_compare_vectors")
     return np.float32(out.value)
+
+
+def _np_at(ptr, dtype, count):
+    """numpy view of `count` items of `dtype` at a raw address handed to a callback."""
+    if count == 0:
+        return np.empty(0, dtype=dtype)
+    dt = np.dtype(dtype)
+    buf = (C.c_ubyte * (count * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=count)
+
+
+def make_allgather_cb(fn, world: int):
+    """Wrap fn(send_u8, recv_u8) as a C svdb_allgather_fn; exceptions become a non-zero return code."""
+    def cb(_ctx, send, recv, nbytes):
+        try:
+            fn(_np_at(send, np.uint8, nbytes), _np_at(recv, np.uint8, nbytes * world))
+            return 0
+        except Exception as ex:                  # never unwind through the C frames
+            import traceback
+            traceback.print_exc()
+            return -5
+    return ALLGATHER_FN(cb)
+
+
+def tie_resolve(backend: TieBackend, Q, merged: np.ndarray) -> int:
+    """svdb_tie_resolve with a caller-supplied backend (tests drive it with a numpy backend). Returns levels walked."""
+    Q = _f64(Q)
+    Q = Q.reshape(-1, Q.shape[-1])
+    levels = C.c_uint64()
+    _check(lib().svdb_tie_resolve(C.byref(backend), C.c_void_p(Q.ctypes.data), len(Q), Q.shape[1],
+                                  C.c_void_p(merged.ctypes.data), merged.shape[1], C.byref(levels)), "svdb_tie_resolve")
+    return levels.value
 
 
 def merge_candidates_device(device: int, stream: int | None, in_ptr: int, nshards: int, nq: int, k: int,

@@ -6,7 +6,9 @@ shard (K1) and re-ranks its survivors, the per-rank top-k candidate blocks (k x 
 query) are exchanged with ONE all-gather, and every rank merges them (K7).  The exchange is
 latency-bound (16..320 bytes per rank and query), so it rides the same stream directly behind
 the scan epilogue.  The key (reference-order distance, global sequence number) is exact, so
-the merged answer is identical to a single-GPU scan of all rows.
+the merged answer is identical to a single-GPU scan of all rows.  When distinct kd-points tie at
+exactly the minimal distance, the shards additionally walk the path of the reference's GLOBAL tree
+together (csrc/tie_protocol.cu) so that position 0 is the entry the reference itself returns.
 """
 from __future__ import annotations
 
@@ -33,7 +35,13 @@ def merge_candidates_host(gathered: np.ndarray, k: int) -> np.ndarray:
         c = gathered[:, q, :].reshape(-1)
         order = np.lexsort((c["seq"], c["dist"]))[:k]
         out[q] = c[order]
-        out[q]["flags"] = np.bitwise_or.reduce(c["flags"])
+        flags = np.bitwise_or.reduce(c["flags"] & ~np.uint64(B.CAND_TIE))
+        # SVDB_CAND_TIE is about the merged minimum: two entries there, or one whose shard flagged it
+        if out[q]["seq"][0] != B.NONE:
+            at_min = (c["seq"] != B.NONE) & (c["dist"] == out[q]["dist"][0])
+            if at_min.sum() >= 2 or np.any(c["flags"][at_min] & np.uint64(B.CAND_TIE)):
+                flags |= np.uint64(B.CAND_TIE)
+        out[q]["flags"] = flags
     return out
 
 
@@ -139,7 +147,22 @@ class ShardedIndex:
             host.copy_(merged, non_blocking=True)
             t.cuda.current_stream(self.device).synchronize()
             res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
-        return res.copy()
+        res = res.copy()
+        if self.world > 1 and np.any(res["flags"][:, 0] & B.CAND_TIE):
+            # distinct kd-points at exactly the minimal distance: all shards walk the global tree's path
+            # together (svdb_resolve_ties_sharded); the flags are the same on every rank
+            q_np = np.ascontiguousarray(q_host.numpy() if hasattr(q_host, "numpy") else q_host)
+            self.engine.resolve_ties_sharded(self.rank, self.world, q_np, res, allgather=self._allgather_host)
+        return res
+
+    def _allgather_host(self, send: np.ndarray, recv: np.ndarray) -> None:
+        """Host bytes in, host bytes of every rank out, over the process group (NCCL moves device tensors)."""
+        t = self.torch
+        dev = t.device("cuda", self.device)
+        mine = t.from_numpy(np.array(send, copy=True)).to(dev)
+        out = t.empty(self.world * mine.numel(), dtype=t.uint8, device=dev)
+        t.distributed.all_gather_into_tensor(out, mine, group=self.group)
+        recv[:] = out.cpu().numpy()
 
 
 class ReplicatedCompare:

@@ -39,7 +39,14 @@ def test_merge_host_orders_by_dist_then_seq():
     c["flags"][1, 0, 2] = 1
     m = merge_candidates_host(c, 3)
     assert list(m["seq"][0]) == [3, 5, 0] and list(m["dist"][0]) == [1.0, 1.0, 2.0]
-    assert np.all(m["flags"][0] == 1)
+    # UNSAFE of any input survives; TIE because two inputs (seq 3 and 5) sit at the merged minimum
+    assert np.all(m["flags"][0] == (B.CAND_UNSAFE | B.CAND_TIE))
+    c["dist"][1, 0, 0] = 1.5
+    c["flags"][0, 0, 1] = B.CAND_TIE          # a shard's own flag counts only if that shard holds the minimum
+    m = merge_candidates_host(c, 3)
+    assert np.all(m["flags"][0] == B.CAND_UNSAFE)
+    c["flags"][0, 0, 0] = B.CAND_TIE
+    assert np.all(merge_candidates_host(c, 3)["flags"][0] == (B.CAND_UNSAFE | B.CAND_TIE))
 
 
 def _worker(rank, world, port_no, n, D, k, out_dir):
@@ -95,3 +102,58 @@ def test_two_rank_exchange_and_merge_equals_single_scan(tmp_path, port):
         np.testing.assert_array_equal(merged[0]["seq"][i].astype(np.int64), seq)
         np.testing.assert_array_equal(merged[0]["dist"][i].view(np.uint64), d.view(np.uint64))
     db.close()
+
+
+# ---- exact ties across shards: the product's walk (svdb_tie_resolve) over a real process group ----
+
+def _tie_worker(rank, world, port_no, seed, n, K, k, out_dir):
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tie_backend_np import NumpyTieShard, local_topk
+    rng = np.random.Generator(np.random.PCG64(seed))        # every rank can regenerate any row range
+    rows = rng.integers(0, 4, size=(n, K)) / 2.0
+    Q = rng.integers(0, 4, size=(48, K)) / 2.0 + 0.25
+    lo, hi = shard_range(n, world, rank)
+    local = local_topk(rows[lo:hi], lo, Q, K, k)
+    t_local = torch.from_numpy(local.view(np.int64).reshape(len(Q), k, 4).copy())
+    gathered = [torch.zeros_like(t_local) for _ in range(world)]
+    dist.all_gather(gathered, t_local)
+    merged = merge_candidates_host(torch.stack(gathered).numpy().view(B.candidate_dtype).reshape(world, len(Q), k), k)
+
+    def allgather(send, recv):
+        mine = torch.from_numpy(np.array(send, copy=True))
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        recv[:] = torch.cat(parts).numpy()
+
+    shard = NumpyTieShard(rows[lo:hi], lo, K, rank, world, allgather)
+    levels = B.tie_resolve(shard.backend, Q, merged)
+    np.save(os.path.join(out_dir, f"tie_{rank}.npy"), merged)
+    np.save(os.path.join(out_dir, f"tie_levels_{rank}.npy"), np.array([levels]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_tie_walk_matches_the_global_tree(tmp_path, port):
+    seed, n, K, k, world = 21, 600, 2, 3, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_tie_worker, args=(world, port_no, seed, n, K, k, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = rng.integers(0, 4, size=(n, K)) / 2.0
+    Q = rng.integers(0, 4, size=(48, K)) / 2.0 + 0.25
+    h = port.build(rows, K)
+    want = port.nearest_batch(h, Q)
+    port.free(h)
+    got = [np.load(tmp_path / f"tie_{r}.npy") for r in range(world)]
+    np.testing.assert_array_equal(got[0], got[1])
+    np.testing.assert_array_equal(got[0]["index"][:, 0], want)
+    assert int(np.load(tmp_path / "tie_levels_0.npy")[0]) > 0      # the walk really ran
+    assert not np.any(got[0]["flags"] & B.CAND_TIE)
