@@ -44,7 +44,9 @@ def main():
         g = torch.Generator().manual_seed(n + levels)
         if levels:
             rows = torch.randint(0, levels, (n, D), generator=g).to(torch.float64) / 2      # same on every rank
-            Q = (torch.randint(0, levels, (16, D), generator=g).to(torch.float64) / 2).pin_memory()
+            Q = torch.randint(0, levels, (16, D), generator=g).to(torch.float64) / 2
+            Q[:, 0] += 0.25                       # between lattice planes: no exact hit, the minimum is shared
+            Q = Q.pin_memory()
         else:
             rows = torch.rand((n, D), dtype=torch.float64, generator=g)
             Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()

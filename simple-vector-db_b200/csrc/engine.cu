@@ -215,6 +215,8 @@ void svdb_engine::destroy() {
     xnorm.release();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
+    tie_state_free(tie);
+    tie = nullptr;
     if (own_stream) cudaStreamDestroy(own_stream);
     own_stream = stream = nullptr;
 }

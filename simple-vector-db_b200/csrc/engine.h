@@ -43,6 +43,8 @@ struct PinnedScratch {
 
 struct svdb_exchange;
 namespace svdb {
+struct TieGpu;                       // device scratch of the cross-shard tie walk (tie_protocol.cu)
+void tie_state_free(TieGpu *t);
 cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candidate *d_local, size_t nq, size_t k,
                              svdb_candidate *out);
 bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k);
@@ -121,6 +123,8 @@ struct svdb_engine {
     unsigned long long opt_gen = 0;          // bumped by svdb_set_option / svdb_set_stream
     size_t last_nq = 0, last_k = 0;          // a shape is captured the second time it shows up in a row
     void drop_graphs();
+
+    svdb::TieGpu *tie = nullptr;             // created by the first tie walk, kept for the next ones
 
     svdb::ScanTuning tune;
     bool force_exact = false;

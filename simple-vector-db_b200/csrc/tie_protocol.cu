@@ -403,6 +403,8 @@ struct TieGpu {
     }
 };
 
+void tie_state_free(TieGpu *t) { delete t; }
+
 #define TCK(call)                                             \
     do {                                                      \
         cudaError_t ce_ = (call);                             \
@@ -564,11 +566,14 @@ int resolve_ties_engine(svdb_engine *e, svdb_exchange *x, int rank, int world, s
     if (rc) return rc;
     cudaError_t ce = cudaSetDevice(e->device);
     if (ce != cudaSuccess) return e->fail_cuda("cudaSetDevice", ce);
-    TieGpu t;
-    t.e = e;
+    if (!e->tie) {
+        e->tie = new (std::nothrow) TieGpu();
+        if (!e->tie) return e->fail(SVDB_ERR_OOM, "tie walk state");
+        e->tie->e = e;
+    }
     XchAg xa{x, e->stream};
     svdb_tie_backend b{};
-    b.ctx = &t;
+    b.ctx = e->tie;
     b.world = world;
     b.rank = rank;
     b.kd_dim = (size_t)e->K;

@@ -98,7 +98,7 @@ def test_sharded_lattice_ties_equal_the_global_tree(port, world, K, D, levels):
         n_flag = np.count_nonzero(merged["flags"][:, 0] & B.CAND_TIE)
         assert n_flag > 0
         got = sh.resolve(Q, merged)
-        np.testing.assert_array_equal(got["index"][:, 0], want)
+        np.testing.assert_array_equal(got["seq"][:, 0], want)      # insert-only data: global row == seq
         assert not np.any(got["flags"] & B.CAND_TIE)
         st = sh.engines[0].stats()
         assert st["tie_events"] == n_flag
@@ -106,7 +106,7 @@ def test_sharded_lattice_ties_equal_the_global_tree(port, world, K, D, levels):
         k = 4
         merged = sh.merged(Q, k)
         got = sh.resolve(Q, merged)
-        np.testing.assert_array_equal(got["index"][:, 0], want)
+        np.testing.assert_array_equal(got["seq"][:, 0], want)      # insert-only data: global row == seq
         for g, m in zip(got, merged):
             rest = [int(s) for s in m["seq"] if s != g["seq"][0]][:k - 1]
             assert [int(s) for s in g["seq"][1:1 + len(rest)]] == rest
@@ -125,7 +125,7 @@ def test_sharded_mass_ties_beyond_any_candidate_list(port, K, n_far):
         merged = sh.merged(Q, 1)
         assert merged["flags"][0, 0] & B.CAND_TIE and merged["dist"][0, 0] == 25.0
         got = sh.resolve(Q, merged)
-        np.testing.assert_array_equal(got["index"][:, 0], want)
+        np.testing.assert_array_equal(got["seq"][:, 0], want)      # insert-only data: global row == seq
     finally:
         sh.close()
 
@@ -155,7 +155,7 @@ def test_duplicate_rows_across_shards_skip_the_walk(port):
         merged = sh.merged(Q, 2)
         assert np.all(merged["flags"][:, 0] & B.CAND_TIE)
         got = sh.resolve(Q, merged)
-        np.testing.assert_array_equal(got["index"][:, 0], want)
+        np.testing.assert_array_equal(got["seq"][:, 0], want)      # insert-only data: global row == seq
         assert sh.engines[0].stats()["tie_levels"] == 0
     finally:
         sh.close()
@@ -168,6 +168,7 @@ def test_one_call_sharded_path_with_peer_exchange_world_1(port, K, D, levels):
     rng = np.random.Generator(np.random.PCG64(77 + K))
     rows = rng.integers(0, levels, size=(5000, D)) / 2.0
     Q = rng.integers(0, levels, size=(33, D)) / 2.0
+    Q[:, 0] += 0.25                                  # half way between lattice planes: never an exact hit
     want = oracle_tree_ids(port, rows, K, Q)
     xch = B.Exchange(0, 0, 1, 4096)
     xch.connect(xch.handle)
