@@ -104,6 +104,9 @@ int svdb_update_batch(svdb_engine *e, const size_t *index, const double *rows, s
 int svdb_delete_batch(svdb_engine *e, const size_t *index, size_t n);      /* applied in order */
 /* Bare log append (n kd-points of ld >= kd_dim doubles, each with the index to report). */
 int svdb_append_kdpoints(svdb_engine *e, const double *pts, const size_t *index, size_t n, size_t ld);
+/* The same with the kd-points already in device memory (SVDB_FLAG_LOG_ONLY engines); entry i reports
+ * index first_index + i. */
+int svdb_append_kdpoints_device(svdb_engine *e, const double *d_pts, size_t first_index, size_t n, size_t ld);
 /* Same as svdb_insert_batch with rows already in device memory (bulk ingest). */
 int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, size_t ld, size_t *first_index);
 /* Push pending deltas to the device (queries do this themselves). */

@@ -39,8 +39,9 @@ def main():
     report = []
     # the last three are coarse lattices: distinct kd-points at exactly equal distance everywhere (and, with
     # 0/1 coordinates, dozens of them per query), so the answer depends on the order of the reference's tree
-    for (n, D, K, levels) in ((400_003, 128, 128, 0), (50_000, 768, 768, 0), (300_000, 16, 3, 0),
-                              (200_000, 16, 3, 7), (100_000, 64, 64, 2), (60_000, 768, 768, 2)):
+    for (n, D, K, levels, replicate) in ((400_003, 128, 128, 0, True), (50_000, 768, 768, 0, True), (300_000, 16, 3, 0, True),
+                                         (200_000, 16, 3, 7, True), (200_000, 16, 3, 7, False), (100_000, 64, 64, 2, True),
+                                         (60_000, 768, 768, 2, True)):
         g = torch.Generator().manual_seed(n + levels)
         if levels:
             rows = torch.randint(0, levels, (n, D), generator=g).to(torch.float64) / 2      # same on every rank
@@ -50,18 +51,22 @@ def main():
         else:
             rows = torch.rand((n, D), dtype=torch.float64, generator=g)
             Q = torch.rand((16, D), dtype=torch.float64, generator=g).pin_memory()
-        idx = ShardedIndex(D, K, n, rank, world, local, exchange=os.environ.get("SVDB_EXCHANGE", "p2p"))
+        idx = ShardedIndex(D, K, n, rank, world, local, exchange=os.environ.get("SVDB_EXCHANGE", "p2p"),
+                           replicate_thin=replicate)
         idx.bind_current_stream()
         idx.ingest_device(rows[idx.lo:idx.hi].to(dev).contiguous())
         for k in (1, 10):
             got = idx.nearest(Q, k)
+            few = idx.nearest(Q[:3], k)           # too few queries to split over replicas / one small pass per shard
             if rank == 0:
                 with B.Engine(D, K, device=local) as e:
                     e.insert_device(rows.to(dev).data_ptr(), n, D)
                     _, wdist, wseq = e.nearest(Q.numpy(), k)
                 same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
+                same = same and np.array_equal(few["seq"], wseq[:3]) and np.array_equal(few["dist"].view(np.uint64), wdist[:3].view(np.uint64))
                 ok &= bool(same)
                 report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels,
+                               "layout": "replicated kd log, queries split" if idx.replicated else "row shards",
                                "identical_to_single_gpu": bool(same), "tie_events": idx.engine.stats()["tie_events"],
                                "tie_levels": idx.engine.stats()["tie_levels"]})
         idx.close()

@@ -904,6 +904,37 @@ int svdb_append_kdpoints(svdb_engine *e, const double *pts, const size_t *index,
     return SVDB_OK;
 }
 
+// kd-points already in device memory -> a bare log (SVDB_FLAG_LOG_ONLY): entry i reports index first_index + i
+int svdb_append_kdpoints_device(svdb_engine *e, const double *d_pts, size_t first_index, size_t n, size_t ld) {
+    if (!e || (!d_pts && n)) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->log_only) return e->fail(SVDB_ERR_ARG, "svdb_append_kdpoints_device needs a SVDB_FLAG_LOG_ONLY engine");
+    if (ld < (size_t)e->K) return e->fail(SVDB_ERR_ARG, "ld < kd_dim");
+    int rc = e->flush();
+    if (rc) return rc;
+    if (n == 0) return SVDB_OK;
+    if (cudaSetDevice(e->device) != cudaSuccess) return e->fail_cuda("cudaSetDevice", cudaGetLastError());
+    const size_t n0 = e->n_versions, n1 = n0 + n;
+    if (n1 > e->max_versions) return e->fail(SVDB_ERR_OOM, "store exceeds the reserved address range");
+    std::string err;
+    if (!e->log_idx.ensure(n1 * 8, e->stream, err) || !e->kdpts.ensure(n1 * (size_t)e->kstride * 8, e->stream, err))
+        return e->fail(SVDB_ERR_OOM, err);
+    double *dst = e->kdpts.as<double>() + n0 * (size_t)e->kstride;
+    cudaError_t ce = cudaSuccess;
+    if (e->kstride != e->K) ce = cudaMemsetAsync(dst, 0, n * (size_t)e->kstride * 8, e->stream);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy2DAsync(dst, (size_t)e->kstride * 8, d_pts, ld * 8, (size_t)e->K * 8, n, cudaMemcpyDeviceToDevice, e->stream);
+    if (ce == cudaSuccess) ce = launch_iota(e->log_idx.as<u64>() + n0, first_index, n, e->stream);
+    if (ce != cudaSuccess) return e->fail_cuda("svdb_append_kdpoints_device", ce);
+    e->stats.kernels_launched++;
+    rc = e->tree_append(n0, n);
+    if (rc) return rc;
+    e->n_versions = n1;
+    e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
+    return SVDB_OK;
+}
+
 int svdb_insert_batch_device(svdb_engine *e, const double *d_rows, size_t n, size_t ld, size_t *first_index) {
     if (!e || (!d_rows && n)) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);

@@ -67,7 +67,7 @@ _lib = None
 NATIVE_SYMBOLS = [
     "svdb_last_error", "svdb_version", "svdb_device_count", "svdb_engine_create", "svdb_engine_destroy",
     "svdb_set_stream", "svdb_insert_batch", "svdb_update_batch", "svdb_delete_batch", "svdb_append_kdpoints",
-    "svdb_insert_batch_device", "svdb_flush", "svdb_size", "svdb_log_size", "svdb_dimension", "svdb_kd_dim",
+    "svdb_insert_batch_device", "svdb_append_kdpoints_device", "svdb_flush", "svdb_size", "svdb_log_size", "svdb_dimension", "svdb_kd_dim",
     "svdb_read_row", "svdb_nearest_batch", "svdb_nearest_batch_device", "svdb_merge_candidates_device",
     "svdb_compare_batch", "svdb_compare_batch_all", "svdb_compare_batch_device", "svdb_compare_vectors",
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.svdb_delete_batch.argtypes = [C.c_void_p, _zp, C.c_size_t]
     L.svdb_append_kdpoints.argtypes = [C.c_void_p, _dp, _zp, C.c_size_t, C.c_size_t]
     L.svdb_insert_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, _zp]
+    L.svdb_append_kdpoints_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.svdb_flush.argtypes = [C.c_void_p]
     for f in (L.svdb_size, L.svdb_log_size, L.svdb_dimension, L.svdb_kd_dim):
         f.restype = C.c_size_t
@@ -213,6 +214,9 @@ class Engine:
         _check(self.L.svdb_insert_batch_device(self.h, C.c_void_p(ptr), n, ld, C.byref(first)),
                "svdb_insert_batch_device")
         return first.value
+
+    def append_kdpoints_device(self, ptr: int, first_index: int, n: int, ld: int) -> None:
+        _check(self.L.svdb_append_kdpoints_device(self.h, C.c_void_p(ptr), first_index, n, ld), "svdb_append_kdpoints_device")
 
     def update(self, index, rows) -> None:
         index = _u64(np.atleast_1d(index))

@@ -9,6 +9,13 @@ the scan epilogue.  The key (reference-order distance, global sequence number) i
 the merged answer is identical to a single-GPU scan of all rows.  When distinct kd-points tie at
 exactly the minimal distance, the shards additionally walk the path of the reference's GLOBAL tree
 together (csrc/tie_protocol.cu) so that position 0 is the entry the reference itself returns.
+
+Thin kd-points (kd_dim <= 8, the reference's default is 3) are different: the tree answers a query
+in O(log N) visits, so scanning row shards would make N GPUs SLOWER than one.  There the 8*kd_dim
+bytes per row that /nearest looks at are replicated on every GPU (all-gathered once at ingest: the
+whole log + the reference-shaped tree over ALL rows), and the QUERIES are split over the ranks:
+no collective in the query path except the all-gather of the answers, answers identical to one
+GPU by construction, throughput scales with the ranks ("replicas").
 """
 from __future__ import annotations
 
@@ -48,22 +55,33 @@ def merge_candidates_host(gathered: np.ndarray, k: int) -> np.ndarray:
 class ShardedIndex:
     """One rank's shard plus the exchange.  world == 1 needs no process group."""
 
+    REPLICATE_MAX_KD = 8        # the engine's tree regime (option nearest.tree_max_k)
+
     def __init__(self, dimension: int, kd_dim: int, n_rows_total: int, rank: int = 0, world: int = 1,
-                 device: int = 0, group=None, exchange: str = "p2p", max_records: int = 32768):
+                 device: int = 0, group=None, exchange: str = "p2p", max_records: int = 32768,
+                 replicate_thin: bool = True):
         import torch
         self.torch = torch
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.D, self.K = dimension, kd_dim
+        self.n_total = n_rows_total
         self.lo, self.hi = shard_range(n_rows_total, world, rank)
+        self.replicated = world > 1 and replicate_thin and kd_dim <= self.REPLICATE_MAX_KD
+        self.merge_launches = 0
+        self._bufs = {}
+        self._pending, self._sealed = [], False
+        self.xch = None
+        self.max_records = max_records
+        if self.replicated:
+            # every rank: the WHOLE kd log (kd_dim doubles per row) and the tree over it; queries are split
+            self.engine = B.Engine(kd_dim, kd_dim, device=device, reserve_rows=max(1, n_rows_total),
+                                   flags=B.FLAG_LOG_ONLY)
+            return
         self.engine = B.Engine(dimension, kd_dim, device=device, seq_base=self.lo,
                                reserve_rows=max(1, self.hi - self.lo),
                                flags=B.FLAG_SHARD if world > 1 else 0)
-        self.merge_launches = 0
-        self._bufs = {}
         # "p2p": candidates are stored into the peers' HBM over NVLink and merged in the same launch
         # (svdb_exchange); "nccl": all_gather_into_tensor + svdb_merge_candidates_device
-        self.xch = None
-        self.max_records = max_records
         if world > 1 and exchange == "p2p":
             self.xch = B.Exchange(device, rank, world, max_records)
             mine = torch.frombuffer(bytearray(self.xch.handle), dtype=torch.uint8).to(torch.device("cuda", device))
@@ -87,7 +105,38 @@ class ShardedIndex:
     def ingest_device(self, rows) -> None:
         """rows: contiguous float64 CUDA tensor [n, D] belonging to this shard, in order."""
         assert rows.dtype == self.torch.float64 and rows.is_contiguous() and rows.shape[1] == self.D
+        if self.replicated:
+            self._pending.append(rows[:, :self.K].contiguous())     # exchanged when the shard is complete
+            if sum(p.shape[0] for p in self._pending) >= self.hi - self.lo:
+                self._seal()
+            return
         self.engine.insert_device(rows.data_ptr(), rows.shape[0], rows.shape[1])
+
+    def _seal(self) -> None:
+        """Replicated mode: all-gather the kd-points of every shard and append them in global row order."""
+        t = self.torch
+        dev = t.device("cuda", self.device)
+        mine = t.cat(self._pending) if self._pending else t.empty((0, self.K), dtype=t.float64, device=dev)
+        self._pending, self._sealed = [], True
+        assert mine.shape[0] == self.hi - self.lo, "a shard must be ingested completely before the first query"
+        per = -(-self.n_total // self.world)
+        padded = t.zeros((per, self.K), dtype=t.float64, device=dev)
+        padded[:mine.shape[0]] = mine
+        everything = t.empty((self.world, per, self.K), dtype=t.float64, device=dev)
+        t.distributed.all_gather_into_tensor(everything, padded, group=self.group)
+        t.cuda.current_stream(self.device).synchronize()
+        for r in range(self.world):
+            lo, hi = shard_range(self.n_total, self.world, r)
+            if hi > lo:
+                self.engine.append_kdpoints_device(everything[r].data_ptr(), lo, hi - lo, self.K)
+        self.engine.flush()
+
+    def _query_span(self, nq: int):
+        """Replicated mode: which queries this rank answers (all of them when there are too few to split)."""
+        if nq < 2 * self.world:
+            return 0, nq, 0
+        per = -(-nq // self.world)
+        return min(nq, self.rank * per), min(nq, (self.rank + 1) * per), per
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)
@@ -105,6 +154,10 @@ class ShardedIndex:
         """dq: float64 CUDA tensor [nq, >=K]. Returns the merged [nq, k, 4] int64 CUDA tensor
         (a view of svdb_candidate records); everything is enqueued on the current stream."""
         nq = dq.shape[0]
+        if self.replicated:
+            if not self._sealed:
+                self._seal()                      # a rank whose shard is empty never saw an ingest call
+            return self._nearest_device_replicated(dq, k, mode)
         local, gathered, merged, _ = self._buffers(nq, k)
         self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), mode)
         if self.world > 1:
@@ -118,6 +171,24 @@ class ShardedIndex:
                 self.merge_launches += 1
         return merged
 
+    def _nearest_device_replicated(self, dq, k: int, mode: int):
+        t = self.torch
+        nq = dq.shape[0]
+        lo, hi, per = self._query_span(nq)
+        key = ("rep", nq, k)
+        if key not in self._bufs:
+            dev = t.device("cuda", self.device)
+            mine = t.zeros((per if per else nq, k, 4), dtype=t.int64, device=dev)
+            everything = t.zeros((self.world, per, k, 4), dtype=t.int64, device=dev) if per else None
+            self._bufs[key] = (mine, everything)
+        mine, everything = self._bufs[key]
+        if hi > lo:
+            self.engine.nearest_device(dq[lo:hi].data_ptr(), hi - lo, dq.stride(0), k, mine.data_ptr(), mode)
+        if per == 0:
+            return mine[:nq]
+        t.distributed.all_gather_into_tensor(everything, mine, group=self.group)
+        return everything.view(self.world * per, k, 4)[:nq]
+
     def nearest(self, q_host, k: int):
         """End-to-end call a user makes: q_host is a float64 CPU tensor (or numpy array) [nq, >=K];
         returns a numpy array of svdb_candidate [nq, k] with the MERGED answers (`seq` is the global
@@ -126,6 +197,15 @@ class ShardedIndex:
         and merge are enqueued -- and from the second call of a shape on replayed as one CUDA graph --
         inside the library.  With exchange="nccl" the steps are driven from here."""
         nq = q_host.shape[0]
+        if self.replicated and not self._sealed:
+            self._seal()
+        if self.replicated and self._query_span(nq)[2] == 0:
+            # too few queries to split: every replica answers them itself, nothing is exchanged
+            q_np = q_host.numpy() if hasattr(q_host, "numpy") else np.asarray(q_host)
+            idx, dist, seq = self.engine.nearest(q_np[:, :self.K], k)
+            res = np.zeros((nq, k), dtype=B.candidate_dtype)
+            res["index"], res["dist"], res["seq"] = idx, dist, seq
+            return res
         if self.xch is not None and nq * k <= self.max_records:
             q_np = q_host.numpy() if hasattr(q_host, "numpy") else np.asarray(q_host)
             idx, dist, seq = self.engine.nearest_sharded(self.xch, q_np, k)
@@ -137,7 +217,12 @@ class ShardedIndex:
             q_host = t.from_numpy(np.ascontiguousarray(q_host))
         dq = q_host.to(t.device("cuda", self.device), non_blocking=True)
         merged = self.nearest_device(dq, k)
-        host = self._buffers(dq.shape[0], k)[3]
+        if self.replicated:
+            if ("host", nq, k) not in self._bufs:
+                self._bufs[("host", nq, k)] = t.zeros((nq, k, 4), dtype=t.int64).pin_memory()
+            host = self._bufs[("host", nq, k)]
+        else:
+            host = self._buffers(dq.shape[0], k)[3]
         host.copy_(merged, non_blocking=True)
         t.cuda.current_stream(self.device).synchronize()
         res = host.numpy().view(B.candidate_dtype).reshape(dq.shape[0], k)
