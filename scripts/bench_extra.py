@@ -170,6 +170,10 @@ def main():
                             extra_opts=(("nearest.tree_max_k", 0),))
         res += nearest_case("thin_20M_x16_k16_scan", 20_000_000, 16, 16, 1, (1,), iters=10,
                             extra_opts=(("nearest.tree_max_k", 0),))
+    if "ksweep" in which:  # one query over a ~1.5 GB kd log at every kd_dim regime (rows are wider: the kd log is compact)
+        for K in (9, 12, 16, 17, 24, 32, 48, 64, 96, 128, 256):
+            n = int(1.5e9 / (K * 8))
+            res += nearest_case(f"ksweep_k{K}", n, K + 16, K, 1, (1, 8), iters=10)
     if "c2" in which:
         res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50)
         res += compare_case("c2_compare_1M_x128", 1_000_000, 128, 100_000)

@@ -139,6 +139,7 @@ int svdb_engine::init(const svdb_config &c) {
     if (prop.major < 10) return fail(SVDB_ERR_CUDA, "kernels are built for sm_100a only; this device is older");
     tune.num_sms = prop.multiProcessorCount;
     if (const char *v = getenv("SVDB_SCAN_VARIANT")) tune.variant = atoi(v);
+    if (const char *v = getenv("SVDB_THIN_MAX_K")) tune.thin_max_k = atoi(v);     // A/B of the exact vs the wide scan at small kd_dim
 
     D = (int)c.dimension;
     K = (int)c.kd_dim;

@@ -20,7 +20,8 @@ struct ScanTuning {
     int ctas_per_sm = 2;
     int assign = 0;         // 0: tiles dealt round-robin over all warps; 1: every CTA streams one contiguous slab
     int nq_per_pass = 4;    // queries sharing one pass over the log (1, 2, 4, 8)
-    int thin_max_k = 16;    // K <= this: thread-per-row exact kernel is the primary path
+    int thin_max_k = 12;    // K <= this: thread-per-row exact kernel is the primary path (measured 0.84-0.92 x HBM peak
+                            // at K = 9..12 but 0.33 x at K = 16, where 128-byte rows make every lane hit its own line)
     int num_sms = 148;
 };
 

@@ -15,7 +15,7 @@
 //                      keeps its 32 best (d~, seq) in registers, one per lane.
 //   scan_ldg_kernel    same contract, rows streamed with ld.global.nc.v2.f64 (A/B variant).
 //   scan_exact_kernel  one thread per entry, the reference's exact operation order.
-//                      Primary path for thin rows (K <= 16), fallback for any K.
+//                      Primary path for thin rows (K <= 12), fallback for any K.
 //   finalize_kernel    per query: merge the per-CTA lists, recompute the survivors in the
 //                      reference's order (exact_sqdist), order by (d, seq), emit top-k and
 //                      prove that no entry outside the candidate set can belong to it.
@@ -42,11 +42,48 @@ __device__ __forceinline__ void cta_merge_emit(WarpList &mine, Cand *mrg, int W,
     __syncthreads();
 }
 
+// ---- reduce TR per-lane partial sums over the warp with TR-1 + (5 - log2 TR) shuffles ------------
+// A plain butterfly costs 5 shuffles (10 SHFL.32) per row, which is what bounds short rows (measured:
+// 0.23-0.65 x HBM peak for kd_dim 17..48).  Here the first log2(TR) steps HALVE the set instead: a lane
+// passes the rows it gives up to its partner and adds what it receives to the rows it keeps.  Every row
+// is still combined by the same tree over the lane indices (xor 16, 8, 4, 2, 1; addition commutes), so a
+// key is the same bits whatever TR is and wherever the row sits in a tile.
+// On return the total of row r is in v[0] of the lanes with (lane >> (5 - log2 TR)) == r.
+template <int TR>
+__device__ __forceinline__ void reduce_rows(double (&v)[TR], int lane) {
+    constexpr int T = TR == 32 ? 5 : TR == 16 ? 4 : TR == 8 ? 3 : TR == 4 ? 2 : TR == 2 ? 1 : 0;
+#pragma unroll
+    for (int s = 0; s < T; s++) {
+        const int m = 16 >> s;
+        const int cnt = TR >> (s + 1);
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; i++) {
+            const double send = up ? v[i] : v[i + cnt];
+            const double keep = up ? v[i + cnt] : v[i];
+            v[i] = keep + shfl_xor_f64(send, m);
+        }
+    }
+#pragma unroll
+    for (int m = 16 >> T; m >= 1; m >>= 1) v[0] += shfl_xor_f64(v[0], m);
+}
+template <int TR>
+struct RowLane {
+    static constexpr int T = TR == 32 ? 5 : TR == 16 ? 4 : TR == 8 ? 3 : TR == 4 ? 2 : TR == 2 ? 1 : 0;
+    static constexpr int SH = 5 - T;
+    __device__ static __forceinline__ int row(int lane) { return lane >> SH; }
+    __device__ static __forceinline__ bool owner(int lane) { return (lane & ((1 << SH) - 1)) == 0; }
+};
+
 // =====================================================================================
 // Wide rows, TMA bulk-copy ring.  TR rows per tile, NQ queries share the pass.
+// LPR = lanes that share one row.  32: a warp walks a row 64 coordinates at a time (rows of any length).
+// 16 / 8 / 4 (rows of <= 32 / 16 / 8 doubles; TR = 32, NQ = 1): 32 / LPR rows are processed side by side, one
+// 128-bit load per lane and step, so that short rows do not leave most of the warp idle (K = 17: 9 of 32 lanes).
 // =====================================================================================
-template <int TR, int NQ>
+template <int TR, int NQ, int LPR = 32>
 __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstages) {
+    static_assert(LPR == 32 || (TR == 32 && NQ == 1), "packed rows: 32-row tiles, one query");
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,51 +153,87 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
     int s = 0;
     uint32_t phase = 0;
     const uint32_t qa0 = smem_u32(qs) + lane * 16;
+    // packed rows: lane = (row within the step) * LPR + (pair of coordinates); the query pair stays in registers
+    constexpr int PR = 32 / LPR;                       // rows side by side
+    const int pj = lane % LPR, pg = lane / LPR;
+    const bool pact = pj * 2 < kpad;
+    double2 pq = make_double2(0.0, 0.0);
+    if (LPR < 32 && pact) pq = lds128(smem_u32(qs) + pj * 16);
     for (u64 t = gw; t < ntiles; t += GW) {
         mbar_wait(my_bar + 8 * s, phase);
-        // two independent accumulation chains per (row, query) while registers allow it
-        constexpr int NA = (TR * NQ <= 4) ? 2 : 1;
-        double acc[TR][NQ][NA];
+        double cd[NQ];
+        int my_row;                                    // row of the tile whose key this lane ends up with
+        bool my_own;
+        if constexpr (LPR < 32) {
+            // step i covers rows i*PR .. i*PR+PR-1; afterwards lane (g, j) holds LPR partial sums, one per step,
+            // and the halving reduction over j leaves exactly one finished row in every lane: row j*PR + g
+            double v[LPR];
+            const uint32_t sa = my_stage + s * tile_bytes + (uint32_t)pg * row_bytes + (uint32_t)pj * 16;
 #pragma unroll
-        for (int r = 0; r < TR; r++)
+            for (int i = 0; i < LPR; i++) {
+                const double2 x = pact ? lds128(sa + (uint32_t)(i * PR) * row_bytes) : pq;
+                const double a = x.x - pq.x;
+                const double b = x.y - pq.y;
+                v[i] = fma(b, b, a * a);
+            }
 #pragma unroll
-            for (int qi = 0; qi < NQ; qi++)
+            for (int st2 = 0, m = LPR / 2; m >= 1; m >>= 1, st2++) {
+                const int cnt = LPR >> (st2 + 1);
+                const bool up = (lane & m) != 0;
 #pragma unroll
-                for (int a = 0; a < NA; a++) acc[r][qi][a] = 0.0;
-
-        uint32_t sa = my_stage + s * tile_bytes + lane * 16;
-        uint32_t qa = qa0;
-#pragma unroll 4
-        for (int off = lane * 2; off < kpad; off += 64, sa += 512, qa += 512) {
-            double2 qv[NQ];
-#pragma unroll
-            for (int qi = 0; qi < NQ; qi++) qv[qi] = lds128(qa + qi * row_bytes);
-#pragma unroll
-            for (int r = 0; r < TR; r++) {
-                const double2 x = lds128(sa + r * row_bytes);
-#pragma unroll
-                for (int qi = 0; qi < NQ; qi++) {
-                    const double a = x.x - qv[qi].x;
-                    const double b = x.y - qv[qi].y;
-                    acc[r][qi][0] = fma(a, a, acc[r][qi][0]);
-                    acc[r][qi][NA - 1] = fma(b, b, acc[r][qi][NA - 1]);
+                for (int i = 0; i < cnt; i++) {
+                    const double send = up ? v[i] : v[i + cnt];
+                    const double keep = up ? v[i + cnt] : v[i];
+                    v[i] = keep + shfl_xor_f64(send, m);
                 }
             }
-        }
-        // butterfly all-reduce; the combination tree is identical for every row, so equal
-        // rows always get equal keys wherever they sit in the log
-        double cd[NQ];
+            cd[0] = v[0];
+            my_row = pj * PR + pg;
+            my_own = true;
+        } else {
+            // two independent accumulation chains per (row, query) while registers allow it
+            constexpr int NA = (TR * NQ <= 4) ? 2 : 1;
+            double acc[TR][NQ][NA];
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) cd[qi] = CUDART_INF;
+            for (int r = 0; r < TR; r++)
 #pragma unroll
-        for (int r = 0; r < TR; r++)
+                for (int qi = 0; qi < NQ; qi++)
+#pragma unroll
+                    for (int a = 0; a < NA; a++) acc[r][qi][a] = 0.0;
+
+            uint32_t sa = my_stage + s * tile_bytes + lane * 16;
+            uint32_t qa = qa0;
+            // tiles of 16 / 32 rows are only picked for rows of <= 64 doubles: a single trip
+#pragma unroll(TR >= 16 ? 1 : 4)
+            for (int off = lane * 2; off < kpad; off += 64, sa += 512, qa += 512) {
+                double2 qv[NQ];
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) qv[qi] = lds128(qa + qi * row_bytes);
+#pragma unroll
+                for (int r = 0; r < TR; r++) {
+                    const double2 x = lds128(sa + r * row_bytes);
+#pragma unroll
+                    for (int qi = 0; qi < NQ; qi++) {
+                        const double a = x.x - qv[qi].x;
+                        const double b = x.y - qv[qi].y;
+                        acc[r][qi][0] = fma(a, a, acc[r][qi][0]);
+                        acc[r][qi][NA - 1] = fma(b, b, acc[r][qi][NA - 1]);
+                    }
+                }
+            }
+            // all-reduce over the lanes (reduce_rows: the combination tree is identical for every row, so
+            // equal rows always get equal keys wherever they sit in the log)
 #pragma unroll
             for (int qi = 0; qi < NQ; qi++) {
-                double v = NA == 2 ? acc[r][qi][0] + acc[r][qi][NA - 1] : acc[r][qi][0];
+                double v[TR];
 #pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
-                if (lane == r) cd[qi] = v;
+                for (int r = 0; r < TR; r++) v[r] = NA == 2 ? acc[r][qi][0] + acc[r][qi][NA - 1] : acc[r][qi][0];
+                reduce_rows<TR>(v, lane);
+                cd[qi] = v[0];
             }
+            my_row = RowLane<TR>::row(lane);
+            my_own = RowLane<TR>::owner(lane);
+        }
         __syncwarp();
         // the stage is consumed: refill it before the (rare) list maintenance
         const u64 tn = t + (u64)nstages * GW;
@@ -169,10 +242,10 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
             s = 0;
             phase ^= 1;
         }
-        const u64 row0 = t * TR;
-        const bool has = lane < TR && row0 + lane < p.n;
+        const u64 row = t * TR + my_row;
+        const bool has = my_own && row < p.n;
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane, p.cap);
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row, lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -249,19 +322,16 @@ __global__ void __launch_bounds__(256, 2) scan_ldg_kernel(ScanArgs p) {
         }
         double cd[NQ];
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) cd[qi] = CUDART_INF;
+        for (int qi = 0; qi < NQ; qi++) {
+            double v[TR];
 #pragma unroll
-        for (int r = 0; r < TR; r++)
+            for (int r = 0; r < TR; r++) v[r] = acc[r][qi];
+            reduce_rows<TR>(v, lane);
+            cd[qi] = v[0];
+        }
+        const bool has = RowLane<TR>::owner(lane) && RowLane<TR>::row(lane) < rows;
 #pragma unroll
-            for (int qi = 0; qi < NQ; qi++) {
-                double v = acc[r][qi];
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
-                if (lane == r) cd[qi] = v;
-            }
-        const bool has = lane < rows;
-#pragma unroll
-        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + lane, lane, p.cap);
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, cd[qi], row0 + RowLane<TR>::row(lane), lane, p.cap);
     }
 
     const int nlists = gridDim.x;
@@ -644,23 +714,26 @@ static int pick_tile_rows(const ScanTuning &t, int row_bytes, int nq) {
     if (tr <= 0) {
         // ~4 KB tiles measured best (profiles/r01_sweep_scan_*.jsonl): enough per bulk copy, more tiles in flight
         tr = 1;
-        while (tr < 8 && tr * 2 * row_bytes <= 4096) tr *= 2;
+        while (tr < 32 && tr * 2 * row_bytes <= 4096) tr *= 2;
     }
-    while (tr > 1 && tr * nq > 16) tr >>= 1;
-    if (tr >= 8) return 8;
-    if (tr >= 4) return 4;
-    if (tr >= 2) return 2;
-    return 1;
+    // registers: TR x NQ accumulators per lane
+    const int budget = nq == 1 ? 32 : 16;
+    while (tr > 1 && tr * nq > budget) tr >>= 1;
+    int p2 = 1;
+    while (p2 * 2 <= tr && p2 < 32) p2 *= 2;
+    return p2;
 }
 
 int scan_num_lists(const ScanTuning &t, bool /*wide*/) { return t.num_sms * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1); }
 
-template <int TR, int NQ>
+template <int TR, int NQ, int LPR = 32>
 static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
     const int row_bytes = a.stride * 8;
     const int grid = scan_num_lists(t, true);
     int W = t.warps < 1 ? 1 : (t.warps > 16 ? 16 : t.warps);
-    if (t.variant == 1) {
+    if constexpr (TR > 8 || LPR != 32) {
+        if (t.variant == 1) return cudaErrorInvalidValue;     // the LDG variant keeps whole tiles in registers: TR <= 8
+    } else if (t.variant == 1) {
         if (W > 8) W = 8;
         const size_t smem = (size_t)NQ * row_bytes + (size_t)W * 32 * sizeof(Cand);
         if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
@@ -695,17 +768,21 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
     const size_t smem = need(W, NS);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_wide_kernel<TR, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(scan_wide_kernel<TR, NQ, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    scan_wide_kernel<TR, NQ><<<grid, W * 32, smem, st>>>(a, NS);
+    scan_wide_kernel<TR, NQ, LPR><<<grid, W * 32, smem, st>>>(a, NS);
     return cudaGetLastError();
 }
 
 template <int NQ>
 static cudaError_t launch_wide_nq(int tr, const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
     switch (tr) {
+        case 32:
+            if constexpr (NQ == 1) return launch_wide_inst<32, NQ>(t, a, st);
+        case 16:
+            if constexpr (NQ == 1) return launch_wide_inst<16, NQ>(t, a, st);
         case 8:
             if constexpr (NQ <= 2) return launch_wide_inst<8, NQ>(t, a, st);
         case 4:
@@ -719,7 +796,14 @@ static cudaError_t launch_wide_nq(int tr, const ScanTuning &t, const ScanArgs &a
 
 cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_t st) {
     if (a.stride & 1) return cudaErrorInvalidValue;
-    const int tr = pick_tile_rows(t, a.stride * 8, a.nq);
+    if (a.nq == 1 && a.stride <= 32 && t.variant == 0 && t.tile_rows <= 0) {
+        // short rows, one query: several rows side by side in every warp step, 32-row tiles
+        if (a.stride <= 8) return launch_wide_inst<32, 1, 4>(t, a, st);
+        if (a.stride <= 16) return launch_wide_inst<32, 1, 8>(t, a, st);
+        return launch_wide_inst<32, 1, 16>(t, a, st);
+    }
+    int tr = pick_tile_rows(t, a.stride * 8, a.nq);
+    if (t.variant == 1 && tr > 8) tr = 8;
     switch (a.nq) {
         case 1: return launch_wide_nq<1>(tr, t, a, st);
         case 2: return launch_wide_nq<2>(tr, t, a, st);

@@ -283,8 +283,15 @@ def test_dropin_save_load_roundtrip(tmp_path):
 
 @pytest.mark.parametrize("n,D,K,k,seed", [
     (20000, 8, 3, 5, 1),        # thin path, prefix subspace
-    (3000, 16, 16, 10, 2),      # thin path at its upper K
-    (5000, 17, 17, 3, 3),       # wide path at its lower K, odd K (zero padded stride)
+    (3000, 12, 12, 10, 2),      # thin path at its upper K
+    (4099, 20, 13, 10, 21),     # packed rows: 8 lanes per row (stride 14 / 16) ...
+    (3000, 16, 16, 10, 22),
+    (5000, 17, 17, 3, 3),       # ... 16 lanes per row, odd K (zero padded stride 18) ...
+    (2777, 40, 24, 7, 23),
+    (6001, 32, 32, 10, 24),     # ... up to 32 doubles
+    (3500, 33, 33, 5, 25),      # 8 / 16-row tiles of a whole warp per row
+    (3100, 63, 63, 5, 26),
+    (2900, 96, 96, 5, 27),
     (12000, 128, 128, 10, 4),   # config-2 shape (K = D = 128), rows alias the kd log
     (2500, 768, 768, 10, 5),    # config-3 row shape
     (3000, 200, 50, 24, 6),     # K < D wide: compact kd array, k = SVDB_MAX_K
@@ -300,7 +307,7 @@ def test_topk_vs_oracle(port, n, D, K, k, seed):
         assert_topk_equal(e.nearest(Q, k), want, k)
         st = e.stats()
         assert st["kernels_launched"] > 0 and st["exact_reruns"] == 0
-        if K > 16:
+        if K > 12:
             e.set_option("nearest.mma_min_queries", 0)      # 13 queries: K1 in passes of 8 + 4 + 1 from here on
             assert_topk_equal(e.nearest(Q, k), want, k)
             for opts in ({"scan.variant": 1}, {"scan.variant": 0, "scan.nq_per_pass": 1},
