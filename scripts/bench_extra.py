@@ -174,6 +174,10 @@ def main():
         for K in (9, 12, 16, 17, 24, 32, 48, 64, 96, 128, 256):
             n = int(1.5e9 / (K * 8))
             res += nearest_case(f"ksweep_k{K}", n, K + 16, K, 1, (1, 8), iters=10)
+    if "dsweep" in which:  # /compare over a ~3 GB store at every row length; 2M random pairs (or 1M for long rows)
+        for D in (3, 16, 48, 128, 200, 256, 768, 1536, 4096):
+            n = int(3e9 / (max(D, 16) * 8))
+            res += compare_case(f"dsweep_d{D}", n, D, 2_000_000 if D <= 768 else 1_000_000, iters=5)
     if "c2" in which:
         res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50)
         res += compare_case("c2_compare_1M_x128", 1_000_000, 128, 100_000)
