@@ -174,6 +174,14 @@ def main():
         for K in (9, 12, 16, 17, 24, 32, 48, 64, 96, 128, 256):
             n = int(1.5e9 / (K * 8))
             res += nearest_case(f"ksweep_k{K}", n, K + 16, K, 1, (1, 8), iters=10)
+    if "ktop" in which:    # result size: top-1 / 10 / 24 of one query and of a 64-query call
+        for k in (1, 10, 24):
+            res += nearest_case(f"ktop{k}_2M_x768", 2_000_000, 768, 768, k, (1, 64), iters=10)
+            res += nearest_case(f"ktop{k}_4M_x32", 4_000_000, 48, 32, k, (1,), iters=10)
+    if "nsweep" in which:  # store size: where does the fixed cost of a query stop mattering
+        for n in (1_000, 10_000, 100_000, 1_000_000):
+            res += nearest_case(f"nsweep_{n}_x768", n, 768, 768, 1, (1,), iters=50)
+            res += nearest_case(f"nsweep_{n}_x128", n, 128, 128, 1, (1,), iters=50)
     if "dsweep" in which:  # /compare over a ~3 GB store at every row length; 2M random pairs (or 1M for long rows)
         for D in (3, 16, 48, 128, 200, 256, 768, 1536, 4096):
             n = int(3e9 / (max(D, 16) * 8))

@@ -19,3 +19,6 @@ echo "bench exit $?"; cat gpurun_out/bench_n$N.json; grep -v "OMP_NUM_THREADS\|^
 echo "== bench on $N GPUs (nccl exchange)"
 SVDB_EXCHANGE=nccl timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 20 --warmup 3 --batch-queries 0 > gpurun_out/bench_n${N}_nccl.json 2> gpurun_out/bench_n${N}_nccl.err
 echo "bench exit $?"; cat gpurun_out/bench_n${N}_nccl.json | cut -c1-330
+echo "== thin kd-points on $N GPUs: replicated kd log vs row shards"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 scripts/bench_thin_multi.py > gpurun_out/thin_multi_$N.json 2> gpurun_out/thin_multi_$N.err
+echo "thin exit $?"; cat gpurun_out/thin_multi_$N.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/thin_multi_$N.err | tail -5
