@@ -43,7 +43,7 @@ def timed(idx, dq, k, iters, dev):
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-    nq = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
     D, K = 16, 3
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -61,6 +61,19 @@ def main():
         idx.ingest_device(rows)
         nqi = nq if replicate else min(nq, 1024)          # the scan path is ~100x slower per query: keep it short
         ms = timed(idx, dq[:nqi], 1, iters, dev)
+        if replicate:
+            # the same call answered by ONE replica alone (what a single GPU does), timed on every rank
+            one = torch.zeros((nqi, 1, 4), dtype=torch.int64, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it in range(3 + iters):
+                if it == 3:
+                    e0.record()
+                idx.engine.nearest_device(dq.data_ptr(), nqi, dq.stride(0), 1, one.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            t1 = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            out["one_replica_alone"] = {"queries": nqi, "ms_per_call": float(t1), "queries_per_s": nqi / (float(t1) / 1e3)}
         res = idx.nearest_device(dq[:1024], 1)
         torch.cuda.synchronize()
         answers[name] = res.clone()
