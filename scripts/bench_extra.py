@@ -171,7 +171,7 @@ def main():
         res += nearest_case("thin_20M_x16_k16_scan", 20_000_000, 16, 16, 1, (1,), iters=10,
                             extra_opts=(("nearest.tree_max_k", 0),))
     if "ksweep" in which:  # one query over a ~1.5 GB kd log at every kd_dim regime (rows are wider: the kd log is compact)
-        for K in (9, 12, 16, 17, 24, 32, 48, 64, 96, 128, 256):
+        for K in (9, 12, 16, 17, 24, 32, 40, 48, 56, 64, 80, 96, 100, 128, 200, 256, 384, 500):
             n = int(1.5e9 / (K * 8))
             res += nearest_case(f"ksweep_k{K}", n, K + 16, K, 1, (1, 8), iters=10)
     if "ktop" in which:    # result size: top-1 / 10 / 24 of one query and of a 64-query call

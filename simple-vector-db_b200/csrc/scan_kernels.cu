@@ -712,9 +712,10 @@ __global__ void pad_queries_kernel(const double *src, int ldq, double *dst, int 
 static int pick_tile_rows(const ScanTuning &t, int row_bytes, int nq) {
     int tr = t.tile_rows;
     if (tr <= 0) {
-        // ~4 KB tiles measured best (profiles/r01_sweep_scan_*.jsonl): enough per bulk copy, more tiles in flight
+        // 5-8 KB tiles measured best (profiles/r01_ksweep_*: 3 KB tiles 0.88-0.90 x peak, 4 KB 1.04-1.05, 5-8 KB
+        // 1.06-1.09, 10 KB 1.03): the smallest power of two rows that reaches 5 KB
         tr = 1;
-        while (tr < 32 && tr * 2 * row_bytes <= 4096) tr *= 2;
+        while (tr < 32 && tr * row_bytes < 5120) tr *= 2;
     }
     // registers: TR x NQ accumulators per lane
     const int budget = nq == 1 ? 32 : 16;
@@ -747,6 +748,8 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
         return cudaGetLastError();
     }
     int NS = t.stages < 2 ? 2 : t.stages;
+    // row lengths that do not divide 4 KB leave ~3 KB tiles (K = 48, 96: 0.88-0.90 x peak): keep >= 8 KB per warp in flight
+    while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
     const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
     auto need = [&](int w, int ns) {
         return (size_t)w * ns * TR * row_bytes + (size_t)NQ * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)(w * ns + 1) * 8;
