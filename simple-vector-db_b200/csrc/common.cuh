@@ -110,6 +110,29 @@ struct WarpList {
         kd = __shfl_sync(FULL, d, pos);
         ks = __shfl_sync(FULL, seq, pos);
     }
+    // Merge another ascending list (one key per lane, empty slots = (+inf, SEQ_NONE)): afterwards this list holds
+    // the 32 smallest of the 64 keys.  Bitonic: min(mine[i], other[31-i]) is a bitonic sequence of exactly those
+    // keys, five compare-exchange stages sort it.  Cost is fixed (24 SHFL), unlike offer(), whose serial inserts
+    // cost ~100 cycles per key that gets in -- the better choice when many keys of the other list qualify.
+    __device__ __forceinline__ void merge_sorted(double od, u64 os, int lane) {
+        const double rd = __shfl_sync(FULL, od, 31 - lane);
+        const u64 rs = __shfl_sync(FULL, os, 31 - lane);
+        if (key_less(rd, rs, d, seq)) {
+            d = rd;
+            seq = rs;
+        }
+#pragma unroll
+        for (int j = 16; j >= 1; j >>= 1) {
+            const double pd = __shfl_xor_sync(FULL, d, j);
+            const u64 ps = __shfl_xor_sync(FULL, seq, j);
+            const bool upper = (lane & j) != 0;
+            // the lower lane of a pair keeps the smaller key, the upper lane the larger one
+            if (key_less(pd, ps, d, seq) != upper) {
+                d = pd;
+                seq = ps;
+            }
+        }
+    }
     // Offer one candidate per lane (has = this lane holds one).  Only the best `lim` keys are
     // maintained (tau = key at lane lim-1); lanes beyond hold sorted leftovers nobody reads.
     __device__ __forceinline__ void offer(bool has, double cd, u64 cs, int lane, int lim = 32) {

@@ -429,7 +429,25 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     WarpList wl;
     wl.reset();
     double bound = CUDART_INF;
-    {
+    if (p.cap >= 16) {
+        // long lists (k >= 8): most keys of a list qualify while the running list fills up, and every one of them
+        // would be a serial insert -- merge list by list with the fixed-cost bitonic network instead
+        const int per = (p.nlists + FIN_WARPS - 1) / FIN_WARPS;
+        const int lo = warp * per, hi = min(p.nlists, lo + per);
+        for (int base = lo; base < hi; base += 4) {
+            Cand c[4];                                   // four independent loads in flight per lane
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                c[u] = Cand{CUDART_INF, SEQ_NONE};
+                if (base + u < hi && lane < p.cap) c[u] = L[(size_t)(base + u) * p.cap + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (lane == p.cap - 1 && c[u].seq != SEQ_NONE) bound = fmin(bound, c[u].d);   // that list was full
+                wl.merge_sorted(c[u].d, c[u].seq, lane);
+            }
+        }
+    } else {
         const int per = ((total + FIN_WARPS - 1) / FIN_WARPS + 31) & ~31;
         const int lo = warp * per, hi = min(total, lo + per);
         for (int base = lo; base < hi; base += 128) {
@@ -455,11 +473,14 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     if (lane == 0) wbound[warp] = bound;
     __syncthreads();
     if (warp == 0) {
+        // only the best `cap` keys of a slice list are meaningful; the slice lists are sorted: bitonic merges
+        if (lane >= p.cap) wl.reset();
         for (int w = 1; w < FIN_WARPS; w++) {
-            const Cand c = mrg[w * 32 + lane];
+            Cand c = mrg[w * 32 + lane];
             // a slice list that is full may itself have dropped keys >= its last one
             if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
-            wl.offer(c.seq != SEQ_NONE && lane < p.cap, c.d, c.seq, lane, p.cap);
+            if (lane >= p.cap) c = Cand{CUDART_INF, SEQ_NONE};
+            wl.merge_sorted(c.d, c.seq, lane);
             bound = fmin(bound, wbound[w]);
         }
 #pragma unroll
