@@ -527,24 +527,37 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
             // work items = (candidate, 256-coordinate segment), dealt round-robin to the warps; every
             // lane keeps 8 row loads and 8 query loads in flight
             const int nseg = (len + 255) >> 8;
-            for (int w = warp; w < nneed * nseg; w += FIN_WARPS) {
-                const int j = w / nseg, s0 = (w % nseg) << 8;
-                const double *row = p.pts + cseq[j] * (u64)p.stride + c0 + s0;
-                const double *qq = qv + c0 + s0;
-                double *t = tbuf + j * ld + s0;
-                const int slen = min(256, len - s0);
-                double x[8], y[8];
+            // two items per trip: 16 row loads + 16 query loads in flight per lane (the loop is DRAM-latency bound)
+            for (int w = warp; w < nneed * nseg; w += 2 * FIN_WARPS) {
+                double x[2][8], y[2][8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = u * 32 + lane;
-                    x[u] = i < slen ? __ldg(row + i) : 0.0;
-                    y[u] = i < slen ? __ldg(qq + i) : 0.0;
+                for (int h = 0; h < 2; h++) {
+                    const int wi = w + h * FIN_WARPS;
+                    const bool on = wi < nneed * nseg;
+                    const int j = on ? wi / nseg : 0, s0 = on ? (wi % nseg) << 8 : 0;
+                    const double *row = p.pts + cseq[j] * (u64)p.stride + c0 + s0;
+                    const double *qq = qv + c0 + s0;
+                    const int slen = on ? min(256, len - s0) : 0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = u * 32 + lane;
+                        x[h][u] = i < slen ? __ldg(row + i) : 0.0;
+                        y[h][u] = i < slen ? __ldg(qq + i) : 0.0;
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = u * 32 + lane;
-                    const double df = __dsub_rn(x[u], y[u]);
-                    if (i < slen) t[i] = __dmul_rn(df, df);
+                for (int h = 0; h < 2; h++) {
+                    const int wi = w + h * FIN_WARPS;
+                    if (wi >= nneed * nseg) break;
+                    const int j = wi / nseg, s0 = (wi % nseg) << 8;
+                    double *t = tbuf + j * ld + s0;
+                    const int slen = min(256, len - s0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = u * 32 + lane;
+                        const double df = __dsub_rn(x[h][u], y[h][u]);
+                        if (i < slen) t[i] = __dmul_rn(df, df);
+                    }
                 }
             }
             __syncthreads();
