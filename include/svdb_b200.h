@@ -256,7 +256,9 @@ typedef struct svdb_stats {
     uint64_t tie_levels;         /* tree levels walked for them, summed */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
-/* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm". */
+/* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
+ * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
+ * row i is global row lo + i sets it to lo, so that merged answers carry global row numbers). */
 int svdb_set_option(svdb_engine *e, const char *name, long value);
 /* Scan the log for nq queries already on the device, timing the scan kernel alone with
  * CUDA events on the engine's stream: returns average milliseconds per launch. */

@@ -55,20 +55,39 @@ def main():
                            replicate_thin=replicate)
         idx.bind_current_stream()
         idx.ingest_device(rows[idx.lo:idx.hi].to(dev).contiguous())
-        for k in (1, 10):
-            got = idx.nearest(Q, k)
-            few = idx.nearest(Q[:3], k)           # too few queries to split over replicas / one small pass per shard
-            if rank == 0:
-                with B.Engine(D, K, device=local) as e:
-                    e.insert_device(rows.to(dev).data_ptr(), n, D)
-                    _, wdist, wseq = e.nearest(Q.numpy(), k)
-                same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
-                same = same and np.array_equal(few["seq"], wseq[:3]) and np.array_equal(few["dist"].view(np.uint64), wdist[:3].view(np.uint64))
-                ok &= bool(same)
-                report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels,
-                               "layout": "replicated kd log, queries split" if idx.replicated else "row shards",
-                               "identical_to_single_gpu": bool(same), "tie_events": idx.engine.stats()["tie_events"],
-                               "tie_levels": idx.engine.stats()["tie_levels"]})
+        ref = None
+        if rank == 0:
+            ref = B.Engine(D, K, device=local)
+            ref.insert_device(rows.to(dev).data_ptr(), n, D)
+        gm = torch.Generator().manual_seed(99 + n)
+        for phase in ("bulk", "after inserts+updates"):
+            if phase != "bulk":
+                # vector_db_insert x 5 and vector_db_update x 7 (stale kd-points stay searchable): the log grows at its tail
+                mk = (lambda m: torch.randint(0, levels, (m, D), generator=gm).to(torch.float64) / 2) if levels else \
+                     (lambda m: torch.rand((m, D), dtype=torch.float64, generator=gm))
+                new_rows, upd_rows = mk(5).numpy(), mk(7).numpy()
+                upd_ids = torch.randint(0, n, (7,), generator=gm).numpy().astype(np.uint64)
+                first = idx.append_rows(new_rows)
+                idx.append_update(upd_ids, upd_rows)
+                if rank == 0:
+                    assert ref.insert(new_rows) == first
+                    ref.update(upd_ids, upd_rows)
+                Q = torch.cat([Q[:9], torch.from_numpy(new_rows[:3]), torch.from_numpy(upd_rows[:4])]).pin_memory()
+            for k in (1, 10):
+                got = idx.nearest(Q, k)
+                few = idx.nearest(Q[:3], k)       # too few queries to split over replicas / one small pass per shard
+                if rank == 0:
+                    widx, wdist, wseq = ref.nearest(Q.numpy(), k)
+                    same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
+                    same = same and np.array_equal(got["index"], widx)
+                    same = same and np.array_equal(few["seq"], wseq[:3]) and np.array_equal(few["dist"].view(np.uint64), wdist[:3].view(np.uint64))
+                    ok &= bool(same)
+                    report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels, "phase": phase,
+                                   "layout": "replicated kd log, queries split" if idx.replicated else "row shards",
+                                   "identical_to_single_gpu": bool(same), "tie_events": idx.engine.stats()["tie_events"],
+                                   "tie_levels": idx.engine.stats()["tie_levels"]})
+        if ref is not None:
+            ref.close()
         idx.close()
     # /compare: replicas, pairs split over the ranks, results all-gathered
     n, D = 20_000, 256
@@ -91,7 +110,11 @@ def main():
                 report.append({"compare_metric": metric, "pairs": i1.numel(), "identical_to_single_gpu": same})
     dist.barrier()
     if rank == 0:
-        print(json.dumps({"check": "sharded_vs_single", "world": world, "ok": ok, "cases": report}), flush=True)
+        line = json.dumps({"check": "sharded_vs_single", "world": world, "ok": ok, "cases": report})
+        print(line, flush=True)
+        if os.environ.get("SVDB_CHECK_OUT"):      # stdout also carries NCCL's version banner
+            with open(os.environ["SVDB_CHECK_OUT"], "w") as f:
+                f.write(line + "\n")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -764,7 +764,7 @@ int svdb_engine::ingest_device_rows(const double *d_rows, size_t n, size_t ld, s
     if (ce != cudaSuccess) return e->fail_cuda("cudaMemcpy2DAsync", ce);
     const size_t base_index = e->cur_host.size();
     if (!e->no_log) {
-        ce = launch_iota(e->log_idx.as<u64>() + n0, base_index, n, e->stream);
+        ce = launch_iota(e->log_idx.as<u64>() + n0, base_index + e->index_base, n, e->stream);
         if (ce != cudaSuccess) return e->fail_cuda("iota", ce);
         e->stats.kernels_launched++;
     }
@@ -856,7 +856,7 @@ int svdb_insert_batch(svdb_engine *e, const double *rows, size_t n, size_t ld, s
     for (size_t i = 0; i < n; i++) {
         // vector_database.c:113-115: the entry carries index = size before the increment
         const uint64_t ver = e->n_versions + e->stage_n;
-        int rc = e->stage_one(rows + i * ld, e->D, e->cur_host.size());
+        int rc = e->stage_one(rows + i * ld, e->D, e->cur_host.size() + e->index_base);
         if (rc) return rc;
         e->cur_host.push_back(ver);
         e->uuids.emplace_back();
@@ -872,7 +872,7 @@ int svdb_update_batch(svdb_engine *e, const size_t *index, const double *rows, s
     for (size_t i = 0; i < n; i++) {
         if (index[i] >= e->cur_host.size()) continue;   // vector_database.c:171: silent no-op
         const uint64_t ver = e->n_versions + e->stage_n;
-        int rc = e->stage_one(rows + i * ld, e->D, index[i]);   // :174 re-append with the same index
+        int rc = e->stage_one(rows + i * ld, e->D, index[i] + e->index_base);   // :174 re-append with the same index
         if (rc) return rc;
         e->cur_host[index[i]] = ver;
         e->cur_dirty_lo = std::min(e->cur_dirty_lo, index[i]);
@@ -1315,6 +1315,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.nq_per_pass") e->tune.nq_per_pass = (int)value;
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
+    else if (n == "log.index_base") e->index_base = (uint64_t)value;
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;

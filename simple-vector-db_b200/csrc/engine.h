@@ -72,6 +72,7 @@ struct svdb_engine {
     int mma_min_q = 4;                   // AUTO: batches of at least this many queries take the DMMA path (K2)
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
+    uint64_t index_base = 0;             // added to the index a log entry reports (a shard's rows are global rows lo..)
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::mutex mu;

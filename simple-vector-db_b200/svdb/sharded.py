@@ -80,6 +80,7 @@ class ShardedIndex:
         self.engine = B.Engine(dimension, kd_dim, device=device, seq_base=self.lo,
                                reserve_rows=max(1, self.hi - self.lo),
                                flags=B.FLAG_SHARD if world > 1 else 0)
+        self.engine.set_option("log.index_base", self.lo)      # merged answers carry global row numbers
         # "p2p": candidates are stored into the peers' HBM over NVLink and merged in the same launch
         # (svdb_exchange); "nccl": all_gather_into_tensor + svdb_merge_candidates_device
         if world > 1 and exchange == "p2p":
@@ -111,6 +112,46 @@ class ShardedIndex:
                 self._seal()
             return
         self.engine.insert_device(rows.data_ptr(), rows.shape[0], rows.shape[1])
+
+    # -- the log after the bulk ingest: inserts and updates append to its END ------------------
+    def append_rows(self, rows) -> int:
+        """vector_db_insert for a sharded store (collective: every rank passes the same rows, a float64 numpy
+        array [m, D]).  New rows get the next global row numbers and go to the TAIL of the log, i.e. to the last
+        shard (sequence numbers stay global and ordered); replicas append them everywhere.  Returns the first
+        new row number."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.D)
+        first = self.n_total
+        index = np.arange(first, first + len(rows), dtype=np.uint64)
+        self._append_log(rows, index, new_rows=True)
+        self.n_total += len(rows)
+        return first
+
+    def append_update(self, index, rows) -> None:
+        """vector_db_update: the reference re-inserts the updated kd-point with the SAME index and never removes
+        the old one (vector_database.c:174) -- one more log entry at the tail per update (collective)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.D)
+        index = np.ascontiguousarray(index, dtype=np.uint64).reshape(-1)
+        keep = index < self.n_total                     # :171 out of range: silent no-op
+        self._append_log(rows[keep], index[keep], new_rows=False)
+
+    def _append_log(self, rows, index, new_rows: bool) -> None:
+        if len(rows) == 0:
+            return
+        if self.replicated:
+            if not self._sealed:
+                self._seal()
+            self.engine.append_kdpoints(rows[:, :self.K], index)
+        elif self.world == 1:
+            if new_rows:
+                self.engine.insert(rows)
+            else:
+                self.engine.update(index, rows)
+        elif self.rank == self.world - 1:
+            # the tail shard: its sequence numbers are the largest, so global log order is preserved
+            if new_rows and int(index[0]) == self.lo + self.engine.size:
+                self.engine.insert(rows)                # keeps the shard's rows indexable as well
+            else:
+                self.engine.append_kdpoints(rows[:, :self.K], index)      # reported verbatim: global row numbers
 
     def _seal(self) -> None:
         """Replicated mode: all-gather the kd-points of every shard and append them in global row order."""

@@ -21,12 +21,14 @@ from test_tie_protocol import ThreadRanks  # noqa: E402
 
 
 class GpuShards:
-    def __init__(self, rows, K, world):
+    def __init__(self, rows, K, world, global_index=False):
         self.rows, self.K, self.world = rows, K, world
         self.spans = [shard_range(len(rows), world, r) for r in range(world)]
         self.engines = []
         for lo, hi in self.spans:
             e = B.Engine(rows.shape[1], K, seq_base=lo, flags=B.FLAG_SHARD)
+            if global_index:
+                e.set_option("log.index_base", lo)       # log entries report global row numbers
             if hi > lo:
                 e.insert(rows[lo:hi])
             self.engines.append(e)
@@ -185,3 +187,42 @@ def test_one_call_sharded_path_with_peer_exchange_world_1(port, K, D, levels):
             assert st["tie_events"] > 0 and st["tie_levels"] > 0
     finally:
         xch.close()
+
+
+# ---- inserts and updates after the bulk ingest: the log grows at its tail (the last shard) ------------------
+
+def test_sharded_store_follows_inserts_and_updates(port):
+    """A mutable sharded store: vector_db_insert / vector_db_update append kd-points to the END of the global log
+    (the tail shard), old points stay searchable (vector_database.c:174), answers == the reference-shaped tree
+    over the whole log after every step -- on lattice values, so stale and tied entries do turn up."""
+    from oracle.binding import PortDB
+    rng = np.random.Generator(np.random.PCG64(31))
+    K, D, world, n0 = 3, 5, 3, 600
+    rows = rng.integers(0, 6, size=(n0, D)) / 2.0
+    sh = GpuShards(rows, K, world, global_index=True)
+    db = PortDB(port, D, K)
+    for r in rows:
+        db.insert(r)
+    n_rows = n0
+    try:
+        for step in range(40):
+            v = rng.integers(0, 6, size=D) / 2.0
+            tail = sh.engines[-1]
+            if step % 3 == 0:                                    # insert: a new global row
+                assert db.insert(v) == n_rows
+                tail.insert(v[None, :])
+                n_rows += 1
+            else:                                                # update of a random existing row: re-append, same index
+                j = int(rng.integers(0, n_rows))
+                db.update(j, v)
+                tail.append_kdpoints(v[None, :K], np.array([j], dtype=np.uint64))
+            Q = rng.integers(0, 6, size=(6, D)) / 2.0
+            Q[:, 0] += 0.25
+            want = np.array([db.nearest(q) for q in Q], dtype=np.uint64)
+            merged = sh.merged(Q, 1)
+            got = sh.resolve(Q, merged)
+            np.testing.assert_array_equal(got["index"][:, 0], want, err_msg=f"step {step}")
+        assert sh.engines[0].stats()["tie_events"] > 0
+    finally:
+        sh.close()
+        db.close()
