@@ -31,6 +31,16 @@ def shard_range(n_rows: int, world: int, rank: int):
     return lo, min(n_rows, lo + per)
 
 
+def query_span(nq: int, world: int, rank: int):
+    """Replicated stores split the QUERIES: rank r answers [lo, hi) of a call, `per` = slots per rank in the
+    all-gather of the answers.  Calls with fewer than 2 x world queries are answered by every replica itself
+    (per == 0: nothing is exchanged)."""
+    if nq < 2 * world:
+        return 0, nq, 0
+    per = -(-nq // world)
+    return min(nq, rank * per), min(nq, (rank + 1) * per), per
+
+
 def merge_candidates_host(gathered: np.ndarray, k: int) -> np.ndarray:
     """Host restatement of the K7 merge for a gathered [nshards, nq, k] candidate array.
 
@@ -174,10 +184,7 @@ class ShardedIndex:
 
     def _query_span(self, nq: int):
         """Replicated mode: which queries this rank answers (all of them when there are too few to split)."""
-        if nq < 2 * self.world:
-            return 0, nq, 0
-        per = -(-nq // self.world)
-        return min(nq, self.rank * per), min(nq, (self.rank + 1) * per), per
+        return query_span(nq, self.world, self.rank)
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)

@@ -15,7 +15,7 @@ from conftest import ROOT, PKG
 
 from svdb import binding as B
 from svdb import synth
-from svdb.sharded import merge_candidates_host, shard_range
+from svdb.sharded import merge_candidates_host, query_span, shard_range
 
 
 def test_shard_ranges_cover_exactly():
@@ -27,6 +27,22 @@ def test_shard_ranges_cover_exactly():
                 assert b == c and a <= b
             per = -(-n // world) if n else 0
             assert all(b - a <= per for a, b in spans)
+
+
+def test_query_spans_of_replicated_stores_cover_every_query_once():
+    for world in (1, 2, 3, 8):
+        for nq in (0, 1, 2 * world - 1, 2 * world, 17, 1000, 65536):
+            spans = [query_span(nq, world, r) for r in range(world)]
+            if nq < 2 * world:                       # too few to split: everybody answers everything, no exchange
+                assert all(s == (0, nq, 0) for s in spans)
+                continue
+            per = spans[0][2]
+            assert all(s[2] == per for s in spans) and per * world >= nq
+            assert spans[0][0] == 0 and spans[-1][1] == nq
+            for (a, b, _), (c, d, _) in zip(spans, spans[1:]):
+                assert b == c and a <= b <= a + per
+            # the all-gather lays rank r's answers at r*per: query i sits at slot i
+            assert all(lo == min(nq, r * per) for r, (lo, _, _) in enumerate(spans))
 
 
 def test_merge_host_orders_by_dist_then_seq():
