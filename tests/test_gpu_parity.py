@@ -766,3 +766,31 @@ def test_host_path_graph_replay_tracks_store_and_options(port):
         port.free(h)
         for _ in range(5):
             assert e.nearest(q, 1)[0][0, 0] == want1
+
+
+def test_random_shapes_vs_oracle(port):
+    """Forty random (rows, kd_dim, k, queries) shapes -- every tile size / lanes-per-row variant of K1, the exact
+    kernel, the tree, K2 groups, long and short candidate lists in finalize -- with duplicated rows mixed in."""
+    rng = np.random.Generator(np.random.PCG64(20261017))
+    for it in range(40):
+        K = int(rng.choice([1, 2, 3, 5, 8, 9, 12, 13, 14, 15, 16, 17, 18, 23, 31, 32, 33, 40, 47, 64, 65, 96, 130]))
+        D = K + int(rng.integers(0, 4))
+        n = int(rng.choice([1, 2, 31, 32, 33, 100, 257, 1000, 3001, 5000]))
+        k = int(rng.integers(1, 25))
+        nq = int(rng.choice([1, 2, 3, 4, 5, 9, 17]))
+        rows = synth.uniform_rows(1000 + it, n, D)
+        if n >= 100:                                     # exact duplicates: (dist, seq) ties of the harmless kind
+            dup = rng.integers(0, n, size=n // 10)
+            rows[rng.integers(0, n, size=n // 10)] = rows[dup]
+        Q = synth.uniform_rows(2000 + it, nq, D)
+        Q[0] = rows[int(rng.integers(0, n))]             # an exact hit
+        want = oracle_topk(port, rows, K, Q, k)
+        with B.Engine(D, K) as e:
+            e.insert(rows)
+            try:
+                assert_topk_equal(e.nearest(Q, k), want, k)
+                e.set_option("nearest.tree_max_k", 0)    # thin kd-points through the scan as well
+                e.set_option("nearest.mma_min_queries", 0)
+                assert_topk_equal(e.nearest(Q, k), want, k)
+            except AssertionError as ex:
+                raise AssertionError(f"shape {it}: n={n} D={D} K={K} k={k} nq={nq}: {ex}") from ex
