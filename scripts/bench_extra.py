@@ -174,6 +174,8 @@ def main():
         for K in (9, 12, 16, 17, 24, 32, 40, 48, 56, 64, 80, 96, 100, 128, 200, 256, 384, 500):
             n = int(1.5e9 / (K * 8))
             res += nearest_case(f"ksweep_k{K}", n, K + 16, K, 1, (1, 8), iters=10)
+    if "k6" in which:      # the tree traversal (K6) on a big thin store, one large call
+        res += nearest_case("k6_10M_x16_k3", 10_000_000, 16, 3, 1, (65536, 1048576), iters=5)
     if "ktop" in which:    # result size: top-1 / 10 / 24 of one query and of a 64-query call
         for k in (1, 10, 24):
             res += nearest_case(f"ktop{k}_2M_x768", 2_000_000, 768, 768, k, (1, 64), iters=10)
