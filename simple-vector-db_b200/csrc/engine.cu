@@ -214,7 +214,7 @@ void svdb_engine::destroy() {
     cur.release();
     child.release();
     xnorm.release();
-    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &tree_sort, &qnorm, &xnmax}) s->free_();
+    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
     tie_state_free(tie);
     tie = nullptr;
@@ -341,16 +341,9 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         return fail(SVDB_ERR_ARG, "tree traversal needs an engine that keeps the tree");
     // K6: thin kd-points prune well, and the traversal IS the reference's algorithm
     if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && !force_exact && K <= tree_max_k)) {
-        uint32_t *sort_scratch = nullptr;
-        const size_t sw = tree_sort_order ? tree_sort_scratch_words((int)nq) : 0;
-        if (sw) {
-            std::string terr;
-            if (!tree_sort.ensure(sw * 4, terr)) return fail(SVDB_ERR_OOM, terr);
-            sort_scratch = tree_sort.as<uint32_t>();
-        }
         CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
-                               log_idx.as<u64>(), cfg.seq_base, d_out, sort_scratch, stream));
-        stats.kernels_launched += (sort_scratch && n_versions >= 65536) ? 4 : 1;
+                               log_idx.as<u64>(), cfg.seq_base, d_out, stream));
+        stats.kernels_launched++;
         return SVDB_OK;
     }
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
@@ -1323,7 +1316,6 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
     else if (n == "log.index_base") e->index_base = (uint64_t)value;
-    else if (n == "tree.sort_queries") e->tree_sort_order = value != 0;
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;

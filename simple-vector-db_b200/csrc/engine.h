@@ -71,7 +71,6 @@ struct svdb_engine {
     bool log_only = false, no_log = false, alias = false, wide = false, use_tree = false;
     int mma_min_q = 4;                   // AUTO: batches of at least this many queries take the DMMA path (K2)
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
-    bool tree_sort_order = true;         // K6: big calls walk the tree in subtree order of the queries
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
     uint64_t index_base = 0;             // added to the index a log entry reports (a shard's rows are global rows lo..)
     int device = 0;
@@ -89,7 +88,7 @@ struct svdb_engine {
     size_t stage_ld = 0, stage_n = 0, stage_cap = 0;
 
     // query scratch
-    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag, tree_sort, qnorm, xnmax;
+    svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag, qnorm, xnmax;
     svdb::PinnedScratch hq, hout, hidx, hf, tree_hflag;
 
     // host-side uuid of each index (file round trip); shifts with deletes like the reference's structs

@@ -98,10 +98,7 @@ cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *c
 // K6: the reference's traversal, one thread per query (k = 1), or its k-smallest generalisation (k > 1).
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
-                                uint32_t *sort_scratch /* tree_sort_scratch_words(nq) words, or NULL */, cudaStream_t st);
-// Calls of at least this many queries are processed in subtree order (counting sort on the first path turns).
-constexpr int TREE_SORT_MIN_QUERIES = 8192;
-size_t tree_sort_scratch_words(int nq);
+                                cudaStream_t st);
 
 struct CompareArgs {
     const double *rows;     // version rows, row s at rows + s * ldr; ldr % 16 == 0, zero padded

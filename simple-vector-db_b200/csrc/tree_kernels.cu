@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
                                                            const uint32_t *__restrict__ child, u64 n,
                                                            const double *__restrict__ Q, int ldq, int nq,
                                                            const u64 *__restrict__ log_index, u64 seq_base,
-                                                           svdb_candidate *out, const uint32_t *__restrict__ order) {
+                                                           svdb_candidate *out) {
     struct Frame {
         uint32_t node, depth;
         double plane;
@@ -145,9 +145,8 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
     // host memory, zero-copy); longer ones are read in place (L1-resident after the first node)
     double ql[16];
     const double *q = ql;                      // (no __restrict__: q may point at ql)
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq) return;
-    const int qi = order ? (int)order[t] : t;  // big calls: neighbouring threads take queries of the same subtree
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
     const double *qg = Q + (size_t)qi * ldq;
     if (K <= 16)
         for (int i = 0; i < K; i++) ql[i] = qg[i];
@@ -229,10 +228,9 @@ __global__ void __launch_bounds__(128) tree_knn_kernel(const double *__restrict_
                                                        const uint32_t *__restrict__ child, u64 n,
                                                        const double *__restrict__ Q, int ldq, int nq, int k,
                                                        const u64 *__restrict__ log_index, u64 seq_base,
-                                                       svdb_candidate *out, const uint32_t *__restrict__ order) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq) return;
-    const int qi = order ? (int)order[t] : t;
+                                                       svdb_candidate *out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
     double ql[16];
     const double *qg = Q + (size_t)qi * ldq;
     if (K <= 16)
@@ -334,84 +332,15 @@ __global__ void __launch_bounds__(128) tree_knn_kernel(const double *__restrict_
     }
 }
 
-// ---- big calls: process the queries in the order of the subtrees they fall into -------------------------
-// Random queries make every lane of a warp chase its own path: 32 distinct sectors per load and nothing reused
-// (profiles/r01_ncu_tree_nearest_*: L2 hit rate 35 %, 12 KB of sectors per query).  The answers do not depend on
-// the order in which queries are processed, so they are bucketed by the first `levels` turns of their own near
-// path (which subtree of depth `levels` the query point lies in) with a counting sort, and thread t takes the
-// t-th query of that order: a warp's lanes walk the same subtree, their loads fall into the same lines.
-__global__ void __launch_bounds__(256) tree_bucket_kernel(const double *__restrict__ pts, int stride, int K,
-                                                          const uint32_t *__restrict__ child, u64 n,
-                                                          const double *__restrict__ Q, int ldq, int nq, int levels,
-                                                          uint32_t *__restrict__ bucket, uint32_t *hist) {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    const double *q = Q + (size_t)qi * ldq;
-    uint32_t b = 0, cur = n ? 0u : NODE_NONE;
-    for (int d = 0; d < levels; d++) {
-        uint32_t side = 0;
-        if (cur != NODE_NONE) {
-            const int cd = d % K;
-            side = q[cd] < __ldg(pts + (size_t)cur * stride + cd) ? 0u : 1u;
-            cur = child[2 * (size_t)cur + side];
-        }
-        b = (b << 1) | side;
-    }
-    bucket[qi] = b;
-    atomicAdd(hist + b, 1u);
-}
-// exclusive scan of hist[0..nb) in place, one CTA (nb <= 65536)
-__global__ void __launch_bounds__(1024) tree_bucket_scan_kernel(uint32_t *hist, int nb) {
-    __shared__ uint32_t part[1024];
-    const int per = (nb + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(nb, lo + per);
-    uint32_t s = 0;
-    for (int i = lo; i < hi; i++) s += hist[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = part[threadIdx.x] - s;          // exclusive prefix of this thread's slice
-    for (int i = lo; i < hi; i++) {
-        const uint32_t c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
-}
-__global__ void __launch_bounds__(256) tree_bucket_scatter_kernel(const uint32_t *__restrict__ bucket, uint32_t *offs, int nq,
-                                                                  uint32_t *__restrict__ order) {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    order[atomicAdd(offs + bucket[qi], 1u)] = (uint32_t)qi;     // any order inside a bucket will do
-}
-
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
-                                uint32_t *sort_scratch, cudaStream_t st) {
+                                cudaStream_t st) {
     if (nq == 0) return cudaSuccess;
-    const uint32_t *order = nullptr;
-    if (sort_scratch && nq >= TREE_SORT_MIN_QUERIES && n >= 65536) {
-        int levels = 4;
-        while (levels < 16 && (nq >> (levels + 1)) >= 32) levels++;      // ~32-64 queries per bucket
-        const int nb = 1 << levels;
-        uint32_t *bucket = sort_scratch, *ord = sort_scratch + nq, *hist = sort_scratch + 2 * (size_t)nq;
-        cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)nb * 4, st);
-        if (e != cudaSuccess) return e;
-        tree_bucket_kernel<<<(nq + 255) / 256, 256, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, levels, bucket, hist);
-        tree_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, nb);
-        tree_bucket_scatter_kernel<<<(nq + 255) / 256, 256, 0, st>>>(bucket, hist, nq, ord);
-        order = ord;
-    }
-    if (k == 1)
-        tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out, order);
-    else
-        tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out, order);
+    if (k == 1) {
+        tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out);
+    } else
+        tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out);
     return cudaGetLastError();
 }
-size_t tree_sort_scratch_words(int nq) { return nq >= TREE_SORT_MIN_QUERIES ? 2 * (size_t)nq + 65536 : 0; }
 
 }  // namespace svdb

@@ -794,24 +794,3 @@ def test_random_shapes_vs_oracle(port):
                 assert_topk_equal(e.nearest(Q, k), want, k)
             except AssertionError as ex:
                 raise AssertionError(f"shape {it}: n={n} D={D} K={K} k={k} nq={nq}: {ex}") from ex
-
-
-def test_big_tree_calls_in_subtree_order_give_the_same_answers(port):
-    """Calls of >= 8192 queries over >= 65536 rows walk the tree in the order of the subtrees the queries fall
-    into (a counting sort on the first turns of each near path): same answers, query for query."""
-    n, D, K, nq = 150_000, 5, 3, 20_000
-    rows = synth.script_values(91, (n, D))               # short decimals: duplicates and exact ties included
-    Q = synth.script_values(92, (nq, D))
-    with B.Engine(D, K) as e:
-        e.insert(rows)
-        got1 = e.nearest(Q, 1)
-        got3 = e.nearest(Q, 3)
-        st = e.stats()
-        e.set_option("tree.sort_queries", 0)
-        ref1 = e.nearest(Q, 1)
-        ref3 = e.nearest(Q, 3)
-        for a, b in zip(got1 + got3, ref1 + ref3):
-            np.testing.assert_array_equal(a, b)
-        assert e.stats()["kernels_launched"] - st["kernels_launched"] < st["kernels_launched"]   # 4 launches vs 1 per call
-    want = oracle_tree_ids(port, rows, K, Q[:3000])
-    np.testing.assert_array_equal(got1[0][:3000, 0], want)
