@@ -67,24 +67,50 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
     const u64 gw = (u64)blockIdx.x * CMP_WARPS + warp, GW = (u64)gridDim.x * CMP_WARPS;
     const int sub = lane >> 3, piece = lane & 7;
 
-    for (u64 g = gw; g < ngroups; g += GW) {
-        const u64 pid = g * 32 + lane;
-        bool ok = pid < p.n;
-        u64 ra = 0, rb = 0;  // version rows
-        if (ok) {
+    // Which rows a pair needs is two dependent loads deep (pair index -> current version) before the rows
+    // themselves can be requested.  Both are taken off a group's critical path: the indices are loaded two
+    // groups ahead, the versions looked up one group ahead, in registers.
+    constexpr u64 NO_ROW = ~0ull;
+    auto load_pair = [&](u64 gg, u64 &x, u64 &y) {
+        x = y = NO_ROW;
+        const u64 pid = gg * 32 + lane;
+        if (gg < ngroups && pid < p.n) {
             if (MODE == 4) {
-                ra = rb = p.first + pid;
+                x = y = p.first + pid;
             } else {
-                const u64 x = p.i1[pid], y = p.i2[pid];
-                ok = x < p.nrows && y < p.nrows;
-                if (ok) {
-                    ra = p.cur ? p.cur[x] : x;
-                    rb = p.cur ? p.cur[y] : y;
-                }
+                x = p.i1[pid];
+                y = p.i2[pid];
             }
         }
+    };
+    auto look_up = [&](u64 x, u64 y, u64 &r1, u64 &r2) {
+        r1 = r2 = NO_ROW;
+        if (MODE == 4) {
+            r1 = r2 = x;
+        } else if (x < p.nrows && y < p.nrows) {       // NO_ROW fails this too
+            r1 = p.cur ? p.cur[x] : x;
+            r2 = p.cur ? p.cur[y] : y;
+        }
+    };
+    u64 nx, ny, nra, nrb;                              // indices of the group after next / rows of the next group
+    load_pair(gw, nx, ny);
+    look_up(nx, ny, nra, nrb);
+    load_pair(gw + GW, nx, ny);
+
+    for (u64 g = gw; g < ngroups; g += GW) {
+        const u64 pid = g * 32 + lane;
+        const bool ok = nra != NO_ROW;
+        const u64 ra = ok ? nra : 0, rb = ok ? nrb : 0;  // out-of-range pairs fetch row 0 and answer the sentinel
+        look_up(nx, ny, nra, nrb);                      // next group: in flight while this one is processed
+        load_pair(g + 2 * GW, nx, ny);
         const double *pa = p.rows + ra * (u64)p.ldr;
         const double *pb = p.rows + rb * (u64)p.ldr;
+        // cosine: the two norms are one more dependent random load each -- ask for them now, use them at the end
+        float na = 0.0f, nb = 0.0f;
+        if ((MODE == 0 || MODE == 3) && ok) {
+            na = __ldg(p.norm + ra);
+            nb = __ldg(p.norm + rb);
+        }
 
         // rows are padded to 16 doubles; a CH > 16 segment may reach past the padded row end: clamp
         auto issue = [&](int c) {
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
             if (MODE == 3) {
                 float *o = p.out + pid * 3;
                 if (ok) {
-                    o[0] = finish_cosine(acc.dot, p.norm[ra], p.norm[rb]);
+                    o[0] = finish_cosine(acc.dot, na, nb);
                     o[1] = finish_euclid(acc.sum);
                     o[2] = acc.dot;
                 } else {
@@ -157,7 +183,7 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) compare_kernel(CompareArgs p) 
             } else {
                 float r = -1.0f;  // vector_database.c:302-305 sentinel
                 if (ok) {
-                    if (MODE == 0) r = finish_cosine(acc.dot, p.norm[ra], p.norm[rb]);
+                    if (MODE == 0) r = finish_cosine(acc.dot, na, nb);
                     if (MODE == 1) r = finish_euclid(acc.sum);
                     if (MODE == 2 || MODE == 4) r = acc.dot;
                 }
