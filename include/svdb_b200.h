@@ -125,7 +125,9 @@ int svdb_read_row(svdb_engine *e, size_t index, double *out /* dimension doubles
 int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, size_t k,
                        size_t *index_out, double *dist_out, uint64_t *seq_out);
 /* Device buffers, asynchronous on the engine's stream: d_out receives nq x k candidates.
- * mode: SVDB_MODE_AUTO   tree traversal for thin kd-points (kd_dim <= 8), else scan + exact re-rank;
+ * mode: SVDB_MODE_AUTO   tree traversal for thin kd-points (kd_dim <= 8; k = 1: the balanced median tree, with
+ *                        the queries it flags as distinct-point ties re-answered by the reference's traversal),
+ *                        else scan + exact re-rank;
  *       SVDB_MODE_EXACT  reference-order scan of every entry (no approximation to prove complete);
  *       SVDB_MODE_TREE   the reference's own traversal on the GPU tree (k > 1: its k-smallest generalisation,
  *                        position 0 is still the reference's answer).
@@ -134,6 +136,7 @@ int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, s
 #define SVDB_MODE_AUTO  0
 #define SVDB_MODE_EXACT 1
 #define SVDB_MODE_TREE  2
+#define SVDB_MODE_MTREE 3        /* k = 1, thin kd-points: balanced median tree + the reference's traversal for flagged ties */
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k,
                               svdb_candidate *d_out, int mode);
 /* Cross-shard merge: d_in holds nshards blocks of nq x k candidates (an allgather result);
@@ -254,9 +257,13 @@ typedef struct svdb_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t tie_events;         /* sharded queries whose exact tie went through svdb_resolve_ties_sharded */
     uint64_t tie_levels;         /* tree levels walked for them, summed */
+    uint64_t mtree_builds;       /* (re)builds of the balanced median tree (K8) */
+    uint64_t mtree_levels;       /* its internal levels after the last build (2^levels leaves of <= 32 points) */
+    uint64_t mtree_rows;         /* log entries it covers; later ones are scanned as a tail */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
+ * "nearest.mtree" (AUTO may use the median tree), "mtree.lanes" (32/16/8 lanes per query), "mtree.tail_max";
  * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
  * row i is global row lo + i sets it to lo, so that merged answers carry global row numbers). */
 int svdb_set_option(svdb_engine *e, const char *name, long value);

@@ -153,6 +153,9 @@ int svdb_engine::init(const svdb_config &c) {
     max_versions = std::min<size_t>(va / main_row_bytes, 0xfffffffeull);   // tree links are u32
     use_tree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !getenv("SVDB_NO_TREE");
     graphs_enabled = !getenv("SVDB_NO_GRAPH");
+    use_mtree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !wide && K <= 8 && !getenv("SVDB_NO_MTREE");
+    if (const char *v = getenv("SVDB_MTREE")) mtree_auto = atoi(v);
+    if (const char *v = getenv("SVDB_MTREE_LANES")) mtree_lanes = atoi(v);
     std::string err;
     if (!log_only) {
         if (!rows.init(device, max_versions * (size_t)Dpad * 8, err)) return fail(SVDB_ERR_CUDA, err);
@@ -214,7 +217,8 @@ void svdb_engine::destroy() {
     cur.release();
     child.release();
     xnorm.release();
-    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax}) s->free_();
+    for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
+                       &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
     tie_state_free(tie);
     tie = nullptr;
@@ -262,6 +266,38 @@ int svdb_engine::tree_append(size_t n0, size_t m) {
     }
     stats.tree_rounds += rounds;
     stats.kernels_launched += rounds + 1;
+    return SVDB_OK;
+}
+
+bool svdb_engine::mtree_wanted(size_t k, int mode) const {
+    if (k != 1 || !use_mtree) return false;
+    return mode == SVDB_MODE_MTREE || (mode == SVDB_MODE_AUTO && mtree_auto && !force_exact && K <= tree_max_k);
+}
+
+// K8: the median tree covers log entries [0, mt.n_built); what was appended since is scanned as a tail by K9.
+// Rebuild (from scratch: the tree is static) once the tail exceeds clamp(n_built / 8, tail_min, tail_max).
+int svdb_engine::mtree_update() {
+    if (!use_mtree) return SVDB_OK;
+    const size_t n = n_versions, tail = n - (size_t)mt.n_built;
+    const size_t limit = std::min(std::max((size_t)mt.n_built / 8, mtree_tail_min), std::max(mtree_tail_max, mtree_tail_min));
+    if (tail <= limit) return SVDB_OK;
+    std::string err;
+    if (!mt_split.ensure(mtree_split_count(n) * 8, err) || !mt_pts.ensure(n * (size_t)K * 8, err) || !mt_seq.ensure(n * 4, err))
+        return fail(SVDB_ERR_OOM, err);
+    int levels = 0, launches = 0;
+    mt = MtreeView{};                    // nothing usable until the build has finished
+    CK(launch_mtree_build(kd_ptr(), kstride, K, n, mt_split.as<double>(), mt_pts.as<double>(), mt_seq.as<uint32_t>(),
+                          tune.num_sms, stream, &levels, &launches));
+    mt.split = mt_split.as<double>();
+    mt.mpts = mt_pts.as<double>();
+    mt.mseq = mt_seq.as<uint32_t>();
+    mt.n_built = n;
+    mt.levels = levels;
+    opt_gen++;                           // captured graphs baked the old view in
+    stats.mtree_builds++;
+    stats.mtree_levels = (uint64_t)levels;
+    stats.mtree_rows = n;
+    stats.kernels_launched += launches;
     return SVDB_OK;
 }
 
@@ -339,6 +375,24 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     CK(cudaSetDevice(device));
     if (mode == SVDB_MODE_TREE && !use_tree)
         return fail(SVDB_ERR_ARG, "tree traversal needs an engine that keeps the tree");
+    if (mode == SVDB_MODE_MTREE && !mtree_wanted(k, mode))
+        return fail(SVDB_ERR_ARG, "the median tree serves k = 1 on engines with thin kd-points (kd_dim <= 8, not a shard)");
+    // K9: balanced median tree; the queries it flags (distinct points tied at the minimum) go through K6
+    if (mtree_wanted(k, mode)) {
+        rc = mtree_update();
+        if (rc) return rc;
+        std::string err;
+        if (use_tree && !mt_marks.ensure(nq * 4, err)) return fail(SVDB_ERR_OOM, err);
+        CK(launch_mtree_nearest(mt, kd_ptr(), kstride, K, n_versions, d_Q, (int)ldq, (int)nq, log_idx.as<u64>(), cfg.seq_base,
+                                use_tree ? 1 : 0, mtree_lanes, use_tree ? mt_marks.as<unsigned>() : nullptr, d_out, stream));
+        stats.kernels_launched++;
+        if (use_tree) {
+            CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, 1,
+                                   log_idx.as<u64>(), cfg.seq_base, d_out, stream, mt_marks.as<unsigned>()));
+            stats.kernels_launched++;
+        }
+        return SVDB_OK;
+    }
     // K6: thin kd-points prune well, and the traversal IS the reference's algorithm
     if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && !force_exact && K <= tree_max_k)) {
         CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
@@ -508,6 +562,10 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     for (size_t i = 0; i < nq; i++) memcpy(hq.as<double>() + i * K, Q + i * ldq, (size_t)K * 8);
     int rc = flush();
     if (rc) return rc;
+    if (mtree_wanted(k, SVDB_MODE_AUTO)) {       // before any capture: a rebuild allocates and synchronizes
+        rc = mtree_update();
+        if (rc) return rc;
+    }
     stats.h2d_bytes += nq * (size_t)K * 8;
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
 
@@ -1002,7 +1060,7 @@ int svdb_nearest_batch_sharded(svdb_engine *e, svdb_exchange *x, const double *Q
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out,
                               int mode) {
     if (!e) return SVDB_ERR_ARG;
-    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_TREE) return e->fail(SVDB_ERR_ARG, "unknown mode");
+    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_MTREE) return e->fail(SVDB_ERR_ARG, "unknown mode");
     std::lock_guard<std::mutex> g(e->mu);
     return e->nearest_device(d_Q, nq, ldq, k, d_out, mode);
 }
@@ -1316,6 +1374,13 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.force_exact") e->force_exact = value != 0;
     else if (n == "nearest.tree_max_k") e->tree_max_k = (int)value;
     else if (n == "log.index_base") e->index_base = (uint64_t)value;
+    else if (n == "nearest.mtree") e->mtree_auto = value != 0;
+    else if (n == "mtree.lanes") {
+        if (value != 32 && value != 16 && value != 8) return e->fail(SVDB_ERR_ARG, "mtree.lanes must be 32, 16 or 8");
+        e->mtree_lanes = (int)value;
+    }
+    else if (n == "mtree.tail_max") e->mtree_tail_max = (size_t)std::max(0l, value);
+    else if (n == "mtree.tail_min") e->mtree_tail_min = (size_t)std::max(0l, value);
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;

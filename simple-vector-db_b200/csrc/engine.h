@@ -72,6 +72,11 @@ struct svdb_engine {
     int mma_min_q = 4;                   // AUTO: batches of at least this many queries take the DMMA path (K2)
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
+    // K8/K9: balanced median tree over thin kd-points (median_tree.cu); serves k = 1, flags distinct-point ties for K6
+    bool use_mtree = false;              // engine may keep one (thin log, kd_dim <= 8, not a shard)
+    int mtree_auto = 1;                  // AUTO prefers it over K6 for k = 1
+    int mtree_lanes = 32;                // lanes per query in K9 (32, 16, 8)
+    size_t mtree_tail_min = 256, mtree_tail_max = 4096;   // rebuild once the unindexed tail exceeds clamp(n_built/8, min, max)
     uint64_t index_base = 0;             // added to the index a log entry reports (a shard's rows are global rows lo..)
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -89,6 +94,8 @@ struct svdb_engine {
 
     // query scratch
     svdb::Scratch qpad, qraw, lists, outc, idx1, idx2, fout, tree_pn, tree_pds, tree_flag, qnorm, xnmax;
+    svdb::Scratch mt_split, mt_pts, mt_seq, mt_marks;
+    svdb::MtreeView mt;
     svdb::PinnedScratch hq, hout, hidx, hf, tree_hflag;
 
     // host-side uuid of each index (file round trip); shifts with deletes like the reference's structs
@@ -144,6 +151,8 @@ struct svdb_engine {
     int flush();
     int upload_cur();
     int tree_append(size_t n0, size_t m);
+    bool mtree_wanted(size_t k, int mode) const;
+    int mtree_update();                  // (re)build the median tree when the unindexed tail has outgrown its limit
     int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode);
     // x != NULL: this engine is one shard; the local candidates go through the peer-memory exchange and the
     // outputs are the merged answers (collective: every rank calls with the same nq and k)

@@ -96,9 +96,35 @@ cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *c
                                uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
                                int max_rounds, int *rounds_out);
 // K6: the reference's traversal, one thread per query (k = 1), or its k-smallest generalisation (k > 1).
+// only_marked (k = 1; device array of nq words, or NULL): answer only the queries whose word is non-zero (K9 left a
+// distinct-point tie there), leave the other entries of out[] as they are.
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
-                                cudaStream_t st);
+                                cudaStream_t st, const unsigned *only_marked = nullptr);
+
+// K8/K9: balanced median KD tree over thin kd-points (median_tree.cu).  Implicit layout: node (level l, j) has heap id
+// 2^l + j and covers positions [(j*n)>>l, ((j+1)*n)>>l) of the leaf-ordered point array; only split values are stored.
+struct MtreeView {
+    const double *split = nullptr;    // [2^levels], heap order, entry 0 unused
+    const double *mpts = nullptr;     // [n_built][K] kd-points in leaf order
+    const uint32_t *mseq = nullptr;   // [n_built] log sequence number of each
+    u64 n_built = 0;                  // log entries [0, n_built) are in the tree
+    int levels = 0;                   // internal levels; 2^levels leaves of <= 32 points
+};
+int mtree_levels(u64 n);
+size_t mtree_split_count(u64 n);
+// Build over log entries [0, n): median splits by radix-select partitioning (large segments) and in-CTA sorts (segments
+// of <= 2048).  split/mpts/mseq: mtree_split_count(n) doubles, n*K doubles, n u32.  Allocates and frees its own scratch
+// (~17 bytes per entry) and synchronizes the stream.
+cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, double *split, double *mpts, uint32_t *mseq,
+                               int num_sms, cudaStream_t st, int *levels_out, int *launches_out);
+// k = 1, K <= 8.  `lanes` (32, 16 or 8) lanes per query.  Entries [t.n_built, n) of the raw log are scanned after the tree.
+// Answers: smallest (reference-order distance, seq); SVDB_CAND_TIE (if mark_ties) when entries with different
+// coordinates tie at the minimum -- only then can the reference's answer differ (rerun those through K6);
+// marks (device, nq words, may be NULL) receives 1 for every flagged query, else 0.
+cudaError_t launch_mtree_nearest(const MtreeView &t, const double *pts, int stride, int K, u64 n, const double *Q, int ldq,
+                                 int nq, const u64 *log_index, u64 seq_base, int mark_ties, int lanes, unsigned *marks,
+                                 svdb_candidate *out, cudaStream_t st);
 
 struct CompareArgs {
     const double *rows;     // version rows, row s at rows + s * ldr; ldr % 16 == 0, zero padded

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
                                                            const uint32_t *__restrict__ child, u64 n,
                                                            const double *__restrict__ Q, int ldq, int nq,
                                                            const u64 *__restrict__ log_index, u64 seq_base,
-                                                           svdb_candidate *out) {
+                                                           svdb_candidate *out, const unsigned *__restrict__ only_marked) {
     struct Frame {
         uint32_t node, depth;
         double plane;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(128) tree_nearest_kernel(const double *__restr
     const double *q = ql;                      // (no __restrict__: q may point at ql)
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
+    if (only_marked && !only_marked[qi]) return;   // K9 answered this one already
     const double *qg = Q + (size_t)qi * ldq;
     if (K <= 16)
         for (int i = 0; i < K; i++) ql[i] = qg[i];
@@ -334,10 +335,11 @@ __global__ void __launch_bounds__(128) tree_knn_kernel(const double *__restrict_
 
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
-                                cudaStream_t st) {
+                                cudaStream_t st, const unsigned *only_marked) {
     if (nq == 0) return cudaSuccess;
     if (k == 1) {
-        tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out);
+        tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out,
+                                                              only_marked);
     } else
         tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out);
     return cudaGetLastError();

@@ -17,7 +17,7 @@ NONE = (1 << 64) - 1
 MAX_K = 24
 COSINE, EUCLIDEAN, DOT, ALL_METRICS = 0, 1, 2, 3
 FLAG_LOG_ONLY, FLAG_NO_LOG, FLAG_SHARD = 1, 2, 4
-MODE_AUTO, MODE_EXACT, MODE_TREE = 0, 1, 2
+MODE_AUTO, MODE_EXACT, MODE_TREE, MODE_MTREE = 0, 1, 2, 3
 CAND_UNSAFE, CAND_TIE = 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -37,7 +37,8 @@ class Stats(C.Structure):
     _fields_ = [("kernels_launched", C.c_uint64), ("exact_reruns", C.c_uint64), ("tree_reruns", C.c_uint64),
                 ("tree_rounds", C.c_uint64), ("coalesced_calls", C.c_uint64), ("coalesced_passes", C.c_uint64),
                 ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("tie_events", C.c_uint64), ("tie_levels", C.c_uint64)]
+                ("tie_events", C.c_uint64), ("tie_levels", C.c_uint64), ("mtree_builds", C.c_uint64),
+                ("mtree_levels", C.c_uint64), ("mtree_rows", C.c_uint64)]
 
 
 # ---- exact ties on a sharded store (svdb_tie_resolve / svdb_resolve_ties_sharded) ----
