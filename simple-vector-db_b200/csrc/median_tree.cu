@@ -446,7 +446,7 @@ __device__ __forceinline__ void mt_visit(const unsigned mask, const int gl, cons
 }
 
 template <int LPQ>
-__global__ void __launch_bounds__(128) mtree_nearest_kernel(const double *__restrict__ split, const double *__restrict__ mpts,
+__global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__restrict__ split, const double *__restrict__ mpts,
                                                             const uint32_t *__restrict__ mseq, u64 nb, int L,
                                                             const double *__restrict__ pts, int stride, u64 n, int K,
                                                             const double *__restrict__ Q, int ldq, int nq,
@@ -464,8 +464,12 @@ __global__ void __launch_bounds__(128) mtree_nearest_kernel(const double *__rest
     b.p = nullptr;
     b.tie = false;
     if (nb) {
-        uint32_t st_node[32];
-        double st_plane[32];
+        // the far-side stack is the same in every lane of the group: one copy per group in shared memory (every lane
+        // writes the same value and reads back what it wrote); thread-local arrays cost 32 copies of the traffic
+        __shared__ uint32_t s_node[128 / LPQ][32];
+        __shared__ double s_plane[128 / LPQ][32];
+        uint32_t *st_node = s_node[threadIdx.x / LPQ];
+        double *st_plane = s_plane[threadIdx.x / LPQ];
         int sp = 0;
         uint32_t h = 1;
         for (;;) {
