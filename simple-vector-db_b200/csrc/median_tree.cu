@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
     b.tie = false;
     if (nb) {
         // the far-side stack is the same in every lane of the group: one copy per group in shared memory (every lane
-        // writes the same value and reads back what it wrote); thread-local arrays cost 32 copies of the traffic
+        // writes the same value and reads back what it wrote; the __syncwarp keeps a lane that runs ahead from
+        // pushing over frames a slower lane has not popped yet); thread-local arrays cost 32 copies of the traffic
         __shared__ uint32_t s_node[128 / LPQ][32];
         __shared__ double s_plane[128 / LPQ][32];
         uint32_t *st_node = s_node[threadIdx.x / LPQ];
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
         int sp = 0;
         uint32_t h = 1;
         for (;;) {
+            __syncwarp(mask);
             int lev = 31 - __clz(h);
             int cd = lev % K;
             while (lev < L) {

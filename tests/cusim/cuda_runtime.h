@@ -105,6 +105,10 @@ void launch(unsigned grid, unsigned block, void (*kernel)(P...), A... args) {
 #define gridDim (cusim::tls.gdim)
 
 inline void __syncthreads() { cusim::tls.bar->wait(); }
+inline void __syncwarp(unsigned mask) {
+    uint64_t s[32];
+    cusim::tls.warp->gather(mask, cusim::tls.lane, 0, s);
+}
 inline unsigned __shfl_up_sync(unsigned mask, unsigned v, int o) {
     uint64_t s[32];
     cusim::tls.warp->gather(mask, cusim::tls.lane, v, s);
