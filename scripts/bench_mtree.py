@@ -90,6 +90,17 @@ def case(name, n, D, K, nqs, out):
                 rec[f"K9_lanes{lanes}_qps"] = nq / ms9 * 1e3
                 rec[f"K9_lanes{lanes}_identical_to_K6"] = same
             rec["best_speedup_vs_K6"] = ms6 / min(rec[f"K9_lanes{l}_ms"] for l in (32, 16, 8))
+            if nq <= 65536:                                         # top-10: K6's k-smallest traversal vs a warp per query
+                k = 10
+                r6 = torch.zeros((nq, k, 4), dtype=torch.int64, device=DEV)
+                r9 = torch.zeros((nq, k, 4), dtype=torch.int64, device=DEV)
+                e.set_option("nearest.mtree", 0)
+                rec["K6_top10_ms"] = timed(lambda: e.nearest_device(q.data_ptr(), nq, D, k, r6.data_ptr()), max(2, iters // 5))
+                e.set_option("nearest.mtree", 1)
+                rec["K9_top10_ms"] = timed(lambda: e.nearest_device(q.data_ptr(), nq, D, k, r9.data_ptr()), max(2, iters // 5))
+                torch.cuda.synchronize()
+                rec["K9_top10_identical_to_K6"] = bool(torch.equal(r6, r9))
+                rec["top10_speedup_vs_K6"] = rec["K6_top10_ms"] / rec["K9_top10_ms"]
             print(json.dumps(rec), flush=True)
             out.append(rec)
 

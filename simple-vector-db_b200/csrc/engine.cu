@@ -270,7 +270,7 @@ int svdb_engine::tree_append(size_t n0, size_t m) {
 }
 
 bool svdb_engine::mtree_wanted(size_t k, int mode) const {
-    if (k != 1 || !use_mtree) return false;
+    if (k < 1 || k > SVDB_MAX_K || !use_mtree) return false;
     return mode == SVDB_MODE_MTREE || (mode == SVDB_MODE_AUTO && mtree_auto && !force_exact && K <= tree_max_k);
 }
 
@@ -376,18 +376,19 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     if (mode == SVDB_MODE_TREE && !use_tree)
         return fail(SVDB_ERR_ARG, "tree traversal needs an engine that keeps the tree");
     if (mode == SVDB_MODE_MTREE && !mtree_wanted(k, mode))
-        return fail(SVDB_ERR_ARG, "the median tree serves k = 1 on engines with thin kd-points (kd_dim <= 8, not a shard)");
+        return fail(SVDB_ERR_ARG, "the median tree serves engines with thin kd-points (kd_dim <= 8, not a shard)");
     // K9: balanced median tree; the queries it flags (distinct points tied at the minimum) go through K6
     if (mtree_wanted(k, mode)) {
         rc = mtree_update();
         if (rc) return rc;
         std::string err;
         if (use_tree && !mt_marks.ensure(nq * 4, err)) return fail(SVDB_ERR_OOM, err);
-        CK(launch_mtree_nearest(mt, kd_ptr(), kstride, K, n_versions, d_Q, (int)ldq, (int)nq, log_idx.as<u64>(), cfg.seq_base,
-                                use_tree ? 1 : 0, mtree_lanes, use_tree ? mt_marks.as<unsigned>() : nullptr, d_out, stream));
+        CK(launch_mtree_nearest(mt, kd_ptr(), kstride, K, n_versions, d_Q, (int)ldq, (int)nq, (int)k, log_idx.as<u64>(),
+                                cfg.seq_base, use_tree ? 1 : 0, mtree_lanes, use_tree ? mt_marks.as<unsigned>() : nullptr, d_out,
+                                stream));
         stats.kernels_launched++;
         if (use_tree) {
-            CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, 1,
+            CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
                                    log_idx.as<u64>(), cfg.seq_base, d_out, stream, mt_marks.as<unsigned>()));
             stats.kernels_launched++;
         }

@@ -96,7 +96,7 @@ cudaError_t launch_tree_insert(const double *pts, int stride, int K, uint32_t *c
                                uint32_t *pds, unsigned *d_flag, unsigned *h_flag_pinned, int num_sms, cudaStream_t st,
                                int max_rounds, int *rounds_out);
 // K6: the reference's traversal, one thread per query (k = 1), or its k-smallest generalisation (k > 1).
-// only_marked (k = 1; device array of nq words, or NULL): answer only the queries whose word is non-zero (K9 left a
+// only_marked (device array of nq words, or NULL): answer only the queries whose word is non-zero (K9 left a
 // distinct-point tie there), leave the other entries of out[] as they are.
 cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint32_t *child, u64 n, const double *Q,
                                 int ldq, int nq, int k, const u64 *log_index, u64 seq_base, svdb_candidate *out,
@@ -118,12 +118,13 @@ size_t mtree_split_count(u64 n);
 // (~17 bytes per entry) and synchronizes the stream.
 cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, double *split, double *mpts, uint32_t *mseq,
                                int num_sms, cudaStream_t st, int *levels_out, int *launches_out);
-// k = 1, K <= 8.  `lanes` (32, 16 or 8) lanes per query.  Entries [t.n_built, n) of the raw log are scanned after the tree.
+// K <= 8.  k = 1: `lanes` (32, 16 or 8) lanes per query; k > 1: a warp per query keeps the k smallest (distance, seq),
+// nq x k candidates.  Entries [t.n_built, n) of the raw log are scanned after the tree.
 // Answers: smallest (reference-order distance, seq); SVDB_CAND_TIE (if mark_ties) when entries with different
 // coordinates tie at the minimum -- only then can the reference's answer differ (rerun those through K6);
 // marks (device, nq words, may be NULL) receives 1 for every flagged query, else 0.
 cudaError_t launch_mtree_nearest(const MtreeView &t, const double *pts, int stride, int K, u64 n, const double *Q, int ldq,
-                                 int nq, const u64 *log_index, u64 seq_base, int mark_ties, int lanes, unsigned *marks,
+                                 int nq, int k, const u64 *log_index, u64 seq_base, int mark_ties, int lanes, unsigned *marks,
                                  svdb_candidate *out, cudaStream_t st);
 
 struct CompareArgs {

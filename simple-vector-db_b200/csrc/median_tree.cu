@@ -16,7 +16,7 @@
 //     (shared-memory histograms per 2048-element chunk, one pick per segment and pass), then a stable 3-way
 //     partition (count, scan, scatter) moves the u32 permutation.  Segments of <= 2048 entries finish ALL
 //     their remaining levels inside one CTA: a shared-memory bitonic sort by (sub-segment, key) per level.
-//   * traversal (K9): LPQ lanes (32, 16 or 8) per query.  The descent reads one split value per level (no
+//   * traversal (K9): LPQ lanes (32, 16 or 8) per query (k = 1), a full warp per query for k > 1.  The descent reads one split value per level (no
 //     point fetch, no child links), a leaf visit is ONE coalesced read of up to 32 points, each lane forms
 //     its point's distance in the reference's operation order (kdtree.c:134-137: rounded sub, mul, add, in
 //     index order), and three REDUX min-reductions pick the leaf's smallest (distance, seq).  The far side of
@@ -398,9 +398,11 @@ struct MtBest {
 };
 
 // One coalesced visit of up to LPQ entries (one per lane of the group): base + (pos0 + lane) * stride.
-template <int LPQ>
+// KNN (full warps only): every finite candidate is also offered to the warp's sorted list of the klim smallest keys.
+template <int LPQ, bool KNN>
 __device__ __forceinline__ void mt_visit(const unsigned mask, const int gl, const double *__restrict__ base, int stride, u64 pos0,
-                                         unsigned count, const uint32_t *__restrict__ seqs, const double *q, int K, MtBest &b) {
+                                         unsigned count, const uint32_t *__restrict__ seqs, const double *q, int K, MtBest &b,
+                                         WarpList *list = nullptr, int klim = 0) {
     const bool has = (unsigned)gl < count;
     const double *p = base + (pos0 + (has ? gl : 0)) * (size_t)stride;
     double d = 0.0;
@@ -410,6 +412,7 @@ __device__ __forceinline__ void mt_visit(const unsigned mask, const int gl, cons
     }
     const uint32_t s = seqs ? __ldg(seqs + pos0 + (has ? gl : 0)) : (uint32_t)(pos0 + gl);
     const bool valid = has && d < CUDART_INF;                      // NaN and +inf never win (kdtree.c:139 against INFINITY)
+    if (KNN) list->offer(valid, d, (u64)s, gl, klim);
     const unsigned hi = valid ? (unsigned)__double2hiint(d) : 0xffffffffu;
     const unsigned m_hi = __reduce_min_sync(mask, hi);
     if (m_hi == 0xffffffffu) return;
@@ -445,13 +448,16 @@ __device__ __forceinline__ void mt_visit(const unsigned mask, const int gl, cons
     }
 }
 
-template <int LPQ>
-__global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__restrict__ split, const double *__restrict__ mpts,
+// KNN = false: k = 1.  KNN = true (LPQ = 32): the k smallest (distance, seq) in a warp-distributed list; the far side
+// of a split is visited while its plane is not beyond the k-th key; the minimum and its tie flag are tracked as for k = 1.
+template <int LPQ, bool KNN>
+__global__ void __launch_bounds__(128, KNN ? 8 : 12) mtree_nearest_kernel(const double *__restrict__ split, const double *__restrict__ mpts,
                                                             const uint32_t *__restrict__ mseq, u64 nb, int L,
                                                             const double *__restrict__ pts, int stride, u64 n, int K,
-                                                            const double *__restrict__ Q, int ldq, int nq,
+                                                            const double *__restrict__ Q, int ldq, int nq, int k,
                                                             const u64 *__restrict__ log_index, u64 seq_base, int mark_ties,
                                                             unsigned *__restrict__ marks, svdb_candidate *out) {
+    static_assert(!KNN || LPQ == 32, "the k-smallest list is one key per lane of a full warp");
     const int qi = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPQ);
     if (qi >= nq) return;                                          // whole groups leave together
     const int lane = threadIdx.x & 31, gl = lane & (LPQ - 1);
@@ -463,6 +469,8 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
     b.s = 0xffffffffu;
     b.p = nullptr;
     b.tie = false;
+    WarpList list;
+    list.reset();
     if (nb) {
         // the far-side stack is the same in every lane of the group: one copy per group in shared memory (every lane
         // writes the same value and reads back what it wrote; the __syncwarp keeps a lane that runs ahead from
@@ -493,11 +501,16 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
             const u64 lo = mt_bound(j, nb, L);
             const unsigned cnt = (unsigned)(mt_bound(j + 1, nb, L) - lo);
             for (unsigned off = 0; off < cnt; off += LPQ)
-                mt_visit<LPQ>(mask, gl, mpts, K, lo + off, min((unsigned)LPQ, cnt - off), mseq, q, K, b);
+                mt_visit<LPQ, KNN>(mask, gl, mpts, K, lo + off, min((unsigned)LPQ, cnt - off), mseq, q, K, b, &list, k);
+            double bound = b.d;
+            if (KNN) {                                             // k-th smallest key so far (+inf while fewer than k)
+                u64 ts;
+                list.key_at(k - 1, bound, ts);
+            }
             bool found = false;
             while (sp > 0) {
                 sp--;
-                if (st_plane[sp] <= b.d) {                         // '<=': equal distances must be seen (lowest seq, tie detection)
+                if (st_plane[sp] <= bound) {                       // '<=': equal distances must be seen (lowest seq, tie detection)
                     h = st_node[sp];
                     found = true;
                     break;
@@ -507,7 +520,22 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
         }
     }
     for (u64 pos = nb; pos < n; pos += LPQ)                        // entries appended since the build
-        mt_visit<LPQ>(mask, gl, pts, stride, pos, (unsigned)min((u64)LPQ, n - pos), nullptr, q, K, b);
+        mt_visit<LPQ, KNN>(mask, gl, pts, stride, pos, (unsigned)min((u64)LPQ, n - pos), nullptr, q, K, b, &list, k);
+    if (KNN) {
+        // lane i holds the i-th smallest (distance, seq); position 0 is the minimum, i.e. the reference's answer unless flagged
+        const u64 fl = (b.tie && mark_ties) ? SVDB_CAND_TIE : 0ull;
+        if (gl < k) {
+            svdb_candidate c;
+            const bool none = list.seq == SEQ_NONE;
+            c.dist = none ? CUDART_INF : list.d;
+            c.seq = none ? SEQ_NONE : list.seq + seq_base;
+            c.index = none ? (u64)SVDB_NONE : log_index[list.seq];
+            c.flags = none ? 0ull : fl;
+            out[(size_t)qi * k + gl] = c;
+        }
+        if (gl == 0 && marks) marks[qi] = fl ? 1u : 0u;
+        return;
+    }
     if (gl == 0) {
         svdb_candidate c;
         if (b.s == 0xffffffffu) {
@@ -527,23 +555,25 @@ __global__ void __launch_bounds__(128, 12) mtree_nearest_kernel(const double *__
 }
 
 cudaError_t launch_mtree_nearest(const MtreeView &t, const double *pts, int stride, int K, u64 n, const double *Q, int ldq,
-                                 int nq, const u64 *log_index, u64 seq_base, int mark_ties, int lanes, unsigned *marks,
+                                 int nq, int k, const u64 *log_index, u64 seq_base, int mark_ties, int lanes, unsigned *marks,
                                  svdb_candidate *out, cudaStream_t st) {
     if (nq == 0) return cudaSuccess;
-    if (K > 8) return cudaErrorInvalidValue;
+    if (K > 8 || k < 1 || k > 32) return cudaErrorInvalidValue;
+    if (k > 1) lanes = 32;
     const int gpb = 128 / lanes;
     const unsigned grid = (unsigned)((nq + gpb - 1) / gpb);
-    if (lanes == 32)
-        mtree_nearest_kernel<32><<<grid, 128, 0, st>>>(t.split, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq,
-                                                       log_index, seq_base, mark_ties, marks, out);
+#define MT_ARGS t.split, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq, k, log_index, seq_base, mark_ties, marks, out
+    if (k > 1)
+        mtree_nearest_kernel<32, true><<<grid, 128, 0, st>>>(MT_ARGS);
+    else if (lanes == 32)
+        mtree_nearest_kernel<32, false><<<grid, 128, 0, st>>>(MT_ARGS);
     else if (lanes == 16)
-        mtree_nearest_kernel<16><<<grid, 128, 0, st>>>(t.split, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq,
-                                                       log_index, seq_base, mark_ties, marks, out);
+        mtree_nearest_kernel<16, false><<<grid, 128, 0, st>>>(MT_ARGS);
     else if (lanes == 8)
-        mtree_nearest_kernel<8><<<grid, 128, 0, st>>>(t.split, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq,
-                                                      log_index, seq_base, mark_ties, marks, out);
+        mtree_nearest_kernel<8, false><<<grid, 128, 0, st>>>(MT_ARGS);
     else
         return cudaErrorInvalidValue;
+#undef MT_ARGS
     return cudaGetLastError();
 }
 

@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(128) tree_knn_kernel(const double *__restrict_
                                                        const uint32_t *__restrict__ child, u64 n,
                                                        const double *__restrict__ Q, int ldq, int nq, int k,
                                                        const u64 *__restrict__ log_index, u64 seq_base,
-                                                       svdb_candidate *out) {
+                                                       svdb_candidate *out, const unsigned *__restrict__ only_marked) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
+    if (only_marked && !only_marked[qi]) return;                 // K9 answered this one already
     double ql[16];
     const double *qg = Q + (size_t)qi * ldq;
     if (K <= 16)
@@ -341,7 +342,8 @@ cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint
         tree_nearest_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, log_index, seq_base, out,
                                                               only_marked);
     } else
-        tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out);
+        tree_knn_kernel<<<(nq + 127) / 128, 128, 0, st>>>(pts, stride, K, child, n, Q, ldq, nq, k, log_index, seq_base, out,
+                                                          only_marked);
     return cudaGetLastError();
 }
 

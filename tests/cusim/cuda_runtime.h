@@ -109,10 +109,22 @@ inline void __syncwarp(unsigned mask) {
     uint64_t s[32];
     cusim::tls.warp->gather(mask, cusim::tls.lane, 0, s);
 }
-inline unsigned __shfl_up_sync(unsigned mask, unsigned v, int o) {
+template <typename T> inline uint64_t cusim_bits(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof v); return b; }
+template <typename T> inline T cusim_from(uint64_t b) { T v; memcpy(&v, &b, sizeof v); return v; }
+template <typename T> inline T __shfl_up_sync(unsigned mask, T v, int o) {
     uint64_t s[32];
-    cusim::tls.warp->gather(mask, cusim::tls.lane, v, s);
-    return cusim::tls.lane >= o ? (unsigned)s[cusim::tls.lane - o] : v;
+    cusim::tls.warp->gather(mask, cusim::tls.lane, cusim_bits(v), s);
+    return cusim::tls.lane >= o ? cusim_from<T>(s[cusim::tls.lane - o]) : v;
+}
+template <typename T> inline T __shfl_sync(unsigned mask, T v, int src) {
+    uint64_t s[32];
+    cusim::tls.warp->gather(mask, cusim::tls.lane, cusim_bits(v), s);
+    return cusim_from<T>(s[src & 31]);
+}
+template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int x) {
+    uint64_t s[32];
+    cusim::tls.warp->gather(mask, cusim::tls.lane, cusim_bits(v), s);
+    return cusim_from<T>(s[(cusim::tls.lane ^ x) & 31]);
 }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     uint64_t s[32];

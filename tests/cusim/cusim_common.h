@@ -7,3 +7,4 @@ typedef unsigned long long u64;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr u64 SEQ_NONE = ~0ull;
 }
+#include "warplist.cuh"

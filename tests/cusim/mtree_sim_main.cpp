@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <random>
+#include <utility>
 
 #include "median_tree_sim.inc"
 
@@ -85,7 +86,7 @@ int main(int argc, char **argv) {
         std::vector<svdb_candidate> out(nq);
         std::vector<unsigned> marks(nq, 77u);
         memset(out.data(), 0xEE, out.size() * sizeof(svdb_candidate));
-        if (svdb::launch_mtree_nearest(t, pts.data(), stride, K, nt, Q.data(), K, nq, log_index.data(), 5000, 1, lanes, marks.data(), out.data(), nullptr)) return 3;
+        if (svdb::launch_mtree_nearest(t, pts.data(), stride, K, nt, Q.data(), K, nq, 1, log_index.data(), 5000, 1, lanes, marks.data(), out.data(), nullptr)) return 3;
         for (int i = 0; i < nq; i++) {
             const double *q = &Q[(size_t)i * K];
             double bd = INFINITY;
@@ -109,6 +110,37 @@ int main(int argc, char **argv) {
                 return 1;
             }
             flagged += tie && lanes == 32;
+        }
+    }
+    // k > 1: the k smallest (distance, seq), flagged like k = 1
+    for (int k : {2, 5, 24}) {
+        std::vector<svdb_candidate> out((size_t)nq * k);
+        std::vector<unsigned> marks(nq, 77u);
+        memset(out.data(), 0xEE, out.size() * sizeof(svdb_candidate));
+        if (svdb::launch_mtree_nearest(t, pts.data(), stride, K, nt, Q.data(), K, nq, k, log_index.data(), 5000, 1, 32, marks.data(), out.data(), nullptr)) return 3;
+        for (int i = 0; i < nq; i++) {
+            const double *q = &Q[(size_t)i * K];
+            std::vector<std::pair<double, u64>> all;
+            for (u64 e = 0; e < nt; e++) {
+                const double d = sqdist(&pts[e * stride], q, K);
+                if (d < INFINITY) all.push_back({d, e});
+            }
+            std::sort(all.begin(), all.end());
+            bool tie = false;
+            for (size_t a = 1; a < all.size() && all[a].first == all[0].first; a++)
+                for (int c = 0; c < K; c++) tie |= pts[all[a].second * stride + c] != pts[all[0].second * stride + c];
+            for (int r = 0; r < k; r++) {
+                const svdb_candidate &c = out[(size_t)i * k + r];
+                const bool ok = (size_t)r < all.size()
+                                    ? (c.seq == all[r].second + 5000 && c.index == 1000 + all[r].second &&
+                                       memcmp(&c.dist, &all[r].first, 8) == 0 && c.flags == (tie ? SVDB_CAND_TIE : 0ull))
+                                    : (c.seq == ~0ull && c.index == (u64)SVDB_NONE && c.dist == INFINITY && c.flags == 0);
+                if (!ok || marks[i] != (tie ? 1u : 0u)) {
+                    printf("k %d query %d rank %d: got seq %llu dist %.17g flags %llu mark %u (tie %d)\n", k, i, r,
+                           (unsigned long long)c.seq, c.dist, (unsigned long long)c.flags, marks[i], (int)tie);
+                    return 1;
+                }
+            }
         }
     }
     printf("OK n=%llu K=%d tail=%llu levels=%d launches=%d flagged=%d/%d\n", (unsigned long long)n, K, (unsigned long long)tail, L,

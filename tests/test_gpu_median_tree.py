@@ -88,6 +88,15 @@ def test_median_tree_returns_the_reference_id(port, kind, n, K, nq):
             assert d9[i, 0] == exact_dist(rows, K, Q[i], int(i9[i, 0]))
         one = e.nearest(Q[:1], 1)                                      # single-query host call (coalescing + graph path)
         assert one[0][0, 0] == want[0]
+        # k > 1: a warp per query keeps the k smallest (distance, seq); position 0 stays the reference's answer
+        for k in (2, 10, 24):
+            e.set_option("nearest.mtree", 0)
+            a = e.nearest(Q[:120], k)                                  # K6's k-smallest traversal
+            e.set_option("nearest.mtree", 1)
+            b = e.nearest(Q[:120], k)
+            np.testing.assert_array_equal(b[0][:, 0], want[:120], err_msg=f"k {k}")
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x.view(np.uint64), y.view(np.uint64), err_msg=f"k {k}")
 
 
 def test_median_tree_follows_the_growing_log(port):
@@ -179,8 +188,12 @@ def test_median_tree_device_api_and_errors(port):
         np.testing.assert_array_equal(res["index"], want + 7)
         assert not np.any(res["flags"])
         assert e.stats()["mtree_builds"] == 1
-        with pytest.raises(B.SvdbError):
-            e.nearest_device(dq.data_ptr(), 4, D, 2, out.data_ptr(), B.MODE_MTREE)   # k = 1 only
+        out5 = torch.zeros((len(Q), 5, 4), dtype=torch.int64, device="cuda")
+        e.nearest_device(dq.data_ptr(), len(Q), D, 5, out5.data_ptr(), B.MODE_MTREE)
+        torch.cuda.synchronize()
+        res5 = out5.cpu().numpy().view(B.candidate_dtype).reshape(len(Q), 5)
+        np.testing.assert_array_equal(res5["index"][:, 0], want + 7)
+        assert np.all(np.diff(res5["dist"], axis=1) >= 0)
     with B.Engine(16, 16) as e:                                        # wide kd-points: no median tree
         e.insert(synth.uniform_rows(1, 100, 16))
         q16 = torch.zeros((1, 16), dtype=torch.float64, device="cuda")

@@ -20,8 +20,8 @@ def sim_binary(tmp_path_factory):
     src = open(os.path.join(CSRC, "median_tree.cu")).read()
     src = src.replace('#include "common.cuh"', '#include "cusim_common.h"')
     # kernel<<<grid, block, smem, stream>>>(args)  ->  cusim::launch(grid, block, kernel, args)
-    src, n = re.subn(r"(\w+(?:<\d+>)?)<<<(.*?), (\w+), 0, st>>>\(", r"cusim::launch(\2, \3, \1, ", src)
-    assert n == 12, n
+    src, n = re.subn(r"(\w+(?:<[\w, ]+>)?)<<<(.*?), (\w+), 0, st>>>\(", r"cusim::launch(\2, \3, \1, ", src)
+    assert n == 13, n
     assert "<<<" not in src
     (tmp / "median_tree_sim.inc").write_text(src)
     exe = str(tmp / "mtree_sim")
