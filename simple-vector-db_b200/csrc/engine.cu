@@ -153,9 +153,10 @@ int svdb_engine::init(const svdb_config &c) {
     max_versions = std::min<size_t>(va / main_row_bytes, 0xfffffffeull);   // tree links are u32
     use_tree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !getenv("SVDB_NO_TREE");
     graphs_enabled = !getenv("SVDB_NO_GRAPH");
-    use_mtree = !no_log && !(c.flags & SVDB_FLAG_SHARD) && !wide && K <= 8 && !getenv("SVDB_NO_MTREE");
+    use_mtree = !no_log && !wide && K <= 8 && !getenv("SVDB_NO_MTREE");
     if (const char *v = getenv("SVDB_MTREE")) mtree_auto = atoi(v);
     if (const char *v = getenv("SVDB_MTREE_LANES")) mtree_lanes = atoi(v);
+    if (const char *v = getenv("SVDB_MTREE_BLOCK")) mtree_block = atoi(v) == 1 ? 1 : 3;
     std::string err;
     if (!log_only) {
         if (!rows.init(device, max_versions * (size_t)Dpad * 8, err)) return fail(SVDB_ERR_CUDA, err);
@@ -278,17 +279,19 @@ bool svdb_engine::mtree_wanted(size_t k, int mode) const {
 // Rebuild (from scratch: the tree is static) once the tail exceeds clamp(n_built / 8, tail_min, tail_max).
 int svdb_engine::mtree_update() {
     if (!use_mtree) return SVDB_OK;
+    if (mt.n_built && mt.block_levels != mtree_block) mt = MtreeView{};      // layout option changed: rebuild
     const size_t n = n_versions, tail = n - (size_t)mt.n_built;
     const size_t limit = std::min(std::max((size_t)mt.n_built / 8, mtree_tail_min), std::max(mtree_tail_max, mtree_tail_min));
     if (tail <= limit) return SVDB_OK;
     std::string err;
-    if (!mt_split.ensure(mtree_split_count(n) * 8, err) || !mt_pts.ensure(n * (size_t)K * 8, err) || !mt_seq.ensure(n * 4, err))
+    if (!mt_split.ensure(mtree_split_count(n, mtree_block) * 8, err) || !mt_pts.ensure(n * (size_t)K * 8, err) || !mt_seq.ensure(n * 4, err))
         return fail(SVDB_ERR_OOM, err);
     int levels = 0, launches = 0;
     mt = MtreeView{};                    // nothing usable until the build has finished
-    CK(launch_mtree_build(kd_ptr(), kstride, K, n, mt_split.as<double>(), mt_pts.as<double>(), mt_seq.as<uint32_t>(),
+    CK(launch_mtree_build(kd_ptr(), kstride, K, n, mtree_block, mt_split.as<double>(), mt_pts.as<double>(), mt_seq.as<uint32_t>(),
                           tune.num_sms, stream, &levels, &launches));
     mt.split = mt_split.as<double>();
+    mt.block_levels = mtree_block;
     mt.mpts = mt_pts.as<double>();
     mt.mseq = mt_seq.as<uint32_t>();
     mt.n_built = n;
@@ -376,16 +379,23 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     if (mode == SVDB_MODE_TREE && !use_tree)
         return fail(SVDB_ERR_ARG, "tree traversal needs an engine that keeps the tree");
     if (mode == SVDB_MODE_MTREE && !mtree_wanted(k, mode))
-        return fail(SVDB_ERR_ARG, "the median tree serves engines with thin kd-points (kd_dim <= 8, not a shard)");
+        return fail(SVDB_ERR_ARG, "the median tree serves engines with thin kd-points (kd_dim <= 8)");
     // K9: balanced median tree; the queries it flags (distinct points tied at the minimum) go through K6
     if (mtree_wanted(k, mode)) {
         rc = mtree_update();
         if (rc) return rc;
         std::string err;
         if (use_tree && !mt_marks.ensure(nq * 4, err)) return fail(SVDB_ERR_OOM, err);
+        // a shard keeps no reference-shaped tree: its flag travels with the candidates and the tie is settled
+        // across the shards (tie_protocol.cu); plain (distance, seq) order is what the merge wants anyway
+        const bool shard = (cfg.flags & SVDB_FLAG_SHARD) != 0;
+        // lanes per query (k = 1): a full warp answers one query fastest, narrower groups keep more queries in flight --
+        // measured best (profiles/r01_mtree_K6_vs_K9_ab.jsonl): 32 up to a few thousand queries per call, 16 up to a few
+        // hundred thousand, 8 beyond
+        const int lanes = mtree_lanes ? mtree_lanes : (nq < 8192 ? 32 : (nq < 524288 ? 16 : 8));
         CK(launch_mtree_nearest(mt, kd_ptr(), kstride, K, n_versions, d_Q, (int)ldq, (int)nq, (int)k, log_idx.as<u64>(),
-                                cfg.seq_base, use_tree ? 1 : 0, mtree_lanes, use_tree ? mt_marks.as<unsigned>() : nullptr, d_out,
-                                stream));
+                                cfg.seq_base, (use_tree || shard) ? 1 : 0, lanes,
+                                use_tree ? mt_marks.as<unsigned>() : nullptr, d_out, stream));
         stats.kernels_launched++;
         if (use_tree) {
             CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
@@ -1377,8 +1387,12 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "log.index_base") e->index_base = (uint64_t)value;
     else if (n == "nearest.mtree") e->mtree_auto = value != 0;
     else if (n == "mtree.lanes") {
-        if (value != 32 && value != 16 && value != 8) return e->fail(SVDB_ERR_ARG, "mtree.lanes must be 32, 16 or 8");
+        if (value != 0 && value != 32 && value != 16 && value != 8) return e->fail(SVDB_ERR_ARG, "mtree.lanes must be 0 (auto), 32, 16 or 8");
         e->mtree_lanes = (int)value;
+    }
+    else if (n == "mtree.block_levels") {
+        if (value != 1 && value != 3) return e->fail(SVDB_ERR_ARG, "mtree.block_levels must be 1 or 3");
+        e->mtree_block = (int)value;
     }
     else if (n == "mtree.tail_max") e->mtree_tail_max = (size_t)std::max(0l, value);
     else if (n == "mtree.tail_min") e->mtree_tail_min = (size_t)std::max(0l, value);

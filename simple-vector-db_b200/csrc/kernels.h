@@ -105,18 +105,20 @@ cudaError_t launch_tree_nearest(const double *pts, int stride, int K, const uint
 // K8/K9: balanced median KD tree over thin kd-points (median_tree.cu).  Implicit layout: node (level l, j) has heap id
 // 2^l + j and covers positions [(j*n)>>l, ((j+1)*n)>>l) of the leaf-ordered point array; only split values are stored.
 struct MtreeView {
-    const double *split = nullptr;    // [2^levels], heap order, entry 0 unused
+    const double *split = nullptr;    // split values; block_levels = 1: [2^levels] in heap order (entry 0 unused);
+                                      // 3: 64-byte blocks of three levels each (median_tree.cu: mt_slot)
+    int block_levels = 1;
     const double *mpts = nullptr;     // [n_built][K] kd-points in leaf order
     const uint32_t *mseq = nullptr;   // [n_built] log sequence number of each
     u64 n_built = 0;                  // log entries [0, n_built) are in the tree
     int levels = 0;                   // internal levels; 2^levels leaves of <= 32 points
 };
 int mtree_levels(u64 n);
-size_t mtree_split_count(u64 n);
+size_t mtree_split_count(u64 n, int block_levels);
 // Build over log entries [0, n): median splits by radix-select partitioning (large segments) and in-CTA sorts (segments
-// of <= 2048).  split/mpts/mseq: mtree_split_count(n) doubles, n*K doubles, n u32.  Allocates and frees its own scratch
+// of <= 2048).  split/mpts/mseq: mtree_split_count(n, block_levels) doubles, n*K doubles, n u32.  Allocates and frees its own scratch
 // (~17 bytes per entry) and synchronizes the stream.
-cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, double *split, double *mpts, uint32_t *mseq,
+cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, int block_levels, double *split, double *mpts, uint32_t *mseq,
                                int num_sms, cudaStream_t st, int *levels_out, int *launches_out);
 // K <= 8.  k = 1: `lanes` (32, 16 or 8) lanes per query; k > 1: a warp per query keeps the k smallest (distance, seq),
 // nq x k candidates.  Entries [t.n_built, n) of the raw log are scanned after the tree.

@@ -46,6 +46,21 @@ constexpr int MT_PER_THREAD = MT_CHUNK / MT_THREADS;
 
 __host__ __device__ __forceinline__ u64 mt_bound(u64 j, u64 n, int level) { return (j * n) >> level; }
 
+// Where node (level, j) keeps its split value.  blk = 1: heap order (2^level + j).  blk = 3: three levels per 64-byte
+// block -- block (t, jt) holds the 7 nodes of the subtree rooted at node (3t, jt) in heap order (slot 7 unused), blocks
+// of super-level t start at (8^t - 1) / 7 -- so that a descent pays one memory round trip per THREE levels.
+__host__ __device__ __forceinline__ u64 mt_slot(int level, u64 j, int blk) {
+    if (blk == 1) return (1ull << level) + j;
+    const int t = level / 3, r = level - 3 * t;
+    const u64 block = ((1ull << (3 * t)) - 1) / 7 + (j >> r);
+    return block * 8 + ((1ull << r) - 1) + (j & ((1ull << r) - 1));
+}
+__device__ __forceinline__ void mt_prefetch(const void *p) {
+#ifndef SVDB_CUSIM
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 // double -> u64 whose unsigned order is the numeric order (-0 < +0, which is harmless: a partition
 // that is valid in key order is valid in numeric order).  NaNs sort with +inf: their points never win.
 __device__ __forceinline__ u64 mt_key(double x) {
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_count_kernel(const u64 *__restr
 // one CTA per segment: exclusive scan of the chunk counts, totals, and the node's split value
 __global__ void __launch_bounds__(MT_THREADS) mt_scan_kernel(const unsigned *__restrict__ cnt, unsigned *offs, unsigned *tot,
                                                              unsigned cps, int level, const u64 *__restrict__ prefix,
-                                                             double *split) {
+                                                             double *split, int blk) {
     __shared__ unsigned wt[8];
     const u64 j = blockIdx.x;
     unsigned carry_l = 0, carry_e = 0;
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_scan_kernel(const unsigned *__r
     if (threadIdx.x == 0) {
         tot[j * 2] = carry_l;
         tot[j * 2 + 1] = carry_e;
-        split[(1ull << level) + j] = mt_unkey(prefix[j]);
+        split[mt_slot(level, j, blk)] = mt_unkey(prefix[j]);
     }
 }
 
@@ -246,7 +261,7 @@ __device__ __forceinline__ bool mt_after(u64 ka, u64 va, u64 kb, u64 vb) {     /
 
 __global__ void __launch_bounds__(MT_THREADS) mt_small_kernel(const double *__restrict__ pts, int stride, int K,
                                                               const uint32_t *__restrict__ perm, u64 n, int level0, int L,
-                                                              double *split, double *__restrict__ mpts,
+                                                              double *split, int blk, double *__restrict__ mpts,
                                                               uint32_t *__restrict__ mseq) {
     __shared__ u64 skey[MT_SMALL];
     __shared__ u64 sval[MT_SMALL];            // sub-segment id << 32 | log entry
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_small_kernel(const double *__re
         for (u64 x = threadIdx.x; x < nsub; x += MT_THREADS) {
             const u64 jj = sub0 + x;
             const u64 mpos = mt_bound(2 * jj + 1, n, lev + 1) - lo;
-            split[(1ull << lev) + jj] = mt_unkey(skey[mpos]);
+            split[mt_slot(lev, jj, blk)] = mt_unkey(skey[mpos]);
         }
         __syncthreads();
     }
@@ -309,7 +324,12 @@ int mtree_levels(u64 n) {
     return L;
 }
 
-size_t mtree_split_count(u64 n) { return (size_t)1 << mtree_levels(n); }
+size_t mtree_split_count(u64 n, int blk) {
+    const int L = mtree_levels(n);
+    if (blk == 1 || L == 0) return (size_t)1 << L;
+    const int T = (L + 2) / 3;                                   // super-levels; the last one may be partly used
+    return (size_t)(((1ull << (3 * T)) - 1) / 7) * 8;
+}
 
 #define MT_CK(call)                         \
     do {                                    \
@@ -320,8 +340,9 @@ size_t mtree_split_count(u64 n) { return (size_t)1 << mtree_levels(n); }
         }                                   \
     } while (0)
 
-cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, double *split, double *mpts, uint32_t *mseq,
+cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, int blk, double *split, double *mpts, uint32_t *mseq,
                                int num_sms, cudaStream_t st, int *levels_out, int *launches_out) {
+    if (blk != 1 && blk != 3) return cudaErrorInvalidValue;
     std::vector<void *> blocks;
     const int L = mtree_levels(n);
     if (levels_out) *levels_out = L;
@@ -373,14 +394,14 @@ cudaError_t launch_mtree_build(const double *pts, int stride, int K, u64 n, doub
                 mt_pick_kernel<<<(unsigned)S, MT_THREADS, 0, st>>>(hist, prefix, rank, pass);
             }
             mt_count_kernel<<<grid, MT_THREADS, 0, st>>>(keys, n, l, cps, prefix, cnt);
-            mt_scan_kernel<<<(unsigned)S, MT_THREADS, 0, st>>>(cnt, offs, tot, cps, l, prefix, split);
+            mt_scan_kernel<<<(unsigned)S, MT_THREADS, 0, st>>>(cnt, offs, tot, cps, l, prefix, split, blk);
             mt_scatter_kernel<<<grid, MT_THREADS, 0, st>>>(keys, perm[cur], perm[cur ^ 1], n, l, cps, prefix, rank, offs, tot);
             launches += 21;
             cur ^= 1;
             MT_CK(cudaGetLastError());
         }
     }
-    mt_small_kernel<<<(unsigned)(1ull << levels_a), MT_THREADS, 0, st>>>(pts, stride, K, perm[cur], n, levels_a, L, split, mpts, mseq);
+    mt_small_kernel<<<(unsigned)(1ull << levels_a), MT_THREADS, 0, st>>>(pts, stride, K, perm[cur], n, levels_a, L, split, blk, mpts, mseq);
     launches++;
     MT_CK(cudaGetLastError());
     MT_CK(cudaStreamSynchronize(st));
@@ -451,7 +472,7 @@ __device__ __forceinline__ void mt_visit(const unsigned mask, const int gl, cons
 // KNN = false: k = 1.  KNN = true (LPQ = 32): the k smallest (distance, seq) in a warp-distributed list; the far side
 // of a split is visited while its plane is not beyond the k-th key; the minimum and its tie flag are tracked as for k = 1.
 template <int LPQ, bool KNN>
-__global__ void __launch_bounds__(128, KNN ? 8 : 12) mtree_nearest_kernel(const double *__restrict__ split, const double *__restrict__ mpts,
+__global__ void __launch_bounds__(128, KNN ? 8 : 12) mtree_nearest_kernel(const double *__restrict__ split, int blk, const double *__restrict__ mpts,
                                                             const uint32_t *__restrict__ mseq, u64 nb, int L,
                                                             const double *__restrict__ pts, int stride, u64 n, int K,
                                                             const double *__restrict__ Q, int ldq, int nq, int k,
@@ -486,7 +507,9 @@ __global__ void __launch_bounds__(128, KNN ? 8 : 12) mtree_nearest_kernel(const 
             int lev = 31 - __clz(h);
             int cd = lev % K;
             while (lev < L) {
-                const double s = __ldg(split + h);
+                const double *sp_ = split + mt_slot(lev, h - (1u << lev), blk);
+                if (blk == 3 && lev % 3 == 0) mt_prefetch(sp_ + 4);   // second sector of the block: levels +1/+2 hit L1
+                const double s = __ldg(sp_);
                 const double qc = q[cd];
                 const bool left = qc < s;
                 const double t = __dsub_rn(qc, s);
@@ -562,7 +585,7 @@ cudaError_t launch_mtree_nearest(const MtreeView &t, const double *pts, int stri
     if (k > 1) lanes = 32;
     const int gpb = 128 / lanes;
     const unsigned grid = (unsigned)((nq + gpb - 1) / gpb);
-#define MT_ARGS t.split, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq, k, log_index, seq_base, mark_ties, marks, out
+#define MT_ARGS t.split, t.block_levels, t.mpts, t.mseq, t.n_built, t.levels, pts, stride, n, K, Q, ldq, nq, k, log_index, seq_base, mark_ties, marks, out
     if (k > 1)
         mtree_nearest_kernel<32, true><<<grid, 128, 0, st>>>(MT_ARGS);
     else if (lanes == 32)

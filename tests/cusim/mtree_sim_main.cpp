@@ -1,7 +1,7 @@
 // Runs the K8/K9 kernel source of csrc/median_tree.cu under the CPU emulation in cuda_runtime.h (this directory)
 // and checks: the build is a permutation with valid median splits at every node; the traversal returns the
 // smallest (reference-order distance, seq) of tree + tail and flags exactly the queries whose minimum is
-// shared by entries with different coordinates.   usage: mtree_sim <n> <K> <tail> <nq> <dist> <seed>
+// shared by entries with different coordinates.   usage: mtree_sim <n> <K> <tail> <nq> <dist> <seed> [levels per block: 3 | 1]
 #include <stdio.h>
 
 #include <random>
@@ -26,6 +26,7 @@ int main(int argc, char **argv) {
     const int K = atoi(argv[2]);
     const u64 tail = strtoull(argv[3], 0, 10);
     const int nq = atoi(argv[4]);
+    const int blk = argc > 7 ? atoi(argv[7]) : 3;
     const int dist = atoi(argv[5]);       // 0 uniform, 1 coarse grid (ties, duplicates), 2 sorted, 3 uniform with non-finite rows
     std::mt19937_64 rng(strtoull(argv[6], 0, 10));
     std::uniform_real_distribution<double> U(-1.0, 1.0);
@@ -49,10 +50,10 @@ int main(int argc, char **argv) {
     for (u64 i = 0; i < nt; i++) log_index[i] = 1000 + i;
 
     const int L = svdb::mtree_levels(n);
-    std::vector<double> split(svdb::mtree_split_count(n), NAN), mpts(std::max<u64>(n, 1) * K, NAN);
+    std::vector<double> split(svdb::mtree_split_count(n, blk), NAN), mpts(std::max<u64>(n, 1) * K, NAN);
     std::vector<uint32_t> mseq(std::max<u64>(n, 1), 0xdeadbeefu);
     int levels = -1, launches = 0;
-    if (svdb::launch_mtree_build(pts.data(), stride, K, n, split.data(), mpts.data(), mseq.data(), 4, nullptr, &levels, &launches)) return 3;
+    if (svdb::launch_mtree_build(pts.data(), stride, K, n, blk, split.data(), mpts.data(), mseq.data(), 4, nullptr, &levels, &launches)) return 3;
     if (levels != L) { printf("levels %d != %d\n", levels, L); return 1; }
     // permutation + payload
     std::vector<char> seen(n, 0);
@@ -65,7 +66,7 @@ int main(int argc, char **argv) {
     for (int l = 0; l < L; l++)
         for (u64 j = 0; j < (1ull << l); j++) {
             const u64 lo = svdb::mt_bound(j, n, l), hi = svdb::mt_bound(j + 1, n, l), mid = svdb::mt_bound(2 * j + 1, n, l + 1);
-            const double s = split[(1ull << l) + j];
+            const double s = split[svdb::mt_slot(l, j, blk)];
             if (!(lo < mid && mid < hi)) { printf("empty side at level %d seg %llu\n", l, (unsigned long long)j); return 1; }
             for (u64 p = lo; p < hi; p++) {
                 double x = mpts[p * K + l % K];
@@ -80,7 +81,7 @@ int main(int argc, char **argv) {
         if (svdb::mt_bound(j + 1, n, L) - svdb::mt_bound(j, n, L) > 32) { printf("leaf too large\n"); return 1; }
 
     svdb::MtreeView t;
-    t.split = split.data(); t.mpts = mpts.data(); t.mseq = mseq.data(); t.n_built = n; t.levels = L;
+    t.split = split.data(); t.mpts = mpts.data(); t.mseq = mseq.data(); t.n_built = n; t.levels = L; t.block_levels = blk;
     int flagged = 0;
     for (int lanes : {32, 16, 8}) {
         std::vector<svdb_candidate> out(nq);

@@ -76,14 +76,16 @@ def test_median_tree_returns_the_reference_id(port, kind, n, K, nq):
         np.testing.assert_array_equal(i6[:, 0], want)
         assert e.stats()["mtree_builds"] == 0
         e.set_option("nearest.mtree", 1)
-        for lanes in (32, 16, 8):
-            e.set_option("mtree.lanes", lanes)
-            i9, d9, s9 = e.nearest(Q, 1)
-            np.testing.assert_array_equal(i9[:, 0], want, err_msg=f"lanes {lanes}")
-            np.testing.assert_array_equal(s9, s6)
-            np.testing.assert_array_equal(d9.view(np.uint64), d6.view(np.uint64))
+        for blk in (1, 3):                                             # split values in heap order / 64-byte blocks of 3 levels
+            e.set_option("mtree.block_levels", blk)
+            for lanes in (32, 16, 8, 0):
+                e.set_option("mtree.lanes", lanes)
+                i9, d9, s9 = e.nearest(Q, 1)
+                np.testing.assert_array_equal(i9[:, 0], want, err_msg=f"block {blk} lanes {lanes}")
+                np.testing.assert_array_equal(s9, s6)
+                np.testing.assert_array_equal(d9.view(np.uint64), d6.view(np.uint64))
         st = e.stats()
-        assert st["mtree_builds"] == (1 if n > 256 else 0) and st["mtree_rows"] == (n if n > 256 else 0)
+        assert st["mtree_builds"] == (2 if n > 256 else 0) and st["mtree_rows"] == (n if n > 256 else 0)
         for i in (0, nq // 2, nq - 1):
             assert d9[i, 0] == exact_dist(rows, K, Q[i], int(i9[i, 0]))
         one = e.nearest(Q[:1], 1)                                      # single-query host call (coalescing + graph path)

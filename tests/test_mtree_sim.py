@@ -49,6 +49,7 @@ CASES = [
 
 @pytest.mark.parametrize("n,K,tail,nq,dist,seed", CASES)
 def test_kernel_source_under_cpu_emulation(sim_binary, n, K, tail, nq, dist, seed):
-    r = subprocess.run([sim_binary, str(n), str(K), str(tail), str(nq), str(dist), str(seed)], capture_output=True, text=True,
-                       timeout=180)
+    blk = "1" if seed % 4 == 0 else "3"          # split values in heap order / in 64-byte blocks of three levels
+    r = subprocess.run([sim_binary, str(n), str(K), str(tail), str(nq), str(dist), str(seed), blk], capture_output=True,
+                       text=True, timeout=180)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
