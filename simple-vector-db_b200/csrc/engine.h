@@ -76,7 +76,7 @@ struct svdb_engine {
     bool use_mtree = false;              // engine may keep one (thin log, kd_dim <= 8)
     int mtree_auto = 1;                  // AUTO prefers it over K6 for k = 1
     int mtree_lanes = 0;                 // lanes per query in K9 (32, 16, 8); 0: chosen from the number of queries in the call
-    int mtree_block = 3;                 // tree levels per 64-byte block of split values (1: heap order)
+    int mtree_block = 1;                 // 1: split values in heap order; 3: 64-byte blocks of three levels (measured slower, kept as an option)
     size_t mtree_tail_min = 256, mtree_tail_max = 4096;   // rebuild once the unindexed tail exceeds clamp(n_built/8, min, max)
     uint64_t index_base = 0;             // added to the index a log entry reports (a shard's rows are global rows lo..)
     int device = 0;
