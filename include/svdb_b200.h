@@ -263,6 +263,8 @@ typedef struct svdb_stats {
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
+ * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never),
+ * "nearest.umma_min_kd_dim",
  * "nearest.mtree" (AUTO may use the median tree), "mtree.lanes" (32/16/8 lanes per query), "mtree.tail_max";
  * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
  * row i is global row lo + i sets it to lo, so that merged answers carry global row numbers). */
@@ -273,6 +275,10 @@ int svdb_time_scan(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, siz
 /* With option "profile.scan_events" = 1 every scan launch is bracketed by CUDA events on the
  * engine's stream; this returns their summed duration and count since the last call. */
 int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches);
+/* Diagnostics of the tcgen05 batch path (K10): after a batch call made with option "umma.debug_keys" = 1, copies
+ * the approximate keys of log rows 0..127 against the first bn queries of that call ([128][bn] floats, bn = 64,
+ * 128 or 256 by batch size) to keys_out -- tests use it to check the key error bound. */
+int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count);
 
 #ifdef __cplusplus
 }

@@ -218,6 +218,10 @@ void svdb_engine::destroy() {
     cur.release();
     child.release();
     xnorm.release();
+    shadow.release();
+    shadow_ready = false;
+    shadow_n = 0;
+    for (Scratch *s : {&qsplit, &ubuf, &udbg}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
                        &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
@@ -413,6 +417,12 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     }
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
     const int cap = (int)std::min<size_t>(32, k + 8);
+    // K10: larger batches go to the tcgen05 tensor cores (split-bf16 keys, same exact re-rank)
+    if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_min_q > 0 && nq >= (size_t)umma_min_q &&
+        K >= umma_min_k && n_versions < (1ull << 31)) {
+        const int r = nearest_umma(d_Q, nq, ldq, k, d_out);
+        if (r != -1000) return r;
+    }
     // K2: a batch large enough to be compute-bound goes to the FP64 tensor cores
     if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
         const int G = mma_group_size(nq);
@@ -556,6 +566,113 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         stats.kernels_launched++;
         done += nqp;
     }
+    return SVDB_OK;
+}
+
+// K10 (umma_filter.cu).  Returns -1000 when the path cannot serve this engine (no HBM for the shadow, no tensor-map
+// entry point): the caller falls through to K2.
+int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out) {
+    std::string err;
+    const int Kp = umma_kpad(K);
+    const size_t row_bytes = (size_t)2 * Kp * 2;
+    if (!shadow_ready) {
+        if (!shadow.init(device, max_versions * row_bytes, err)) {
+            umma_ok = false;
+            return -1000;
+        }
+        shadow_ready = true;
+    }
+    if (shadow_n < n_versions) {
+        if (!shadow.ensure(n_versions * row_bytes, stream, err)) {
+            umma_ok = false;                 // not enough HBM next to the store: K2 serves, nothing is lost
+            cudaGetLastError();
+            return -1000;
+        }
+        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow.as<uint16_t>(), tune.num_sms, stream));
+        stats.kernels_launched++;
+        shadow_n = n_versions;
+    }
+    const int bn = umma_group_size(nq);
+    const int cap = (int)std::min<size_t>(32, k + 14);
+    const int ldp = kstride;
+    size_t done = 0;
+    while (done < nq) {
+        const size_t nqp = std::min<size_t>(nq - done, (size_t)bn * tune.num_sms);
+        const int ngroups = (int)((nqp + bn - 1) / bn);
+        const int nstreams = std::max(1, tune.num_sms / ngroups);
+        const size_t nq_pad = (size_t)ngroups * bn;
+        if (!qpad.ensure(nq_pad * (size_t)ldp * 8, err) || !qnorm.ensure(nq_pad * 8, err) || !qsplit.ensure(nq_pad * row_bytes, err) ||
+            !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err) || !ubuf.ensure(umma_buf_bytes(ngroups, nstreams, bn), err))
+            return fail(SVDB_ERR_OOM, err);
+        if (umma_debug && !udbg.ensure((size_t)128 * 256 * 4, err)) return fail(SVDB_ERR_OOM, err);
+        CK(launch_prep_queries(d_Q + done * ldq, (int)ldq, K, (int)nqp, (int)nq_pad, qpad.as<double>(), ldp, qnorm.as<double>(), stream));
+        CK(launch_split_bf16(qpad.as<double>(), ldp, K, Kp, 0, nq_pad, qsplit.as<uint16_t>(), tune.num_sms, stream));
+        UmmaArgs ua{};
+        ua.xsplit = shadow.as<uint16_t>();
+        ua.n = n_versions;
+        ua.K = K;
+        ua.Kp = Kp;
+        ua.xnorm = xnorm.as<double>();
+        ua.qsplit = qsplit.as<uint16_t>();
+        ua.qnorm = qnorm.as<double>();
+        ua.nq = (int)nqp;
+        ua.bn = bn;
+        ua.ngroups = ngroups;
+        ua.nstreams = nstreams;
+        ua.cap = cap;
+        ua.lists = lists.as<Cand>();
+        ua.bufs = ubuf.p;
+        ua.dbg_keys = (umma_debug && done == 0) ? udbg.as<float>() : nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (profile_scan) {
+            if (scan_events_used == scan_events.size()) {
+                cudaEvent_t a, b;
+                CK(cudaEventCreate(&a));
+                CK(cudaEventCreate(&b));
+                scan_events.emplace_back(a, b);
+            }
+            ev0 = scan_events[scan_events_used].first;
+            ev1 = scan_events[scan_events_used].second;
+            scan_events_used++;
+            CK(cudaEventRecord(ev0, stream));
+        }
+        cudaError_t ce = launch_umma_filter(ua, stream, &err);
+        if (ce == cudaErrorNotSupported && done == 0) {     // no cuTensorMapEncodeTiled in this driver
+            umma_ok = false;
+            if (profile_scan) scan_events_used--;
+            return -1000;
+        }
+        CK(ce);
+        if (ev1) CK(cudaEventRecord(ev1, stream));
+        FinalArgs fa{};
+        fa.lists = lists.as<Cand>();
+        fa.nlists = nstreams;
+        fa.cap = cap;
+        fa.nq = (int)nqp;
+        fa.k = (int)k;
+        fa.pts = kd_ptr();
+        fa.K = K;
+        fa.stride = kstride;
+        fa.q = qpad.as<double>();
+        fa.ldq = ldp;
+        fa.log_index = log_idx.as<u64>();
+        fa.seq_base = cfg.seq_base;
+        fa.eps = 0.0;
+        fa.eabs_coef = umma_eabs_coef(K);
+        fa.qnorm = qnorm.as<double>();
+        fa.xn_max_bits = xnmax.as<unsigned long long>();
+        // fp32 keys: products of coordinates below ~1e-19 underflow, squares above ~1e38 overflow; outside this range
+        // of max|x|^2 + |q|^2 the error bound does not hold and the query is answered by the exact scan
+        fa.scale_lo = 1e-24;
+        fa.scale_hi = 1e30;
+        fa.child = use_tree ? child.as<uint32_t>() : nullptr;
+        fa.mark_ties = (cfg.flags & SVDB_FLAG_SHARD) ? 1 : 0;
+        fa.out = d_out + done * k;
+        CK(launch_finalize(fa, stream));
+        stats.kernels_launched += 4;
+        done += nqp;
+    }
+    umma_debug = false;
     return SVDB_OK;
 }
 
@@ -1398,6 +1515,9 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "mtree.tail_min") e->mtree_tail_min = (size_t)std::max(0l, value);
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
+    else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
+    else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
+    else if (n == "umma.debug_keys") e->umma_debug = value != 0;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;
@@ -1471,6 +1591,19 @@ int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches) {
     *total_ms = sum;
     *launches = e->scan_events_used;
     e->scan_events_used = 0;
+    return SVDB_OK;
+}
+
+/* Diagnostics of K10: after a batch call made with option "umma.debug_keys" = 1, the approximate keys of log rows
+ * 0..127 against the first `bn` queries of that call, [128][bn] floats (bn = 64, 128 or 256 by batch size). */
+int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count) {
+    if (!e || !keys_out) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->udbg.p || count > (size_t)128 * 256) return e->fail(SVDB_ERR_ARG, "no K10 debug capture (set umma.debug_keys before the call)");
+    cudaSetDevice(e->device);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(keys_out, e->udbg.p, count * 4, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) return e->fail_cuda("debug_filter_keys", ce);
     return SVDB_OK;
 }
 

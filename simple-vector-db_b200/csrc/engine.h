@@ -70,6 +70,16 @@ struct svdb_engine {
     int D = 0, K = 0, Dpad = 0, kstride = 0;
     bool log_only = false, no_log = false, alias = false, wide = false, use_tree = false;
     int mma_min_q = 4;                   // AUTO: batches of at least this many queries take the DMMA path (K2)
+    // K10: batches of at least umma_min_q queries over kd-points of at least umma_min_k coordinates take the tcgen05 path
+    // (split-bf16 keys + the same exact re-rank); 0 switches it off.  Needs a bf16 shadow of the log (4 bytes per
+    // coordinate, built on first use and extended incrementally); if that does not fit, K2 keeps serving.
+    int umma_min_q = 0, umma_min_k = 32;
+    bool umma_ok = true, shadow_ready = false;
+    size_t shadow_n = 0;                 // log entries present in the shadow
+    svdb::DeviceBuffer shadow;           // [versions][2*Kp] bf16
+    svdb::Scratch qsplit, ubuf, udbg;
+    bool umma_debug = false;             // next K10 launch dumps the keys of its first tile into udbg
+    int nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out);   // SVDB_OK, an error, or -1000: not available
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)
     // K8/K9: balanced median tree over thin kd-points (median_tree.cu); serves k = 1, flags distinct-point ties for K6

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/svdb_b200.h"
 
 namespace svdb {
@@ -58,6 +60,7 @@ struct FinalArgs {
     double eabs_coef;       // GEMM-form keys (K2): absolute error bound = eabs_coef * (xn_max + |q|^2); 0 otherwise
     const double *qnorm;    // |q|^2 per query of this launch (K2), else NULL
     const unsigned long long *xn_max_bits;   // largest |x|^2 in the log, as double bits (K2), else NULL
+    double scale_lo, scale_hi;   // K10 (fp32 keys): queries whose max|x|^2 + |q|^2 lies outside [lo, hi] are flagged UNSAFE; 0, 0: no check
     const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
     int mark_ties;          // shards (child == NULL): flag SVDB_CAND_TIE when distinct kd-points may tie at the minimum
     svdb_candidate *out;    // [nq][k]
@@ -87,6 +90,29 @@ cudaError_t launch_rownorm(const double *pts, int stride, int K, u64 first, u64 
                            int num_sms, cudaStream_t st);
 cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int nq_pad, double *dst, int ldp, double *qnorm,
                                 cudaStream_t st);
+
+// K10: batched queries on the 5th-generation tensor cores (tcgen05 + TMEM) with split-bf16 keys (umma_filter.cu)
+struct UmmaArgs {
+    const uint16_t *xsplit; // [n][2*Kp] bf16: hi plane | lo plane of every log row (launch_split_bf16)
+    u64 n;                  // log entries, < 2^31
+    int K, Kp;              // Kp = umma_kpad(K)
+    const double *xnorm;    // |x_r|^2 per log entry (fp64, as for K2)
+    const uint16_t *qsplit; // [ngroups*bn][2*Kp] bf16 planes of the padded queries
+    const double *qnorm;    // |q|^2 per padded query
+    int nq;                 // real queries
+    int bn;                 // queries per CTA group: 64, 128 or 256 (umma_group_size)
+    int ngroups, nstreams;  // grid = ngroups * nstreams CTAs
+    int cap;
+    Cand *lists;            // [ngroups*bn][nstreams][cap]
+    void *bufs;             // umma_buf_bytes(ngroups, nstreams, bn) of scratch
+    float *dbg_keys;        // NULL, or [128][bn]: the keys of rows 0..127 against the first query group (diagnostics)
+};
+int umma_kpad(int K);
+int umma_group_size(size_t nq);
+size_t umma_buf_bytes(int ngroups, int nstreams, int bn);
+double umma_eabs_coef(int K);   // absolute key error <= coef * (max|x|^2 + |q|^2)
+cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst, int num_sms, cudaStream_t st);
+cudaError_t launch_umma_filter(const UmmaArgs &a, cudaStream_t st, std::string *why);
 
 // K5: insert log entries [n0, n0+m) into the reference-shaped tree (level-synchronous; see tree_kernels.cu).
 // pn/pds: m-entry u32 scratch; d_flag: device word; h_flag_pinned: pinned host word. Synchronizes the stream.

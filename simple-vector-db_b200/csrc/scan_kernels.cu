@@ -596,6 +596,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
         // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
         unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
     }
+    if (p.scale_hi > 0.0) {
+        // fp32 keys (K10): their error bound only holds while neither squares overflow nor products underflow
+        const double scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
+        if (!(scale >= p.scale_lo && scale <= p.scale_hi)) unsafe = true;
+    }
 
     // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----
     bool tie_flag = false;

@@ -1,0 +1,398 @@
+// umma_filter.cu -- K10: batched-query distance keys on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as K2 (mma_kernels.cu): per-CTA lists of the best APPROXIMATE keys for every query of a batch,
+// finished by finalize_kernel's reference-order re-rank (kdtree.c:134-137) and completeness proof.  K2 forms the
+// keys on the FP64 tensor cores (DMMA, 37 TFLOP/s); tcgen05 has no FP64 kind, but the keys only have to be good
+// enough to keep every row that could be in the top-k, so K10 forms them from a SPLIT-BF16 copy of the log:
+//
+//   x = xh + xl + r,  xh = bf16(x), xl = bf16(fl32(x) - xh), |r| <= (2^-16 + 2^-24) |x|        (same for q)
+//   <x, q> ~ <xh, qh> + <xh, ql> + <xl, qh>            three kind::f16 UMMAs per 16 coordinates, fp32 accumulators in TMEM
+//   d~(r, q) = |x_r|^2 + |q|^2 - 2 <x_r, q>            |x|^2, |q|^2 from the fp64 rows (precomputed, rounded to fp32 once)
+//
+// Error: the dropped terms are bounded by 3.1 * 2^-16 sum|x_i q_i|, the fp32 accumulation of 3K exact bf16 products in
+// K/16 chained instructions by (3K/16) 2^-21 sum|x_i q_i| (a deliberately loose model of the tensor core's aligned
+// adder; umma_eabs_coef doubles it again), the three fp32 roundings of the key by 2^-21 (|x|^2 + |q|^2).  With
+// sum|x_i q_i| <= |x||q| <= (|x|^2 + |q|^2)/2 the key error is ABSOLUTE, E = coef (max|x|^2 + |q|^2) like K2's, and
+// finalize_kernel widens its re-rank window and its proof by it.  Non-finite keys (overflow of bf16/fp32 on huge
+// values) are kept as candidates, never dropped, so extreme data ends in the exact fallback instead of a wrong answer.
+//
+// Kernel: one persistent CTA per SM; CTA c serves query group c % ngroups (bn = 64/128/256 queries) over row tiles
+// stream, stream + nstreams, ... (CTAs of one stream run together, so a row tile comes from HBM once and from L2 after).
+//   warp 0   : TMA producer  -- four 2-D tiled loads per stage (row hi/lo planes 128 x 64, query hi/lo planes bn x 64,
+//              SWIZZLE_128B) completing on the stage's mbarrier
+//   warp 1   : MMA issuer    -- one lane issues 12 tcgen05.mma (M=128, N=bn, K=16) per stage into one of two TMEM
+//              accumulator stages; tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 4-7: epilogue      -- tcgen05.ld 32 lanes x 32 columns, key = |x|^2 + |q|^2 - 2 acc, compare with the query's
+//              threshold in shared memory; the rare survivor is appended to the (CTA, query) buffer in global memory;
+//              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (WarpList) and
+//              tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace svdb {
+
+constexpr int UF_M = 128;                       // rows per tile = TMEM lanes
+constexpr int UF_NMAX = 256;                    // queries per CTA group, at most
+constexpr int UF_KC = 64;                       // bf16 coordinates per stage row = one 128-byte swizzle row
+constexpr int UF_STAGES = 2;
+constexpr int UF_A_BYTES = UF_M * 128;          // one plane of a row tile
+constexpr int UF_B_BYTES = UF_NMAX * 128;       // one plane of a query tile
+constexpr int UF_STAGE_BYTES = 2 * UF_A_BYTES + 2 * UF_B_BYTES;     // 96 KB
+constexpr int UF_BUF = 256;                     // append-buffer entries per (CTA, query)
+constexpr int UF_THREADS = 256;
+constexpr int UF_TAIL = 64 + 64 + 3 * UF_NMAX * 4;                   // barriers, tmem pointer, cnt / tau / qn
+constexpr int UF_SMEM = UF_STAGES * UF_STAGE_BYTES + UF_TAIL + 1024; // + slack to align the stages to 1024 bytes
+
+int umma_kpad(int K) { return (K + UF_KC - 1) / UF_KC * UF_KC; }
+int umma_group_size(size_t nq) { return nq <= 64 ? 64 : (nq <= 128 ? 128 : 256); }
+size_t umma_buf_bytes(int ngroups, int nstreams, int bn) { return (size_t)ngroups * nstreams * bn * UF_BUF * 8; }
+double umma_eabs_coef(int K) { return 3.2 * ldexp(1.0, -16) + (3.0 * K / 16.0 + 8.0) * ldexp(1.0, -20); }
+
+// ---- PTX wrappers (tcgen05 / TMA); the mbarrier ones live in common.cuh ----
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives lane (base lane + t), register i = column i
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile stored as rows of 128 bytes (64 bf16), SWIZZLE_128B:
+// 8-row groups 1024 bytes apart (SBO), version 1 (sm_100), layout type 2.  Stepping 16 coordinates along K inside
+// the 128-byte row advances the start address by 32 bytes (the swizzle is applied to the address bits by the hardware).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// Instruction descriptor: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9 / 10-12 = 1), both K-major (bits 15, 16 = 0),
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UF_M >> 4) << 24);
+}
+
+struct UfEntry {
+    float key;
+    uint32_t row;
+};
+
+// The `cap` smallest of the first cnt entries of one (CTA, query) buffer, as a warp-distributed sorted list.
+__device__ __forceinline__ WarpList uf_select(const UfEntry *buf, unsigned cnt, int cap, int lane) {
+    WarpList wl;
+    wl.reset();
+    for (unsigned i = 0; i < cnt; i += 32) {
+        const bool has = i + lane < cnt;
+        UfEntry e{0.f, 0u};
+        if (has) e = buf[i + lane];
+        wl.offer(has, (double)e.key, (u64)e.row, lane, cap);
+    }
+    return wl;
+}
+
+__global__ void __launch_bounds__(UF_THREADS, 1)
+umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q, UmmaArgs p) {
+    extern __shared__ unsigned char uf_smem_raw[];
+    const uint32_t raw = smem_u32(uf_smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B tiles want 1024-byte alignment
+    unsigned char *sgen = uf_smem_raw + (sbase - raw);
+    unsigned char *tail = sgen + UF_STAGES * UF_STAGE_BYTES;
+    const uint32_t tail_u = sbase + UF_STAGES * UF_STAGE_BYTES;
+    // barriers: full[2] (TMA -> MMA), empty[2] (MMA -> TMA), tfull[2] (MMA -> epilogue), tempty[2] (epilogue -> MMA)
+    const uint32_t bar_full = tail_u, bar_empty = tail_u + 16, bar_tfull = tail_u + 32, bar_tempty = tail_u + 48;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 64);
+    unsigned *cnt_s = reinterpret_cast<unsigned *>(tail + 128);
+    float *tau_s = reinterpret_cast<float *>(tail + 128 + UF_NMAX * 4);
+    float *qn_s = reinterpret_cast<float *>(tail + 128 + 2 * UF_NMAX * 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bn = p.bn;
+    const int group = blockIdx.x % p.ngroups, stream = blockIdx.x / p.ngroups;
+    const int q0 = group * bn;
+    const int nchunks = p.Kp / UF_KC;
+    const u64 ntiles = (p.n + UF_M - 1) / UF_M;
+
+    if (tid == 0) {
+        for (int s = 0; s < UF_STAGES; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);            // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {                                     // the whole warp allocates all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = tid; j < UF_NMAX; j += UF_THREADS) {
+        cnt_s[j] = 0;
+        tau_s[j] = CUDART_INF_F;
+        qn_s[j] = j < bn ? (float)p.qnorm[q0 + j] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t stage_tx = 2 * UF_A_BYTES + 2 * (uint32_t)bn * 128u;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
+                const int row0 = (int)(tile * UF_M);
+                for (int kc = 0; kc < nchunks; kc++) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t st = sbase + stage * UF_STAGE_BYTES;
+                    mbar_arrive_expect_tx(full, stage_tx);
+                    tma_load_2d(st, &map_x, kc * UF_KC, row0, full);                                   // row tile, hi plane
+                    tma_load_2d(st + UF_A_BYTES, &map_x, p.Kp + kc * UF_KC, row0, full);               //           lo plane
+                    tma_load_2d(st + 2 * UF_A_BYTES, &map_q, kc * UF_KC, q0, full);                    // queries, hi plane
+                    tma_load_2d(st + 2 * UF_A_BYTES + UF_B_BYTES, &map_q, p.Kp + kc * UF_KC, q0, full);  //        lo plane
+                    if (++stage == UF_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(bn);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);      // the epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)as * UF_NMAX;
+                for (int kc = 0; kc < nchunks; kc++) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t st = sbase + stage * UF_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < UF_KC / 16; j++) {
+                        const uint64_t xh = umma_desc(st + j * 32), xl = umma_desc(st + UF_A_BYTES + j * 32);
+                        const uint64_t qh = umma_desc(st + 2 * UF_A_BYTES + j * 32);
+                        const uint64_t ql = umma_desc(st + 2 * UF_A_BYTES + UF_B_BYTES + j * 32);
+                        tc_mma(acc, xh, ql, idesc, (kc | j) != 0);      // the small products first
+                        tc_mma(acc, xl, qh, idesc, 1);
+                        tc_mma(acc, xh, qh, idesc, 1);
+                    }
+                    tc_commit(bar_empty + 8 * stage);            // smem stage free once these MMAs have read it
+                    if (++stage == UF_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(bar_tfull + 8 * as);                   // accumulator complete
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: keys, thresholds, candidate buffers =====================
+        const int ew = warp - 4;                                  // = warp % 4: the TMEM lane quarter this warp may read
+        UfEntry *bufs = reinterpret_cast<UfEntry *>(p.bufs) + (size_t)blockIdx.x * bn * UF_BUF;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const u64 row = tile * UF_M + ew * 32 + lane;
+            const bool ok = row < p.n;
+            const float xn = ok ? (float)__ldg(p.xnorm + row) : 0.f;
+            const bool dbg = p.dbg_keys != nullptr && blockIdx.x == 0 && tile == (u64)stream;
+            for (int c = 0; c < bn / 32; c++) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * UF_NMAX + c * 32), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const int j = c * 32 + i;
+                    float key = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[j]);
+                    if (dbg) p.dbg_keys[(size_t)(ew * 32 + lane) * bn + j] = key;
+                    if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;           // NaN / inf: keep it, never drop it
+                    if (ok && !(key >= tau_s[j])) {
+                        const unsigned pos = atomicAdd(&cnt_s[j], 1u);
+                        if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);      // this warp is done with the accumulator stage
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+            // ---- prune the buffers that could overflow during the next tile (warp ew owns queries ew, ew+4, ...) ----
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int t0 = 0; t0 < bn / 4; t0 += 32) {
+                const int t = t0 + lane;
+                unsigned m = __ballot_sync(FULL, t < bn / 4 && cnt_s[ew + 4 * t] > (unsigned)(UF_BUF - UF_M));
+                while (m) {
+                    const int j = ew + 4 * (t0 + __ffs(m) - 1);
+                    m &= m - 1;
+                    const unsigned cnt = cnt_s[j];
+                    UfEntry *b = bufs + (size_t)j * UF_BUF;
+                    WarpList wl = uf_select(b, cnt, p.cap, lane);
+                    if (lane < p.cap && wl.seq != SEQ_NONE) b[lane] = UfEntry{(float)wl.d, (uint32_t)wl.seq};
+                    double dk;
+                    u64 sk;
+                    wl.key_at(p.cap - 1, dk, sk);
+                    __syncwarp();
+                    if (lane == 0) {
+                        cnt_s[j] = min(cnt, (unsigned)p.cap);
+                        if (sk != SEQ_NONE) tau_s[j] = (float)dk;           // from now on only keys below the cap-th smallest
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
+        for (int j = ew; j < bn; j += 4) {
+            WarpList wl = uf_select(bufs + (size_t)j * UF_BUF, cnt_s[j], p.cap, lane);
+            if (lane < p.cap) p.lists[((size_t)(q0 + j) * p.nstreams + stream) * p.cap + lane] = Cand{wl.d, wl.seq};
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- fp64 rows -> [hi plane | lo plane] bf16 rows of 2*Kp entries (zeros beyond K) ----
+__global__ void __launch_bounds__(256) split_bf16_kernel(const double *__restrict__ src, int ld, int K, int Kp, u64 first, u64 n,
+                                                         __nv_bfloat16 *__restrict__ dst) {
+    constexpr int ROWS = 32;                                       // rows per block step
+    const int hp = Kp / 2;
+    for (u64 r0 = (u64)blockIdx.x * ROWS; r0 < n; r0 += (u64)gridDim.x * ROWS) {
+        const int rows = (int)min((u64)ROWS, n - r0);
+        for (int li = threadIdx.x; li < rows * hp; li += blockDim.x) {
+            const int rr = li / hp, c = (li - rr * hp) * 2;
+            const u64 r = first + r0 + rr;
+            const double *row = src + r * (u64)ld;
+            const double v0 = c < K ? row[c] : 0.0, v1 = c + 1 < K ? row[c + 1] : 0.0;
+            const float f0 = __double2float_rn(v0), f1 = __double2float_rn(v1);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+            __nv_bfloat16 *out = dst + r * (u64)(2 * Kp) + c;
+            *reinterpret_cast<__nv_bfloat162 *>(out) = __nv_bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162 *>(out + Kp) = __nv_bfloat162(l0, l1);
+        }
+    }
+}
+
+cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst, int num_sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    u64 grid = (n + 31) / 32;
+    if (grid > (u64)num_sms * 16) grid = (u64)num_sms * 16;
+    split_bf16_kernel<<<(unsigned)grid, 256, 0, st>>>(src, ld, K, Kp, first, n, reinterpret_cast<__nv_bfloat16 *>(dst));
+    return cudaGetLastError();
+}
+
+// ---- host: tensor maps (driver entry point resolved at run time, like arena.cu) and the launch ----
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled(std::string &why) {
+    static EncodeTiledFn fn = nullptr;
+    static std::string err;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr)
+            err = std::string("cannot resolve driver entry point cuTensorMapEncodeTiled: ") + cudaGetErrorString(e);
+        else
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    if (!fn) why = err;
+    return fn;
+}
+// [rows][2*Kp] bf16, box = 64 coordinates x box_rows rows, 128-byte swizzle, zeros out of bounds
+bool make_map(CUtensorMap *m, const void *base, u64 rows, int Kp, int box_rows, std::string &why) {
+    EncodeTiledFn fn = encode_tiled(why);
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * Kp), (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)(2 * Kp) * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)UF_KC, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        why = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+        return false;
+    }
+    return true;
+}
+}  // namespace
+
+cudaError_t launch_umma_filter(const UmmaArgs &a, cudaStream_t st, std::string *why) {
+    std::string err;
+    if ((a.bn != 64 && a.bn != 128 && a.bn != 256) || a.ngroups < 1 || a.nstreams < 1 || a.Kp % UF_KC || a.Kp < a.K || a.cap < 1 ||
+        a.cap > 32 || a.n == 0 || a.n >= (1ull << 31)) {
+        if (why) *why = "umma filter: bad launch shape";
+        return cudaErrorInvalidValue;
+    }
+    CUtensorMap mx, mq;
+    if (!make_map(&mx, a.xsplit, a.n, a.Kp, UF_M, err) || !make_map(&mq, a.qsplit, (u64)a.ngroups * a.bn, a.Kp, a.bn, err)) {
+        if (why) *why = err;
+        return cudaErrorNotSupported;
+    }
+    cudaError_t e = cudaFuncSetAttribute(umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
+    if (e != cudaSuccess) return e;
+    umma_filter_kernel<<<a.ngroups * a.nstreams, UF_THREADS, UF_SMEM, st>>>(mx, mq, a);
+    return cudaGetLastError();
+}
+
+}  // namespace svdb

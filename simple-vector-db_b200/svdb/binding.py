@@ -71,7 +71,7 @@ NATIVE_SYMBOLS = [
     "svdb_insert_batch_device", "svdb_append_kdpoints_device", "svdb_flush", "svdb_size", "svdb_log_size", "svdb_dimension", "svdb_kd_dim",
     "svdb_read_row", "svdb_nearest_batch", "svdb_nearest_batch_device", "svdb_merge_candidates_device",
     "svdb_compare_batch", "svdb_compare_batch_all", "svdb_compare_batch_device", "svdb_compare_vectors",
-    "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time",
+    "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time", "svdb_debug_filter_keys",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
     "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
     "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded",
@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
     L.svdb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
     L.svdb_time_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _fp]
     L.svdb_take_scan_time.argtypes = [C.c_void_p, _fp, _u64p]
+    L.svdb_debug_filter_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.svdb_engine_load_file.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
     L.svdb_save_file.argtypes = [C.c_void_p, C.c_char_p]
     L.svdb_exchange_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
@@ -332,6 +333,11 @@ class Engine:
         ms = C.c_float()
         _check(self.L.svdb_time_scan(self.h, C.c_void_p(q_ptr), nq, ldq, k, iters, C.byref(ms)), "svdb_time_scan")
         return ms.value
+
+    def debug_filter_keys(self, bn: int) -> np.ndarray:
+        out = np.empty((128, bn), dtype=np.float32)
+        _check(self.L.svdb_debug_filter_keys(self.h, C.c_void_p(out.ctypes.data), out.size), "svdb_debug_filter_keys")
+        return out
 
     def take_scan_time(self):
         ms = C.c_float()

@@ -336,6 +336,7 @@ def test_batched_dmma_path_vs_oracle(port, n, D, K, nq, k, seed):
     with B.Engine(D, K) as e:
         e.insert(rows)
         e.flush()
+        e.set_option("nearest.umma_min_queries", 0)             # K10 (tests/test_gpu_umma.py) would take the 100-query case
         l0 = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q, k), want, k)
         assert e.stats()["exact_reruns"] == 0

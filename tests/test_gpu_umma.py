@@ -1,0 +1,119 @@
+"""GPU parity of K10 (csrc/umma_filter.cu): batched /nearest on the tcgen05 tensor cores with split-bf16 keys.
+The keys are approximate by design; the answers, after finalize's reference-order re-rank (kdtree.c:134-137),
+must be bit-identical to the oracle's -- and the measured key error must stay inside the bound the proof uses."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from svdb import binding as B  # noqa: E402
+from svdb import synth  # noqa: E402
+from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
+
+
+def umma_on(e):
+    e.set_option("nearest.umma_min_queries", 1)
+    e.set_option("nearest.umma_min_kd_dim", 1)
+
+
+@pytest.mark.parametrize("n,D,K,nq,k,seed", [
+    (20000, 128, 128, 100, 10, 1),     # one group of 128 queries, 28 of them padding
+    (9000, 768, 768, 64, 10, 2),       # config-3 rows, group of 64
+    (6000, 100, 100, 300, 5, 3),       # K not a multiple of the 64-coordinate stage (zero-filled tail); two groups of 256
+    (5000, 200, 50, 33, 24, 4),        # compact kd array (K < D), k = SVDB_MAX_K
+    (100, 40, 40, 16, 3, 5),           # fewer rows than one 128-row tile
+    (40000, 96, 96, 1024, 10, 6),      # config-3 batch shape: four groups of 256
+    (129, 64, 64, 5, 1, 7),            # one full tile + one row
+])
+def test_umma_path_vs_oracle(port, n, D, K, nq, k, seed):
+    rows = synth.uniform_rows(seed, n, D)
+    Q = synth.uniform_rows(seed + 70, nq, D)
+    want = oracle_topk(port, rows, K, Q, k)
+    with B.Engine(D, K) as e:
+        e.insert(rows)
+        e.flush()
+        umma_on(e)
+        l0 = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q, k), want, k)
+        assert e.stats()["exact_reruns"] == 0
+        assert e.stats()["kernels_launched"] - l0 == 5          # shadow split + (prep, query split, filter, finalize)
+        l0 = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q, k), want, k)             # shadow is kept
+        assert e.stats()["kernels_launched"] - l0 == 4
+
+
+def test_umma_key_error_is_inside_the_bound():
+    n, K, nq = 4096, 768, 256
+    rows = synth.uniform_rows(21, n, K)
+    Q = synth.uniform_rows(22, nq, K)
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        umma_on(e)
+        e.set_option("umma.debug_keys", 1)
+        e.nearest(Q, 1)
+        keys = e.debug_filter_keys(256).astype(np.float64)
+    d = ((rows[:128, None, :] - Q[None, :, :]) ** 2).sum(-1)
+    scale = (rows ** 2).sum(1).max() + (Q ** 2).sum(1)[None, :]
+    coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0 + 8.0) * 2.0 ** -20
+    rel = np.abs(keys - d) / scale
+    assert rel.max() < coef / 4, (rel.max(), coef)              # the proof's bound with a margin of at least 4
+
+
+def test_umma_shadow_follows_inserts_and_updates(port):
+    D = 64
+    rows = synth.uniform_rows(31, 3000, D)
+    more = synth.uniform_rows(32, 500, D)
+    Q = synth.uniform_rows(33, 80, D)
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        umma_on(e)
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
+        e.insert(more)
+        allrows = np.vstack([rows, more])
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, allrows, D, Q, 5), 5)
+        # a query that IS a freshly inserted row must find it at distance 0
+        idx, dist, _ = e.nearest(np.vstack([more[:70], rows[:10]]), 1)
+        assert np.array_equal(idx[:70, 0], 3000 + np.arange(70)) and np.all(dist[:, 0] == 0.0)
+
+
+def test_umma_cancellation_and_huge_values_fall_back(port):
+    """Rows far from the origin (the GEMM form cancels) and rows beyond fp32 range: the proof fails or the scale check
+    trips, the exact scan answers, results still identical to the oracle."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    rows = 1.0e6 + rng.random((4000, 64))
+    Q = 1.0e6 + rng.random((70, 64))
+    with B.Engine(64, 64) as e:
+        e.insert(rows)
+        umma_on(e)
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, 64, Q, 5), 5)
+        assert e.stats()["exact_reruns"] > 0
+    rows = rng.random((2000, 64)) * 1.0e25
+    Q = rng.random((70, 64)) * 1.0e25
+    with B.Engine(64, 64) as e:
+        e.insert(rows)
+        umma_on(e)
+        assert_topk_equal(e.nearest(Q, 3), oracle_topk(port, rows, 64, Q, 3), 3)
+        assert e.stats()["exact_reruns"] > 0
+    rows = rng.random((2000, 64)) * 1.0e-20
+    Q = rng.random((70, 64)) * 1.0e-20
+    with B.Engine(64, 64) as e:
+        e.insert(rows)
+        umma_on(e)
+        assert_topk_equal(e.nearest(Q, 3), oracle_topk(port, rows, 64, Q, 3), 3)
+
+
+def test_umma_mass_duplicates(port):
+    """More identical rows than a candidate list holds: completeness cannot be proven from approximate keys; the
+    escalation chain must still return the lowest sequence numbers."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    base = rng.random((1, 48))
+    rows = np.vstack([np.repeat(base, 200, axis=0), rng.random((3000, 48))])
+    Q = np.vstack([base + 1e-9, rng.random((69, 48))])
+    with B.Engine(48, 48) as e:
+        e.insert(rows)
+        umma_on(e)
+        assert_topk_equal(e.nearest(Q, 10), oracle_topk(port, rows, 48, Q, 10), 10)
