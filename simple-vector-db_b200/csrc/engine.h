@@ -73,7 +73,7 @@ struct svdb_engine {
     // K10: batches of at least umma_min_q queries over kd-points of at least umma_min_k coordinates take the tcgen05 path
     // (split-bf16 keys + the same exact re-rank); 0 switches it off.  Needs a bf16 shadow of the log (4 bytes per
     // coordinate, built on first use and extended incrementally); if that does not fit, K2 keeps serving.
-    int umma_min_q = 0, umma_min_k = 32;
+    int umma_min_q = 65, umma_min_k = 32;
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the shadow
     svdb::DeviceBuffer shadow;           // [versions][2*Kp] bf16
