@@ -24,8 +24,8 @@
 //              accumulator stages; tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 4-7: epilogue      -- tcgen05.ld 32 lanes x 32 columns, key = |x|^2 + |q|^2 - 2 acc, compare with the query's
 //              threshold in shared memory; the rare survivor is appended to the (CTA, query) buffer in global memory;
-//              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (WarpList) and
-//              tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
+//              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (bitwise selection of
+//              the cap-th smallest key, uf_prune) and tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <float.h>
@@ -111,17 +111,76 @@ struct UfEntry {
     uint32_t row;
 };
 
-// The `cap` smallest of the first cnt entries of one (CTA, query) buffer, as a warp-distributed sorted list.
-__device__ __forceinline__ WarpList uf_select(const UfEntry *buf, unsigned cnt, int cap, int lane) {
-    WarpList wl;
-    wl.reset();
-    for (unsigned i = 0; i < cnt; i += 32) {
-        const bool has = i + lane < cnt;
-        UfEntry e{0.f, 0u};
-        if (has) e = buf[i + lane];
-        wl.offer(has, (double)e.key, (u64)e.row, lane, cap);
+// float <-> u32 whose unsigned order is the numeric order (keys are finite: non-finite ones were clamped to -FLT_MAX)
+__device__ __forceinline__ uint32_t uf_ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float uf_unord(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// Keep the `keep` smallest of the cnt (<= UF_BUF) entries of one (CTA, query) buffer, compacted to its front in no
+// particular order; returns how many are left.  When something was dropped, tau = the largest key kept (every dropped
+// key is >= tau).  One warp, entries in registers (8 per lane); the keep-th smallest key is found by a 32-step
+// bitwise search with a warp-wide count per step -- a fixed ~2k cycles, where sorted insertion paid ~200 cycles of
+// dependent shuffles for every key that entered the list.
+__device__ __forceinline__ unsigned uf_prune(UfEntry *b, unsigned cnt, int keep, int lane, float &tau, bool &dropped) {
+    constexpr int PER = UF_BUF / 32;
+    dropped = false;
+    if (cnt <= (unsigned)keep) return cnt;
+    uint32_t u[PER], r[PER];
+#pragma unroll
+    for (int s = 0; s < PER; s++) {
+        const unsigned i = s * 32 + lane;
+        u[s] = 0xffffffffu;                                  // never a valid key (that would be a NaN pattern)
+        r[s] = 0;
+        if (i < cnt) {
+            const UfEntry e = b[i];
+            u[s] = uf_ord(e.key);
+            r[s] = e.row;
+        }
     }
-    return wl;
+    uint32_t T = 0;                                          // becomes the keep-th smallest key
+    for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t t = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < PER; s++) c += u[s] < t;
+        if (__reduce_add_sync(FULL, c) < keep) T = t;
+    }
+    int nlt = 0;
+#pragma unroll
+    for (int s = 0; s < PER; s++) nlt += u[s] < T;
+    unsigned eq_left = (unsigned)(keep - __reduce_add_sync(FULL, nlt));   // keys equal to T that still fit
+    __syncwarp();                                            // every lane holds its entries: the buffer may be overwritten
+    const unsigned below = (1u << lane) - 1u;
+    unsigned base = 0;
+#pragma unroll
+    for (int s = 0; s < PER; s++) {
+        const bool eq = u[s] == T;
+        const unsigned me = __ballot_sync(FULL, eq);
+        const bool k = u[s] < T || (eq && (unsigned)__popc(me & below) < eq_left);
+        const unsigned mk = __ballot_sync(FULL, k);
+        if (k) b[base + __popc(mk & below)] = UfEntry{uf_unord(u[s]), r[s]};
+        base += __popc(mk);
+        eq_left -= min(eq_left, (unsigned)__popc(me));
+    }
+    tau = uf_unord(T);
+    dropped = true;
+    return base;
+}
+
+// Ascending bitonic sort of one 64-bit key per lane.
+__device__ __forceinline__ u64 uf_sort32(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 o = __shfl_xor_sync(FULL, v, j);
+            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+            v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+        }
+    }
+    return v;
 }
 
 __global__ void __launch_bounds__(UF_THREADS, 1)
@@ -275,16 +334,13 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int j = ew + 4 * (t0 + __ffs(m) - 1);
                     m &= m - 1;
                     const unsigned cnt = cnt_s[j];
-                    UfEntry *b = bufs + (size_t)j * UF_BUF;
-                    WarpList wl = uf_select(b, cnt, p.cap, lane);
-                    if (lane < p.cap && wl.seq != SEQ_NONE) b[lane] = UfEntry{(float)wl.d, (uint32_t)wl.seq};
-                    double dk;
-                    u64 sk;
-                    wl.key_at(p.cap - 1, dk, sk);
+                    float tau;
+                    bool dropped;
+                    const unsigned kept = uf_prune(bufs + (size_t)j * UF_BUF, cnt, p.cap, lane, tau, dropped);
                     __syncwarp();
                     if (lane == 0) {
-                        cnt_s[j] = min(cnt, (unsigned)p.cap);
-                        if (sk != SEQ_NONE) tau_s[j] = (float)dk;           // from now on only keys below the cap-th smallest
+                        cnt_s[j] = kept;
+                        if (dropped) tau_s[j] = tau;                        // from now on only keys below the cap-th smallest
                     }
                 }
             }
@@ -292,8 +348,22 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
         for (int j = ew; j < bn; j += 4) {
-            WarpList wl = uf_select(bufs + (size_t)j * UF_BUF, cnt_s[j], p.cap, lane);
-            if (lane < p.cap) p.lists[((size_t)(q0 + j) * p.nstreams + stream) * p.cap + lane] = Cand{wl.d, wl.seq};
+            UfEntry *b = bufs + (size_t)j * UF_BUF;
+            float tau;
+            bool dropped;
+            const unsigned kept = uf_prune(b, cnt_s[j], p.cap, lane, tau, dropped);
+            __syncwarp();
+            u64 v = ~0ull;                                        // (key, row) in one word; empty slots sort last
+            if ((unsigned)lane < kept) {
+                const UfEntry e = b[lane];
+                v = ((u64)uf_ord(e.key) << 32) | e.row;
+            }
+            v = uf_sort32(v, lane);
+            if (lane < p.cap) {
+                Cand c{CUDART_INF, SEQ_NONE};
+                if (v != ~0ull) c = Cand{(double)uf_unord((uint32_t)(v >> 32)), v & 0xffffffffull};
+                p.lists[((size_t)(q0 + j) * p.nstreams + stream) * p.cap + lane] = c;
+            }
         }
     }
 
