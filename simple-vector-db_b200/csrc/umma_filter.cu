@@ -22,8 +22,9 @@
 //              SWIZZLE_128B) completing on the stage's mbarrier
 //   warp 1   : MMA issuer    -- one lane issues 12 tcgen05.mma (M=128, N=bn, K=16) per stage into one of two TMEM
 //              accumulator stages; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 4-7: epilogue      -- tcgen05.ld 32 lanes x 32 columns, key = |x|^2 + |q|^2 - 2 acc, compare with the query's
-//              threshold in shared memory; the rare survivor is appended to the (CTA, query) buffer in global memory;
+//   warps 4-11: epilogue     -- tcgen05.ld 32 lanes x 32 columns, |x|^2 - 2 acc against the query's threshold (tau - |q|^2, in
+//              shared memory), one ballot per key; the rare survivors of a warp are appended to the (CTA, query) buffer
+//              in global memory with ONE shared-memory atomic per warp;
 //              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (bitwise selection of
 //              the cap-th smallest key, uf_prune) and tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
 #include <cuda.h>
@@ -46,7 +47,7 @@ constexpr int UF_A_BYTES = UF_M * 128;          // one plane of a row tile
 constexpr int UF_B_BYTES = UF_NMAX * 128;       // one plane of a query tile
 constexpr int UF_STAGE_BYTES = 2 * UF_A_BYTES + 2 * UF_B_BYTES;     // 96 KB
 constexpr int UF_BUF = 256;                     // append-buffer entries per (CTA, query)
-constexpr int UF_THREADS = 256;
+constexpr int UF_THREADS = 384;                  // TMA warp, MMA warp, two idle, eight epilogue warps
 constexpr int UF_TAIL = 64 + 64 + 3 * UF_NMAX * 4;                   // barriers, tmem pointer, cnt / tau / qn
 constexpr int UF_SMEM = UF_STAGES * UF_STAGE_BYTES + UF_TAIL + 1024; // + slack to align the stages to 1024 bytes
 
@@ -117,6 +118,11 @@ __device__ __forceinline__ uint32_t uf_ord(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float uf_unord(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// The epilogue tests |x|^2 - 2 acc < thr instead of forming the key first.  thr = tau - |q|^2 plus a slack that covers
+// the roundings of both sides (2^-23 relative each), so that every row whose key is below tau passes; a row that
+// passes with a key slightly above tau is just one more candidate.  tau = +inf gives +inf.
+__device__ __forceinline__ float uf_thr(float tau, float qn) { return (tau - qn) + ldexpf(fabsf(tau) + fabsf(qn), -20); }
 
 // Keep the `keep` smallest of the cnt (<= UF_BUF) entries of one (CTA, query) buffer, compacted to its front in no
 // particular order; returns how many are left.  When something was dropped, tau = the largest key kept (every dropped
@@ -195,7 +201,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t bar_full = tail_u, bar_empty = tail_u + 16, bar_tfull = tail_u + 32, bar_tempty = tail_u + 48;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 64);
     unsigned *cnt_s = reinterpret_cast<unsigned *>(tail + 128);
-    float *tau_s = reinterpret_cast<float *>(tail + 128 + UF_NMAX * 4);
+    float *thr_s = reinterpret_cast<float *>(tail + 128 + UF_NMAX * 4);   // per query: tau - |q|^2, tau = cap-th smallest key so far
     float *qn_s = reinterpret_cast<float *>(tail + 128 + 2 * UF_NMAX * 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,7 +216,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);            // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 8);            // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -221,7 +227,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     for (int j = tid; j < UF_NMAX; j += UF_THREADS) {
         cnt_s[j] = 0;
-        tau_s[j] = CUDART_INF_F;
+        thr_s[j] = CUDART_INF_F;
         qn_s[j] = j < bn ? (float)p.qnorm[q0 + j] : 0.f;
     }
     tc_fence_before();
@@ -291,8 +297,12 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue: keys, thresholds, candidate buffers =====================
-        const int ew = warp - 4;                                  // = warp % 4: the TMEM lane quarter this warp may read
+        // Eight warps: warp % 4 is the TMEM lane quarter (32 rows) a warp may read, (warp - 4) / 4 the half of the
+        // group's query columns it looks at.
+        const int wi = warp - 4, ew = warp & 3, half = wi >> 2;
+        const unsigned below = (1u << lane) - 1u;
         UfEntry *bufs = reinterpret_cast<UfEntry *>(p.bufs) + (size_t)blockIdx.x * bn * UF_BUF;
+        const int c_lo = half * (bn / 64), c_hi = c_lo + bn / 64;  // 32-column chunks of this warp
         int as = 0;
         uint32_t aphase = 0;
         for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
@@ -302,20 +312,39 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const bool ok = row < p.n;
             const float xn = ok ? (float)__ldg(p.xnorm + row) : 0.f;
             const bool dbg = p.dbg_keys != nullptr && blockIdx.x == 0 && tile == (u64)stream;
-            for (int c = 0; c < bn / 32; c++) {
+            for (int c = c_lo; c < c_hi; c++) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * UF_NMAX + c * 32), v);
+                float th[32];                                     // thresholds of these 32 queries (constant during the tile)
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 t4 = reinterpret_cast<const float4 *>(thr_s + c * 32)[i];
+                    th[4 * i] = t4.x, th[4 * i + 1] = t4.y, th[4 * i + 2] = t4.z, th[4 * i + 3] = t4.w;
+                }
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                    const int j = c * 32 + i;
-                    float key = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[j]);
-                    if (dbg) p.dbg_keys[(size_t)(ew * 32 + lane) * bn + j] = key;
-                    if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;           // NaN / inf: keep it, never drop it
-                    if (ok && !(key >= tau_s[j])) {
-                        const unsigned pos = atomicAdd(&cnt_s[j], 1u);
-                        if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                    // key < tau  <=>  |x|^2 - 2 acc < tau - |q|^2 =: thr (kept conservative, see uf_thr); NaN passes
+                    const float acc = __uint_as_float(v[i]);
+                    const bool pass = ok && !(fmaf(-2.f, acc, xn) >= th[i]);
+                    const unsigned m = __ballot_sync(FULL, pass);
+                    if (m) {                                      // rare, and uniform over the warp
+                        const int j = c * 32 + i;
+                        unsigned base = 0;
+                        if (lane == 0) base = atomicAdd(&cnt_s[j], (unsigned)__popc(m));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (pass) {
+                            float key = fmaf(-2.f, acc, xn + qn_s[j]);
+                            if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;       // NaN / inf: keep it, never drop it
+                            const unsigned pos = base + __popc(m & below);
+                            if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                        }
                     }
+                }
+                if (dbg) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        p.dbg_keys[(size_t)(ew * 32 + lane) * bn + c * 32 + i] = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[c * 32 + i]);
                 }
             }
             tc_fence_before();
@@ -325,13 +354,13 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 as = 0;
                 aphase ^= 1;
             }
-            // ---- prune the buffers that could overflow during the next tile (warp ew owns queries ew, ew+4, ...) ----
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int t0 = 0; t0 < bn / 4; t0 += 32) {
+            // ---- prune the buffers that could overflow during the next tile (warp wi owns queries wi, wi+8, ...) ----
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int t0 = 0; t0 < bn / 8; t0 += 32) {
                 const int t = t0 + lane;
-                unsigned m = __ballot_sync(FULL, t < bn / 4 && cnt_s[ew + 4 * t] > (unsigned)(UF_BUF - UF_M));
+                unsigned m = __ballot_sync(FULL, t < bn / 8 && cnt_s[wi + 8 * t] > (unsigned)(UF_BUF - UF_M));
                 while (m) {
-                    const int j = ew + 4 * (t0 + __ffs(m) - 1);
+                    const int j = wi + 8 * (t0 + __ffs(m) - 1);
                     m &= m - 1;
                     const unsigned cnt = cnt_s[j];
                     float tau;
@@ -340,14 +369,14 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     __syncwarp();
                     if (lane == 0) {
                         cnt_s[j] = kept;
-                        if (dropped) tau_s[j] = tau;                        // from now on only keys below the cap-th smallest
+                        if (dropped) thr_s[j] = uf_thr(tau, qn_s[j]);       // from now on only keys below the cap-th smallest
                     }
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
-        for (int j = ew; j < bn; j += 4) {
+        for (int j = wi; j < bn; j += 8) {
             UfEntry *b = bufs + (size_t)j * UF_BUF;
             float tau;
             bool dropped;
