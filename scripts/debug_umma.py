@@ -83,6 +83,17 @@ def main():
                 torch.cuda.synchronize()
                 out[f"{label}_ms_per_call_host"] = (time.perf_counter() - t0) / reps * 1e3
             out["speedup_vs_k2"] = out["k2_ms_per_call_host"] / out["k10_ms_per_call_host"]
+            # the filter kernel alone (CUDA events around its launch on the engine's stream)
+            e.set_option("nearest.umma_min_queries", 1)
+            e.set_option("profile.scan_events", 1)
+            e.take_scan_time()
+            for _ in range(3):
+                e.nearest(Q, k)
+            ms, launches = e.take_scan_time()
+            e.set_option("profile.scan_events", 0)
+            out["k10_filter_kernel_ms"] = ms / max(1, launches)
+            kp = -(-K // 64) * 64
+            out["k10_filter_executed_tflops"] = 3 * 2.0 * nq * n * kp / (ms / max(1, launches) / 1e3) / 1e12
     print(json.dumps(out), flush=True)
 
 
