@@ -387,9 +387,17 @@ def ours(args):
                     "unsafe_flags": int(np.count_nonzero(res_b["flags"] & B.CAND_UNSAFE)),
                     "result_checksum": int(np.bitwise_xor.reduce(res_b["seq"].astype(np.uint64).ravel()))}
 
-        batch = run_batch(True)
-        batch_dmma = run_batch(False)
-        batch["identical_to_dmma_path"] = batch["result_checksum"] == batch_dmma["result_checksum"]
+        # the batch figures are extras next to the headline: a failure here must not take the headline line with it
+        try:
+            batch = run_batch(True)
+        except Exception as ex:  # noqa: BLE001
+            batch = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            batch_dmma = run_batch(False)
+        except Exception as ex:  # noqa: BLE001
+            batch_dmma = {"error": f"{type(ex).__name__}: {ex}"}
+        if "result_checksum" in batch and "result_checksum" in batch_dmma:
+            batch["identical_to_dmma_path"] = batch["result_checksum"] == batch_dmma["result_checksum"]
         e.set_option("nearest.umma_min_queries", 65)
 
     if rank != 0:

@@ -117,3 +117,31 @@ def test_umma_mass_duplicates(port):
         e.insert(rows)
         umma_on(e)
         assert_topk_equal(e.nearest(Q, 10), oracle_topk(port, rows, 48, Q, 10), 10)
+
+
+def test_umma_on_row_shards_and_merge(port):
+    """Two row-range SHARD engines on one GPU take a 200-query batch through K10 each; K7's merge of their candidates
+    equals one engine over all rows (what bench.py's batch does per rank at N > 1)."""
+    n, D, k, nq = 8000, 96, 10, 200
+    rows = synth.uniform_rows(41, n, D)
+    Q = synth.uniform_rows(42, nq, D)
+    want = oracle_topk(port, rows, D, Q, k)
+    half = n // 2
+    dev_rows = torch.from_numpy(rows).cuda()
+    dq = torch.from_numpy(Q).cuda()
+    shards = [B.Engine(D, D, seq_base=0, flags=B.FLAG_SHARD), B.Engine(D, D, seq_base=half, flags=B.FLAG_SHARD)]
+    stream = torch.cuda.current_stream().cuda_stream
+    gathered = torch.zeros((2, nq, k, 4), dtype=torch.int64, device="cuda")
+    for s, e in enumerate(shards):
+        e.set_stream(stream)
+        umma_on(e)
+        e.insert_device(dev_rows[s * half:(s + 1) * half].data_ptr(), half, D)
+        e.nearest_device(dq.data_ptr(), nq, D, k, gathered[s].data_ptr())
+    merged = torch.zeros((nq, k, 4), dtype=torch.int64, device="cuda")
+    B.merge_candidates_device(0, stream, gathered.data_ptr(), 2, nq, k, merged.data_ptr())
+    torch.cuda.synchronize()
+    res = merged.cpu().numpy().view(B.candidate_dtype).reshape(nq, k)
+    assert not np.any(res["flags"] & B.CAND_UNSAFE)
+    assert_topk_equal((res["seq"], res["dist"], res["seq"]), want, k)
+    for e in shards:
+        e.close()
