@@ -24,7 +24,7 @@
 //              accumulator stages; tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 4-11: epilogue     -- tcgen05.ld 32 lanes x 32 columns, |x|^2 - 2 acc against the query's threshold (tau - |q|^2, in
 //              shared memory), one ballot per key; the rare survivors of a warp are appended to the (CTA, query) buffer
-//              in global memory with ONE shared-memory atomic per warp;
+//              in global memory, their slots reserved by ONE shared-memory atomic instruction per warp and chunk;
 //              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (bitwise selection of
 //              the cap-th smallest key, uf_prune) and tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
 #include <cuda.h>
@@ -322,22 +322,32 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     th[4 * i] = t4.x, th[4 * i + 1] = t4.y, th[4 * i + 2] = t4.z, th[4 * i + 3] = t4.w;
                 }
                 tc_wait_ld();
+                // key < tau  <=>  |x|^2 - 2 acc < tau - |q|^2 =: thr (kept conservative, see uf_thr); NaN passes.
+                // One ballot per key; lane i keeps the mask of the chunk's query i.
+                unsigned mine = 0;
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                    // key < tau  <=>  |x|^2 - 2 acc < tau - |q|^2 =: thr (kept conservative, see uf_thr); NaN passes
-                    const float acc = __uint_as_float(v[i]);
-                    const bool pass = ok && !(fmaf(-2.f, acc, xn) >= th[i]);
+                    const bool pass = ok && !(fmaf(-2.f, __uint_as_float(v[i]), xn) >= th[i]);
                     const unsigned m = __ballot_sync(FULL, pass);
-                    if (m) {                                      // rare, and uniform over the warp
-                        const int j = c * 32 + i;
-                        unsigned base = 0;
-                        if (lane == 0) base = atomicAdd(&cnt_s[j], (unsigned)__popc(m));
-                        base = __shfl_sync(FULL, base, 0);
-                        if (pass) {
-                            float key = fmaf(-2.f, acc, xn + qn_s[j]);
-                            if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;       // NaN / inf: keep it, never drop it
-                            const unsigned pos = base + __popc(m & below);
-                            if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                    if (lane == i) mine = m;
+                }
+                const unsigned any = __ballot_sync(FULL, mine != 0);
+                if (any) {                                        // rare after the first tiles, and uniform over the warp
+                    // ONE shared-memory atomic instruction reserves the buffer slots of every query that has survivors
+                    unsigned base_mine = 0;
+                    if (mine) base_mine = atomicAdd(&cnt_s[c * 32 + lane], (unsigned)__popc(mine));
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if ((any >> i) & 1u) {
+                            const unsigned m = __shfl_sync(FULL, mine, i);
+                            const unsigned base = __shfl_sync(FULL, base_mine, i);
+                            if ((m >> lane) & 1u) {
+                                const int j = c * 32 + i;
+                                float key = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[j]);
+                                if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;   // NaN / inf: keep it, never drop it
+                                const unsigned pos = base + __popc(m & below);
+                                if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                            }
                         }
                     }
                 }
