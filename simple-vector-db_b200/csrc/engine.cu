@@ -602,7 +602,7 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         const int nstreams = std::max(1, tune.num_sms / ngroups);
         const size_t nq_pad = (size_t)ngroups * bn;
         if (!qpad.ensure(nq_pad * (size_t)ldp * 8, err) || !qnorm.ensure(nq_pad * 8, err) || !qsplit.ensure(nq_pad * row_bytes, err) ||
-            !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err) || !ubuf.ensure(umma_buf_bytes(ngroups, nstreams, bn), err))
+            !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err) || !ubuf.ensure(umma_buf_bytes(ngroups, nstreams, bn) + nq_pad * 4, err))
             return fail(SVDB_ERR_OOM, err);
         if (umma_debug && !udbg.ensure((size_t)128 * 256 * 4, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_prep_queries(d_Q + done * ldq, (int)ldq, K, (int)nqp, (int)nq_pad, qpad.as<double>(), ldp, qnorm.as<double>(), stream));
@@ -622,6 +622,8 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         ua.cap = cap;
         ua.lists = lists.as<Cand>();
         ua.bufs = ubuf.p;
+        ua.gtau = reinterpret_cast<uint32_t *>(static_cast<char *>(ubuf.p) + umma_buf_bytes(ngroups, nstreams, bn));
+        CK(cudaMemsetAsync(ua.gtau, 0xff, nq_pad * 4, stream));
         ua.dbg_keys = (umma_debug && done == 0) ? udbg.as<float>() : nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (profile_scan) {

@@ -105,6 +105,7 @@ struct UmmaArgs {
     int cap;
     Cand *lists;            // [ngroups*bn][nstreams][cap]
     void *bufs;             // umma_buf_bytes(ngroups, nstreams, bn) of scratch
+    uint32_t *gtau;         // [ngroups*bn] words, all 0xffffffff at launch: per query the smallest cap-th key published so far
     float *dbg_keys;        // NULL, or [128][bn]: the keys of rows 0..127 against the first query group (diagnostics)
 };
 int umma_kpad(int K);

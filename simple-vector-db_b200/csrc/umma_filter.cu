@@ -25,6 +25,8 @@
 //   warps 4-11: epilogue     -- tcgen05.ld 32 lanes x 32 columns, |x|^2 - 2 acc against the query's threshold (tau - |q|^2, in
 //              shared memory), one ballot per key; the rare survivors of a warp are appended to the (CTA, query) buffer
 //              in global memory, their slots reserved by ONE shared-memory atomic instruction per warp and chunk;
+//              the CTAs of a query group share the smallest cap-th key any of them has seen (one u32 per query in global
+//              memory, atomicMin / refreshed every few tiles), so their thresholds converge as one;
 //              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (bitwise selection of
 //              the cap-th smallest key, uf_prune) and tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
 #include <cuda.h>
@@ -303,7 +305,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const unsigned below = (1u << lane) - 1u;
         UfEntry *bufs = reinterpret_cast<UfEntry *>(p.bufs) + (size_t)blockIdx.x * bn * UF_BUF;
         const int c_lo = half * (bn / 64), c_hi = c_lo + bn / 64;  // 32-column chunks of this warp
-        int as = 0;
+        int as = 0, it = 0;
         uint32_t aphase = 0;
         for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
             mbar_wait(bar_tfull + 8 * as, aphase);
@@ -366,11 +368,18 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             // ---- prune the buffers that could overflow during the next tile (warp wi owns queries wi, wi+8, ...) ----
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int t0 = 0; t0 < bn / 8; t0 += 32) {
-                const int t = t0 + lane;
-                unsigned m = __ballot_sync(FULL, t < bn / 8 && cnt_s[wi + 8 * t] > (unsigned)(UF_BUF - UF_M));
+            {
+                // bn / 8 <= 32 queries per warp: lane t looks after query wi + 8 t
+                const int jmine = wi + 8 * lane;
+                const bool mineok = lane < bn / 8;
+                // the smallest cap-th key any CTA of this query group has published so far: an upper bound of the
+                // group's cap-th smallest key, so keys above it are nobody's candidates (37 CTAs converge as one)
+                const bool refresh = it < 16 || (it & 3) == 0;
+                uint32_t g = 0xffffffffu;
+                if (refresh && mineok) g = __ldcg(p.gtau + q0 + jmine);
+                unsigned m = __ballot_sync(FULL, mineok && cnt_s[jmine] > (unsigned)(UF_BUF - UF_M));
                 while (m) {
-                    const int j = wi + 8 * (t0 + __ffs(m) - 1);
+                    const int j = wi + 8 * (__ffs(m) - 1);
                     m &= m - 1;
                     const unsigned cnt = cnt_s[j];
                     float tau;
@@ -379,11 +388,17 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     __syncwarp();
                     if (lane == 0) {
                         cnt_s[j] = kept;
-                        if (dropped) thr_s[j] = uf_thr(tau, qn_s[j]);       // from now on only keys below the cap-th smallest
+                        if (dropped) {
+                            thr_s[j] = fminf(thr_s[j], uf_thr(tau, qn_s[j]));   // from now on only keys below the cap-th smallest
+                            atomicMin(p.gtau + q0 + j, uf_ord(tau));
+                        }
                     }
                 }
+                __syncwarp();
+                if (g != 0xffffffffu) thr_s[jmine] = fminf(thr_s[jmine], uf_thr(uf_unord(g), qn_s[jmine]));
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            it++;
         }
         // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
         for (int j = wi; j < bn; j += 8) {
