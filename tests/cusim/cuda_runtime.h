@@ -165,3 +165,5 @@ inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 using std::max;
 using std::min;
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
