@@ -498,12 +498,28 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     const int nlists = n_versions ? scan_num_lists(tune, !use_exact) : 0;
     std::string err;
 
+    // K11 (option scan.shadow): 1-3 queries stream the split-bf16 shadow (half the bytes of the fp64 rows)
+    bool use_shadow = false;
+    if (!use_exact && mode == SVDB_MODE_AUTO && scan_shadow && n_versions && umma_ok && K >= umma_min_k && n_versions < (1ull << 31)) {
+        const int sr = ensure_shadow();
+        if (sr == SVDB_OK) use_shadow = true;
+        else if (sr != -1000) return sr;
+    }
+
     const double *qbase = d_Q;
     int qld = (int)ldq;
+    if (use_shadow) {
+        // padded fp64 copies (the re-rank reads them) and |q|^2 per query (the key error bound scales with it)
+        if (!qpad.ensure(nq * (size_t)kstride * 8, err) || !qnorm.ensure(nq * 8, err)) return fail(SVDB_ERR_OOM, err);
+        CK(launch_prep_queries(d_Q, (int)ldq, K, (int)nq, (int)nq, qpad.as<double>(), kstride, qnorm.as<double>(), stream));
+        stats.kernels_launched++;
+        qbase = qpad.as<double>();
+        qld = kstride;
+    }
     // the wide scan stages whole query rows of kstride doubles with 16-byte bulk copies:
     // use the caller's buffer in place when it already has that shape, else pad a copy
     const bool q_in_place = K == kstride && (ldq % 2) == 0 && (reinterpret_cast<uintptr_t>(d_Q) % 16) == 0;
-    if (!use_exact && !q_in_place) {
+    if (!use_exact && !use_shadow && !q_in_place) {
         if (!qpad.ensure(nq * (size_t)kstride * 8, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_pad_queries(d_Q, (int)ldq, qpad.as<double>(), kstride, K, (int)nq, stream));
         stats.kernels_launched++;
@@ -541,7 +557,21 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
                 scan_events_used++;
                 CK(cudaEventRecord(ev0, stream));
             }
-            CK(use_exact ? launch_scan_exact(tune, sa, stream) : launch_scan_wide(tune, sa, stream));
+            if (use_shadow) {
+                ShadowScanArgs ha{};
+                ha.xsplit = shadow.as<uint16_t>();
+                ha.n = n_versions;
+                ha.K = K;
+                ha.Kp = umma_kpad(K);
+                ha.q = sa.q;
+                ha.ldq = qld;
+                ha.nq = nqp;
+                ha.cap = cap;
+                ha.lists = lists.as<Cand>();
+                CK(launch_scan_shadow(tune, ha, stream));
+            } else {
+                CK(use_exact ? launch_scan_exact(tune, sa, stream) : launch_scan_wide(tune, sa, stream));
+            }
             if (ev1) CK(cudaEventRecord(ev1, stream));
             stats.kernels_launched++;
         }
@@ -559,6 +589,14 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         fa.log_index = log_idx.as<u64>();
         fa.seq_base = cfg.seq_base;
         fa.eps = use_exact ? -1.0 : 4.0 * (double)(K + 2) * ldexp(1.0, -53);
+        if (use_shadow) {
+            fa.eps = shadow_eps(K);
+            fa.eabs_coef = shadow_eabs_coef();
+            fa.qnorm = qnorm.as<double>() + done;
+            fa.xn_max_bits = xnmax.as<unsigned long long>();
+            fa.scale_lo = 1e-24;               // fp32 keys: see nearest_umma
+            fa.scale_hi = 1e30;
+        }
         fa.child = use_tree ? child.as<uint32_t>() : nullptr;
         fa.mark_ties = (cfg.flags & SVDB_FLAG_SHARD) ? 1 : 0;
         fa.out = d_out + done * k;
@@ -569,9 +607,9 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     return SVDB_OK;
 }
 
-// K10 (umma_filter.cu).  Returns -1000 when the path cannot serve this engine (no HBM for the shadow, no tensor-map
-// entry point): the caller falls through to K2.
-int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out) {
+// The split-bf16 shadow of the kd log ([versions][2*Kp] bf16, K10 and K11 read it): created on first use, extended by
+// the entries appended since.  -1000: no HBM for it (or no address space) -- the fp64 paths keep serving.
+int svdb_engine::ensure_shadow() {
     std::string err;
     const int Kp = umma_kpad(K);
     const size_t row_bytes = (size_t)2 * Kp * 2;
@@ -584,7 +622,7 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
     }
     if (shadow_n < n_versions) {
         if (!shadow.ensure(n_versions * row_bytes, stream, err)) {
-            umma_ok = false;                 // not enough HBM next to the store: K2 serves, nothing is lost
+            umma_ok = false;                 // not enough HBM next to the store: nothing is lost
             cudaGetLastError();
             return -1000;
         }
@@ -592,6 +630,17 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         stats.kernels_launched++;
         shadow_n = n_versions;
     }
+    return SVDB_OK;
+}
+
+// K10 (umma_filter.cu).  Returns -1000 when the path cannot serve this engine (no HBM for the shadow, no tensor-map
+// entry point): the caller falls through to K2.
+int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out) {
+    std::string err;
+    const int Kp = umma_kpad(K);
+    const size_t row_bytes = (size_t)2 * Kp * 2;
+    const int sr = ensure_shadow();
+    if (sr) return sr;
     const int bn = umma_group_size(nq);
     const int cap = (int)std::min<size_t>(32, k + 14);
     const int ldp = kstride;
@@ -1520,6 +1569,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "umma.debug_keys") e->umma_debug = value != 0;
+    else if (n == "scan.shadow") e->scan_shadow = value != 0;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;

@@ -78,6 +78,8 @@ struct svdb_engine {
     size_t shadow_n = 0;                 // log entries present in the shadow
     svdb::DeviceBuffer shadow;           // [versions][2*Kp] bf16
     svdb::Scratch qsplit, ubuf, udbg;
+    bool scan_shadow = false;            // K11: 1-3 queries per call scan the shadow instead of the fp64 rows (option scan.shadow)
+    int ensure_shadow();                 // SVDB_OK, an error, or -1000: not available
     bool umma_debug = false;             // next K10 launch dumps the keys of its first tile into udbg
     int nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out);   // SVDB_OK, an error, or -1000: not available
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped

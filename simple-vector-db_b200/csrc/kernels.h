@@ -47,6 +47,21 @@ cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_
 // Reference-order exact scan, one thread per log entry (primary for thin rows, fallback for any).
 cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
 
+// K11: the scan over the split-bf16 shadow of the log (4 bytes per coordinate instead of 8)
+struct ShadowScanArgs {
+    const uint16_t *xsplit; // [n][2*Kp] bf16: hi plane | lo plane (launch_split_bf16)
+    u64 n;
+    int K, Kp;
+    const double *q;        // device queries (fp64), query i at q + i * ldq
+    int ldq;
+    int nq;                 // 1, 2, 4 or 8 queries share the pass
+    int cap;
+    Cand *lists;            // [nq][nlists][cap]
+};
+cudaError_t launch_scan_shadow(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st);
+double shadow_eps(int K);
+double shadow_eabs_coef();
+
 struct FinalArgs {
     const Cand *lists;
     int nlists, cap, nq, k;

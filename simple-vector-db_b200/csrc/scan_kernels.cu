@@ -255,6 +255,138 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
 }
 
 // =====================================================================================
+// K11: the same scan over the split-bf16 SHADOW of the log (umma_filter.cu: [hi plane | lo plane] bf16 rows of
+// 2*Kp entries, 4 bytes per coordinate) -- HALF the bytes of the fp64 rows, and the scan is HBM-bound.
+// Per coordinate x^ = hi + lo (exact in fp32, |x^ - x| <= (2^-16 + 2^-24)|x|), diff = x^ - fl32(q), key = sum diff^2
+// accumulated in fp32 (FFMA, lane-parallel, butterfly).  With e_i = x^_i - x_i + q_i - q^_i:
+//   |key - d| <= 2 sqrt(d) |e| + |e|^2 + (K/32 + 12) 2^-24 d  <=  (eta + ...) d + (1 + 1/eta) |e|^2,   eta = 2^-13,
+// i.e. the (eps, eabs) form finalize_kernel already proves completeness for (shadow_eps / shadow_eabs_coef).
+// Same ring of per-warp shared-memory stages fed by 1-D bulk async copies as scan_wide_kernel; TR <= 32 rows per tile,
+// lane r keeps the key of row r of the tile, one offer per tile and query.
+// =====================================================================================
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(512, 1) scan_shadow_kernel(ShadowScanArgs p, int nstages, int TR) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = p.Kp;
+    const uint32_t row_bytes = (uint32_t)Kp * 4u;
+    const uint32_t tile_bytes = (uint32_t)TR * row_bytes;
+    const int trips = (Kp + 255) >> 8;                 // a warp covers 256 coordinates per trip, 8 per lane
+
+    // queries in fp32, laid out so that lane l reads its 8 coordinates of a trip with two conflict-free 128-bit loads:
+    // float4 index ((query * trips + trip) * 2 + half) * 32 + lane
+    float *qs = reinterpret_cast<float *>(smem + (size_t)W * nstages * tile_bytes);
+    Cand *mrg = reinterpret_cast<Cand *>(reinterpret_cast<unsigned char *>(qs) + (size_t)NQ * trips * 1024);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(mrg) + (size_t)W * 32 * sizeof(Cand));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W * nstages; i++) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < NQ * trips * 256; i += blockDim.x) {
+        const int qi = i / (trips * 256), c = i - qi * (trips * 256);
+        const float v = c < p.K ? (float)p.q[(size_t)qi * p.ldq + c] : 0.f;
+        qs[((qi * trips + (c >> 8)) * 2 + ((c & 7) >> 2)) * 128 + ((c & 255) >> 3) * 4 + (c & 3)] = v;
+    }
+    __syncthreads();
+
+    const u64 ntiles = (p.n + TR - 1) / TR;
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const uint32_t my_stage = smem_u32(smem) + (uint32_t)warp * nstages * tile_bytes;
+    const uint32_t my_bar = smem_u32(bars + warp * nstages);
+    const uint32_t qs_u = smem_u32(qs) + lane * 16;
+
+    auto issue = [&](u64 t, int s) {
+        const u64 row0 = t * TR;
+        const u64 left = p.n - row0;
+        const uint32_t rows = left < (u64)TR ? (uint32_t)left : (uint32_t)TR;
+        const uint32_t bytes = rows * row_bytes;
+        mbar_arrive_expect_tx(my_bar + 8 * s, bytes);
+        bulk_g2s(my_stage + s * tile_bytes, reinterpret_cast<const unsigned char *>(p.xsplit) + row0 * (u64)row_bytes, bytes,
+                 my_bar + 8 * s);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < nstages; s++) {
+            const u64 t = gw + (u64)s * GW;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (u64 t = gw; t < ntiles; t += GW) {
+        mbar_wait(my_bar + 8 * s, phase);
+        const u64 row0 = t * TR;
+        const int rows = (int)(p.n - row0 < (u64)TR ? p.n - row0 : (u64)TR);
+        float mykey[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) mykey[qi] = 0.f;
+        for (int r = 0; r < rows; r++) {
+            float acc[NQ];
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) acc[qi] = 0.f;
+            const uint32_t base = my_stage + s * tile_bytes + (uint32_t)r * row_bytes + lane * 16;
+            for (int trip = 0, c0 = lane * 8; c0 < Kp; trip++, c0 += 256) {
+                const uint4 h = lds_u128(base + trip * 512);
+                const uint4 l = lds_u128(base + (uint32_t)Kp * 2u + trip * 512);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {          // a 32-bit word holds coordinates 2j (low half) and 2j+1 (high half)
+                    x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                    x[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) {
+                    const uint32_t qa = qs_u + (uint32_t)((qi * trips + trip) * 2) * 512u;
+                    float4 a, b;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(qa));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(qa + 512u));
+                    const float q8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float d = x[j] - q8[j];
+                        acc[qi] = fmaf(d, d, acc[qi]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) acc[qi] += __shfl_xor_sync(FULL, acc[qi], m);
+                if (lane == r) mykey[qi] = acc[qi];
+            }
+        }
+        __syncwarp();
+        // the stage is consumed: refill it before the (rare) list maintenance
+        const u64 tn = t + (u64)nstages * GW;
+        if (lane == 0 && tn < ntiles) issue(tn, s);
+        if (++s == nstages) {
+            s = 0;
+            phase ^= 1;
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(lane < rows, (double)mykey[qi], row0 + lane, lane, p.cap);
+    }
+
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+}
+
+// =====================================================================================
 // Wide rows, direct LDG.128 streaming (A/B variant of the same contract).
 // =====================================================================================
 template <int TR, int NQ>
@@ -853,6 +985,60 @@ cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_
         case 8: return launch_wide_nq<8>(tr, t, a, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+template <int NQ>
+static cudaError_t launch_shadow_inst(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st) {
+    const size_t row_bytes = (size_t)a.Kp * 4;
+    int TR = (int)(6144 / row_bytes);                  // ~6 KB per bulk copy, like K1's tiles
+    TR = TR < 1 ? 1 : (TR > 32 ? 32 : TR);
+    const int trips = (a.Kp + 255) / 256;
+    const int grid = scan_num_lists(t, true);
+    int W = t.warps < 1 ? 1 : (t.warps > 16 ? 16 : t.warps);
+    int NS = t.stages < 2 ? 2 : t.stages;
+    while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
+    const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
+    auto need = [&](int w, int ns) {
+        return (size_t)w * ns * TR * row_bytes + (size_t)NQ * trips * 1024 + (size_t)w * 32 * sizeof(Cand) + (size_t)w * ns * 8;
+    };
+    size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    const int W0 = W, NS0 = NS;
+    while (need(W, NS) > budget && NS > 2) NS--;
+    while (need(W, NS) > budget && W > 2) W--;
+    if (need(W, NS) > budget) {
+        budget = (size_t)MAX_SMEM;
+        W = W0;
+        NS = NS0;
+        while (need(W, NS) > budget && NS > 2) NS--;
+        while (need(W, NS) > budget && W > 1) W--;
+        if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    }
+    const size_t smem = need(W, NS);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(scan_shadow_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    scan_shadow_kernel<NQ><<<grid, W * 32, smem, st>>>(a, NS, TR);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_shadow(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st) {
+    if (a.Kp % 64 || a.Kp < a.K || a.n >= (1ull << 32)) return cudaErrorInvalidValue;
+    switch (a.nq) {
+        case 1: return launch_shadow_inst<1>(t, a, st);
+        case 2: return launch_shadow_inst<2>(t, a, st);
+        case 4: return launch_shadow_inst<4>(t, a, st);
+        case 8: return launch_shadow_inst<8>(t, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+// key error of K11: |key - d| <= shadow_eps(K) * d + shadow_eabs_coef() * (max|x|^2 + |q|^2)
+double shadow_eps(int K) { return ldexp(1.0, -13) + ((double)K / 32.0 + 12.0) * ldexp(1.0, -24); }
+double shadow_eabs_coef() {
+    const double delta = ldexp(1.0, -16) + ldexp(1.0, -24);
+    return (1.0 + 8192.0) * 2.0 * delta * delta * 1.01;
 }
 
 template <int NQ>

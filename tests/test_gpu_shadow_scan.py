@@ -1,0 +1,64 @@
+"""GPU parity of K11 (scan_shadow_kernel, csrc/scan_kernels.cu): the single-query / small-batch scan over the split-bf16
+shadow of the log instead of the fp64 rows (option scan.shadow, off by default in this round).  Approximate fp32 keys,
+answers after finalize's reference-order re-rank (kdtree.c:134-137) bit-identical to the oracle's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from svdb import binding as B  # noqa: E402
+from svdb import synth  # noqa: E402
+from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
+
+
+@pytest.mark.parametrize("n,D,K,nq,k,seed", [
+    (20000, 128, 128, 1, 1, 1),        # the headline shape in small: one query, top-1
+    (9000, 768, 768, 3, 10, 2),        # config-3 rows; passes of 2 + 1 queries
+    (6000, 100, 100, 2, 5, 3),         # K not a multiple of 64 (zero-filled tail), half-empty last trip
+    (5000, 200, 50, 1, 24, 4),         # compact kd array (K < D), k = SVDB_MAX_K
+    (37, 40, 40, 1, 3, 5),             # fewer rows than one tile
+    (7000, 320, 320, 3, 10, 6),        # two trips, the second one partial
+])
+def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed):
+    rows = synth.uniform_rows(seed, n, D)
+    Q = synth.uniform_rows(seed + 70, nq, D)
+    want = oracle_topk(port, rows, K, Q, k)
+    with B.Engine(D, K) as e:
+        e.insert(rows)
+        e.flush()
+        e.set_option("scan.shadow", 1)
+        e.set_option("nearest.umma_min_kd_dim", 1)
+        for _ in range(3):                                      # plain launches, then the captured graph
+            assert_topk_equal(e.nearest(Q, k), want, k)
+        assert e.stats()["exact_reruns"] == 0
+        e.set_option("scan.shadow", 0)
+        assert_topk_equal(e.nearest(Q, k), want, k)
+
+
+def test_shadow_scan_follows_inserts_and_extremes(port):
+    D = 64
+    rng = np.random.Generator(np.random.PCG64(7))
+    rows = synth.uniform_rows(31, 3000, D)
+    more = synth.uniform_rows(32, 300, D)
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        e.set_option("scan.shadow", 1)
+        Q = synth.uniform_rows(33, 2, D)
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
+        e.insert(more)
+        allrows = np.vstack([rows, more])
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, allrows, D, Q, 5), 5)
+        idx, dist, _ = e.nearest(more[7:8], 1)                  # a freshly inserted row finds itself
+        assert idx[0, 0] == 3007 and dist[0, 0] == 0.0
+    # far from the origin the fp32 keys cancel: the proof fails and the exact scan answers
+    rows = 1.0e6 + rng.random((4000, D))
+    Q = 1.0e6 + rng.random((2, D))
+    with B.Engine(D, D) as e:
+        e.insert(rows)
+        e.set_option("scan.shadow", 1)
+        assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
+        assert e.stats()["exact_reruns"] > 0
