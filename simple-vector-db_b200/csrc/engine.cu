@@ -501,9 +501,14 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     // K11 (option scan.shadow): 1-3 queries stream the split-bf16 shadow (half the bytes of the fp64 rows)
     bool use_shadow = false;
     if (!use_exact && mode == SVDB_MODE_AUTO && scan_shadow && n_versions && umma_ok && K >= umma_min_k && n_versions < (1ull << 31)) {
-        const int sr = ensure_shadow();
-        if (sr == SVDB_OK) use_shadow = true;
-        else if (sr != -1000) return sr;
+        // never build or extend the shadow under stream capture (see nearest_host): fall back to the fp64 rows there
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        if (cs == cudaStreamCaptureStatusNone || (shadow_ready && shadow_n == n_versions)) {
+            const int sr = ensure_shadow();
+            if (sr == SVDB_OK) use_shadow = true;
+            else if (sr != -1000) return sr;
+        }
     }
 
     const double *qbase = d_Q;
@@ -744,6 +749,12 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     if (mtree_wanted(k, SVDB_MODE_AUTO)) {       // before any capture: a rebuild allocates and synchronizes
         rc = mtree_update();
         if (rc) return rc;
+    }
+    if (scan_shadow && wide && !force_exact && umma_ok && K >= umma_min_k && n_versions && n_versions < (1ull << 31)) {
+        // K11's shadow likewise: building it inside a capture that is later discarded would leave shadow_n ahead of
+        // what was actually converted
+        rc = ensure_shadow();
+        if (rc && rc != -1000) return rc;
     }
     stats.h2d_bytes += nq * (size_t)K * 8;
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
