@@ -423,6 +423,18 @@ def ours(args):
                          f"on {r['cores']} threads; value = measured {r['qps_sample']:.3f} q/s x {n_sample}/{N} (linear in rows)",
                "value_on_sample": r["qps_sample"], "one_query_one_core_s": r["one_query_one_core_s"]}
 
+    # ---- K11 A/B beside it (N=1, full runs only): the single-query scan over the split-bf16 shadow of the log (opt-in
+    # this round, option scan.shadow) against the fp64-row scan, in a process of its own on a 2M-row store ----
+    shadow_ab = None
+    if world == 1 and not args.no_cpu_baseline and not args.no_shadow_ab:
+        try:
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "debug_shadow.py"), "2000000", str(D)],
+                               capture_output=True, text=True, timeout=180)
+            shadow_ab = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            shadow_ab = {"error": f"{type(ex).__name__}: {ex}"}
+
     rows_per_rank = idx.hi - idx.lo
     algo_bytes = rows_per_rank * K * 8
     peak, peak_src = measured_peak_gbs()
@@ -450,6 +462,7 @@ def ours(args):
         "clocks": sampler.summary(),
         "batch": batch,
         "batch_dmma": batch_dmma,
+        "single_query_shadow_ab": shadow_ab,
         "store": {"rows_per_rank": rows_per_rank, "build_s": build_s, "hbm_gib_mapped": e.stats()["hbm_bytes_mapped"] / 2**30,
                   "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0]),
                   "e2e_entry_point": "svdb_nearest_batch (C-ABI, host buffers)" if world == 1 else "svdb.sharded.ShardedIndex.nearest"},
@@ -493,6 +506,7 @@ def main():
     ap.add_argument("--batch-queries", type=int, default=1024)
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shadow-ab", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. scan.variant=1)")
     args = ap.parse_args()
     if args.kd_dim <= 0:
