@@ -264,7 +264,8 @@ typedef struct svdb_stats {
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
  * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never),
- * "nearest.umma_min_kd_dim",
+ * "nearest.umma_min_kd_dim", "scan.shadow" (1: calls of 1-3 queries scan the split-bf16 shadow of the log, K11 -- half the
+ * bytes of the fp64 rows, same answers; off by default in this release),
  * "nearest.mtree" (AUTO may use the median tree), "mtree.lanes" (32/16/8 lanes per query), "mtree.tail_max";
  * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
  * row i is global row lo + i sets it to lo, so that merged answers carry global row numbers). */

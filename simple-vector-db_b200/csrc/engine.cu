@@ -221,6 +221,7 @@ void svdb_engine::destroy() {
     shadow.release();
     shadow_ready = false;
     shadow_n = 0;
+    shadow_mapped_counted = 0;
     for (Scratch *s : {&qsplit, &ubuf, &udbg}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
                        &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
@@ -346,7 +347,8 @@ int svdb_engine::flush() {
     CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
     n_versions = n1;
     stage_n = 0;
-    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped();
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped() + shadow.mapped();
+    shadow_mapped_counted = shadow.mapped();
     return SVDB_OK;
 }
 
@@ -633,6 +635,8 @@ int svdb_engine::ensure_shadow() {
         }
         CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow.as<uint16_t>(), tune.num_sms, stream));
         stats.kernels_launched++;
+        stats.hbm_bytes_mapped += shadow.mapped() - shadow_mapped_counted;
+        shadow_mapped_counted = shadow.mapped();
         shadow_n = n_versions;
     }
     return SVDB_OK;
@@ -1039,7 +1043,8 @@ int svdb_engine::ingest_device_rows(const double *d_rows, size_t n, size_t ld, s
     e->uuids.resize(e->cur_host.size(), std::array<char, 37>{});
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow.mapped();
+    e->shadow_mapped_counted = e->shadow.mapped();
     return SVDB_OK;
 }
 
@@ -1180,7 +1185,8 @@ int svdb_append_kdpoints_device(svdb_engine *e, const double *d_pts, size_t firs
     if (rc) return rc;
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow.mapped();
+    e->shadow_mapped_counted = e->shadow.mapped();
     return SVDB_OK;
 }
 

@@ -76,6 +76,7 @@ struct svdb_engine {
     int umma_min_q = 65, umma_min_k = 32;
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the shadow
+    size_t shadow_mapped_counted = 0;    // part of shadow.mapped() already included in stats.hbm_bytes_mapped
     svdb::DeviceBuffer shadow;           // [versions][2*Kp] bf16
     svdb::Scratch qsplit, ubuf, udbg;
     bool scan_shadow = false;            // K11: 1-3 queries per call scan the shadow instead of the fp64 rows (option scan.shadow)
