@@ -648,6 +648,10 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
     std::string err;
     const int Kp = umma_kpad(K);
     const size_t row_bytes = (size_t)2 * Kp * 2;
+    // never build or extend the shadow under stream capture (see nearest_host): K2 serves that call
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone && !(shadow_ready && shadow_n == n_versions)) return -1000;
     const int sr = ensure_shadow();
     if (sr) return sr;
     const int bn = umma_group_size(nq);
@@ -754,9 +758,10 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         rc = mtree_update();
         if (rc) return rc;
     }
-    if (scan_shadow && wide && !force_exact && umma_ok && K >= umma_min_k && n_versions && n_versions < (1ull << 31)) {
-        // K11's shadow likewise: building it inside a capture that is later discarded would leave shadow_n ahead of
-        // what was actually converted
+    if ((scan_shadow || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
+        n_versions && n_versions < (1ull << 31)) {
+        // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
+        // ahead of what was actually converted
         rc = ensure_shadow();
         if (rc && rc != -1000) return rc;
     }
