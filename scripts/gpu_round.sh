@@ -15,9 +15,14 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 echo "== ncu: full capture of the scan kernel (one launch at full size)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:scan_wide_kernel -s 4 -c 1 -o gpurun_out/prof_scan_full \
     python bench.py --steps 3 --warmup 3 --batch-queries 0 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1; echo "exit $?"
-echo "== ncu: K2 and compare kernels"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_mma_kernel -c 1 -o gpurun_out/prof_mma \
-    python bench.py --rows 1000000 --steps 3 --warmup 3 --batch-queries 1024 --no-cpu-baseline > gpurun_out/ncu_mma.log 2>&1; echo "exit $?"
+echo "== ncu: K2, K10, K11 (bench.py stops the profiler after its timed region, so these come from the bring-up scripts)"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_mma_kernel -c 1 -o gpurun_out/prof_mma -f \
+    python scripts/debug_umma.py time_1M > gpurun_out/ncu_mma.log 2>&1; echo "exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma_filter_kernel -c 1 -o gpurun_out/prof_umma -f \
+    python scripts/debug_umma.py time_1M > gpurun_out/ncu_umma.log 2>&1; echo "exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_shadow_kernel -s 2 -c 1 -o gpurun_out/prof_shadow -f \
+    python scripts/debug_shadow.py 2000000 768 > gpurun_out/ncu_shadow.log 2>&1; echo "exit $?"
+echo "== which kernel for which batch size"; timeout 600 python scripts/sweep_batch_paths.py > gpurun_out/sweep_batch_paths.jsonl 2> gpurun_out/sweep_batch_paths.err; cut -c1-400 gpurun_out/sweep_batch_paths.jsonl
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:compare_kernel -s 12 -c 1 -o gpurun_out/prof_compare \
     python scripts/bench_extra.py c4 --out=gpurun_out/tmp.jsonl > gpurun_out/ncu_compare.log 2>&1; echo "exit $?"
 ls -la gpurun_out
