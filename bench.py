@@ -381,6 +381,8 @@ def ours(args):
                         "note": "whole step incl. re-rank; per-GPU flops = 2*queries*rows_per_rank*K"}
                 what = "K2: GEMM-form keys on FP64 DMMA (64 queries per CTA group) + exact re-rank"
             return {"workload": f"{nb}-query batch, top-{kb}, {what}",
+                    "dtype": "filter keys: split bf16 x 3 products, fp32 accumulate (tcgen05); answers: f64, reference operation order, "
+                             "bit-identical to the f64 paths" if umma else "f64",
                     "queries": nb, "k": kb, "value": nb / sec, "unit": UNIT, "ms": float(b_ms),
                     "e2e": {"value": nb / (float(b_e2e) / 1e3), "unit": UNIT, "h2d_bytes": nb * D * 8, "d2h_bytes": nb * kb * 32},
                     "gpu_launches": int(b_launches), "roofline": roof, "clocks": bsampler.summary(),
@@ -460,6 +462,7 @@ def ours(args):
             sms_avg = sms / max(1, sl)
             shadow_full = {"workload": "the headline's single-query steps with option scan.shadow = 1 (K11: scan of the split-bf16 "
                                        "shadow, 4 bytes per coordinate; opt-in this round)",
+                           "dtype": "filter keys: fp32 from the split-bf16 shadow; answers: f64, reference operation order",
                            "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "scan_ms": sms_avg,
                            "roofline": {"bound": "hbm", "kernel": "scan_shadow_kernel<1>", "algorithmic_bytes_per_launch": N * kp * 4,
                                         "achieved": N * kp * 4 / (sms_avg / 1e3) / 1e9 if sms_avg > 0 else 0.0, "peak": pk, "unit": "GB/s",
