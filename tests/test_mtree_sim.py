@@ -40,9 +40,9 @@ CASES = [
     (2048, 3, 0, 16, 1, 6),        # largest single-CTA build, coarse grid: duplicates and distinct ties
     (2049, 2, 33, 16, 0, 7),       # one radix-select level, uneven halves
     (9001, 3, 100, 24, 0, 8),      # three radix-select levels
-    (9001, 3, 0, 24, 1, 9),        # the same on a grid: medians inside long runs of equal keys
-    (5000, 8, 10, 12, 0, 10),      # K = 8
-    (6000, 2, 0, 12, 2, 11),       # sorted insertion order
+    (4600, 3, 0, 16, 1, 9),        # two radix-select levels on a grid: medians inside long runs of equal keys
+    (4200, 8, 10, 8, 0, 10),       # K = 8
+    (4200, 2, 0, 12, 2, 11),       # sorted insertion order
     (4500, 3, 64, 16, 3, 12),      # NaN / +-inf coordinates
 ]
 
