@@ -446,7 +446,6 @@ def ours(args):
             e.set_option("scan.shadow", 1)
             got = [idx.nearest_device(q_dev[i], k).clone() for i in range(min(pool, 4))]      # also the warm-up
             torch.cuda.synchronize()
-            r0 = e.stats()["exact_reruns"]
             e.set_option("profile.scan_events", 1)
             e.take_scan_time()
             ev0.record()
@@ -468,7 +467,8 @@ def ours(args):
                                         "achieved": N * kp * 4 / (sms_avg / 1e3) / 1e9 if sms_avg > 0 else 0.0, "peak": pk, "unit": "GB/s",
                                         "frac": (N * kp * 4 / (sms_avg / 1e3) / 1e9 / pk) if sms_avg > 0 else 0.0},
                            "identical_to_fp64_row_scan": all(bool(torch.equal(a, b)) for a, b in zip(want, got)),
-                           "exact_reruns": e.stats()["exact_reruns"] - r0}
+                           # the device API hands UNSAFE flags to its caller instead of re-running the query itself
+                           "unsafe_flags": int(sum(int(((g[..., 3] & B.CAND_UNSAFE) != 0).sum()) for g in got))}
         except Exception as ex:  # noqa: BLE001
             shadow_full = {"error": f"{type(ex).__name__}: {ex}"}
         try:
