@@ -1,6 +1,8 @@
+"""K11 against K1 against a torch fp64 brute force on the device, 300k and 2M rows x 768: prints the three answers side by
+side (the run that showed the shadow-built-under-a-discarded-capture bug: K11 returned rows 0..8).  GPU box only."""
 import json, os, sys
 import numpy as np
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "simple-vector-db_b200")]
 from svdb import binding as B
 import torch
