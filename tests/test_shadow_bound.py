@@ -48,6 +48,9 @@ def bound(K, x, q, d):
     ("near_query", 256, 4),        # rows within 1e-3 of the query: d tiny against the norms (the absolute term must carry it)
     ("offset", 128, 5),            # 1000 + U[0,1): cancellation in the differences
     ("mixed_magnitudes", 512, 6),  # coordinates spread over six decades
+    ("cauchy", 200, 7),            # heavy tails: a few coordinates carry the norms
+    ("sparse", 1000, 8),           # 5 % non-zeros
+    ("small_integers", 50, 9),     # exact ties galore
 ])
 def test_shadow_key_error_within_bound(kind, K, seed):
     rng = np.random.default_rng(seed)
@@ -61,8 +64,15 @@ def test_shadow_key_error_within_bound(kind, K, seed):
         x = np.repeat(q, n // nq, axis=0) + 1e-3 * rng.standard_normal((n, K))
     elif kind == "offset":
         x, q = 1000.0 + rng.random((n, K)), 1000.0 + rng.random((nq, K))
+    elif kind == "cauchy":
+        x, q = rng.standard_cauchy((n, K)).clip(-1e3, 1e3), rng.standard_cauchy((nq, K)).clip(-1e3, 1e3)
+    elif kind == "sparse":
+        x = np.where(rng.random((n, K)) < 0.05, rng.standard_normal((n, K)) * 100, 0.0)
+        q = np.where(rng.random((nq, K)) < 0.05, rng.standard_normal((nq, K)) * 100, 0.0)
+    elif kind == "small_integers":
+        x, q = rng.integers(-3, 4, (n, K)).astype(float), rng.integers(-3, 4, (nq, K)).astype(float)
     else:
-        mag = 10.0 ** rng.integers(-3, 3, size=K)
+        mag = 10.0 ** rng.integers(-3, 3, size=K).astype(float)
         x, q = rng.standard_normal((n, K)) * mag, rng.standard_normal((nq, K)) * mag
     d = ((x[:, None, :] - q[None, :, :]) ** 2).sum(-1)
     err = np.abs(shadow_keys(x, q) - d)

@@ -38,3 +38,32 @@ def test_split_residual_and_product_bound(scale, seed):
     coef_repr = 3.2 * 2.0 ** -16
     scale2 = (x ** 2).sum(1)[:, None] + (q ** 2).sum(1)[None, :]
     assert np.all(2 * np.abs(approx - exact) <= coef_repr * scale2)
+
+
+@pytest.mark.parametrize("kind,seed", [("uniform", 1), ("cauchy", 2), ("near_query", 3), ("scaled", 4)])
+def test_key_error_with_sequential_fp32_accumulation_within_umma_eabs_coef(kind, seed):
+    """The whole K10 key, emulated with the WORST accumulation order fp32 allows (one running sum over all 3K bf16 products;
+    the tensor core adds in trees of 16): still inside coef * (max|x|^2 + |q|^2), coef = umma_eabs_coef(K)."""
+    rng = np.random.default_rng(seed)
+    n, nq, K = 48, 3, 256
+    if kind == "uniform":
+        x, q = rng.random((n, K)), rng.random((nq, K))
+    elif kind == "cauchy":
+        x, q = rng.standard_cauchy((n, K)).clip(-1e3, 1e3), rng.standard_cauchy((nq, K)).clip(-1e3, 1e3)
+    elif kind == "near_query":
+        q = rng.standard_normal((nq, K))
+        x = np.repeat(q, n // nq, axis=0) * (1 + 1e-5 * rng.standard_normal((n, K)))
+    else:
+        x, q = rng.standard_normal((n, K)) * 1e7, rng.standard_normal((nq, K)) * 1e7
+    xh, xl = split(x)
+    qh, ql = split(q)
+    prod = np.zeros((n, nq), np.float32)
+    for i in range(K):
+        for a, b in ((xh, ql), (xl, qh), (xh, qh)):
+            prod = (prod + a[:, i:i + 1].astype(np.float32) * b[:, i].astype(np.float32)[None, :]).astype(np.float32)
+    xn, qn = (x ** 2).sum(1).astype(np.float32), (q ** 2).sum(1).astype(np.float32)
+    key = (xn[:, None] + qn[None, :]).astype(np.float32) + np.float32(-2) * prod
+    d = ((x[:, None, :] - q[None, :, :]) ** 2).sum(-1)
+    coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0 + 8.0) * 2.0 ** -20
+    scale = (x ** 2).sum(1).max() + (q ** 2).sum(1)[None, :]
+    assert np.all(np.abs(key.astype(np.float64) - d) <= coef * scale)
