@@ -121,7 +121,7 @@ def load_peaks() -> dict:
 
 
 def profile_traffic():
-    """dram bytes per scan launch from the committed ncu capture, if one exists."""
+    """dram bytes per scan launch from the committed ncu captures ({kernel: {dram_bytes_per_launch, rows, source}})."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
     except Exception:
@@ -131,9 +131,20 @@ def profile_traffic():
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's own kdtree_nearest on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_rows(n: int, D: int) -> np.ndarray:
+def cpu_rows(n: int, D: int):
+    """The first n rows of the synthetic store.  On a GPU box they are generated exactly like the GPU arm's store
+    (torch.rand on the device with the per-chunk seeds, copied to the host), so both arms see the SAME rows; without a
+    device (this arm also runs on CPU-only hosts) numpy PCG64 draws from the same distribution."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            parts = [part.cpu() for _, part in store_chunks(dev, 0, n, n, D)]
+            return torch.cat(parts)[:n].numpy(), "identical to the GPU arm's rows (torch.rand on the device, per-chunk seeds)"
+    except Exception:  # noqa: BLE001
+        pass
     rng = np.random.Generator(np.random.PCG64(SEED))
-    return rng.random((n, D), dtype=np.float64)
+    return rng.random((n, D), dtype=np.float64), "same distribution (numpy PCG64; no CUDA device to generate the GPU arm's rows)"
 
 
 def run_cpu_reference(rows: np.ndarray, K: int, n_total: int, steps: int, warmup: int, budget_s: float):
@@ -161,12 +172,13 @@ def run_cpu_reference(rows: np.ndarray, K: int, n_total: int, steps: int, warmup
     for i in range(steps):
         drv.nearest_batch(h, np.roll(Q, i, axis=0), cores)
     dt = time.perf_counter() - t0
+    ids = drv.nearest_batch(h, Q, cores)          # the reference's answers on the sample (compared with the GPU engine's)
     drv.free(h)
     qps_sample = steps * cores / dt
     scale = rows.shape[0] / n_total
     return {"kind": drv.kind, "cores": cores, "qps_sample": qps_sample, "qps_full": qps_sample * scale,
             "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "build_s": build_s,
-            "one_query_one_core_s": one}
+            "one_query_one_core_s": one, "Q": Q, "ids": ids}
 
 
 def reference_arm(args):
@@ -174,9 +186,9 @@ def reference_arm(args):
     if rank != 0:
         return
     n_sample = min(args.rows, args.cpu_sample_rows)
-    rows = cpu_rows(n_sample, args.dim)
+    rows, rows_how = cpu_rows(n_sample, args.dim)
     r = run_cpu_reference(rows, args.kd_dim, args.rows, args.steps, args.warmup, budget_s=90.0)
-    sample = (f"first {n_sample} of {args.rows} rows (same distribution, numpy PCG64), {r['cores']} concurrent "
+    sample = (f"first {n_sample} of {args.rows} rows ({rows_how}), {r['cores']} concurrent "
               f"queries per step on {r['cores']} threads; value = q/s on the sample x {n_sample}/{args.rows} "
               f"(linear in rows: at K={args.kd_dim} kdtree_nearest visits ~every node)")
     line = {
@@ -192,13 +204,37 @@ def reference_arm(args):
     emit(line)
 
 
+def store_chunks(dev, lo: int, hi: int, N: int, D: int):
+    """The synthetic store, U[0,1) fp64, generated on the device chunk by chunk; seeds are per chunk, so any sharding
+    (and the parity check, which regenerates the rows instead of reading them back) sees the same rows."""
+    import torch
+    c = lo // CHUNK_ROWS
+    while c * CHUNK_ROWS < hi:
+        g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + c)
+        chunk = torch.rand((CHUNK_ROWS, D), dtype=torch.float64, device=dev, generator=g)
+        a, b = max(lo, c * CHUNK_ROWS), min(hi, (c + 1) * CHUNK_ROWS, N)
+        yield a, chunk[a - c * CHUNK_ROWS: b - c * CHUNK_ROWS]
+        del chunk
+        c += 1
+
+
+PLANE_KERNEL = {0: "scan_wide_kernel<TR,1> (K1, fp64 rows)", 1: "scan_shadow_kernel<1> (K11, hi + lo bf16 planes of the shadow)",
+                2: "scan_plane_kernel<1,TRIPS,32,TR> (K12, bf16 hi plane of the shadow)"}
+
+
+def plane_bytes(plane: int, rows: int, K: int) -> int:
+    """Algorithmic bytes one scan launch reads: the copy of the log the kernel streams, once."""
+    kp = -(-K // 64) * 64
+    return rows * K * 8 if plane == 0 else rows * kp * (4 if plane == 1 else 2)
+
+
 def workload_config(args):
     return {"workload": f"config3: {args.rows}x{args.dim} fp64 store, kd_dim={args.kd_dim}, single-query nearest top-1 "
                         f"per step, row-sharded over n_gpus",
             "rows": args.rows, "dim": args.dim, "kd_dim": args.kd_dim, "k": 1, "queries_per_step": 1,
             "parallelism": f"row-shards x{args.gpus}", "exchange": os.environ.get("SVDB_EXCHANGE", "p2p") if args.gpus > 1 else None,
-            "l2": "store per GPU >> 126 MB L2 (no flush needed)" if args.rows * args.dim * 8 // max(1, args.gpus) > 4 * L2_BYTES
-                  else "store fits L2: flushed between steps"}
+            "l2": "bytes streamed per GPU and step >> 126 MB L2 (no flush needed)"
+                  if plane_bytes(2, args.rows // max(1, args.gpus), args.kd_dim) > 4 * L2_BYTES else "store fits L2: flushed between steps"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -234,23 +270,16 @@ def ours(args):
     # ---- synthetic store: U[0,1) fp64, generated on the device chunk by chunk -------------
     t0 = time.perf_counter()
     lo, hi = idx.lo, idx.hi
-    c = lo // CHUNK_ROWS
-    while c * CHUNK_ROWS < hi:
-        g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + c)
-        chunk = torch.rand((CHUNK_ROWS, D), dtype=torch.float64, device=dev, generator=g)
-        a, b = max(lo, c * CHUNK_ROWS), min(hi, (c + 1) * CHUNK_ROWS, N)
-        part = chunk[a - c * CHUNK_ROWS: b - c * CHUNK_ROWS]
+    for _, part in store_chunks(dev, lo, hi, N, D):
         idx.ingest_device(part)
         torch.cuda.synchronize()
-        del chunk, part
-        c += 1
     build_s = time.perf_counter() - t0
     torch.cuda.empty_cache()
     if rank == 0:
         log(f"[bench] store built: {hi - lo} rows/rank in {build_s:.1f}s, {e.stats()['hbm_bytes_mapped'] / 2**30:.1f} GiB mapped")
 
     flush_buf = None
-    if (hi - lo) * K * 8 <= 4 * L2_BYTES:
+    if plane_bytes(2, hi - lo, K) <= 4 * L2_BYTES:      # the smallest copy of the log a scan may stream
         flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
 
     # ---- queries: a pool of distinct ones, in pinned host memory and in HBM --------------
@@ -321,14 +350,59 @@ def ours(args):
     st1 = e.stats()
     launches = st1["kernels_launched"] - st0["kernels_launched"] + (idx.merge_launches - m0)
 
+    plane_used = int(e.stats()["scan_plane_last"])
+
     times = torch.tensor([dev_ms, e2e_s * 1e3, scan_ms / max(1, scan_launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, scan_ms_avg = (float(x) for x in times.cpu())
 
+    # ---- the same steps on the fp64 rows (K1, option scan.plane = 0): BASELINE.json's "fp64 scan at >= 80 % of HBM peak"
+    # reading keeps its number next to the headline, whatever copy of the log the default path streams ----
+    fp64_scan = None
+    if plane_used != 0 and not args.no_fp64_scan:
+        try:
+            e.set_option("scan.plane", 0)
+            for i in range(3):
+                step_dev(i)
+            barrier()
+            e.set_option("profile.scan_events", 1)
+            e.take_scan_time()
+            fsampler = ClockSampler(local)
+            fsampler.start()
+            ev0.record()
+            for i in range(args.steps):
+                step_dev(args.warmup + i)
+            ev1.record()
+            barrier()
+            fsampler.stop()
+            f_ms = ev0.elapsed_time(ev1)
+            f_scan_ms, f_launches = e.take_scan_time()
+            e.set_option("profile.scan_events", 0)
+            ft = torch.tensor([f_ms, f_scan_ms / max(1, f_launches)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+            f_ms, f_scan_avg = (float(x) for x in ft.cpu())
+            fb = plane_bytes(0, hi - lo, K)
+            pk, pk_src = measured_peak_gbs()
+            fp64_scan = {"workload": "the headline's steps with option scan.plane = 0: K1 streams the fp64 rows (8 bytes per coordinate)",
+                         "dtype": "f64", "value": args.steps / (f_ms / 1e3), "unit": UNIT, "ms_per_step": f_ms / args.steps,
+                         "roofline": {"bound": "hbm", "kernel": PLANE_KERNEL[0], "algorithmic_bytes_per_launch": fb,
+                                      "avg_launch_ms": f_scan_avg, "achieved": fb / (f_scan_avg / 1e3) / 1e9 if f_scan_avg > 0 else 0.0,
+                                      "peak": pk, "unit": "GB/s", "frac": fb / (f_scan_avg / 1e3) / 1e9 / pk if f_scan_avg > 0 else 0.0,
+                                      "peak_source": pk_src, "launches_timed": int(f_launches)},
+                         "clocks": fsampler.summary()}
+        except Exception as ex:  # noqa: BLE001
+            fp64_scan = {"error": f"{type(ex).__name__}: {ex}"}
+        finally:
+            e.set_option("scan.plane", 2 if not any(kv.startswith("scan.plane=") or kv.startswith("scan.shadow=") for kv in args.opt)
+                         else plane_used)
+            e.set_option("profile.scan_events", 0)
+
     # ---- config 3 batch: 1024 queries, top-10 -- K10 (tcgen05, split-bf16 keys) and K2 (FP64 DMMA) side by side ----
     batch = None
     batch_dmma = None
+    batch_results = {}
     if args.batch_queries > 0:
         nb, kb = args.batch_queries, 10
         qb_host = torch.rand((nb, D), dtype=torch.float64, generator=gq).pin_memory()
@@ -380,6 +454,7 @@ def ours(args):
                         "peak_source": "profiles/r01_fp64_peak_dfma_vs_dmma.txt (DMMA.8x8x4 microbenchmark on this pool)",
                         "note": "whole step incl. re-rank; per-GPU flops = 2*queries*rows_per_rank*K"}
                 what = "K2: GEMM-form keys on FP64 DMMA (64 queries per CTA group) + exact re-rank"
+            batch_results["K10" if umma else "K2"] = res_b
             return {"workload": f"{nb}-query batch, top-{kb}, {what}",
                     "dtype": "filter keys: split bf16 x 3 products, fp32 accumulate (tcgen05); answers: f64, reference operation order, "
                              "bit-identical to the f64 paths" if umma else "f64",
@@ -402,6 +477,55 @@ def ours(args):
             batch["identical_to_dmma_path"] = batch["result_checksum"] == batch_dmma["result_checksum"]
         e.set_option("nearest.umma_min_queries", 65)
 
+    # ---- parity at THIS size: outside every timed region, at every N.  For 8 pool queries the product's
+    # answers -- top-1 through the timed path's entry point and top-10 through the public host call -- and, for 8 queries of
+    # the 1024-batch, K10's top-10, are checked against an independent brute force over the whole store + the CPU oracle
+    # (oracle/bigcheck.py): ids and fp64 distance bits ==. ----
+    parity = None
+    if not args.no_parity_check:
+        try:
+            from oracle import bigcheck
+            npq, kp10 = 8, 10
+            def public_call(i, kk):
+                """the call a user makes (step_e2e's entry point), with k = kk"""
+                if world == 1:
+                    ix, ds, sq = e.nearest(q_np[i], kk)
+                    return {"index": ix, "dist": ds, "seq": sq}
+                return idx.nearest(q_host[i], kk)
+
+            got1 = [public_call(i, 1) for i in range(npq)]
+            got10 = [public_call(i, kp10) for i in range(npq)]
+            Qs = [q_dev[i, 0, :K] for i in range(npq)]
+            have_batch = args.batch_queries >= npq and len(batch_results) > 0
+            if have_batch:
+                Qs += [qb_dev[i, :K] for i in range(npq)]
+            Qd = torch.stack(Qs).contiguous()
+            cand = bigcheck.brute_candidates(store_chunks(dev, lo, hi, N, D), Qd, 64)
+            torch.cuda.empty_cache()
+            if world > 1:
+                allc = [None] * world
+                dist.all_gather_object(allc, cand)
+            else:
+                allc = [cand]
+            if rank == 0:
+                Qn = Qd.cpu().numpy()
+                ids10 = np.stack([g["index"][0] for g in got10])
+                d10 = np.stack([g["dist"][0] for g in got10])
+                parity = bigcheck.verdict(allc, Qn[:npq], ids10, d10, kp10, N)
+                ids1 = np.stack([g["index"][0] for g in got1])
+                d1 = np.stack([g["dist"][0] for g in got1])
+                p1 = bigcheck.verdict(allc, Qn[:npq], ids1, d1, 1, N)
+                parity["single_query_top1_ok"] = p1["ok"]
+                parity["ok"] = parity["ok"] and p1["ok"]
+                for name, rb in batch_results.items():             # the 1024-query batch: K10 (tcgen05) and K2 (DMMA) answers
+                    pb = bigcheck.verdict([tuple(a[npq:] for a in c) for c in allc], Qn[npq:], rb["index"][:npq], rb["dist"][:npq], kp10, N)
+                    parity[f"batch_{name}_top10_ok"] = pb["ok"]
+                    parity["ok"] = parity["ok"] and pb["ok"]
+                parity["exact_reruns"] = e.stats()["exact_reruns"]
+                parity["fp64_reruns"] = e.stats()["fp64_reruns"]
+        except Exception as ex:  # noqa: BLE001
+            parity = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -412,107 +536,68 @@ def ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_sample = min(N, args.cpu_sample_rows)
-        g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + 0)
-        need_chunks = -(-n_sample // CHUNK_ROWS)
-        parts = []
-        for c in range(need_chunks):
-            g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003 + c)
-            parts.append(torch.rand((CHUNK_ROWS, D), dtype=torch.float64, device=dev, generator=g).cpu())
-        rows = torch.cat(parts)[:n_sample].numpy()
+        rows = torch.cat([part.cpu() for _, part in store_chunks(dev, 0, n_sample, n_sample, D)])[:n_sample].numpy()
         r = run_cpu_reference(rows, K, N, steps=3, warmup=1, budget_s=25.0)
         cpu = {"value": r["qps_full"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                "sample": f"first {n_sample} of {N} rows of the same store, {r['cores']} concurrent queries/step x {r['steps']} steps "
                          f"on {r['cores']} threads; value = measured {r['qps_sample']:.3f} q/s x {n_sample}/{N} (linear in rows)",
                "value_on_sample": r["qps_sample"], "one_query_one_core_s": r["one_query_one_core_s"]}
-
-    # ---- K11 A/B beside it (N=1, full runs only): the single-query scan over the split-bf16 shadow of the log (opt-in
-    # this round, option scan.shadow) against the fp64-row scan, in a process of its own on a 2M-row store ----
-    shadow_ab = None
-    if world == 1 and not args.no_cpu_baseline and not args.no_shadow_ab:
+        # and the two arms agree on that sample: the reference's kdtree_nearest ids == the GPU engine's on the same rows
         try:
-            import subprocess
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "debug_shadow.py"), "2000000", str(D)],
-                               capture_output=True, text=True, timeout=180)
-            shadow_ab = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+            with B.Engine(D, K, device=local) as es:
+                rows_dev = torch.from_numpy(rows).to(dev)
+                es.insert_device(rows_dev.data_ptr(), n_sample, D)
+                torch.cuda.synchronize()
+                ix, _, _ = es.nearest(r["Q"], 1)
+                del rows_dev
+            cpu["ids_equal_gpu_engine_on_sample"] = bool(np.array_equal(ix[:, 0].astype(np.uint64), r["ids"].astype(np.uint64)))
         except Exception as ex:  # noqa: BLE001
-            shadow_ab = {"error": f"{type(ex).__name__}: {ex}"}
-
-    # ---- and the same K11 scan at the headline's own size, in this process, after everything else has been measured:
-    # the same single-query steps with scan.shadow = 1 (the shadow exists already: the K10 batch built it) ----
-    shadow_full = None
-    if world == 1 and not args.no_shadow_ab and args.batch_queries > 0 and not any("scan.shadow" in kv for kv in args.opt):
-        try:
-            want = [idx.nearest_device(q_dev[i], k).clone() for i in range(min(pool, 4))]
-            e.set_option("scan.shadow", 1)
-            got = [idx.nearest_device(q_dev[i], k).clone() for i in range(min(pool, 4))]      # also the warm-up
-            torch.cuda.synchronize()
-            e.set_option("profile.scan_events", 1)
-            e.take_scan_time()
-            ev0.record()
-            for i in range(args.steps):
-                step_dev(args.warmup + i)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / args.steps
-            sms, sl = e.take_scan_time()
-            e.set_option("profile.scan_events", 0)
-            kp = -(-K // 64) * 64
-            pk, _ = measured_peak_gbs()
-            sms_avg = sms / max(1, sl)
-            shadow_full = {"workload": "the headline's single-query steps with option scan.shadow = 1 (K11: scan of the split-bf16 "
-                                       "shadow, 4 bytes per coordinate; opt-in this round)",
-                           "dtype": "filter keys: fp32 from the split-bf16 shadow; answers: f64, reference operation order",
-                           "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "scan_ms": sms_avg,
-                           "roofline": {"bound": "hbm", "kernel": "scan_shadow_kernel<1>", "algorithmic_bytes_per_launch": N * kp * 4,
-                                        "achieved": N * kp * 4 / (sms_avg / 1e3) / 1e9 if sms_avg > 0 else 0.0, "peak": pk, "unit": "GB/s",
-                                        "frac": (N * kp * 4 / (sms_avg / 1e3) / 1e9 / pk) if sms_avg > 0 else 0.0},
-                           "identical_to_fp64_row_scan": all(bool(torch.equal(a, b)) for a, b in zip(want, got)),
-                           # the device API hands UNSAFE flags to its caller instead of re-running the query itself
-                           "unsafe_flags": int(sum(int(((g[..., 3] & B.CAND_UNSAFE) != 0).sum()) for g in got))}
-        except Exception as ex:  # noqa: BLE001
-            shadow_full = {"error": f"{type(ex).__name__}: {ex}"}
-        try:
-            e.set_option("scan.shadow", 0)
-            e.set_option("profile.scan_events", 0)
-        except Exception:  # noqa: BLE001
-            pass
+            cpu["ids_equal_gpu_engine_on_sample"] = f"{type(ex).__name__}: {ex}"
 
     rows_per_rank = idx.hi - idx.lo
-    # --opt scan.shadow=1: the timed steps ran K11, whose launch reads the split-bf16 shadow (4 bytes per coordinate,
-    # Kp = K rounded up to 64) instead of the fp64 rows; the roofline is then stated on ITS bytes
-    shadow_path = any(kv.replace(" ", "") == "scan.shadow=1" for kv in args.opt)
-    algo_bytes = rows_per_rank * (-(-K // 64) * 64) * 4 if shadow_path else rows_per_rank * K * 8
+    # the roofline is stated on the bytes of the copy of the log the timed launches actually streamed (engine stat
+    # scan_plane_last: 2 = bf16 hi plane, K12, the default; 1 = hi + lo planes, K11; 0 = the fp64 rows, K1)
+    algo_bytes = plane_bytes(plane_used, rows_per_rank, K)
     peak, peak_src = measured_peak_gbs()
     achieved = algo_bytes / (scan_ms_avg / 1e3) / 1e9 if scan_ms_avg > 0 else 0.0
-    traffic = None if shadow_path else profile_traffic()
+    traffic = profile_traffic()
+    tr = (traffic or {}).get({0: "scan_wide", 1: "scan_shadow", 2: "scan_plane"}[plane_used])
     qps = args.steps / (dev_ms / 1e3)
+    dtype = {0: "f64",
+             1: "answers f64 (reference operation order, bit-identical to the reference); scan keys fp32 from the hi + lo bf16 planes",
+             2: "answers f64 (reference operation order, bit-identical to the reference); scan keys fp32 from the bf16 hi plane of "
+                "the log's split-bf16 shadow, completeness proven per query, unproven queries re-answered from the fp64 rows"}[plane_used]
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "dtype": dtype, "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": D * 8,
                 "d2h_bytes_per_step": k * 32, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "scan_shadow_kernel<1> (K11, split-bf16 shadow of the log)" if shadow_path
-                     else "scan_wide_kernel<TR,1> (variant %d)" % e_variant(args),
+        "roofline": {"bound": "hbm", "kernel": PLANE_KERNEL[plane_used] + (" (variant %d)" % e_variant(args) if plane_used == 0 else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # ncu dram__bytes_read+write of one launch; the capture streams traffic["rows"] rows,
-                     # this launch streams rows_per_rank (pure streaming: bytes scale with rows)
-                     "traffic": traffic["dram_bytes_per_launch"] * rows_per_rank / traffic["rows"] if traffic else None,
-                     "traffic_source": traffic["source"] if traffic else None,
+                     # ncu dram__bytes_read+write of ONE launch of this kernel, captured once (profiles/scan_traffic.json) on
+                     # tr["rows"] rows and scaled to this launch's rows (pure streaming: bytes scale with rows) -- a STATIC
+                     # figure, not measured in this run
+                     "traffic": tr["dram_bytes_per_launch"] * rows_per_rank / tr["rows"] if tr else None,
+                     "traffic_kind": "static: one ncu capture scaled by rows" if tr else None,
+                     "traffic_source": tr["source"] if tr else None,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms_avg,
                      "launches_timed": int(scan_launches), "peak_source": peak_src,
                      "scan_share_of_step": scan_ms_avg / (dev_ms / args.steps),
+                     "launch_includes": "scan + (fused tail: merge of the CTA lists, reference-order re-rank, proof"
+                                        + (", peer-memory exchange + cross-shard merge)" if world > 1 else ")"),
                      "fp64_rows_equivalent_gbs": rows_per_rank * K * 8 / (scan_ms_avg / 1e3) / 1e9 if scan_ms_avg > 0 else 0.0},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
+        "parity_check": parity,
+        "fp64_scan": fp64_scan,
         "batch": batch,
         "batch_dmma": batch_dmma,
-        "single_query_shadow_ab": shadow_ab,
-        "single_query_shadow_full_size": shadow_full,
         "store": {"rows_per_rank": rows_per_rank, "build_s": build_s, "hbm_gib_mapped": e.stats()["hbm_bytes_mapped"] / 2**30,
-                  "exact_reruns": e.stats()["exact_reruns"], "last_result_seq": int(last["seq"][0, 0]),
+                  "exact_reruns": e.stats()["exact_reruns"], "fp64_reruns": e.stats()["fp64_reruns"],
+                  "last_result_seq": int(last["seq"][0, 0]),
                   "e2e_entry_point": "svdb_nearest_batch (C-ABI, host buffers)" if world == 1 else "svdb.sharded.ShardedIndex.nearest"},
     }
     emit(line)
@@ -554,7 +639,8 @@ def main():
     ap.add_argument("--batch-queries", type=int, default=1024)
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-shadow-ab", action="store_true")
+    ap.add_argument("--no-fp64-scan", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. scan.variant=1)")
     args = ap.parse_args()
     if args.kd_dim <= 0:

@@ -137,8 +137,17 @@ int svdb_nearest_batch(svdb_engine *e, const double *Q, size_t nq, size_t ldq, s
 #define SVDB_MODE_EXACT 1
 #define SVDB_MODE_TREE  2
 #define SVDB_MODE_MTREE 3        /* k = 1, thin kd-points: balanced median tree + the reference's traversal for flagged ties */
+#define SVDB_MODE_FP64  4        /* the scan of the fp64 rows + exact re-rank, whatever the batch size: no low-precision
+                                    keys (bf16 planes, tensor cores).  First step of the escalation for answers that a
+                                    low-precision path could not prove complete: AUTO -> FP64 -> EXACT -> TREE */
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k,
                               svdb_candidate *d_out, int mode);
+/* Sharded store (one process per GPU): the same with the cross-shard exchange inside -- this shard's scan, the
+ * peer-memory exchange and the merge; d_out receives the MERGED nq x k candidates.  A single-query call is ONE kernel
+ * launch (the scan's last CTA re-ranks, stores to the peers, waits and merges).  Collective. */
+struct svdb_exchange;
+int svdb_nearest_batch_device_sharded(svdb_engine *e, struct svdb_exchange *x, const double *d_Q, size_t nq, size_t ldq,
+                                      size_t k, svdb_candidate *d_out, int mode);
 /* Cross-shard merge: d_in holds nshards blocks of nq x k candidates (an allgather result);
  * d_out receives nq x k, the k smallest of each query under (dist, seq). */
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards,
@@ -260,12 +269,21 @@ typedef struct svdb_stats {
     uint64_t mtree_builds;       /* (re)builds of the balanced median tree (K8) */
     uint64_t mtree_levels;       /* its internal levels after the last build (2^levels leaves of <= 32 points) */
     uint64_t mtree_rows;         /* log entries it covers; later ones are scanned as a tail */
+    uint64_t fp64_reruns;        /* queries a low-precision path flagged and the fp64 scan (K1) re-answered */
+    uint64_t scan_plane_last;    /* what the last scan pass read: 0 fp64 rows (K1 / exact), 1 hi + lo bf16 planes (K11), 2 hi plane (K12) */
+    uint64_t tree_dropped;       /* 1: the reference-shaped tree was deeper than "tree.max_depth" (degenerate insertion
+                                    order, e.g. sorted input) and has been dropped: distinct kd-points at exactly equal
+                                    minimal distance now resolve to the lowest seq, not to the reference's traversal order */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
  * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never),
- * "nearest.umma_min_kd_dim", "scan.shadow" (1: calls of 1-3 queries scan the split-bf16 shadow of the log, K11 -- half the
- * bytes of the fp64 rows, same answers; off by default in this release),
+ * "nearest.umma_min_kd_dim",
+ * "scan.plane" (which copy of the log calls of 1-3 queries scan: 2 = the bf16 hi plane of the split-bf16 shadow, K12, 2 bytes
+ * per coordinate -- the default; 1 = hi + lo planes, K11, 4 bytes; 0 = the fp64 rows, K1, 8 bytes.  Same answers on every
+ * setting: the survivors are re-ranked from the fp64 rows in the reference's operation order and whatever cannot be proven
+ * complete is re-answered from the fp64 rows), "scan.shadow" (round-1 name: 1 = scan.plane 1, 0 = scan.plane 0),
+ * "scan.fuse_tail" (1, default: the scan's last CTA runs the re-rank and the cross-shard exchange itself),
  * "nearest.mtree" (AUTO may use the median tree), "mtree.lanes" (32/16/8 lanes per query), "mtree.tail_max";
  * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
  * row i is global row lo + i sets it to lo, so that merged answers carry global row numbers). */

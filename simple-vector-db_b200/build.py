@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsvdb_b200.so")
-SOURCES = ["scan_kernels.cu", "compare_kernels.cu", "tree_kernels.cu", "median_tree.cu", "mma_kernels.cu", "umma_filter.cu", "arena.cu", "engine.cu", "exchange.cu", "tie_protocol.cu", "dropin.cu"]
+SOURCES = ["scan_kernels.cu", "plane_scan.cu", "compare_kernels.cu", "tree_kernels.cu", "median_tree.cu", "mma_kernels.cu", "umma_filter.cu", "arena.cu", "engine.cu", "exchange.cu", "tie_protocol.cu", "dropin.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "smem_optin.h"
 
 namespace svdb {
 
@@ -200,7 +201,8 @@ static cudaError_t launch_compare_inst(const CompareArgs &a, int num_sms, cudaSt
     u64 grid = (ngroups + W - 1) / W;
     const u64 maxgrid = (u64)num_sms * (smem <= 100 * 1024 ? 2 : 1);
     if (grid > maxgrid) grid = maxgrid;
-    cudaError_t e = cudaFuncSetAttribute(compare_kernel<MODE, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(compare_kernel<MODE, CH, W>, smem);
     if (e != cudaSuccess) return e;
     compare_kernel<MODE, CH, W><<<(unsigned)grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();

@@ -218,11 +218,12 @@ void svdb_engine::destroy() {
     cur.release();
     child.release();
     xnorm.release();
-    shadow.release();
+    shadow_hi.release();
+    shadow_lo.release();
     shadow_ready = false;
     shadow_n = 0;
     shadow_mapped_counted = 0;
-    for (Scratch *s : {&qsplit, &ubuf, &udbg}) s->free_();
+    for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
                        &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
@@ -268,6 +269,7 @@ int svdb_engine::tree_append(size_t n0, size_t m) {
         fprintf(stderr, "svdb_b200: KD tree deeper than %d levels (degenerate insertion order); tree dropped, "
                         "nearest is answered by the scan from now on\n", tree_max_depth);
         use_tree = false;
+        stats.tree_dropped = 1;              // svdb_get_stats: callers can see that exact-tie order is no longer the reference's
         rounds = -rounds;
     }
     stats.tree_rounds += rounds;
@@ -347,8 +349,8 @@ int svdb_engine::flush() {
     CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
     n_versions = n1;
     stage_n = 0;
-    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped() + shadow.mapped();
-    shadow_mapped_counted = shadow.mapped();
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped() + shadow_hi.mapped() + shadow_lo.mapped();
+    shadow_mapped_counted = shadow_hi.mapped() + shadow_lo.mapped();
     return SVDB_OK;
 }
 
@@ -374,7 +376,34 @@ static int largest_pass(size_t remaining, int limit) {
     return p;
 }
 
-int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode) {
+// Sharded stores: the local answers go through the peer-memory exchange (exchange.cu) and d_out receives the merged
+// ones.  A call that is ONE scan pass (the single-query step) does all of it inside the scan launch (scan_tail);
+// everything else exchanges once, after its local answers are complete -- one epoch per call on every path, so the
+// ranks stay in step even if they took different paths.
+int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode,
+                                svdb_exchange *x) {
+    if (!x) return nearest_local(d_Q, nq, ldq, k, d_out, mode, nullptr, nullptr, nullptr);
+    if (!exchange_fits(x, nq, k)) return fail(SVDB_ERR_ARG, "nq * k exceeds the exchange capacity");
+    if (nq == 0) return SVDB_OK;
+    std::string err;
+    if (!xlocal.ensure(nq * k * sizeof(svdb_candidate), err)) return fail(SVDB_ERR_OOM, err);
+    bool exchanged = false;
+    if (!d_out) return fail(SVDB_ERR_ARG, "NULL output");
+    int rc = nearest_local(d_Q, nq, ldq, k, xlocal.as<svdb_candidate>(), mode, x, d_out, &exchanged);
+    if (rc) return rc;
+    if (!exchanged) {
+        CK(exchange_enqueue(x, stream, xlocal.as<svdb_candidate>(), nq, k, d_out));
+        stats.kernels_launched += 2;
+    }
+    return SVDB_OK;
+}
+
+// d_out: this engine's own answers.  x != NULL: the caller will exchange them and merge into d_merged afterwards; a
+// call that is a single scan pass does that itself in the scan's tail and reports *exchanged = true.
+int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode,
+                               svdb_exchange *x, svdb_candidate *d_merged, bool *exchanged) {
+    const bool fp64_only = mode == SVDB_MODE_FP64;       // escalation step: wide fp64 scan + re-rank, no low-precision keys
+    if (fp64_only) mode = SVDB_MODE_AUTO;
     if (k < 1 || k > SVDB_MAX_K) return fail(SVDB_ERR_ARG, "k must be in 1..SVDB_MAX_K");
     if (no_log) return fail(SVDB_ERR_ARG, "this engine was created without a log (SVDB_FLAG_NO_LOG)");
     if (nq == 0) return SVDB_OK;
@@ -387,7 +416,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     if (mode == SVDB_MODE_MTREE && !mtree_wanted(k, mode))
         return fail(SVDB_ERR_ARG, "the median tree serves engines with thin kd-points (kd_dim <= 8)");
     // K9: balanced median tree; the queries it flags (distinct points tied at the minimum) go through K6
-    if (mtree_wanted(k, mode)) {
+    if (!fp64_only && mtree_wanted(k, mode)) {
         rc = mtree_update();
         if (rc) return rc;
         std::string err;
@@ -411,7 +440,7 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         return SVDB_OK;
     }
     // K6: thin kd-points prune well, and the traversal IS the reference's algorithm
-    if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && use_tree && !force_exact && K <= tree_max_k)) {
+    if (mode == SVDB_MODE_TREE || (mode == SVDB_MODE_AUTO && !fp64_only && use_tree && !force_exact && K <= tree_max_k)) {
         CK(launch_tree_nearest(kd_ptr(), kstride, K, child.as<uint32_t>(), n_versions, d_Q, (int)ldq, (int)nq, (int)k,
                                log_idx.as<u64>(), cfg.seq_base, d_out, stream));
         stats.kernels_launched++;
@@ -420,13 +449,13 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
     const int cap = (int)std::min<size_t>(32, k + 8);
     // K10: larger batches go to the tcgen05 tensor cores (split-bf16 keys, same exact re-rank)
-    if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_min_q > 0 && nq >= (size_t)umma_min_q &&
+    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_min_q > 0 && nq >= (size_t)umma_min_q &&
         K >= umma_min_k && n_versions < (1ull << 31)) {
         const int r = nearest_umma(d_Q, nq, ldq, k, d_out);
         if (r != -1000) return r;
     }
     // K2: a batch large enough to be compute-bound goes to the FP64 tensor cores
-    if (!use_exact && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
+    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
         const int G = mma_group_size(nq);
         std::string err;
         const int ldp = kstride;
@@ -500,22 +529,27 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     const int nlists = n_versions ? scan_num_lists(tune, !use_exact) : 0;
     std::string err;
 
-    // K11 (option scan.shadow): 1-3 queries stream the split-bf16 shadow (half the bytes of the fp64 rows)
-    bool use_shadow = false;
-    if (!use_exact && mode == SVDB_MODE_AUTO && scan_shadow && n_versions && umma_ok && K >= umma_min_k && n_versions < (1ull << 31)) {
+    // Which copy of the log the scan reads (option scan.plane): 2 = the bf16 hi plane (K12, 2 bytes per coordinate),
+    // 1 = hi + lo planes (K11, 4 bytes), 0 = the fp64 rows (K1, 8 bytes).  Same answers; see engine.h.
+    const int Kp = umma_kpad(K);
+    int plane = 0;
+    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && scan_plane > 0 && n_versions && umma_ok && K >= umma_min_k &&
+        n_versions < (1ull << 31)) {
         // never build or extend the shadow under stream capture (see nearest_host): fall back to the fp64 rows there
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         if (cs == cudaStreamCaptureStatusNone || (shadow_ready && shadow_n == n_versions)) {
             const int sr = ensure_shadow();
-            if (sr == SVDB_OK) use_shadow = true;
+            if (sr == SVDB_OK) plane = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
             else if (sr != -1000) return sr;
         }
     }
+    last_scan_plane = plane;
+    stats.scan_plane_last = (uint64_t)plane;
 
     const double *qbase = d_Q;
     int qld = (int)ldq;
-    if (use_shadow) {
+    if (plane == 1) {
         // padded fp64 copies (the re-rank reads them) and |q|^2 per query (the key error bound scales with it)
         if (!qpad.ensure(nq * (size_t)kstride * 8, err) || !qnorm.ensure(nq * 8, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_prep_queries(d_Q, (int)ldq, K, (int)nq, (int)nq, qpad.as<double>(), kstride, qnorm.as<double>(), stream));
@@ -526,62 +560,26 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
     // the wide scan stages whole query rows of kstride doubles with 16-byte bulk copies:
     // use the caller's buffer in place when it already has that shape, else pad a copy
     const bool q_in_place = K == kstride && (ldq % 2) == 0 && (reinterpret_cast<uintptr_t>(d_Q) % 16) == 0;
-    if (!use_exact && !use_shadow && !q_in_place) {
+    if (!use_exact && plane == 0 && !q_in_place) {
         if (!qpad.ensure(nq * (size_t)kstride * 8, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_pad_queries(d_Q, (int)ldq, qpad.as<double>(), kstride, K, (int)nq, stream));
         stats.kernels_launched++;
         qbase = qpad.as<double>();
         qld = kstride;
     }
-    const int limit = std::max(1, tune.nq_per_pass);
+    int limit = std::max(1, tune.nq_per_pass);
+    if (plane == 2) limit = plane_scan_supports(Kp, 2) ? std::min(limit, 2) : 1;
     if (nlists && !lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return fail(SVDB_ERR_OOM, err);
+    // the scan's last CTA finalizes (and exchanges) itself -- every wide scan but the LDG variant and the exact kernel
+    const bool fuse = fuse_tail && nlists && !use_exact && (plane > 0 || tune.variant == 0);
+    if (fuse && !ticket.p) {
+        if (!ticket.ensure(16, err)) return fail(SVDB_ERR_OOM, err);
+        CK(cudaMemsetAsync(ticket.p, 0, 16, stream));
+    }
 
     size_t done = 0;
     while (done < nq) {
         const int nqp = largest_pass(nq - done, limit);
-        if (nlists) {
-            ScanArgs sa{};
-            sa.pts = kd_ptr();
-            sa.n = n_versions;
-            sa.K = K;
-            sa.stride = kstride;
-            sa.q = qbase + done * (size_t)qld;
-            sa.ldq = qld;
-            sa.nq = nqp;
-            sa.cap = cap;
-            sa.lists = lists.as<Cand>();
-            sa.assign = tune.assign;
-            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-            if (profile_scan) {
-                if (scan_events_used == scan_events.size()) {
-                    cudaEvent_t a, b;
-                    CK(cudaEventCreate(&a));
-                    CK(cudaEventCreate(&b));
-                    scan_events.emplace_back(a, b);
-                }
-                ev0 = scan_events[scan_events_used].first;
-                ev1 = scan_events[scan_events_used].second;
-                scan_events_used++;
-                CK(cudaEventRecord(ev0, stream));
-            }
-            if (use_shadow) {
-                ShadowScanArgs ha{};
-                ha.xsplit = shadow.as<uint16_t>();
-                ha.n = n_versions;
-                ha.K = K;
-                ha.Kp = umma_kpad(K);
-                ha.q = sa.q;
-                ha.ldq = qld;
-                ha.nq = nqp;
-                ha.cap = cap;
-                ha.lists = lists.as<Cand>();
-                CK(launch_scan_shadow(tune, ha, stream));
-            } else {
-                CK(use_exact ? launch_scan_exact(tune, sa, stream) : launch_scan_wide(tune, sa, stream));
-            }
-            if (ev1) CK(cudaEventRecord(ev1, stream));
-            stats.kernels_launched++;
-        }
         FinalArgs fa{};
         fa.lists = lists.as<Cand>();
         fa.nlists = nlists;
@@ -596,47 +594,130 @@ int svdb_engine::nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t
         fa.log_index = log_idx.as<u64>();
         fa.seq_base = cfg.seq_base;
         fa.eps = use_exact ? -1.0 : 4.0 * (double)(K + 2) * ldexp(1.0, -53);
-        if (use_shadow) {
+        if (plane == 1) {
             fa.eps = shadow_eps(K);
             fa.eabs_coef = shadow_eabs_coef();
             fa.qnorm = qnorm.as<double>() + done;
             fa.xn_max_bits = xnmax.as<unsigned long long>();
             fa.scale_lo = 1e-24;               // fp32 keys: see nearest_umma
             fa.scale_hi = 1e30;
+        } else if (plane == 2) {
+            fa.sq_mode = 1;
+            fa.sq_gamma = plane_gamma(Kp);
+            fa.plane_err_bits = plane_err.as<unsigned long long>();
+            fa.xn_max_bits = xnmax.as<unsigned long long>();
+            fa.scale_lo = 0.0;                 // underflow is inside the bound (tail.cuh); squares must not overflow fp32
+            fa.scale_hi = 1e30;
         }
         fa.child = use_tree ? child.as<uint32_t>() : nullptr;
         fa.mark_ties = (cfg.flags & SVDB_FLAG_SHARD) ? 1 : 0;
         fa.out = d_out + done * k;
-        CK(launch_finalize(fa, stream));
-        stats.kernels_launched++;
+        TailArgs ta{};
+        bool fused_exchange = false;
+        if (fuse) {
+            ta.ticket = ticket.as<unsigned>();
+            ta.fin = fa;
+            if (x && exchanged && done == 0 && (size_t)nqp == nq) {      // the whole call is this one pass
+                exchange_fill_tail(x, ta, d_merged);
+                fused_exchange = true;
+            }
+        }
+        if (nlists) {
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profile_scan) {
+                if (scan_events_used == scan_events.size()) {
+                    cudaEvent_t a, b;
+                    CK(cudaEventCreate(&a));
+                    CK(cudaEventCreate(&b));
+                    scan_events.emplace_back(a, b);
+                }
+                ev0 = scan_events[scan_events_used].first;
+                ev1 = scan_events[scan_events_used].second;
+                scan_events_used++;
+                CK(cudaEventRecord(ev0, stream));
+            }
+            if (plane == 2) {
+                PlaneScanArgs pa{};
+                pa.xhi = shadow_hi.as<uint16_t>();
+                pa.n = n_versions;
+                pa.K = K;
+                pa.Kp = Kp;
+                pa.q = fa.q;
+                pa.ldq = qld;
+                pa.nq = nqp;
+                pa.cap = cap;
+                pa.lists = lists.as<Cand>();
+                pa.tail = ta;
+                CK(launch_scan_plane(tune, pa, stream));
+            } else if (plane == 1) {
+                ShadowScanArgs ha{};
+                ha.xhi = shadow_hi.as<uint16_t>();
+                ha.xlo = shadow_lo.as<uint16_t>();
+                ha.n = n_versions;
+                ha.K = K;
+                ha.Kp = Kp;
+                ha.q = fa.q;
+                ha.ldq = qld;
+                ha.nq = nqp;
+                ha.cap = cap;
+                ha.lists = lists.as<Cand>();
+                ha.tail = ta;
+                CK(launch_scan_shadow(tune, ha, stream));
+            } else {
+                ScanArgs sa{};
+                sa.pts = kd_ptr();
+                sa.n = n_versions;
+                sa.K = K;
+                sa.stride = kstride;
+                sa.q = fa.q;
+                sa.ldq = qld;
+                sa.nq = nqp;
+                sa.cap = cap;
+                sa.lists = lists.as<Cand>();
+                sa.assign = tune.assign;
+                sa.tail = ta;
+                CK(use_exact ? launch_scan_exact(tune, sa, stream) : launch_scan_wide(tune, sa, stream));
+            }
+            if (ev1) CK(cudaEventRecord(ev1, stream));
+            stats.kernels_launched++;
+        }
+        if (!fuse) {
+            CK(launch_finalize(fa, stream));
+            stats.kernels_launched++;
+        }
+        if (fused_exchange) *exchanged = true;
         done += nqp;
     }
     return SVDB_OK;
 }
 
-// The split-bf16 shadow of the kd log ([versions][2*Kp] bf16, K10 and K11 read it): created on first use, extended by
+// The split-bf16 shadow of the kd log (two planes of [versions][Kp] bf16; K10, K11 and K12 read it): created on first use, extended by
 // the entries appended since.  -1000: no HBM for it (or no address space) -- the fp64 paths keep serving.
 int svdb_engine::ensure_shadow() {
     std::string err;
     const int Kp = umma_kpad(K);
-    const size_t row_bytes = (size_t)2 * Kp * 2;
+    const size_t plane_row = (size_t)Kp * 2;
     if (!shadow_ready) {
-        if (!shadow.init(device, max_versions * row_bytes, err)) {
+        if (!plane_err.ensure(8, err)) return fail(SVDB_ERR_OOM, err);
+        CK(cudaMemsetAsync(plane_err.p, 0, 8, stream));
+        if (!shadow_hi.init(device, max_versions * plane_row, err) || !shadow_lo.init(device, max_versions * plane_row, err)) {
             umma_ok = false;
             return -1000;
         }
         shadow_ready = true;
     }
     if (shadow_n < n_versions) {
-        if (!shadow.ensure(n_versions * row_bytes, stream, err)) {
+        if (!shadow_hi.ensure(n_versions * plane_row, stream, err) || !shadow_lo.ensure(n_versions * plane_row, stream, err)) {
             umma_ok = false;                 // not enough HBM next to the store: nothing is lost
             cudaGetLastError();
             return -1000;
         }
-        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow.as<uint16_t>(), tune.num_sms, stream));
+        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow_hi.as<uint16_t>(),
+                             shadow_lo.as<uint16_t>(), plane_err.as<unsigned long long>(), tune.num_sms, stream));
         stats.kernels_launched++;
-        stats.hbm_bytes_mapped += shadow.mapped() - shadow_mapped_counted;
-        shadow_mapped_counted = shadow.mapped();
+        const size_t mapped = shadow_hi.mapped() + shadow_lo.mapped();
+        stats.hbm_bytes_mapped += mapped - shadow_mapped_counted;
+        shadow_mapped_counted = mapped;
         shadow_n = n_versions;
     }
     return SVDB_OK;
@@ -647,7 +728,7 @@ int svdb_engine::ensure_shadow() {
 int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out) {
     std::string err;
     const int Kp = umma_kpad(K);
-    const size_t row_bytes = (size_t)2 * Kp * 2;
+    const size_t row_bytes = (size_t)2 * Kp * 2;         // both planes of one query
     // never build or extend the shadow under stream capture (see nearest_host): K2 serves that call
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -668,14 +749,17 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
             return fail(SVDB_ERR_OOM, err);
         if (umma_debug && !udbg.ensure((size_t)128 * 256 * 4, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_prep_queries(d_Q + done * ldq, (int)ldq, K, (int)nqp, (int)nq_pad, qpad.as<double>(), ldp, qnorm.as<double>(), stream));
-        CK(launch_split_bf16(qpad.as<double>(), ldp, K, Kp, 0, nq_pad, qsplit.as<uint16_t>(), tune.num_sms, stream));
+        uint16_t *qhi = qsplit.as<uint16_t>(), *qlo = qhi + nq_pad * (size_t)Kp;
+        CK(launch_split_bf16(qpad.as<double>(), ldp, K, Kp, 0, nq_pad, qhi, qlo, nullptr, tune.num_sms, stream));
         UmmaArgs ua{};
-        ua.xsplit = shadow.as<uint16_t>();
+        ua.xhi = shadow_hi.as<uint16_t>();
+        ua.xlo = shadow_lo.as<uint16_t>();
         ua.n = n_versions;
         ua.K = K;
         ua.Kp = Kp;
         ua.xnorm = xnorm.as<double>();
-        ua.qsplit = qsplit.as<uint16_t>();
+        ua.qhi = qhi;
+        ua.qlo = qlo;
         ua.qnorm = qnorm.as<double>();
         ua.nq = (int)nqp;
         ua.bn = bn;
@@ -758,7 +842,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         rc = mtree_update();
         if (rc) return rc;
     }
-    if ((scan_shadow || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
+    if ((scan_plane > 0 || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
@@ -775,13 +859,8 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     const bool q_zero_copy = !wide && nq * (size_t)K * 8 <= 2048;
     const double *d_q = q_zero_copy ? hq.as<double>() : qraw.as<double>();
     auto enqueue_mode = [&](int mode) -> int {
-        if (!x) return nearest_device(d_q, nq, K, k, hout.as<svdb_candidate>(), mode);
-        // sharded: local candidates stay in HBM, the exchange stores them to the peers and writes the merge
-        int r = nearest_device(d_q, nq, K, k, outc.as<svdb_candidate>(), mode);
-        if (r) return r;
-        CK(exchange_enqueue(x, stream, outc.as<svdb_candidate>(), nq, k, hout.as<svdb_candidate>()));
-        stats.kernels_launched += 2;
-        return SVDB_OK;
+        // sharded (x): this shard's scan, the peer-memory exchange and the merge; the merged answers land in hout
+        return nearest_device(d_q, nq, K, k, hout.as<svdb_candidate>(), mode, x);
     };
     auto enqueue = [&]() -> int {
         if (!q_zero_copy) CK(cudaMemcpyAsync(qraw.p, hq.p, nq * (size_t)K * 8, cudaMemcpyHostToDevice, stream));
@@ -829,13 +908,23 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     CK(cudaStreamSynchronize(stream));
     svdb_candidate *res = hout.as<svdb_candidate>();
     // Escalation for queries whose answer could not be proven complete:
-    //   AUTO -> EXACT (mass near-ties defeated the approximate candidate set, or the traversal
-    //   stack overflowed) -> TREE (more exactly-tied entries than a candidate list holds; k = 1).
+    //   low-precision keys (K10 / K11 / K12 / K2) -> FP64 (K1: fp64 rows, relative error ~K 2^-53) -> EXACT (mass
+    //   near-ties defeated every approximate candidate set, or the traversal stack overflowed) -> TREE (more
+    //   exactly-tied entries than a candidate list holds; k = 1).
     if (x) {
-        // merged flags are identical on every rank, so every rank takes (or skips) this branch together
-        bool any = false;
-        for (size_t i = 0; i < nq; i++) any = any || (res[i * k].flags & SVDB_CAND_UNSAFE);
-        if (any) {
+        // merged flags are identical on every rank, so every rank takes (or skips) these branches together
+        auto any_flag = [&](uint64_t f) {
+            for (size_t i = 0; i < nq; i++)
+                if (res[i * k].flags & f) return true;
+            return false;
+        };
+        if (any_flag(SVDB_CAND_UNSAFE) && wide) {
+            stats.fp64_reruns += nq;
+            rc = enqueue_mode(SVDB_MODE_FP64);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(stream));
+        }
+        if (any_flag(SVDB_CAND_UNSAFE)) {
             stats.exact_reruns += nq;
             rc = enqueue_mode(SVDB_MODE_EXACT);
             if (rc) return rc;
@@ -843,17 +932,23 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         }
         // distinct kd-points at exactly the minimal distance: which one does the reference's (global) tree reach
         // first?  Decided by all shards together; again every rank sees the same flags.
-        any = false;
-        for (size_t i = 0; i < nq; i++) any = any || (res[i * k].flags & SVDB_CAND_TIE);
-        if (any) {
+        if (any_flag(SVDB_CAND_TIE)) {
             rc = resolve_ties_engine(this, x, exchange_rank(x), exchange_world(x), nullptr, nullptr, hq.as<double>(), nq,
                                      (size_t)K, res, k);
             if (rc) return rc;
         }
     }
+    const bool low_precision_first = wide && (last_scan_plane > 0 || nq >= (size_t)std::max(1, mma_min_q));
     for (size_t i = 0; i < nq && !x; i++) {
         svdb_candidate *r = res + i * k;
         if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
+        if (low_precision_first) {
+            stats.fp64_reruns++;
+            rc = nearest_device(d_q + i * K, 1, K, k, r, SVDB_MODE_FP64);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(stream));
+            if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
+        }
         stats.exact_reruns++;
         rc = nearest_device(d_q + i * K, 1, K, k, r, SVDB_MODE_EXACT);
         if (rc) return rc;
@@ -1048,8 +1143,8 @@ int svdb_engine::ingest_device_rows(const double *d_rows, size_t n, size_t ld, s
     e->uuids.resize(e->cur_host.size(), std::array<char, 37>{});
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow.mapped();
-    e->shadow_mapped_counted = e->shadow.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped();
+    e->shadow_mapped_counted = e->shadow_hi.mapped() + e->shadow_lo.mapped();
     return SVDB_OK;
 }
 
@@ -1190,8 +1285,8 @@ int svdb_append_kdpoints_device(svdb_engine *e, const double *d_pts, size_t firs
     if (rc) return rc;
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow.mapped();
-    e->shadow_mapped_counted = e->shadow.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped();
+    e->shadow_mapped_counted = e->shadow_hi.mapped() + e->shadow_lo.mapped();
     return SVDB_OK;
 }
 
@@ -1261,9 +1356,19 @@ int svdb_nearest_batch_sharded(svdb_engine *e, svdb_exchange *x, const double *Q
 int svdb_nearest_batch_device(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out,
                               int mode) {
     if (!e) return SVDB_ERR_ARG;
-    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_MTREE) return e->fail(SVDB_ERR_ARG, "unknown mode");
+    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_FP64) return e->fail(SVDB_ERR_ARG, "unknown mode");
     std::lock_guard<std::mutex> g(e->mu);
     return e->nearest_device(d_Q, nq, ldq, k, d_out, mode);
+}
+
+/* The sharded query with device buffers, asynchronous on the engine's stream: this shard's scan, the peer-memory
+ * exchange and the merge; d_out receives the MERGED nq x k candidates.  Collective (same nq, k on every rank). */
+int svdb_nearest_batch_device_sharded(svdb_engine *e, svdb_exchange *x, const double *d_Q, size_t nq, size_t ldq, size_t k,
+                                      svdb_candidate *d_out, int mode) {
+    if (!e || !x) return SVDB_ERR_ARG;
+    if (mode < SVDB_MODE_AUTO || mode > SVDB_MODE_FP64) return e->fail(SVDB_ERR_ARG, "unknown mode");
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->nearest_device(d_Q, nq, ldq, k, d_out, mode, x);
 }
 
 int svdb_merge_candidates_device(int device, void *stream, const svdb_candidate *d_in, size_t nshards, size_t nq, size_t k,
@@ -1591,7 +1696,12 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "umma.debug_keys") e->umma_debug = value != 0;
-    else if (n == "scan.shadow") e->scan_shadow = value != 0;
+    else if (n == "scan.shadow") e->scan_plane = value != 0 ? 1 : 0;      // round-1 name: 1 = K11 (hi + lo planes), 0 = fp64 rows
+    else if (n == "scan.plane") {
+        if (value < 0 || value > 2) return e->fail(SVDB_ERR_ARG, "scan.plane must be 0 (fp64 rows), 1 (hi + lo planes) or 2 (hi plane)");
+        e->scan_plane = (int)value;
+    }
+    else if (n == "scan.fuse_tail") e->fuse_tail = value != 0;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;

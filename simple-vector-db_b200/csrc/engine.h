@@ -48,6 +48,7 @@ void tie_state_free(TieGpu *t);
 cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candidate *d_local, size_t nq, size_t k,
                              svdb_candidate *out);
 bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k);
+void exchange_fill_tail(const svdb_exchange *x, TailArgs &t, svdb_candidate *xout);
 int exchange_rank(const svdb_exchange *x);
 int exchange_world(const svdb_exchange *x);
 int exchange_allgather_host(svdb_exchange *x, cudaStream_t st, const void *send, void *recv, size_t bytes);
@@ -76,10 +77,15 @@ struct svdb_engine {
     int umma_min_q = 65, umma_min_k = 32;
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the shadow
-    size_t shadow_mapped_counted = 0;    // part of shadow.mapped() already included in stats.hbm_bytes_mapped
-    svdb::DeviceBuffer shadow;           // [versions][2*Kp] bf16
-    svdb::Scratch qsplit, ubuf, udbg;
-    bool scan_shadow = false;            // K11: 1-3 queries per call scan the shadow instead of the fp64 rows (option scan.shadow)
+    size_t shadow_mapped_counted = 0;    // part of the shadow's mapped bytes already included in stats.hbm_bytes_mapped
+    svdb::DeviceBuffer shadow_hi, shadow_lo;   // [versions][Kp] bf16 each: x ~ hi + lo (split_bf16_kernel)
+    svdb::Scratch qsplit, ubuf, udbg, plane_err, ticket, xlocal;
+    // Which copy of the log 1-2 query calls scan (option "scan.plane"): 0 the fp64 rows (K1), 1 the hi + lo shadow (K11, 4 bytes
+    // per coordinate), 2 the hi plane alone (K12, 2 bytes per coordinate; the default).  Same answers on every setting:
+    // whatever the re-rank cannot prove complete is re-answered from the fp64 rows.
+    int scan_plane = 2;
+    bool fuse_tail = true;               // the scan's last CTA runs finalize (and the cross-shard exchange) itself
+    int last_scan_plane = 0;             // what the last scan pass of nearest_device read (escalation: skip a redundant K1 rerun)
     int ensure_shadow();                 // SVDB_OK, an error, or -1000: not available
     bool umma_debug = false;             // next K10 launch dumps the keys of its first tile into udbg
     int nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out);   // SVDB_OK, an error, or -1000: not available
@@ -167,7 +173,11 @@ struct svdb_engine {
     int tree_append(size_t n0, size_t m);
     bool mtree_wanted(size_t k, int mode) const;
     int mtree_update();                  // (re)build the median tree when the unindexed tail has outgrown its limit
-    int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode);
+    // x != NULL (sharded store): d_out receives the MERGED answers of all shards (collective, one exchange epoch per call)
+    int nearest_device(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode,
+                       svdb_exchange *x = nullptr);
+    int nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out, int mode, svdb_exchange *x,
+                      svdb_candidate *d_merged, bool *exchanged);
     // x != NULL: this engine is one shard; the local candidates go through the peer-memory exchange and the
     // outputs are the merged answers (collective: every rank calls with the same nq and k)
     int nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, size_t *index_out, double *dist_out,

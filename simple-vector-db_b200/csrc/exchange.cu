@@ -20,117 +20,26 @@
 #include "common.cuh"
 #include "engine.h"
 #include "kernels.h"
+#include "tail.cuh"
 
 namespace svdb {
 
-constexpr int XCH_MAX_WORLD = 16;
-constexpr size_t XCH_FLAG_BYTES = 32 * 8;
-constexpr int XCH_EPOCH_SLOT = 31;
-
-struct PeerPtrs {
-    unsigned char *p[XCH_MAX_WORLD];
-};
-
-__device__ __forceinline__ void st_release_sys_u64(u64 *p, u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ u64 ld_acquire_sys_u64(const u64 *p) {
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// local results (nrec candidates) -> slot `rank` of every peer's gather buffer, then the flags
+// local results (nrec candidates) -> slot `rank` of every peer's gather buffer, then the flags (tail.cuh: xch_push)
 __global__ void __launch_bounds__(256) exchange_push_kernel(const svdb_candidate *__restrict__ local, int nrec, PeerPtrs peers,
                                                             int rank, int world, size_t max_rec) {
     __shared__ u64 s_epoch;
-    if (threadIdx.x == 0) {
-        u64 *mine = reinterpret_cast<u64 *>(peers.p[rank]);
-        s_epoch = mine[XCH_EPOCH_SLOT] + 1;
-        mine[XCH_EPOCH_SLOT] = s_epoch;               // read back by the merge kernel that follows in the stream
-    }
-    __syncthreads();
-    const u64 epoch = s_epoch;
-    const size_t parity_off = XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate);
-    const int words = nrec * 4;                                    // 8-byte words
-    const u64 *src = reinterpret_cast<const u64 *>(local);
-    for (int r = 0; r < world; r++) {
-        u64 *dst = reinterpret_cast<u64 *>(peers.p[r] + parity_off + (size_t)rank * max_rec * sizeof(svdb_candidate));
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) st_release_sys_u64(reinterpret_cast<u64 *>(peers.p[threadIdx.x]) + rank, epoch);
+    xch_push(local, nrec, peers, rank, world, max_rec, &s_epoch);
 }
 
 // wait until every shard's data of `epoch` has landed locally, then K7 (one warp per query)
 __global__ void __launch_bounds__(32) exchange_merge_kernel(const unsigned char *mine, int world, size_t max_rec,
                                                             int nq, int k, svdb_candidate *out) {
     const int qi = blockIdx.x, lane = threadIdx.x;
-    const u64 *flags = reinterpret_cast<const u64 *>(mine);
-    const u64 epoch = __ldcg(flags + XCH_EPOCH_SLOT);
-    if (lane < world) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys_u64(flags + lane) < epoch) {
-            if (clock64() - t0 > 20000000000ll) __trap();          // a peer died: do not hang the GPU
-        }
-    }
-    __syncwarp();
+    const u64 epoch = __ldcg(reinterpret_cast<const u64 *>(mine) + XCH_EPOCH_SLOT);
+    xch_wait(mine, world, epoch, lane);
     const svdb_candidate *in = reinterpret_cast<const svdb_candidate *>(
         mine + XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate));
-    WarpList wl;
-    wl.reset();
-    u64 fl = 0;
-    const int total = world * k;
-    for (int base = 0; base < total; base += 32) {
-        const int i = base + lane;
-        double d = CUDART_INF;
-        u64 s = SEQ_NONE;
-        if (i < total) {
-            const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
-            d = __ldcg(&c->dist);
-            s = __ldcg(&c->seq);
-            fl |= __ldcg(&c->flags) & ~SVDB_CAND_TIE;
-        }
-        wl.offer(s != SEQ_NONE, d, s, lane);
-    }
-    // SVDB_CAND_TIE of the merged answer: >= 2 entries at the merged minimum, or one that its shard flagged
-    double dmin;
-    u64 smin;
-    wl.key_at(0, dmin, smin);
-    int at_min = 0;
-    if (smin != SEQ_NONE) {
-        for (int base = 0; base < total; base += 32) {
-            const int i = base + lane;
-            if (i < total) {
-                const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
-                if (__ldcg(&c->seq) != SEQ_NONE && __ldcg(&c->dist) == dmin) at_min += (__ldcg(&c->flags) & SVDB_CAND_TIE) ? 2 : 1;
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        fl |= __shfl_xor_sync(FULL, fl, m);
-        at_min += __shfl_xor_sync(FULL, at_min, m);
-    }
-    if (at_min >= 2) fl |= SVDB_CAND_TIE;
-    if (lane < k) {
-        svdb_candidate c;
-        c.dist = wl.d;
-        c.seq = wl.seq;
-        c.index = (u64)SVDB_NONE;
-        c.flags = fl;
-        if (wl.seq != SEQ_NONE) {
-            for (int i = 0; i < total; i++) {
-                const svdb_candidate *src = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
-                if (__ldcg(&src->seq) == wl.seq) {
-                    c.index = __ldcg(&src->index);
-                    break;
-                }
-            }
-        }
-        out[(size_t)qi * k + lane] = c;
-    }
+    merge_gathered(in, world, max_rec, qi, k, lane, out);
 }
 
 // generic all-gather on the same buffers: wait for every rank's `nrec` 32-byte records of this epoch and copy
@@ -176,6 +85,14 @@ cudaError_t exchange_enqueue(svdb_exchange *x, cudaStream_t st, const svdb_candi
 }
 bool exchange_fits(const svdb_exchange *x, size_t nq, size_t k) { return x && nq * k <= x->max_rec; }
 int exchange_rank(const svdb_exchange *x) { return x->rank; }
+// what a scan's fused tail needs to exchange and merge by itself (kernels.h: TailArgs)
+void exchange_fill_tail(const svdb_exchange *x, TailArgs &t, svdb_candidate *xout) {
+    t.world = x->world;
+    t.rank = x->rank;
+    t.peers = x->peers;
+    t.max_rec = x->max_rec;
+    t.xout = xout;
+}
 int exchange_world(const svdb_exchange *x) { return x->world; }
 
 // Host buffers in, host buffers out: recv = world blocks of `bytes`, in rank order.  Collective; synchronizes st.

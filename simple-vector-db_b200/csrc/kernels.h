@@ -27,41 +27,7 @@ struct ScanTuning {
     int num_sms = 148;
 };
 
-struct ScanArgs {
-    const double *pts;      // log: entry s at pts + s * stride
-    u64 n;                  // entries
-    int K;                  // coordinates measured
-    int stride;             // doubles between entries
-    const double *q;        // device queries, query i at q + i * ldq (zero padded to stride for the wide path)
-    int ldq;
-    int nq;                 // queries in this pass (<= 8)
-    int cap;                // candidates each CTA emits per query
-    Cand *lists;            // [nq][nlists][cap]
-    int assign;             // ScanTuning::assign
-};
-
-// Number of per-CTA lists a scan with this tuning writes per query.
-int scan_num_lists(const ScanTuning &t, bool wide);
-// Approximate (FMA, lane-parallel) scan for wide rows; needs stride even and 16-B aligned pts.
-cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
-// Reference-order exact scan, one thread per log entry (primary for thin rows, fallback for any).
-cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
-
-// K11: the scan over the split-bf16 shadow of the log (4 bytes per coordinate instead of 8)
-struct ShadowScanArgs {
-    const uint16_t *xsplit; // [n][2*Kp] bf16: hi plane | lo plane (launch_split_bf16)
-    u64 n;
-    int K, Kp;
-    const double *q;        // device queries (fp64), query i at q + i * ldq
-    int ldq;
-    int nq;                 // 1, 2, 4 or 8 queries share the pass
-    int cap;
-    Cand *lists;            // [nq][nlists][cap]
-};
-cudaError_t launch_scan_shadow(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st);
-double shadow_eps(int K);
-double shadow_eabs_coef();
-
+// ---- what follows a scan: finalize (merge of the per-CTA lists, reference-order re-rank, completeness proof) ----
 struct FinalArgs {
     const Cand *lists;
     int nlists, cap, nq, k;
@@ -76,11 +42,89 @@ struct FinalArgs {
     const double *qnorm;    // |q|^2 per query of this launch (K2), else NULL
     const unsigned long long *xn_max_bits;   // largest |x|^2 in the log, as double bits (K2), else NULL
     double scale_lo, scale_hi;   // K10 (fp32 keys): queries whose max|x|^2 + |q|^2 lies outside [lo, hi] are flagged UNSAFE; 0, 0: no check
+    // sqrt-form keys (K12, the scan of ONE low-precision plane of the log): key = |x^ - q^|^2 in fp32, hence
+    //   |sqrt(key) - sqrt(d)| <= E + gamma (sqrt(d) + E),   E = max_r |x_r - x^_r| + |q - fl32(q)| + underflow slack
+    // sq_mode = 1: eps / eabs_coef / qnorm are ignored; finalize forms |q - fl32(q)| and |q|^2 itself
+    int sq_mode;
+    double sq_gamma;
+    const unsigned long long *plane_err_bits;   // max_r |x_r - x^_r| over the log, as double bits
     const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
     int mark_ties;          // shards (child == NULL): flag SVDB_CAND_TIE when distinct kd-points may tie at the minimum
     svdb_candidate *out;    // [nq][k]
 };
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st);
+
+// ---- the fused tail: the LAST CTA of a scan launch to finish (atomic ticket) runs finalize for the launch's queries
+// itself and, on a sharded store, stores the answers into every peer's gather buffer over NVLink, waits for the
+// peers' and merges (K7) -- the whole single-query step is ONE launch (the fixed ~44 us of
+// finalize + push + merge launches behind a 1 ms scan).
+constexpr int XCH_MAX_WORLD = 16;
+struct PeerPtrs {
+    unsigned char *p[XCH_MAX_WORLD];
+};
+struct TailArgs {
+    unsigned *ticket;       // device word, zero between launches; NULL: no fused tail (finalize_kernel is launched after the scan)
+    FinalArgs fin;          // fin.lists = the launch's lists
+    int world, rank;        // world <= 1: no exchange, fin.out is the answer
+    PeerPtrs peers;         // exchange.cu: every rank's gather buffer
+    size_t max_rec;
+    svdb_candidate *xout;   // merged answers [nq][k]
+};
+
+struct ScanArgs {
+    const double *pts;      // log: entry s at pts + s * stride
+    u64 n;                  // entries
+    int K;                  // coordinates measured
+    int stride;             // doubles between entries
+    const double *q;        // device queries, query i at q + i * ldq (zero padded to stride for the wide path)
+    int ldq;
+    int nq;                 // queries in this pass (<= 8)
+    int cap;                // candidates each CTA emits per query
+    Cand *lists;            // [nq][nlists][cap]
+    int assign;             // ScanTuning::assign
+    TailArgs tail;          // scan_wide_kernel only
+};
+
+// Number of per-CTA lists a scan with this tuning writes per query.
+int scan_num_lists(const ScanTuning &t, bool wide);
+// Approximate (FMA, lane-parallel) scan for wide rows; needs stride even and 16-B aligned pts.
+cudaError_t launch_scan_wide(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
+// Reference-order exact scan, one thread per log entry (primary for thin rows, fallback for any).
+cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream_t st);
+
+// K11: the scan over the split-bf16 shadow of the log (4 bytes per coordinate instead of 8)
+struct ShadowScanArgs {
+    const uint16_t *xhi, *xlo; // [n][Kp] bf16 each: hi plane, lo plane (launch_split_bf16)
+    u64 n;
+    int K, Kp;
+    const double *q;        // device queries (fp64), query i at q + i * ldq
+    int ldq;
+    int nq;                 // 1, 2, 4 or 8 queries share the pass
+    int cap;
+    Cand *lists;            // [nq][nlists][cap]
+    TailArgs tail;
+};
+cudaError_t launch_scan_shadow(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st);
+double shadow_eps(int K);
+double shadow_eabs_coef();
+
+// K12: the single-query scan over the bf16 HI plane alone (2 bytes per coordinate); sqrt-form bound (FinalArgs::sq_mode)
+struct PlaneScanArgs {
+    const uint16_t *xhi;    // [n][Kp] bf16
+    u64 n;
+    int K, Kp;
+    const double *q;        // device queries (fp64), query i at q + i * ldq; K coordinates each are read
+    int ldq;
+    int nq;                 // 1 or 2 queries share the pass (plane_scan_supports)
+    int cap;
+    Cand *lists;            // [nq][nlists][cap]
+    TailArgs tail;
+};
+bool plane_scan_supports(int Kp, int nq);
+double plane_gamma(int Kp);
+cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaStream_t st);
+
+
 
 cudaError_t launch_merge_candidates(const svdb_candidate *in, int nshards, int nq, int k, svdb_candidate *out,
                                     cudaStream_t st);
@@ -108,11 +152,11 @@ cudaError_t launch_prep_queries(const double *src, int ldq, int K, int nq, int n
 
 // K10: batched queries on the 5th-generation tensor cores (tcgen05 + TMEM) with split-bf16 keys (umma_filter.cu)
 struct UmmaArgs {
-    const uint16_t *xsplit; // [n][2*Kp] bf16: hi plane | lo plane of every log row (launch_split_bf16)
+    const uint16_t *xhi, *xlo; // [n][Kp] bf16 each: hi plane and lo plane of the log rows (launch_split_bf16)
     u64 n;                  // log entries, < 2^31
     int K, Kp;              // Kp = umma_kpad(K)
     const double *xnorm;    // |x_r|^2 per log entry (fp64, as for K2)
-    const uint16_t *qsplit; // [ngroups*bn][2*Kp] bf16 planes of the padded queries
+    const uint16_t *qhi, *qlo; // [ngroups*bn][Kp] bf16 each: the planes of the padded queries
     const double *qnorm;    // |q|^2 per padded query
     int nq;                 // real queries
     int bn;                 // queries per CTA group: 64, 128 or 256 (umma_group_size)
@@ -127,7 +171,9 @@ int umma_kpad(int K);
 int umma_group_size(size_t nq);
 size_t umma_buf_bytes(int ngroups, int nstreams, int bn);
 double umma_eabs_coef(int K);   // absolute key error <= coef * (max|x|^2 + |q|^2)
-cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst, int num_sms, cudaStream_t st);
+// fp64 rows [first, first+n) -> the hi / lo bf16 planes; err_bits (may be NULL): running max over the rows of |x - hi|_2 (double bits)
+cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst_hi, uint16_t *dst_lo,
+                              unsigned long long *err_bits, int num_sms, cudaStream_t st);
 cudaError_t launch_umma_filter(const UmmaArgs &a, cudaStream_t st, std::string *why);
 
 // K5: insert log entries [n0, n0+m) into the reference-shaped tree (level-synchronous; see tree_kernels.cu).

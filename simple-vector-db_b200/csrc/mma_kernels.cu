@@ -18,6 +18,7 @@
 // finalize_kernel widens its candidate window and its completeness proof by E (FinalArgs::eabs*).
 #include "common.cuh"
 #include "kernels.h"
+#include "smem_optin.h"
 
 namespace svdb {
 
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) scan_mma_kernel(MmaArgs p) {
 
 template <int NQT>
 static cudaError_t launch_scan_mma_inst(const MmaArgs &a, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaShape<NQT>::SMEM);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_mma_kernel<NQT>, MmaShape<NQT>::SMEM);
     if (e != cudaSuccess) return e;
     scan_mma_kernel<NQT><<<a.ngroups * a.nstreams, MM_THREADS, MmaShape<NQT>::SMEM, st>>>(a);
     return cudaGetLastError();

@@ -1,0 +1,240 @@
+// plane_scan.cu -- K12: the single-query distance scan over ONE low-precision plane of the log, sm_100a.
+//
+// Replaces the reference's nearest-neighbour loop, src/kdtree.c:131-162 (entry :171-178), for wide kd-points.  K1
+// (scan_kernels.cu) streams the fp64 log at the HBM roofline, so a faster answer needs FEWER BYTES: this kernel reads only
+// the bf16 HI plane of the split-bf16 shadow that K10 keeps anyway (umma_filter.cu: x^ = bf16(fl32(x)), [n][Kp] bf16,
+// 2 bytes per coordinate = a quarter of the fp64 rows), forms key = |x^ - fl32(q)|^2 in fp32 and leaves exactness to the
+// re-rank: finalize_query recomputes the survivors from the fp64 rows in the reference's operation order and PROVES that
+// no row outside the candidate lists can belong to the top-k, from the bound in its natural (square-root) form
+//     | sqrt(key) - sqrt(d) |  <=  E + gamma (sqrt(d) + E),
+//     E = max_r |x_r - x^_r|_2 (measured in fp64 when the plane is written, plane_err) + |q - fl32(q)|_2,
+//     gamma = (Kp/32 + 12) 2^-24 (fp32 rounding of differences, squares and the lane-parallel sum; all terms >= 0)
+// -- a triangle inequality, no Cauchy-Schwarz slack on the cross term.  When the proof fails (near-ties closer than the
+// plane resolves) the query is flagged SVDB_CAND_UNSAFE and re-answered from the fp64 rows (K1); answers are identical
+// to the reference either way.
+//
+// HBM-bound: algorithmic bytes per launch = n * Kp * 2.  Same per-warp ring of shared-memory stages fed by 1-D bulk
+// async copies (UBLKCP) as K1; the query lives in REGISTERS (fp32, 8 coordinates per lane and 256-coordinate trip), so
+// the only shared-memory traffic is one LDS.128 per 8 coordinates of the plane.  Short rows (Kp = 64, 128) are packed
+// 4 / 2 to a warp step.  The launch's last CTA runs finalize (and the cross-shard exchange) itself: one launch per query.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "scan_common.cuh"
+#include "tail.cuh"
+
+namespace svdb {
+
+__device__ __forceinline__ uint4 pl_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// eight bf16 (four 32-bit words, even coordinate in the low half) -> fp32, exact
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 &h, float (&x)[8]) {
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        x[2 * j] = __uint_as_float(w[j] << 16);
+        x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+}
+
+// TRIPS >= 1: Kp <= 256 * TRIPS, queries in registers.  LPR = 32: a warp walks one row per step, TR rows per tile.
+// LPR = 16 / 8 (TRIPS = 1, NQ = 1, TR = 32, Kp = 128 / 64): 2 / 4 rows side by side.
+template <int NQ, int TRIPS, int LPR, int TR>
+__global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constant__ PlaneScanArgs p, int nstages, int smem_bytes) {
+    static_assert(LPR == 32 || (TRIPS == 1 && NQ == 1 && TR == 32), "packed rows: one trip, one query, 32-row tiles");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = p.Kp;
+    const uint32_t row_bytes = (uint32_t)Kp * 2u;
+    const uint32_t tile_bytes = (uint32_t)TR * row_bytes;
+    Cand *mrg = reinterpret_cast<Cand *>(smem + (size_t)W * nstages * tile_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(mrg) + (size_t)W * 32 * sizeof(Cand));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W * nstages; i++) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const u64 ntiles = (p.n + TR - 1) / TR;
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const uint32_t my_stage = smem_u32(smem) + (uint32_t)warp * nstages * tile_bytes;
+    const uint32_t my_bar = smem_u32(bars + warp * nstages);
+    auto issue = [&](u64 t, int s) {
+        const u64 row0 = t * TR;
+        const u64 left = p.n - row0;
+        const uint32_t rows = left < (u64)TR ? (uint32_t)left : (uint32_t)TR;
+        const uint32_t bytes = rows * row_bytes;
+        mbar_arrive_expect_tx(my_bar + 8 * s, bytes);
+        bulk_g2s(my_stage + s * tile_bytes, reinterpret_cast<const unsigned char *>(p.xhi) + row0 * (u64)row_bytes, bytes,
+                 my_bar + 8 * s);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < nstages; s++) {
+            const u64 t = gw + (u64)s * GW;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    // the query, fp32, in registers: lane (j = lane % LPR) owns coordinates trip * 256 + j * 8 .. + 7; zeros beyond K
+    // match the zero padding of the plane
+    const int pj = lane % LPR, pg = lane / LPR;
+    float qr[NQ][TRIPS][8];
+    bool act[TRIPS];
+#pragma unroll
+    for (int t = 0; t < TRIPS; t++) {
+        const int c0 = t * 256 + pj * 8;
+        act[t] = c0 < Kp;
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                qr[qi][t][j] = c0 + j < p.K ? __double2float_rn(__ldg(p.q + (size_t)qi * p.ldq + c0 + j)) : 0.f;
+    }
+
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (u64 t = gw; t < ntiles; t += GW) {
+        mbar_wait(my_bar + 8 * s, phase);
+        float key[NQ];
+        int my_row;
+        bool my_own;
+        if constexpr (LPR < 32) {
+            constexpr int PR = 32 / LPR;               // rows side by side
+            float v[LPR];
+            const uint32_t sa = my_stage + s * tile_bytes + (uint32_t)pg * row_bytes + (uint32_t)pj * 16;
+#pragma unroll
+            for (int i = 0; i < LPR; i++) {
+                float x[8];
+                bf16x8_to_f32(pl_lds128(sa + (uint32_t)(i * PR) * row_bytes), x);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float d0 = x[j] - qr[0][0][j], d1 = x[j + 1] - qr[0][0][j + 1];
+                    a0 = fmaf(d0, d0, a0);
+                    a1 = fmaf(d1, d1, a1);
+                }
+                v[i] = a0 + a1;
+            }
+            reduce_packed<LPR>(v, lane);
+            key[0] = v[0];
+            my_row = pj * PR + pg;
+            my_own = true;
+        } else {
+            float acc[TR][NQ];
+#pragma unroll
+            for (int r = 0; r < TR; r++)
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) acc[r][qi] = 0.f;
+            const uint32_t sa = my_stage + s * tile_bytes + lane * 16;
+            constexpr int RC = TR < 4 ? TR : 4;        // rows whose loads are in flight together
+#pragma unroll
+            for (int tr = 0; tr < TRIPS; tr++) {
+#pragma unroll
+                for (int r0 = 0; r0 < TR; r0 += RC) {
+                    uint4 h[RC];
+#pragma unroll
+                    for (int r = 0; r < RC; r++)
+                        h[r] = act[tr] ? pl_lds128(sa + (r0 + r) * row_bytes + tr * 512) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int r = 0; r < RC; r++) {
+                        float x[8];
+                        bf16x8_to_f32(h[r], x);
+#pragma unroll
+                        for (int qi = 0; qi < NQ; qi++) {
+                            float a0 = acc[r0 + r][qi], a1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                const float d0 = x[j] - qr[qi][tr][j], d1 = x[j + 1] - qr[qi][tr][j + 1];
+                                a0 = fmaf(d0, d0, a0);
+                                a1 = fmaf(d1, d1, a1);
+                            }
+                            acc[r0 + r][qi] = a0 + a1;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                float v[TR];
+#pragma unroll
+                for (int r = 0; r < TR; r++) v[r] = acc[r][qi];
+                reduce_rows<TR>(v, lane);
+                key[qi] = v[0];
+            }
+            my_row = RowLane<TR>::row(lane);
+            my_own = RowLane<TR>::owner(lane);
+        }
+        __syncwarp();
+        // the stage is consumed: refill it before the (rare) list maintenance
+        const u64 tn = t + (u64)nstages * GW;
+        if (lane == 0 && tn < ntiles) issue(tn, s);
+        if (++s == nstages) {
+            s = 0;
+            phase ^= 1;
+        }
+        const u64 row = t * TR + my_row;
+        const bool has = my_own && row < p.n;
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, (double)key[qi], row, lane, p.cap);
+    }
+
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    scan_tail(p.tail, smem, smem_bytes);
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+double plane_gamma(int Kp) { return ((double)Kp / 32.0 + 12.0) * ldexp(1.0, -24); }
+
+template <int NQ, int TRIPS, int LPR, int TR>
+static cudaError_t launch_plane_inst(const ScanTuning &t, const PlaneScanArgs &a, cudaStream_t st) {
+    const size_t row_bytes = (size_t)a.Kp * 2;
+    const int grid = scan_num_lists(t, true);
+    int W = t.warps < 1 ? 1 : (t.warps > 8 ? 8 : t.warps);
+    int NS = t.stages < 2 ? 2 : t.stages;
+    while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
+    const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
+    auto need = [&](int w, int ns) { return (size_t)w * ns * TR * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)w * ns * 8; };
+    const size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    while (need(W, NS) > budget && NS > 2) NS--;
+    while (need(W, NS) > budget && W > 1) W--;
+    if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    const size_t smem = std::max(need(W, NS), a.tail.ticket ? fin_head_bytes(W) + FIN_MIN_TBUF : (size_t)0);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_plane_kernel<NQ, TRIPS, LPR, TR>, smem);
+    if (e != cudaSuccess) return e;
+    scan_plane_kernel<NQ, TRIPS, LPR, TR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
+    return cudaGetLastError();
+}
+
+bool plane_scan_supports(int Kp, int nq) { return Kp >= 64 && Kp % 64 == 0 && Kp <= 1024 && (nq == 1 || (nq == 2 && Kp <= 512)); }
+
+// Tiles of 4-8 KB (K1's measurements: 5-8 KB bulk copies stream best).
+cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaStream_t st) {
+    if (!plane_scan_supports(a.Kp, a.nq) || a.Kp < a.K || !a.xhi || a.n == 0) return cudaErrorInvalidValue;
+    const int Kp = a.Kp;
+    if (a.nq == 1) {
+        if (Kp == 64) return launch_plane_inst<1, 1, 8, 32>(t, a, st);
+        if (Kp == 128) return launch_plane_inst<1, 1, 16, 32>(t, a, st);
+        if (Kp <= 256) return launch_plane_inst<1, 1, 32, 16>(t, a, st);
+        if (Kp <= 512) return launch_plane_inst<1, 2, 32, 8>(t, a, st);
+        if (Kp <= 768) return launch_plane_inst<1, 3, 32, 4>(t, a, st);
+        return launch_plane_inst<1, 4, 32, 4>(t, a, st);
+    }
+    if (Kp <= 256) return launch_plane_inst<2, 1, 32, 16>(t, a, st);
+    return launch_plane_inst<2, 2, 32, 8>(t, a, st);
+}
+
+}  // namespace svdb

@@ -19,61 +19,14 @@
 //   finalize_kernel    per query: merge the per-CTA lists, recompute the survivors in the
 //                      reference's order (exact_sqdist), order by (d, seq), emit top-k and
 //                      prove that no entry outside the candidate set can belong to it.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
-#include "tree.cuh"
+#include "scan_common.cuh"
+#include "tail.cuh"
 
 namespace svdb {
-
-constexpr int MAX_SMEM = 232448;  // 227 KB opt-in limit per CTA on sm_100
-
-// ---- CTA-level merge of the per-warp lists, one query -------------------------------
-__device__ __forceinline__ void cta_merge_emit(WarpList &mine, Cand *mrg, int W, int warp, int lane, int cap,
-                                               Cand *out) {
-    mrg[warp * 32 + lane] = Cand{mine.d, mine.seq};
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < W; w++) {
-            const Cand c = mrg[w * 32 + lane];
-            mine.offer(c.seq != SEQ_NONE, c.d, c.seq, lane, cap);
-        }
-        if (lane < cap) out[lane] = Cand{mine.d, mine.seq};
-    }
-    __syncthreads();
-}
-
-// ---- reduce TR per-lane partial sums over the warp with TR-1 + (5 - log2 TR) shuffles ------------
-// A plain butterfly costs 5 shuffles (10 SHFL.32) per row, which is what bounds short rows (measured:
-// 0.23-0.65 x HBM peak for kd_dim 17..48).  Here the first log2(TR) steps HALVE the set instead: a lane
-// passes the rows it gives up to its partner and adds what it receives to the rows it keeps.  Every row
-// is still combined by the same tree over the lane indices (xor 16, 8, 4, 2, 1; addition commutes), so a
-// key is the same bits whatever TR is and wherever the row sits in a tile.
-// On return the total of row r is in v[0] of the lanes with (lane >> (5 - log2 TR)) == r.
-template <int TR>
-__device__ __forceinline__ void reduce_rows(double (&v)[TR], int lane) {
-    constexpr int T = TR == 32 ? 5 : TR == 16 ? 4 : TR == 8 ? 3 : TR == 4 ? 2 : TR == 2 ? 1 : 0;
-#pragma unroll
-    for (int s = 0; s < T; s++) {
-        const int m = 16 >> s;
-        const int cnt = TR >> (s + 1);
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < cnt; i++) {
-            const double send = up ? v[i] : v[i + cnt];
-            const double keep = up ? v[i + cnt] : v[i];
-            v[i] = keep + shfl_xor_f64(send, m);
-        }
-    }
-#pragma unroll
-    for (int m = 16 >> T; m >= 1; m >>= 1) v[0] += shfl_xor_f64(v[0], m);
-}
-template <int TR>
-struct RowLane {
-    static constexpr int T = TR == 32 ? 5 : TR == 16 ? 4 : TR == 8 ? 3 : TR == 4 ? 2 : TR == 2 ? 1 : 0;
-    static constexpr int SH = 5 - T;
-    __device__ static __forceinline__ int row(int lane) { return lane >> SH; }
-    __device__ static __forceinline__ bool owner(int lane) { return (lane & ((1 << SH) - 1)) == 0; }
-};
 
 // =====================================================================================
 // Wide rows, TMA bulk-copy ring.  TR rows per tile, NQ queries share the pass.
@@ -82,7 +35,7 @@ struct RowLane {
 // 128-bit load per lane and step, so that short rows do not leave most of the warp idle (K = 17: 9 of 32 lanes).
 // =====================================================================================
 template <int TR, int NQ, int LPR = 32>
-__global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstages) {
+__global__ void __launch_bounds__(512, 1) scan_wide_kernel(const __grid_constant__ ScanArgs p, int nstages, int smem_bytes) {
     static_assert(LPR == 32 || (TR == 32 && NQ == 1), "packed rows: 32-row tiles, one query");
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5;
@@ -252,11 +205,12 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(ScanArgs p, int nstag
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
         cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    scan_tail(p.tail, smem, smem_bytes);
 }
 
 // =====================================================================================
-// K11: the same scan over the split-bf16 SHADOW of the log (umma_filter.cu: [hi plane | lo plane] bf16 rows of
-// 2*Kp entries, 4 bytes per coordinate) -- HALF the bytes of the fp64 rows, and the scan is HBM-bound.
+// K11: the same scan over the split-bf16 SHADOW of the log (umma_filter.cu: a hi plane and a lo plane of [n][Kp] bf16
+// each, 4 bytes per coordinate together) -- HALF the bytes of the fp64 rows, and the scan is HBM-bound.
 // Per coordinate x^ = hi + lo (exact in fp32, |x^ - x| <= (2^-16 + 2^-24)|x|), diff = x^ - fl32(q), key = sum diff^2
 // accumulated in fp32 (FFMA, lane-parallel, butterfly).  With e_i = x^_i - x_i + q_i - q^_i:
 //   |key - d| <= 2 sqrt(d) |e| + |e|^2 + (K/32 + 12) 2^-24 d  <=  (eta + ...) d + (1 + 1/eta) |e|^2,   eta = 2^-13,
@@ -271,12 +225,13 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(512, 1) scan_shadow_kernel(ShadowScanArgs p, int nstages, int TR) {
+__global__ void __launch_bounds__(512, 1) scan_shadow_kernel(const __grid_constant__ ShadowScanArgs p, int nstages, int TR, int smem_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Kp = p.Kp;
-    const uint32_t row_bytes = (uint32_t)Kp * 4u;
+    const uint32_t plane_bytes = (uint32_t)Kp * 2u;   // one row of one plane
+    const uint32_t row_bytes = 2u * plane_bytes;
     const uint32_t tile_bytes = (uint32_t)TR * row_bytes;
     const int trips = (Kp + 255) >> 8;                 // a warp covers 256 coordinates per trip, 8 per lane
 
@@ -307,10 +262,12 @@ __global__ void __launch_bounds__(512, 1) scan_shadow_kernel(ShadowScanArgs p, i
         const u64 row0 = t * TR;
         const u64 left = p.n - row0;
         const uint32_t rows = left < (u64)TR ? (uint32_t)left : (uint32_t)TR;
-        const uint32_t bytes = rows * row_bytes;
-        mbar_arrive_expect_tx(my_bar + 8 * s, bytes);
-        bulk_g2s(my_stage + s * tile_bytes, reinterpret_cast<const unsigned char *>(p.xsplit) + row0 * (u64)row_bytes, bytes,
+        const uint32_t bytes = rows * plane_bytes;      // per plane; the lo plane of the tile lands behind TR hi rows
+        mbar_arrive_expect_tx(my_bar + 8 * s, 2 * bytes);
+        bulk_g2s(my_stage + s * tile_bytes, reinterpret_cast<const unsigned char *>(p.xhi) + row0 * (u64)plane_bytes, bytes,
                  my_bar + 8 * s);
+        bulk_g2s(my_stage + s * tile_bytes + (uint32_t)TR * plane_bytes,
+                 reinterpret_cast<const unsigned char *>(p.xlo) + row0 * (u64)plane_bytes, bytes, my_bar + 8 * s);
     };
     if (lane == 0) {
         for (int s = 0; s < nstages; s++) {
@@ -336,10 +293,10 @@ __global__ void __launch_bounds__(512, 1) scan_shadow_kernel(ShadowScanArgs p, i
             float acc[NQ];
 #pragma unroll
             for (int qi = 0; qi < NQ; qi++) acc[qi] = 0.f;
-            const uint32_t base = my_stage + s * tile_bytes + (uint32_t)r * row_bytes + lane * 16;
+            const uint32_t base = my_stage + s * tile_bytes + (uint32_t)r * plane_bytes + lane * 16;
             for (int trip = 0, c0 = lane * 8; c0 < Kp; trip++, c0 += 256) {
                 const uint4 h = lds_u128(base + trip * 512);
-                const uint4 l = lds_u128(base + (uint32_t)Kp * 2u + trip * 512);
+                const uint4 l = lds_u128(base + (uint32_t)TR * plane_bytes + trip * 512);
                 const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
                 float x[8];
 #pragma unroll
@@ -384,6 +341,7 @@ __global__ void __launch_bounds__(512, 1) scan_shadow_kernel(ShadowScanArgs p, i
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
         cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    scan_tail(p.tail, smem, smem_bytes);
 }
 
 // =====================================================================================
@@ -531,269 +489,15 @@ __global__ void __launch_bounds__(512, 1) scan_exact_kernel(ScanArgs p) {
 }
 
 // =====================================================================================
-// finalize: one CTA of 8 warps per query.
-//   1. every warp merges a slice of the per-CTA lists into its register list, the slices are
-//      merged through shared memory -> the 32 best approximate keys, plus `bound`, the
-//      smallest approximate key any list may have dropped;
-//   2. only candidates whose approximate key is within the error margin of the k-th can
-//      belong to the exact top-k; those (normally exactly k) are recomputed in the
-//      reference's operation order: the warps fetch each candidate row coalesced and form
-//      the rounded squares t_i = (x_i - q_i)^2 in shared memory, then one lane per
-//      candidate adds them strictly in index order (the serial chain the reference has);
-//   3. rank by (exact distance, seq), emit top-k, prove completeness against `bound`.
+// finalize as a launch of its own: one CTA of 8 warps per query (tail.cuh: finalize_query).  The single-query scans
+// run the same function in their last CTA instead (scan_tail).
 // =====================================================================================
 constexpr int FIN_WARPS = 8;
-constexpr int FIN_CH = 256;                       // coordinates re-ranked per round
-constexpr int FIN_LD = FIN_CH + 1;                // odd stride: conflict-free column walks
-constexpr size_t FIN_SMEM = (size_t)32 * FIN_LD * 8 + FIN_WARPS * 32 * sizeof(Cand) + 64 * 8;
+constexpr size_t FIN_SMEM = fin_head_bytes(FIN_WARPS) + (size_t)32 * 257 * 8;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    double *tbuf = reinterpret_cast<double *>(fsm);                                  // [32][FIN_LD]
-    Cand *mrg = reinterpret_cast<Cand *>(fsm + (size_t)32 * FIN_LD * 8);             // [FIN_WARPS][32]
-    double *wbound = reinterpret_cast<double *>(mrg + FIN_WARPS * 32);               // [FIN_WARPS]
-    u64 *cseq = reinterpret_cast<u64 *>(wbound + FIN_WARPS);                         // [32]
-    const int qi = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Cand *L = p.lists + (size_t)qi * p.nlists * p.cap;
-    const int total = p.nlists * p.cap;
-
-    // ---- 1. merge ----
-    WarpList wl;
-    wl.reset();
-    double bound = CUDART_INF;
-    if (p.cap >= 16) {
-        // long lists (k >= 8): most keys of a list qualify while the running list fills up, and every one of them
-        // would be a serial insert -- merge list by list with the fixed-cost bitonic network instead
-        const int per = (p.nlists + FIN_WARPS - 1) / FIN_WARPS;
-        const int lo = warp * per, hi = min(p.nlists, lo + per);
-        for (int base = lo; base < hi; base += 4) {
-            Cand c[4];                                   // four independent loads in flight per lane
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                c[u] = Cand{CUDART_INF, SEQ_NONE};
-                if (base + u < hi && lane < p.cap) c[u] = L[(size_t)(base + u) * p.cap + lane];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (lane == p.cap - 1 && c[u].seq != SEQ_NONE) bound = fmin(bound, c[u].d);   // that list was full
-                wl.merge_sorted(c[u].d, c[u].seq, lane);
-            }
-        }
-    } else {
-        const int per = ((total + FIN_WARPS - 1) / FIN_WARPS + 31) & ~31;
-        const int lo = warp * per, hi = min(total, lo + per);
-        for (int base = lo; base < hi; base += 128) {
-            Cand c[4];                                   // four independent loads in flight per lane
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = base + u * 32 + lane;
-                c[u] = Cand{CUDART_INF, SEQ_NONE};
-                if (i < hi) c[u] = L[i];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = base + u * 32 + lane;
-                const bool has = c[u].seq != SEQ_NONE;
-                if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c[u].d);   // that list was full
-                wl.offer(has, c[u].d, c[u].seq, lane, p.cap);
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-    mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
-    if (lane == 0) wbound[warp] = bound;
-    __syncthreads();
-    if (warp == 0) {
-        // only the best `cap` keys of a slice list are meaningful; the slice lists are sorted: bitonic merges
-        if (lane >= p.cap) wl.reset();
-        for (int w = 1; w < FIN_WARPS; w++) {
-            Cand c = mrg[w * 32 + lane];
-            // a slice list that is full may itself have dropped keys >= its last one
-            if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
-            if (lane >= p.cap) c = Cand{CUDART_INF, SEQ_NONE};
-            wl.merge_sorted(c.d, c.seq, lane);
-            bound = fmin(bound, wbound[w]);
-        }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-        double dl;
-        u64 sl;
-        wl.key_at(p.cap - 1, dl, sl);
-        if (sl != SEQ_NONE) bound = fmin(bound, dl);     // the final list is full too
-    }
-
-    // ---- 2. which candidates can still belong to the exact top-k ----
-    // GEMM-form keys (K2) carry an absolute error on top of the relative one
-    double eabs = 0.0;
-    if (p.eabs_coef > 0.0) eabs = p.eabs_coef * (__longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi]);
-    int nneed = 0;
-    if (warp == 0) {
-        const bool valid = wl.seq != SEQ_NONE && lane < p.cap;
-        bool need = valid;
-        if (p.eps >= 0.0) {
-            double dk;
-            u64 sk;
-            wl.key_at(p.k - 1, dk, sk);
-            if (sk != SEQ_NONE) need = valid && wl.d <= dk * (1.0 + 3.0 * p.eps) + 2.0 * eabs;
-        }
-        nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
-        cseq[lane] = wl.seq;
-        if (lane == 0) cseq[32] = (u64)nneed;
-    }
-    __syncthreads();
-    nneed = (int)cseq[32];
-
-    double dex = CUDART_INF;
-    if (p.eps < 0.0) {
-        dex = wl.d;                                     // keys are reference-order already
-    } else {
-        dex = 0.0;
-        const double *qv = p.q + (size_t)qi * p.ldq;
-        // as many coordinates per round as the buffer holds for `nneed` candidates (usually all K)
-        int ch = nneed > 0 ? ((32 * FIN_LD) / nneed - 1) & ~31 : FIN_CH;
-        if (ch > p.K) ch = (p.K + 31) & ~31;
-        const int ld = ch + 1;
-        for (int c0 = 0; c0 < p.K; c0 += ch) {
-            const int len = min(ch, p.K - c0);
-            // work items = (candidate, 256-coordinate segment), dealt round-robin to the warps; every
-            // lane keeps 8 row loads and 8 query loads in flight
-            const int nseg = (len + 255) >> 8;
-            // two items per trip: 16 row loads + 16 query loads in flight per lane (the loop is DRAM-latency bound)
-            for (int w = warp; w < nneed * nseg; w += 2 * FIN_WARPS) {
-                double x[2][8], y[2][8];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int wi = w + h * FIN_WARPS;
-                    const bool on = wi < nneed * nseg;
-                    const int j = on ? wi / nseg : 0, s0 = on ? (wi % nseg) << 8 : 0;
-                    const double *row = p.pts + cseq[j] * (u64)p.stride + c0 + s0;
-                    const double *qq = qv + c0 + s0;
-                    const int slen = on ? min(256, len - s0) : 0;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int i = u * 32 + lane;
-                        x[h][u] = i < slen ? __ldg(row + i) : 0.0;
-                        y[h][u] = i < slen ? __ldg(qq + i) : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int wi = w + h * FIN_WARPS;
-                    if (wi >= nneed * nseg) break;
-                    const int j = wi / nseg, s0 = (wi % nseg) << 8;
-                    double *t = tbuf + j * ld + s0;
-                    const int slen = min(256, len - s0);
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int i = u * 32 + lane;
-                        const double df = __dsub_rn(x[h][u], y[h][u]);
-                        if (i < slen) t[i] = __dmul_rn(df, df);
-                    }
-                }
-            }
-            __syncthreads();
-            if (warp == 0 && lane < nneed) {
-                const double *t = tbuf + lane * ld;
-#pragma unroll 8
-                for (int i = 0; i < len; i++) dex = __dadd_rn(dex, t[i]);   // kdtree.c:136, in index order
-            }
-            __syncthreads();
-        }
-    }
-    if (warp != 0) return;
-
-    // ---- 3. rank and emit ----
-    bool valid = lane < nneed && wl.seq != SEQ_NONE;
-    u64 seq = wl.seq;
-    if (valid && !(dex < CUDART_INF)) valid = false;    // kdtree.c:139 strict <: non-finite never wins
-    if (!valid) {
-        dex = CUDART_INF;
-        seq = SEQ_NONE;
-    }
-    int rank = 0;
-#pragma unroll 8
-    for (int j = 0; j < 32; j++) {
-        const double dj = __shfl_sync(FULL, dex, j);
-        const u64 sj = __shfl_sync(FULL, seq, j);
-        rank += key_less(dj, sj, dex, seq) ? 1 : 0;
-    }
-    const int nvalid = __popc(__ballot_sync(FULL, valid));
-    const unsigned mk = __ballot_sync(FULL, valid && rank == p.k - 1);
-    const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
-
-    bool unsafe = false;
-    if (p.eps >= 0.0 && bound < CUDART_INF) {
-        // entries outside the candidate set have approximate key >= bound, hence reference
-        // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
-        unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
-    }
-    if (p.scale_hi > 0.0) {
-        // fp32 keys (K10): their error bound only holds while neither squares overflow nor products underflow
-        const double scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
-        if (!(scale >= p.scale_lo && scale <= p.scale_hi)) unsafe = true;
-    }
-
-    // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----
-    bool tie_flag = false;
-    if ((p.child != nullptr || p.mark_ties) && nvalid >= 2) {
-        const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
-        const int l0 = __ffs(m0) - 1;
-        const double e1 = __shfl_sync(FULL, dex, l0);
-        const u64 seq0 = __shfl_sync(FULL, seq, l0);
-        const bool tied = valid && dex == e1;
-        unsigned tmask = __ballot_sync(FULL, tied);
-        const int nt = __popc(tmask);
-        if (nt >= 2) {
-            // a dropped entry could tie as well: exact keys -> bound <= e1; approximate keys are
-            // already covered by the completeness proof above (e1 <= ek < bound(1-eps))
-            const bool more = p.eps < 0.0 && bound <= e1;
-            if (more && p.child != nullptr) unsafe = true;
-            // identical kd-points? then the earliest insert is an ancestor of the others and wins
-            bool differs = false;
-            const double *r0 = p.pts + seq0 * (u64)p.stride;
-            for (unsigned tm = tmask; tm; tm &= tm - 1) {
-                const u64 st = __shfl_sync(FULL, seq, __ffs(tm) - 1);
-                const double *rt = p.pts + st * (u64)p.stride;
-                for (int i = lane; i < p.K; i += 32) differs |= rt[i] != r0[i];
-            }
-            differs = __any_sync(FULL, differs);
-            if (p.child == nullptr) {
-                // one shard of a larger log: the order of the GLOBAL tree decides (tie_protocol.cu); say so
-                tie_flag = differs || more;
-            } else if (differs) {
-                if (tied) cseq[rank] = seq;            // tied entries hold ranks 0..nt-1
-                __syncwarp();
-                u64 w = 0;
-                if (lane == 0) w = resolve_tie(p.pts, p.stride, p.K, p.child, p.q + (size_t)qi * p.ldq, cseq, nt);
-                w = __shfl_sync(FULL, w, 0);
-                const unsigned mw = __ballot_sync(FULL, tied && seq == w);
-                const int wr = __shfl_sync(FULL, rank, __ffs(mw) - 1);
-                if (tied) {
-                    if (seq == w) rank = 0;
-                    else if (rank < wr) rank++;
-                }
-            }
-        }
-    }
-    const u64 oflags = (unsafe ? SVDB_CAND_UNSAFE : 0ull) | (tie_flag ? SVDB_CAND_TIE : 0ull);
-    svdb_candidate *out = p.out + (size_t)qi * p.k;
-    if (valid && rank < p.k) {
-        svdb_candidate c;
-        c.dist = dex;
-        c.seq = seq + p.seq_base;
-        c.index = p.log_index[seq];
-        c.flags = oflags;
-        out[rank] = c;
-    }
-    if (lane < p.k && lane >= nvalid) {
-        svdb_candidate c;
-        c.dist = CUDART_INF;
-        c.seq = SEQ_NONE;
-        c.index = (u64)SVDB_NONE;
-        c.flags = oflags;
-        out[lane] = c;
-    }
+    finalize_query(p, blockIdx.x, fsm, (int)FIN_SMEM);
 }
 
 // =====================================================================================
@@ -909,12 +613,9 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
         if (W > 8) W = 8;
         const size_t smem = (size_t)NQ * row_bytes + (size_t)W * 32 * sizeof(Cand);
         if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(scan_ldg_kernel<TR, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        static SmemOptIn optin;
+        cudaError_t e = optin.ensure(scan_ldg_kernel<TR, NQ>, smem);
+        if (e != cudaSuccess) return e;
         scan_ldg_kernel<TR, NQ><<<grid, W * 32, smem, st>>>(a);
         return cudaGetLastError();
     }
@@ -939,14 +640,12 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
         while (need(W, NS) > budget && W > 1) W--;
         if (need(W, NS) > budget) return cudaErrorInvalidValue;
     }
-    const size_t smem = need(W, NS);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_wide_kernel<TR, NQ, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    scan_wide_kernel<TR, NQ, LPR><<<grid, W * 32, smem, st>>>(a, NS);
+    // the fused tail (finalize in the last CTA) reuses the ring's shared memory
+    const size_t smem = std::max(need(W, NS), a.tail.ticket ? fin_head_bytes(W) + FIN_MIN_TBUF : (size_t)0);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_wide_kernel<TR, NQ, LPR>, smem);
+    if (e != cudaSuccess) return e;
+    scan_wide_kernel<TR, NQ, LPR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
     return cudaGetLastError();
 }
 
@@ -1013,19 +712,16 @@ static cudaError_t launch_shadow_inst(const ScanTuning &t, const ShadowScanArgs 
         while (need(W, NS) > budget && W > 1) W--;
         if (need(W, NS) > budget) return cudaErrorInvalidValue;
     }
-    const size_t smem = need(W, NS);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_shadow_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    scan_shadow_kernel<NQ><<<grid, W * 32, smem, st>>>(a, NS, TR);
+    const size_t smem = std::max(need(W, NS), a.tail.ticket ? fin_head_bytes(W) + FIN_MIN_TBUF : (size_t)0);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_shadow_kernel<NQ>, smem);
+    if (e != cudaSuccess) return e;
+    scan_shadow_kernel<NQ><<<grid, W * 32, smem, st>>>(a, NS, TR, (int)smem);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan_shadow(const ScanTuning &t, const ShadowScanArgs &a, cudaStream_t st) {
-    if (a.Kp % 64 || a.Kp < a.K || a.n >= (1ull << 32)) return cudaErrorInvalidValue;
+    if (a.Kp % 64 || a.Kp < a.K || a.n >= (1ull << 32) || !a.xhi || !a.xlo) return cudaErrorInvalidValue;
     switch (a.nq) {
         case 1: return launch_shadow_inst<1>(t, a, st);
         case 2: return launch_shadow_inst<2>(t, a, st);
@@ -1048,12 +744,9 @@ static cudaError_t launch_exact_inst(const ScanTuning &t, const ScanArgs &a, cud
     const int grid = scan_num_lists(t, false);
     const size_t smem = (((size_t)NQ * a.K * 8 + 15) & ~(size_t)15) + (size_t)W * 32 * sizeof(Cand);
     if (smem > (size_t)MAX_SMEM) return cudaErrorInvalidValue;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_exact_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_exact_kernel<NQ>, smem);
+    if (e != cudaSuccess) return e;
     scan_exact_kernel<NQ><<<grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -1069,7 +762,8 @@ cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream
 }
 
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(finalize_kernel, FIN_SMEM);
     if (e != cudaSuccess) return e;
     finalize_kernel<<<a.nq, FIN_WARPS * 32, FIN_SMEM, st>>>(a);
     return cudaGetLastError();

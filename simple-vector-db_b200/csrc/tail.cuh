@@ -1,0 +1,475 @@
+// tail.cuh -- what follows a distance scan, as device functions shared by the stand-alone kernels and by the scans'
+// fused tail (the last CTA of a scan launch runs them itself, kernels.h: TailArgs):
+//   finalize_query   per query: merge the per-CTA lists, recompute the survivors in the reference's operation order
+//                    (kdtree.c:134-137), rank by (d, seq), emit top-k, prove that nothing outside the candidate set
+//                    can belong to it, resolve exact ties the way the reference's tree does (kdtree.c:139, :147-159)
+//   xch_push / xch_wait / merge_gathered
+//                    the cross-shard exchange over NVLink peer memory (exchange.cu) and the K7 merge
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+#include "tree.cuh"
+
+namespace svdb {
+
+constexpr size_t XCH_FLAG_BYTES = 32 * 8;
+constexpr int XCH_EPOCH_SLOT = 31;
+
+__device__ __forceinline__ void st_release_sys_u64(u64 *p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_acquire_sys_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// lists are written by other CTAs of the same launch (fused tail): read them past L1
+__device__ __forceinline__ Cand ldcg_cand(const Cand *p) {
+    Cand c;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(*reinterpret_cast<u64 *>(&c.d)), "=l"(c.seq) : "l"(p));
+    return c;
+}
+
+// shared memory finalize_query needs besides the re-rank buffer: [nw][32] Cand, [nw] bounds, 40 words
+__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)nw * 8 + 40 * 8; }
+constexpr int FIN_MIN_TBUF = 32 * 33 * 8;      // room for 32 candidates x 32 coordinates per round
+
+// =====================================================================================
+// finalize of ONE query by the whole CTA (blockDim.x = nw * 32, nw <= 16).  fsm: fsm_bytes of shared memory the
+// caller does not need any more (>= fin_head_bytes(nw) + FIN_MIN_TBUF).  Ends with a __syncthreads().
+//   1. every warp merges a slice of the per-CTA lists into its register list, the slices are merged through shared
+//      memory -> the 32 best approximate keys, plus `bound`, the smallest approximate key any list may have dropped;
+//   2. only candidates whose approximate key is within the error margin of the k-th can belong to the exact top-k;
+//      those (normally exactly k) are recomputed in the reference's operation order: the warps fetch each candidate
+//      row coalesced and form the rounded squares t_i = (x_i - q_i)^2 in shared memory, then one lane per candidate
+//      adds them strictly in index order (the serial chain the reference has);
+//   3. rank by (exact distance, seq), emit top-k, prove completeness against `bound`.
+// =====================================================================================
+static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, unsigned char *fsm, int fsm_bytes) {
+    const int NW = blockDim.x >> 5;
+    Cand *mrg = reinterpret_cast<Cand *>(fsm);                                        // [NW][32]
+    double *wbound = reinterpret_cast<double *>(fsm + (size_t)NW * 32 * sizeof(Cand)); // [NW]
+    u64 *cseq = reinterpret_cast<u64 *>(wbound + NW);                                 // [33] + 4 words of block reductions
+    double *red = reinterpret_cast<double *>(cseq + 34);                              // [4]
+    double *tbuf = reinterpret_cast<double *>(fsm + fin_head_bytes(NW));
+    const int tcap = (fsm_bytes - (int)fin_head_bytes(NW)) / 8;                       // doubles in tbuf
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Cand *L = p.lists + (size_t)qi * p.nlists * p.cap;
+    const int total = p.nlists * p.cap;
+    const double *qv = p.q + (size_t)qi * p.ldq;
+
+    // ---- 1. merge ----
+    WarpList wl;
+    wl.reset();
+    double bound = CUDART_INF;
+    if (p.cap >= 16) {
+        // long lists (k >= 8): most keys of a list qualify while the running list fills up, and every one of them
+        // would be a serial insert -- merge list by list with the fixed-cost bitonic network instead
+        const int per = (p.nlists + NW - 1) / NW;
+        const int lo = warp * per, hi = min(p.nlists, lo + per);
+        for (int base = lo; base < hi; base += 4) {
+            Cand c[4];                                   // four independent loads in flight per lane
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                c[u] = Cand{CUDART_INF, SEQ_NONE};
+                if (base + u < hi && lane < p.cap) c[u] = ldcg_cand(L + (size_t)(base + u) * p.cap + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (lane == p.cap - 1 && c[u].seq != SEQ_NONE) bound = fmin(bound, c[u].d);   // that list was full
+                wl.merge_sorted(c[u].d, c[u].seq, lane);
+            }
+        }
+    } else {
+        const int per = ((total + NW - 1) / NW + 31) & ~31;
+        const int lo = warp * per, hi = min(total, lo + per);
+        for (int base = lo; base < hi; base += 128) {
+            Cand c[4];                                   // four independent loads in flight per lane
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                c[u] = Cand{CUDART_INF, SEQ_NONE};
+                if (i < hi) c[u] = ldcg_cand(L + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                const bool has = c[u].seq != SEQ_NONE;
+                if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c[u].d);   // that list was full
+                wl.offer(has, c[u].d, c[u].seq, lane, p.cap);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
+    mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
+    if (lane == 0) wbound[warp] = bound;
+
+    // sqrt-form keys: |q - fl32(q)| and |q|^2 of this query, formed here (no prep launch in front of the scan)
+    double eq2 = 0.0, qn2 = 0.0;
+    if (p.sq_mode) {
+        for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+            const double v = __ldg(qv + i);
+            const double r = v - (double)__double2float_rn(v);
+            eq2 = fma(r, r, eq2);
+            qn2 = fma(v, v, qn2);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            eq2 += shfl_xor_f64(eq2, m);
+            qn2 += shfl_xor_f64(qn2, m);
+        }
+        if (lane == 0) {
+            tbuf[2 * warp] = eq2;
+            tbuf[2 * warp + 1] = qn2;
+        }
+    }
+    __syncthreads();
+    if (p.sq_mode && threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < NW; w++) {
+            a += tbuf[2 * w];
+            b += tbuf[2 * w + 1];
+        }
+        red[0] = a;
+        red[1] = b;
+    }
+    if (warp == 0) {
+        // only the best `cap` keys of a slice list are meaningful; the slice lists are sorted: bitonic merges
+        if (lane >= p.cap) wl.reset();
+        for (int w = 1; w < NW; w++) {
+            Cand c = mrg[w * 32 + lane];
+            // a slice list that is full may itself have dropped keys >= its last one
+            if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
+            if (lane >= p.cap) c = Cand{CUDART_INF, SEQ_NONE};
+            wl.merge_sorted(c.d, c.seq, lane);
+            bound = fmin(bound, wbound[w]);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
+        double dl;
+        u64 sl;
+        wl.key_at(p.cap - 1, dl, sl);
+        if (sl != SEQ_NONE) bound = fmin(bound, dl);     // the final list is full too
+    }
+    __syncthreads();                                     // red[] is complete; tbuf may be reused
+
+    // ---- 2. which candidates can still belong to the exact top-k ----
+    const double eps64 = 4.0 * (double)(p.K + 2) * 1.1102230246251565e-16;    // reference-order sum vs the real-number sum
+    // GEMM-form keys (K2) carry an absolute error on top of the relative one
+    double eabs = 0.0, E = 0.0, scale = 0.0;
+    if (p.sq_mode) {
+        // E bounds |x - x^| + |q - q^| (2-norms) plus what squares of tiny differences lose to fp32 underflow
+        E = __longlong_as_double((long long)*p.plane_err_bits) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
+        scale = __longlong_as_double((long long)*p.xn_max_bits) + red[1];
+    } else if (p.eabs_coef > 0.0) {
+        scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
+        eabs = p.eabs_coef * scale;
+    }
+    int nneed = 0;
+    if (warp == 0) {
+        const bool valid = wl.seq != SEQ_NONE && lane < p.cap;
+        bool need = valid;
+        double dk;
+        u64 sk;
+        wl.key_at(p.k - 1, dk, sk);
+        if (p.sq_mode) {
+            // the k rows with the smallest keys have sqrt(d) <= U; a row with sqrt(d) <= U has sqrt(key) <= (U + E)(1 + gamma)
+            if (sk != SEQ_NONE) {
+                const double U = sqrt(dk) / (1.0 - p.sq_gamma) + E;
+                const double lim = (U * (1.0 + eps64) + E) * (1.0 + p.sq_gamma);
+                need = valid && !(wl.d > lim * lim * (1.0 + 1e-12));
+            }
+        } else if (p.eps >= 0.0) {
+            // |key - d| <= eps d + eabs: a member of the true top-k has key <= (dk + eabs)(1 + eps)/(1 - eps) + eabs
+            if (sk != SEQ_NONE) need = valid && wl.d <= (dk + eabs) * ((1.0 + p.eps) / (1.0 - p.eps)) * (1.0 + 1e-15) + eabs;
+        }
+        nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
+        cseq[lane] = wl.seq;
+        if (lane == 0) cseq[32] = (u64)nneed;
+    }
+    __syncthreads();
+    nneed = (int)cseq[32];
+
+    const bool approx = p.sq_mode || p.eps >= 0.0;
+    double dex = CUDART_INF;
+    if (!approx) {
+        dex = wl.d;                                     // keys are reference-order already
+    } else {
+        dex = 0.0;
+        // as many coordinates per round as the buffer holds for `nneed` candidates (usually all K)
+        int ch = nneed > 0 ? (tcap / nneed - 1) & ~31 : 256;
+        if (ch > p.K) ch = (p.K + 31) & ~31;
+        const int ld = ch + 1;                          // odd stride: conflict-free column walks
+        for (int c0 = 0; c0 < p.K; c0 += ch) {
+            const int len = min(ch, p.K - c0);
+            // work items = (candidate, 256-coordinate segment), dealt round-robin to the warps; every
+            // lane keeps 8 row loads and 8 query loads in flight
+            const int nseg = (len + 255) >> 8;
+            // two items per trip: 16 row loads + 16 query loads in flight per lane (the loop is DRAM-latency bound)
+            for (int w = warp; w < nneed * nseg; w += 2 * NW) {
+                double x[2][8], y[2][8];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int wi = w + h * NW;
+                    const bool on = wi < nneed * nseg;
+                    const int j = on ? wi / nseg : 0, s0 = on ? (wi % nseg) << 8 : 0;
+                    const double *row = p.pts + cseq[j] * (u64)p.stride + c0 + s0;
+                    const double *qq = qv + c0 + s0;
+                    const int slen = on ? min(256, len - s0) : 0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = u * 32 + lane;
+                        x[h][u] = i < slen ? __ldg(row + i) : 0.0;
+                        y[h][u] = i < slen ? __ldg(qq + i) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int wi = w + h * NW;
+                    if (wi >= nneed * nseg) break;
+                    const int j = wi / nseg, s0 = (wi % nseg) << 8;
+                    double *t = tbuf + j * ld + s0;
+                    const int slen = min(256, len - s0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = u * 32 + lane;
+                        const double df = __dsub_rn(x[h][u], y[h][u]);
+                        if (i < slen) t[i] = __dmul_rn(df, df);
+                    }
+                }
+            }
+            __syncthreads();
+            if (warp == 0 && lane < nneed) {
+                const double *t = tbuf + lane * ld;
+#pragma unroll 8
+                for (int i = 0; i < len; i++) dex = __dadd_rn(dex, t[i]);   // kdtree.c:136, in index order
+            }
+            __syncthreads();
+        }
+    }
+
+    if (warp == 0) {
+        // ---- 3. rank and emit ----
+        bool valid = lane < nneed && wl.seq != SEQ_NONE;
+        u64 seq = wl.seq;
+        if (valid && !(dex < CUDART_INF)) valid = false;    // kdtree.c:139 strict <: non-finite never wins
+        if (!valid) {
+            dex = CUDART_INF;
+            seq = SEQ_NONE;
+        }
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) {
+            const double dj = __shfl_sync(FULL, dex, j);
+            const u64 sj = __shfl_sync(FULL, seq, j);
+            rank += key_less(dj, sj, dex, seq) ? 1 : 0;
+        }
+        const int nvalid = __popc(__ballot_sync(FULL, valid));
+        const unsigned mk = __ballot_sync(FULL, valid && rank == p.k - 1);
+        const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
+
+        bool unsafe = false;
+        if (approx && bound < CUDART_INF) {
+            if (p.sq_mode) {
+                // entries outside the candidate set have key >= bound, hence sqrt(d) >= sqrt(bound)/(1 + gamma) - E
+                const double lb = sqrt(bound) / (1.0 + p.sq_gamma) - E;
+                unsafe = nvalid < p.k || !(lb > 0.0 && ek < lb * lb * (1.0 - eps64 - 1e-12));
+            } else {
+                // entries outside the candidate set have approximate key >= bound, hence reference
+                // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
+                unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
+            }
+        }
+        if (p.scale_hi > 0.0) {
+            // fp32 keys (K10, K11, K12): their error bound only holds while neither squares overflow nor products underflow
+            if (!(scale >= p.scale_lo && scale <= p.scale_hi)) unsafe = true;
+        }
+
+        // ---- exact ties at the minimum: the reference keeps whichever its tree reaches first ----
+        bool tie_flag = false;
+        if ((p.child != nullptr || p.mark_ties) && nvalid >= 2) {
+            const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
+            const int l0 = __ffs(m0) - 1;
+            const double e1 = __shfl_sync(FULL, dex, l0);
+            const u64 seq0 = __shfl_sync(FULL, seq, l0);
+            const bool tied = valid && dex == e1;
+            unsigned tmask = __ballot_sync(FULL, tied);
+            const int nt = __popc(tmask);
+            if (nt >= 2) {
+                // a dropped entry could tie as well: exact keys -> bound <= e1; approximate keys are
+                // already covered by the completeness proof above (e1 <= ek < what a dropped entry can have)
+                const bool more = !approx && bound <= e1;
+                if (more && p.child != nullptr) unsafe = true;
+                // identical kd-points? then the earliest insert is an ancestor of the others and wins
+                bool differs = false;
+                const double *r0 = p.pts + seq0 * (u64)p.stride;
+                for (unsigned tm = tmask; tm; tm &= tm - 1) {
+                    const u64 st = __shfl_sync(FULL, seq, __ffs(tm) - 1);
+                    const double *rt = p.pts + st * (u64)p.stride;
+                    for (int i = lane; i < p.K; i += 32) differs |= rt[i] != r0[i];
+                }
+                differs = __any_sync(FULL, differs);
+                if (p.child == nullptr) {
+                    // one shard of a larger log: the order of the GLOBAL tree decides (tie_protocol.cu); say so
+                    tie_flag = differs || more;
+                } else if (differs) {
+                    if (tied) cseq[rank] = seq;            // tied entries hold ranks 0..nt-1
+                    __syncwarp();
+                    u64 w = 0;
+                    if (lane == 0) w = resolve_tie(p.pts, p.stride, p.K, p.child, qv, cseq, nt);
+                    w = __shfl_sync(FULL, w, 0);
+                    const unsigned mw = __ballot_sync(FULL, tied && seq == w);
+                    const int wr = __shfl_sync(FULL, rank, __ffs(mw) - 1);
+                    if (tied) {
+                        if (seq == w) rank = 0;
+                        else if (rank < wr) rank++;
+                    }
+                }
+            }
+        }
+        const u64 oflags = (unsafe ? SVDB_CAND_UNSAFE : 0ull) | (tie_flag ? SVDB_CAND_TIE : 0ull);
+        svdb_candidate *out = p.out + (size_t)qi * p.k;
+        if (valid && rank < p.k) {
+            svdb_candidate c;
+            c.dist = dex;
+            c.seq = seq + p.seq_base;
+            c.index = p.log_index[seq];
+            c.flags = oflags;
+            out[rank] = c;
+        }
+        if (lane < p.k && lane >= nvalid) {
+            svdb_candidate c;
+            c.dist = CUDART_INF;
+            c.seq = SEQ_NONE;
+            c.index = (u64)SVDB_NONE;
+            c.flags = oflags;
+            out[lane] = c;
+        }
+    }
+    __syncthreads();
+}
+
+// =====================================================================================
+// Cross-shard exchange (exchange.cu describes the buffers).  All by one CTA.
+// =====================================================================================
+// local results (nrec candidates) -> slot `rank` of every peer's gather buffer, then the epoch flags.  Returns the epoch.
+__device__ __forceinline__ u64 xch_push(const svdb_candidate *local, int nrec, const PeerPtrs &peers, int rank, int world,
+                                        size_t max_rec, u64 *s_epoch) {
+    if (threadIdx.x == 0) {
+        u64 *mine = reinterpret_cast<u64 *>(peers.p[rank]);
+        *s_epoch = mine[XCH_EPOCH_SLOT] + 1;
+        mine[XCH_EPOCH_SLOT] = *s_epoch;              // read back by whoever waits for this epoch
+    }
+    __syncthreads();
+    const u64 epoch = *s_epoch;
+    const size_t parity_off = XCH_FLAG_BYTES + (size_t)(epoch & 1) * world * max_rec * sizeof(svdb_candidate);
+    const int words = nrec * 4;                                    // 8-byte words
+    const u64 *src = reinterpret_cast<const u64 *>(local);
+    for (int r = 0; r < world; r++) {
+        u64 *dst = reinterpret_cast<u64 *>(peers.p[r] + parity_off + (size_t)rank * max_rec * sizeof(svdb_candidate));
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys_u64(reinterpret_cast<u64 *>(peers.p[threadIdx.x]) + rank, epoch);
+    return epoch;
+}
+// lanes 0..world-1 of the calling warp spin until every shard's data of `epoch` has landed in the local buffer
+__device__ __forceinline__ void xch_wait(const unsigned char *mine, int world, u64 epoch, int lane) {
+    const u64 *flags = reinterpret_cast<const u64 *>(mine);
+    if (lane < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(flags + lane) < epoch) {
+            if (clock64() - t0 > 20000000000ll) __trap();          // a peer died: do not hang the GPU
+        }
+    }
+    __syncwarp();
+}
+// K7 for one query by one warp: in = the gathered blocks of this epoch ([world] blocks, max_rec records apart)
+__device__ __forceinline__ void merge_gathered(const svdb_candidate *in, int world, size_t max_rec, int qi, int k, int lane,
+                                               svdb_candidate *out) {
+    WarpList wl;
+    wl.reset();
+    u64 fl = 0;
+    const int total = world * k;
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        double d = CUDART_INF;
+        u64 s = SEQ_NONE;
+        if (i < total) {
+            const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+            d = __ldcg(&c->dist);
+            s = __ldcg(&c->seq);
+            fl |= __ldcg(&c->flags) & ~SVDB_CAND_TIE;
+        }
+        wl.offer(s != SEQ_NONE, d, s, lane);
+    }
+    // SVDB_CAND_TIE of the merged answer: >= 2 entries at the merged minimum, or one that its shard flagged
+    double dmin;
+    u64 smin;
+    wl.key_at(0, dmin, smin);
+    int at_min = 0;
+    if (smin != SEQ_NONE) {
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            if (i < total) {
+                const svdb_candidate *c = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+                if (__ldcg(&c->seq) != SEQ_NONE && __ldcg(&c->dist) == dmin) at_min += (__ldcg(&c->flags) & SVDB_CAND_TIE) ? 2 : 1;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        fl |= __shfl_xor_sync(FULL, fl, m);
+        at_min += __shfl_xor_sync(FULL, at_min, m);
+    }
+    if (at_min >= 2) fl |= SVDB_CAND_TIE;
+    if (lane < k) {
+        svdb_candidate c;
+        c.dist = wl.d;
+        c.seq = wl.seq;
+        c.index = (u64)SVDB_NONE;
+        c.flags = fl;
+        if (wl.seq != SEQ_NONE) {
+            for (int i = 0; i < total; i++) {
+                const svdb_candidate *src = in + (size_t)(i / k) * max_rec + (size_t)qi * k + (i % k);
+                if (__ldcg(&src->seq) == wl.seq) {
+                    c.index = __ldcg(&src->index);
+                    break;
+                }
+            }
+        }
+        out[(size_t)qi * k + lane] = c;
+    }
+}
+
+// =====================================================================================
+// The fused tail of a scan launch.  Every CTA calls it after its lists are written (all threads); the last one to
+// arrive finalizes the launch's queries and, on a sharded store, exchanges and merges.  smem: the CTA's dynamic
+// shared memory, free by now.
+// =====================================================================================
+__device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem, int smem_bytes) {
+    if (t.ticket == nullptr) return;
+    __shared__ unsigned s_last;
+    __shared__ u64 s_epoch;
+    __threadfence();                                   // this CTA's lists are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(t.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;   // ... before its ticket is
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *t.ticket = 0;               // re-armed for the next launch on the stream
+    for (int qi = 0; qi < t.fin.nq; qi++) finalize_query(t.fin, qi, smem, smem_bytes);
+    if (t.world <= 1) return;
+    const int nrec = t.fin.nq * t.fin.k;
+    const u64 epoch = xch_push(t.fin.out, nrec, t.peers, t.rank, t.world, t.max_rec, &s_epoch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+    const unsigned char *mine = t.peers.p[t.rank];
+    if (warp < t.fin.nq) xch_wait(mine, t.world, epoch, lane);
+    const svdb_candidate *in = reinterpret_cast<const svdb_candidate *>(
+        mine + XCH_FLAG_BYTES + (size_t)(epoch & 1) * t.world * t.max_rec * sizeof(svdb_candidate));
+    for (int qi = warp; qi < t.fin.nq; qi += NW) merge_gathered(in, t.world, t.max_rec, qi, t.fin.k, lane, t.xout);
+}
+
+}  // namespace svdb

@@ -5,7 +5,7 @@
 // keys on the FP64 tensor cores (DMMA, 37 TFLOP/s); tcgen05 has no FP64 kind, but the keys only have to be good
 // enough to keep every row that could be in the top-k, so K10 forms them from a SPLIT-BF16 copy of the log:
 //
-//   x = xh + xl + r,  xh = bf16(x), xl = bf16(fl32(x) - xh), |r| <= (2^-16 + 2^-24) |x|        (same for q)
+//   x = xh + xl + r,  xh = bf16(x), xl = bf16(fl32(x) - xh)   (two planes of [n][Kp] bf16: hi, lo), |r| <= (2^-16 + 2^-24) |x|        (same for q)
 //   <x, q> ~ <xh, qh> + <xh, ql> + <xl, qh>            three kind::f16 UMMAs per 16 coordinates, fp32 accumulators in TMEM
 //   d~(r, q) = |x_r|^2 + |q|^2 - 2 <x_r, q>            |x|^2, |q|^2 from the fp64 rows (precomputed, rounded to fp32 once)
 //
@@ -38,6 +38,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "smem_optin.h"
 #include "umma_select.cuh"
 
 namespace svdb {
@@ -110,7 +111,8 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 }
 
 __global__ void __launch_bounds__(UF_THREADS, 1)
-umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q, UmmaArgs p) {
+umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                   const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql, UmmaArgs p) {
     extern __shared__ unsigned char uf_smem_raw[];
     const uint32_t raw = smem_u32(uf_smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B tiles want 1024-byte alignment
@@ -168,10 +170,10 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t st = sbase + stage * UF_STAGE_BYTES;
                     mbar_arrive_expect_tx(full, stage_tx);
-                    tma_load_2d(st, &map_x, kc * UF_KC, row0, full);                                   // row tile, hi plane
-                    tma_load_2d(st + UF_A_BYTES, &map_x, p.Kp + kc * UF_KC, row0, full);               //           lo plane
-                    tma_load_2d(st + 2 * UF_A_BYTES, &map_q, kc * UF_KC, q0, full);                    // queries, hi plane
-                    tma_load_2d(st + 2 * UF_A_BYTES + UF_B_BYTES, &map_q, p.Kp + kc * UF_KC, q0, full);  //        lo plane
+                    tma_load_2d(st, &map_xh, kc * UF_KC, row0, full);                                  // row tile, hi plane
+                    tma_load_2d(st + UF_A_BYTES, &map_xl, kc * UF_KC, row0, full);                     //           lo plane
+                    tma_load_2d(st + 2 * UF_A_BYTES, &map_qh, kc * UF_KC, q0, full);                   // queries, hi plane
+                    tma_load_2d(st + 2 * UF_A_BYTES + UF_B_BYTES, &map_ql, kc * UF_KC, q0, full);      //          lo plane
                     if (++stage == UF_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -348,34 +350,50 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
-// ---- fp64 rows -> [hi plane | lo plane] bf16 rows of 2*Kp entries (zeros beyond K) ----
+// ---- fp64 rows -> the two bf16 planes of the shadow, [n][Kp] each (zeros beyond K): hi = bf16(fl32(x)),
+// lo = bf16(fl32(x) - hi).  One warp per row.  err_bits (may be NULL): running maximum over the rows of |x - hi|_2, the
+// error of the HI plane alone, formed in fp64 and rounded up -- what K12's completeness proof needs (plane_scan.cu).
+// Rows with a non-finite coordinate are left out of it: their distance is never finite, so they can never win
+// (kdtree.c:139) and no bound on them is needed. ----
 __global__ void __launch_bounds__(256) split_bf16_kernel(const double *__restrict__ src, int ld, int K, int Kp, u64 first, u64 n,
-                                                         __nv_bfloat16 *__restrict__ dst) {
-    constexpr int ROWS = 32;                                       // rows per block step
-    const int hp = Kp / 2;
-    for (u64 r0 = (u64)blockIdx.x * ROWS; r0 < n; r0 += (u64)gridDim.x * ROWS) {
-        const int rows = (int)min((u64)ROWS, n - r0);
-        for (int li = threadIdx.x; li < rows * hp; li += blockDim.x) {
-            const int rr = li / hp, c = (li - rr * hp) * 2;
-            const u64 r = first + r0 + rr;
-            const double *row = src + r * (u64)ld;
+                                                         __nv_bfloat16 *__restrict__ dst_hi, __nv_bfloat16 *__restrict__ dst_lo,
+                                                         unsigned long long *__restrict__ err_bits) {
+    const int lane = threadIdx.x & 31;
+    const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, GW = ((u64)gridDim.x * blockDim.x) >> 5;
+    double emax = 0.0;
+    for (u64 i = gw; i < n; i += GW) {
+        const u64 r = first + i;
+        const double *row = src + r * (u64)ld;
+        double e2 = 0.0;
+        for (int c = lane * 2; c < Kp; c += 64) {
             const double v0 = c < K ? row[c] : 0.0, v1 = c + 1 < K ? row[c + 1] : 0.0;
             const float f0 = __double2float_rn(v0), f1 = __double2float_rn(v1);
             const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
             const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
             const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-            __nv_bfloat16 *out = dst + r * (u64)(2 * Kp) + c;
-            *reinterpret_cast<__nv_bfloat162 *>(out) = __nv_bfloat162(h0, h1);
-            *reinterpret_cast<__nv_bfloat162 *>(out + Kp) = __nv_bfloat162(l0, l1);
+            *reinterpret_cast<__nv_bfloat162 *>(dst_hi + r * (u64)Kp + c) = __nv_bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162 *>(dst_lo + r * (u64)Kp + c) = __nv_bfloat162(l0, l1);
+            const double d0 = v0 - (double)__bfloat162float(h0), d1 = v1 - (double)__bfloat162float(h1);
+            e2 = fma(d0, d0, e2);
+            e2 = fma(d1, d1, e2);
         }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) e2 += __shfl_xor_sync(FULL, e2, m);
+        if (e2 == e2 && e2 < CUDART_INF) emax = fmax(emax, e2);
+    }
+    if (err_bits != nullptr && lane == 0 && emax > 0.0) {
+        const double e = sqrt(emax) * (1.0 + 1e-12);           // non-negative doubles order like their bit patterns
+        atomicMax(err_bits, (unsigned long long)__double_as_longlong(e));
     }
 }
 
-cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst, int num_sms, cudaStream_t st) {
+cudaError_t launch_split_bf16(const double *src, int ld, int K, int Kp, u64 first, u64 n, uint16_t *dst_hi, uint16_t *dst_lo,
+                              unsigned long long *err_bits, int num_sms, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    u64 grid = (n + 31) / 32;
+    u64 grid = (n + 7) / 8;
     if (grid > (u64)num_sms * 16) grid = (u64)num_sms * 16;
-    split_bf16_kernel<<<(unsigned)grid, 256, 0, st>>>(src, ld, K, Kp, first, n, reinterpret_cast<__nv_bfloat16 *>(dst));
+    split_bf16_kernel<<<(unsigned)grid, 256, 0, st>>>(src, ld, K, Kp, first, n, reinterpret_cast<__nv_bfloat16 *>(dst_hi),
+                                                      reinterpret_cast<__nv_bfloat16 *>(dst_lo), err_bits);
     return cudaGetLastError();
 }
 
@@ -400,12 +418,12 @@ EncodeTiledFn encode_tiled(std::string &why) {
     if (!fn) why = err;
     return fn;
 }
-// [rows][2*Kp] bf16, box = 64 coordinates x box_rows rows, 128-byte swizzle, zeros out of bounds
+// one plane: [rows][Kp] bf16, box = 64 coordinates x box_rows rows, 128-byte swizzle, zeros out of bounds
 bool make_map(CUtensorMap *m, const void *base, u64 rows, int Kp, int box_rows, std::string &why) {
     EncodeTiledFn fn = encode_tiled(why);
     if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)(2 * Kp), (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)(2 * Kp) * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
     const cuuint32_t box[2] = {(cuuint32_t)UF_KC, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
@@ -426,14 +444,17 @@ cudaError_t launch_umma_filter(const UmmaArgs &a, cudaStream_t st, std::string *
         if (why) *why = "umma filter: bad launch shape";
         return cudaErrorInvalidValue;
     }
-    CUtensorMap mx, mq;
-    if (!make_map(&mx, a.xsplit, a.n, a.Kp, UF_M, err) || !make_map(&mq, a.qsplit, (u64)a.ngroups * a.bn, a.Kp, a.bn, err)) {
+    CUtensorMap mxh, mxl, mqh, mql;
+    const u64 nqp = (u64)a.ngroups * a.bn;
+    if (!make_map(&mxh, a.xhi, a.n, a.Kp, UF_M, err) || !make_map(&mxl, a.xlo, a.n, a.Kp, UF_M, err) ||
+        !make_map(&mqh, a.qhi, nqp, a.Kp, a.bn, err) || !make_map(&mql, a.qlo, nqp, a.Kp, a.bn, err)) {
         if (why) *why = err;
         return cudaErrorNotSupported;
     }
-    cudaError_t e = cudaFuncSetAttribute(umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(umma_filter_kernel, UF_SMEM);
     if (e != cudaSuccess) return e;
-    umma_filter_kernel<<<a.ngroups * a.nstreams, UF_THREADS, UF_SMEM, st>>>(mx, mq, a);
+    umma_filter_kernel<<<a.ngroups * a.nstreams, UF_THREADS, UF_SMEM, st>>>(mxh, mxl, mqh, mql, a);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ NONE = (1 << 64) - 1
 MAX_K = 24
 COSINE, EUCLIDEAN, DOT, ALL_METRICS = 0, 1, 2, 3
 FLAG_LOG_ONLY, FLAG_NO_LOG, FLAG_SHARD = 1, 2, 4
-MODE_AUTO, MODE_EXACT, MODE_TREE, MODE_MTREE = 0, 1, 2, 3
+MODE_AUTO, MODE_EXACT, MODE_TREE, MODE_MTREE, MODE_FP64 = 0, 1, 2, 3, 4
 CAND_UNSAFE, CAND_TIE = 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -38,7 +38,8 @@ class Stats(C.Structure):
                 ("tree_rounds", C.c_uint64), ("coalesced_calls", C.c_uint64), ("coalesced_passes", C.c_uint64),
                 ("hbm_bytes_mapped", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("tie_events", C.c_uint64), ("tie_levels", C.c_uint64), ("mtree_builds", C.c_uint64),
-                ("mtree_levels", C.c_uint64), ("mtree_rows", C.c_uint64)]
+                ("mtree_levels", C.c_uint64), ("mtree_rows", C.c_uint64), ("fp64_reruns", C.c_uint64),
+                ("scan_plane_last", C.c_uint64), ("tree_dropped", C.c_uint64)]
 
 
 # ---- exact ties on a sharded store (svdb_tie_resolve / svdb_resolve_ties_sharded) ----
@@ -74,7 +75,7 @@ NATIVE_SYMBOLS = [
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time", "svdb_debug_filter_keys",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
     "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
-    "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded",
+    "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded", "svdb_nearest_batch_device_sharded",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -130,6 +131,8 @@ def lib() -> C.CDLL:
     L.svdb_exchange_destroy.argtypes = [C.c_void_p]
     L.svdb_exchange_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
     L.svdb_nearest_batch_sharded.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_size_t, C.c_size_t, C.c_size_t, _zp, _dp, _u64p]
+    L.svdb_nearest_batch_device_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                    C.c_void_p, C.c_int]
     L.svdb_tie_resolve.argtypes = [C.POINTER(TieBackend), C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, _u64p]
     L.svdb_resolve_ties_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, C.c_void_p,
                                             C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -296,6 +299,11 @@ class Engine:
     def nearest_device(self, q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, mode: int = 0) -> None:
         _check(self.L.svdb_nearest_batch_device(self.h, C.c_void_p(q_ptr), nq, ldq, k, C.c_void_p(out_ptr), int(mode)),
                "svdb_nearest_batch_device")
+
+    def nearest_device_sharded(self, xch: "Exchange", q_ptr: int, nq: int, ldq: int, k: int, out_ptr: int, mode: int = 0) -> None:
+        """Scan of this shard + peer-memory exchange + merge (collective); out receives the merged candidates."""
+        _check(self.L.svdb_nearest_batch_device_sharded(self.h, xch.h, C.c_void_p(q_ptr), nq, ldq, k, C.c_void_p(out_ptr),
+                                                        int(mode)), "svdb_nearest_batch_device_sharded")
 
     # -- compare ------------------------------------------------------------
     def compare(self, metric: int, i1, i2) -> np.ndarray:

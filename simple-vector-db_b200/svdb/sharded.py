@@ -207,16 +207,16 @@ class ShardedIndex:
                 self._seal()                      # a rank whose shard is empty never saw an ingest call
             return self._nearest_device_replicated(dq, k, mode)
         local, gathered, merged, _ = self._buffers(nq, k)
+        if self.world > 1 and self.xch is not None and nq * k <= self.max_records:
+            # scan + peer-memory exchange + merge inside the library (one launch for a single query)
+            self.engine.nearest_device_sharded(self.xch, dq.data_ptr(), nq, dq.stride(0), k, merged.data_ptr(), mode)
+            return merged
         self.engine.nearest_device(dq.data_ptr(), nq, dq.stride(0), k, local.data_ptr(), mode)
         if self.world > 1:
             stream = self.torch.cuda.current_stream(self.device).cuda_stream
-            if self.xch is not None and nq * k <= self.max_records:
-                self.xch.merge(stream, local.data_ptr(), nq, k, merged.data_ptr())
-                self.merge_launches += 2
-            else:
-                self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
-                B.merge_candidates_device(self.device, stream, gathered.data_ptr(), self.world, nq, k, merged.data_ptr())
-                self.merge_launches += 1
+            self.torch.distributed.all_gather_into_tensor(gathered, local, group=self.group)
+            B.merge_candidates_device(self.device, stream, gathered.data_ptr(), self.world, nq, k, merged.data_ptr())
+            self.merge_launches += 1
         return merged
 
     def _nearest_device_replicated(self, dq, k: int, mode: int):

@@ -355,7 +355,7 @@ def test_batched_dmma_cancellation_falls_back(port):
     with B.Engine(64, 64) as e:
         e.insert(rows)
         assert_topk_equal(e.nearest(Q, 5), want, 5)
-        assert e.stats()["exact_reruns"] > 0
+        assert e.stats()["exact_reruns"] + e.stats()["fp64_reruns"] > 0      # low-precision keys -> K1 (fp64 rows) -> exact
 
 
 def test_script_distribution_ties(port):

@@ -1,6 +1,7 @@
-"""GPU parity of K11 (scan_shadow_kernel, csrc/scan_kernels.cu): the single-query / small-batch scan over the split-bf16
-shadow of the log instead of the fp64 rows (option scan.shadow, off by default in this round).  Approximate fp32 keys,
-answers after finalize's reference-order re-rank (kdtree.c:134-137) bit-identical to the oracle's."""
+"""GPU parity of K11 (scan_shadow_kernel, csrc/scan_kernels.cu: hi + lo bf16 planes) and K12 (scan_plane_kernel,
+csrc/plane_scan.cu: the hi plane alone, the default): the single-query / small-batch scans over the split-bf16 shadow of
+the log instead of the fp64 rows (option scan.plane).  Approximate fp32 keys, answers after the reference-order re-rank
+(kdtree.c:134-137) bit-identical to the oracle's; with and without the fused tail (option scan.fuse_tail)."""
 import numpy as np
 import pytest
 
@@ -15,6 +16,7 @@ from svdb import synth  # noqa: E402
 from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
 
 
+@pytest.mark.parametrize("plane,fuse", [(1, 1), (2, 1), (1, 0), (2, 0)])
 @pytest.mark.parametrize("n,D,K,nq,k,seed", [
     (20000, 128, 128, 1, 1, 1),        # the headline shape in small: one query, top-1
     (9000, 768, 768, 3, 10, 2),        # config-3 rows; passes of 2 + 1 queries
@@ -22,32 +24,40 @@ from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
     (5000, 200, 50, 1, 24, 4),         # compact kd array (K < D), k = SVDB_MAX_K
     (37, 40, 40, 1, 3, 5),             # fewer rows than one tile
     (7000, 320, 320, 3, 10, 6),        # two trips, the second one partial
+    (8000, 64, 64, 1, 10, 7),          # K12: four rows packed to a warp step
+    (8001, 192, 192, 2, 2, 8),         # K12: one trip, 24 of 32 lanes
+    (3000, 1000, 1000, 1, 10, 9),      # K12: four trips
+    (2000, 1100, 1100, 1, 5, 10),      # beyond K12's register-resident query: K11 serves plane 2 as well
 ])
-def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed):
+def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed, plane, fuse):
     rows = synth.uniform_rows(seed, n, D)
     Q = synth.uniform_rows(seed + 70, nq, D)
     want = oracle_topk(port, rows, K, Q, k)
     with B.Engine(D, K) as e:
         e.insert(rows)
         e.flush()
+        e.set_option("scan.plane", 0)
+        e.set_option("scan.fuse_tail", fuse)
         assert_topk_equal(e.nearest(Q, k), want, k)             # K1 first: the next call of this shape is the one that gets captured
-        e.set_option("scan.shadow", 1)
+        e.set_option("scan.plane", plane)
         e.set_option("nearest.umma_min_kd_dim", 1)
         for _ in range(3):                                      # the shadow is built before the capture, never inside it
             assert_topk_equal(e.nearest(Q, k), want, k)
-        assert e.stats()["exact_reruns"] == 0
-        e.set_option("scan.shadow", 0)
+        st = e.stats()
+        assert st["exact_reruns"] == 0 and (plane == 2 or st["fp64_reruns"] == 0)
+        e.set_option("scan.plane", 0)
         assert_topk_equal(e.nearest(Q, k), want, k)
 
 
-def test_shadow_scan_follows_inserts_and_extremes(port):
+@pytest.mark.parametrize("plane", [1, 2])
+def test_shadow_scan_follows_inserts_and_extremes(port, plane):
     D = 64
     rng = np.random.Generator(np.random.PCG64(7))
     rows = synth.uniform_rows(31, 3000, D)
     more = synth.uniform_rows(32, 300, D)
     with B.Engine(D, D) as e:
         e.insert(rows)
-        e.set_option("scan.shadow", 1)
+        e.set_option("scan.plane", plane)
         Q = synth.uniform_rows(33, 2, D)
         assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
         e.insert(more)
@@ -60,6 +70,6 @@ def test_shadow_scan_follows_inserts_and_extremes(port):
     Q = 1.0e6 + rng.random((2, D))
     with B.Engine(D, D) as e:
         e.insert(rows)
-        e.set_option("scan.shadow", 1)
+        e.set_option("scan.plane", plane)
         assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
-        assert e.stats()["exact_reruns"] > 0
+        assert e.stats()["exact_reruns"] + e.stats()["fp64_reruns"] > 0      # low-precision keys -> K1 (fp64 rows) -> exact
