@@ -18,6 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsvdb_b200.so")
 SOURCES = ["scan_kernels.cu", "plane_scan.cu", "compare_kernels.cu", "tree_kernels.cu", "median_tree.cu", "mma_kernels.cu", "umma_filter.cu", "arena.cu", "engine.cu", "exchange.cu", "tie_protocol.cu", "dropin.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-cudart", "static"]
 
 
 def nvcc() -> str:
@@ -28,7 +29,13 @@ def nvcc() -> str:
 
 
 def _stamp() -> str:
+    """Hash of everything the library depends on: sources, headers, the source list, the flags and the compiler."""
     h = hashlib.sha256()
+    h.update(repr((SOURCES, ARCH, COMMON_FLAGS)).encode())
+    try:
+        h.update(subprocess.run([nvcc(), "--version"], capture_output=True, text=True).stdout.encode())
+    except Exception:  # noqa: BLE001
+        pass
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
             if name.endswith((".cu", ".cuh", ".h")):
@@ -44,8 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
     cc = nvcc()
-    common = [cc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-cudart", "static"]
+    common = [cc, *ARCH, *COMMON_FLAGS]
     if verbose:
         common += ["-Xptxas", "-v"]
     objs = []
