@@ -1,10 +1,11 @@
 """Which kernel should answer a call of nq queries?  Times one device-resident call (CUDA events, queries in HBM) through
-each path on the same store and prints one JSON line per nq: K1 (fp64 rows, passes of <= 8 queries), K11 (split-bf16
-shadow, passes of <= 8), K2 (FP64 DMMA), K10 (tcgen05).  Answers of every path are compared with K1's.
+each path on the same store and prints one JSON line per nq: K1 (fp64 rows, passes of <= 8 queries), K11 (hi + lo bf16
+planes, passes of <= 8), K12 (hi plane, passes of <= 2), K2 (FP64 DMMA), K10 (tcgen05).  Answers of every path are
+compared with K1's; `hbm_pass_ms` is one pass over the fp64 rows at the measured HBM peak.
 
     python scripts/sweep_batch_paths.py [rows] [dim] [k]          # defaults 2000000 768 10
-AUTO's thresholds (nearest.mma_min_queries = 4, nearest.umma_min_queries = 65, scan.shadow = 0) were set from the
-round-1 measurements of K1/K2/K10 alone; this sweep is what the next change of those defaults should be based on."""
+AUTO's thresholds (nearest.mma_min_queries, nearest.umma_min_queries, scan.plane) are set from this sweep
+(profiles/r02_sweep_batch_paths_*.jsonl)."""
 import json
 import os
 import sys
@@ -15,12 +16,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "simple-vector-db_b200")]
 from svdb import binding as B  # noqa: E402
 
-PATHS = {           # name: (scan.shadow, nearest.mma_min_queries, nearest.umma_min_queries)
+PATHS = {           # name: (scan.plane, nearest.mma_min_queries, nearest.umma_min_queries)
     "K1_fp64_rows": (0, 0, 0),
-    "K11_shadow": (1, 0, 0),
+    "K11_hi_lo_planes": (1, 0, 0),
+    "K12_hi_plane": (2, 0, 0),
     "K2_dmma": (0, 1, 0),
     "K10_tcgen05": (0, 0, 1),
 }
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:  # noqa: BLE001
+    PEAK = 6650.0
 
 
 def main():
@@ -41,14 +47,16 @@ def main():
         Qall = torch.rand((1024, D), dtype=torch.float64, device="cuda", generator=g)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for nq in (1, 2, 3, 4, 8, 16, 32, 64, 65, 128, 256, 1024):
+            if nq > 64 and os.environ.get("SWEEP_MAX_NQ"):
+                break
             Q = Qall[:nq].contiguous()
             out = torch.zeros((nq, k, 4), dtype=torch.int64, device="cuda")
-            line = {"rows": n, "dim": D, "k": k, "nq": nq}
+            line = {"rows": n, "dim": D, "k": k, "nq": nq, "hbm_pass_ms": n * D * 8 / PEAK / 1e6}
             want = None
             for name, (shadow, mma, umma) in PATHS.items():
-                if name in ("K1_fp64_rows", "K11_shadow") and nq > 256:
-                    continue                                   # 128 passes: not a contender
-                e.set_option("scan.shadow", shadow)
+                if name in ("K1_fp64_rows", "K11_hi_lo_planes") and nq > 256 or name == "K12_hi_plane" and nq > 64:
+                    continue                                   # too many passes: not a contender
+                e.set_option("scan.plane", shadow)
                 e.set_option("nearest.mma_min_queries", mma)
                 e.set_option("nearest.umma_min_queries", umma)
                 e.nearest_device(Q.data_ptr(), nq, D, k, out.data_ptr())          # warm-up (builds the shadow once)

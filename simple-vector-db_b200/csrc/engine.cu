@@ -177,6 +177,12 @@ int svdb_engine::init(const svdb_config &c) {
 
     CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
+    // the fused tail's arrival counter: zero between launches.  Allocated and cleared HERE, never lazily: a first use
+    // inside a stream capture (nearest_host) would record the memset into a graph that is then thrown away
+    if (!no_log) {
+        if (!ticket.ensure(16, err)) return fail(SVDB_ERR_OOM, err);
+        CK(cudaMemset(ticket.p, 0, 16));
+    }
 
     stage_ld = log_only ? (size_t)kstride : (size_t)Dpad;
     stage_cap = std::min<size_t>(65536, std::max<size_t>(1, ((size_t)8 << 20) / (stage_ld * 8)));
@@ -571,11 +577,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
     if (plane == 2) limit = plane_scan_supports(Kp, 2) ? std::min(limit, 2) : 1;
     if (nlists && !lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return fail(SVDB_ERR_OOM, err);
     // the scan's last CTA finalizes (and exchanges) itself -- every wide scan but the LDG variant and the exact kernel
-    const bool fuse = fuse_tail && nlists && !use_exact && (plane > 0 || tune.variant == 0);
-    if (fuse && !ticket.p) {
-        if (!ticket.ensure(16, err)) return fail(SVDB_ERR_OOM, err);
-        CK(cudaMemsetAsync(ticket.p, 0, 16, stream));
-    }
+    const bool fuse = fuse_tail && ticket.p && nlists && !use_exact && (plane > 0 || tune.variant == 0);
 
     size_t done = 0;
     while (done < nq) {
@@ -842,7 +844,8 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         rc = mtree_update();
         if (rc) return rc;
     }
-    if ((scan_plane > 0 || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
+    const bool few = mma_min_q <= 0 || nq < (size_t)mma_min_q;            // calls the single-query scans (K12 / K11) serve
+    if (((scan_plane > 0 && few) || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
@@ -893,7 +896,9 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
                 done = true;
             } else {
                 cudaGetLastError();
-                graphs_enabled = false;      // something in the sequence is not capturable here: plain launches from now on
+                // a scratch block grew during the capture (its pointers are baked in): just try again next time; anything
+                // else means something in the sequence is not capturable here -- plain launches from now on
+                if (r != SVDB_OK || ce2 != cudaSuccess || !graph || scratch_generation() + opt_gen == gen) graphs_enabled = false;
                 stats.kernels_launched = l0;
             }
             if (graph) cudaGraphDestroy(graph);
