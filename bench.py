@@ -409,8 +409,10 @@ def ours(args):
         qb_dev = qb_host.to(dev)
         peaks = load_peaks()
 
+        umma_default = 3 if K >= 256 else 32        # the engine's own default (engine.h)
+
         def run_batch(umma: bool):
-            e.set_option("nearest.umma_min_queries", 65 if umma else 0)
+            e.set_option("nearest.umma_min_queries", umma_default if umma else 0)
             # warm-up: K10 builds its bf16 shadow of the log and sizes its scratch on the first full call; the DMMA
             # path (0.6 s per full call) warms up on one query group
             idx.nearest_device(qb_dev if umma else qb_dev[:64], kb)
@@ -475,7 +477,7 @@ def ours(args):
             batch_dmma = {"error": f"{type(ex).__name__}: {ex}"}
         if "result_checksum" in batch and "result_checksum" in batch_dmma:
             batch["identical_to_dmma_path"] = batch["result_checksum"] == batch_dmma["result_checksum"]
-        e.set_option("nearest.umma_min_queries", 65)
+        e.set_option("nearest.umma_min_queries", umma_default)
 
     # ---- parity at THIS size: outside every timed region, at every N.  For 8 pool queries the product's
     # answers -- top-1 through the timed path's entry point and top-10 through the public host call -- and, for 8 queries of

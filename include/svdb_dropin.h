@@ -20,7 +20,12 @@
  *     each row (the reference's own malloc'ed vec.data, whose ownership
  *     vector_db_insert/update take exactly as before);
  *   - KDTree.root is non-NULL once the log is non-empty but is not a walkable
- *     tree (kdtree_create_node / *_rec of src/kdtree.c are not exported);
+ *     tree.  The reference's non-static helpers that no header declares and nothing
+ *     outside their own file calls -- kdtree_create_node, kdtree_insert_rec,
+ *     kdtree_free_rec, kdtree_nearest_rec (src/kdtree.c:15,47,98,131) and the unused
+ *     qsort comparator `compare` (src/vector_database.c:361) -- are deliberately NOT
+ *     exported: they take or return KDTreeNode pointers into a heap tree that does
+ *     not exist here;
  *   - no progress chatter on stdout (the reference prints per insert level);
  *   - kd_dim > vector dimension is rejected ((size_t)-1) instead of reading past
  *     the row (src/kdtree.c:26-28);
@@ -84,6 +89,7 @@ float euclidean_distance(Vector vec1, Vector vec2);
 float dot_product(Vector vec1, Vector vec2);
 
 /* -- batched extensions behind the same semantics (last row) -- */
+#define SVDB_DROPIN_MAX_K 24     /* largest k of kdtree_nearest_batch (= SVDB_MAX_K) */
 /* k nearest log entries for each of nq queries (ldq doubles apart); index_out is nq x k. */
 int kdtree_nearest_batch(KDTree *tree, const double *queries, size_t nq, size_t ldq, size_t k,
                          size_t *index_out, double *dist_out);

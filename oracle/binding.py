@@ -35,6 +35,9 @@ def build(ref_root: str = "/root/reference") -> None:
     # the reference's handlers driven in-process (needs the CUDA library to link the second binary)
     subprocess.run(["make", "-s", "-C", HERE, "handlers", f"REF={ref_root}"], check=False,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # ... and the same handlers with integration/f3_f4_handlers.patch applied (top-k /nearest, batched /compare)
+    subprocess.run(["make", "-s", "-C", HERE, "handlers_patched", f"REF={ref_root}"], check=False,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def _as_f64(a) -> np.ndarray:

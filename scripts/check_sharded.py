@@ -76,15 +76,48 @@ def main():
             for k in (1, 10):
                 got = idx.nearest(Q, k)
                 few = idx.nearest(Q[:3], k)       # too few queries to split over replicas / one small pass per shard
+                # ONE query per call: the whole step is a single scan launch whose last CTA re-ranks, stores to the peers,
+                # waits and merges (scan_tail) -- through the host entry point and through the device entry point
+                ones = [idx.nearest(Q[i:i + 1], k) for i in range(4)]
+                qd = Q.to(dev)
+                ones_dev = []
+                for i in range(4):
+                    r = idx.nearest_device(qd[i:i + 1], k).clone()
+                    torch.cuda.synchronize()
+                    ones_dev.append(r.cpu().numpy().view(B.candidate_dtype).reshape(1, k))
                 if rank == 0:
                     widx, wdist, wseq = ref.nearest(Q.numpy(), k)
                     same = np.array_equal(got["seq"], wseq) and np.array_equal(got["dist"].view(np.uint64), wdist.view(np.uint64))
                     same = same and np.array_equal(got["index"], widx)
                     same = same and np.array_equal(few["seq"], wseq[:3]) and np.array_equal(few["dist"].view(np.uint64), wdist[:3].view(np.uint64))
+                    single = all(np.array_equal(o["seq"][0], wseq[i]) and np.array_equal(o["index"][0], widx[i]) and
+                                 np.array_equal(o["dist"][0].view(np.uint64), wdist[i].view(np.uint64)) for i, o in enumerate(ones))
+                    # the device entry point leaves exact ties between distinct points to its caller (SVDB_CAND_TIE)
+                    single_dev = all((o["flags"][0, 0] & B.CAND_TIE) or
+                                     (np.array_equal(o["seq"][0], wseq[i]) and np.array_equal(o["dist"][0].view(np.uint64), wdist[i].view(np.uint64)))
+                                     for i, o in enumerate(ones_dev))
+                    same = same and single and single_dev
+                    # ... and against the CPU oracle itself (flat (distance, seq) order is the reference's answer wherever
+                    # the minimum is not shared by distinct points: the non-lattice cases)
+                    oracle_ok = None
+                    if not levels and phase == "bulk" and n * K <= 60_000_000:
+                        from oracle import binding as OB
+                        from oracle.binding import PortDB
+                        db = PortDB(OB.load_port(), D, K)
+                        for r in rows.numpy():
+                            db.insert(r)
+                        oracle_ok = True
+                        for i, q in enumerate(Q.numpy()):
+                            oseq, oidx, od = db.topk(q, k)
+                            oracle_ok &= np.array_equal(got["index"][i].astype(np.uint64), np.asarray(oidx, dtype=np.uint64)) and \
+                                np.array_equal(got["dist"][i].view(np.uint64), od.view(np.uint64))
+                        db.close()
+                        same = same and bool(oracle_ok)
                     ok &= bool(same)
                     report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels, "phase": phase,
                                    "layout": "replicated kd log, queries split" if idx.replicated else "row shards",
-                                   "identical_to_single_gpu": bool(same), "tie_events": idx.engine.stats()["tie_events"],
+                                   "identical_to_single_gpu": bool(same), "single_query_calls_identical": bool(single and single_dev),
+                                   "identical_to_cpu_oracle": oracle_ok, "tie_events": idx.engine.stats()["tie_events"],
                                    "tie_levels": idx.engine.stats()["tie_levels"]})
         if ref is not None:
             ref.close()

@@ -145,6 +145,7 @@ int svdb_engine::init(const svdb_config &c) {
     K = (int)c.kd_dim;
     Dpad = (int)round_up(D, 16);
     wide = K > tune.thin_max_k;
+    if (umma_min_q < 0) umma_min_q = K >= 256 ? 3 : 32;
     alias = !log_only && !no_log && wide && K == D;
     kstride = alias ? Dpad : (wide ? (int)round_up(K, 2) : K);
 
@@ -844,8 +845,9 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         rc = mtree_update();
         if (rc) return rc;
     }
-    const bool few = mma_min_q <= 0 || nq < (size_t)mma_min_q;            // calls the single-query scans (K12 / K11) serve
-    if (((scan_plane > 0 && few) || (umma_min_q > 0 && nq >= (size_t)umma_min_q)) && wide && !force_exact && umma_ok && K >= umma_min_k &&
+    const bool to_umma = umma_min_q > 0 && nq >= (size_t)umma_min_q;     // K10 serves the call
+    const bool few = !to_umma && (mma_min_q <= 0 || nq < (size_t)mma_min_q);   // the single-query scans (K12 / K11) do
+    if (((scan_plane > 0 && few) || to_umma) && wide && !force_exact && umma_ok && K >= umma_min_k &&
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted

@@ -74,7 +74,10 @@ struct svdb_engine {
     // K10: batches of at least umma_min_q queries over kd-points of at least umma_min_k coordinates take the tcgen05 path
     // (split-bf16 keys + the same exact re-rank); 0 switches it off.  Needs a bf16 shadow of the log (4 bytes per
     // coordinate, built on first use and extended incrementally); if that does not fit, K2 keeps serving.
-    int umma_min_q = 65, umma_min_k = 32;
+    // Thresholds from profiles/r02_sweep_batch_paths.jsonl: with 64-query CTA groups K10 answers 3..64 queries in the time of
+    // ~0.65 fp64 HBM passes at kd_dim 768 (K2: 1.4 - 4 passes), so it takes over from 3 queries on for kd_dim >= 256; for
+    // shorter rows its per-tile epilogue dominates and K2 stays ahead up to 16 queries (set in init(); -1 = not chosen yet).
+    int umma_min_q = -1, umma_min_k = 32;
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the shadow
     size_t shadow_mapped_counted = 0;    // part of the shadow's mapped bytes already included in stats.hbm_bytes_mapped

@@ -25,6 +25,9 @@ static MHD_AccessHandlerCallback route(const char *method, const char *url) {
     } else if (!strcmp(method, "POST")) {
         if (!strcmp(url, "/vector")) return post_handler;
         if (!strcmp(url, "/nearest")) return nearest_handler;
+#ifdef SVDB_PATCHED_HANDLERS                                 /* integration/f3_f4_handlers.patch: the route it adds to main.c */
+        if (!strncmp(url, "/compare/", 9)) return compare_batch_handler;
+#endif
     } else if (!strcmp(method, "PUT") && !strcmp(url, "/vector")) {
         return put_handler;
     } else if (!strcmp(method, "DELETE") && !strcmp(url, "/vector")) {

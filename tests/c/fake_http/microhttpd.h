@@ -22,6 +22,7 @@ enum MHD_OPTION { MHD_OPTION_END = 0, MHD_OPTION_NOTIFY_COMPLETED = 4 };
 #define MHD_HTTP_BAD_REQUEST 400
 #define MHD_HTTP_NOT_FOUND 404
 #define MHD_HTTP_INTERNAL_SERVER_ERROR 500
+#define MHD_HTTP_NOT_IMPLEMENTED 501
 #define MHD_HTTP_HEADER_CONTENT_TYPE "Content-Type"
 
 typedef enum MHD_Result (*MHD_AccessHandlerCallback)(void *cls, struct MHD_Connection *connection, const char *url,

@@ -38,6 +38,7 @@ def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed, plane, fuse):
         e.flush()
         e.set_option("scan.plane", 0)
         e.set_option("scan.fuse_tail", fuse)
+        e.set_option("nearest.umma_min_queries", 0)             # 3 queries at kd_dim >= 256 would go to K10 (tests/test_gpu_umma.py)
         assert_topk_equal(e.nearest(Q, k), want, k)             # K1 first: the next call of this shape is the one that gets captured
         e.set_option("scan.plane", plane)
         e.set_option("nearest.umma_min_kd_dim", 1)
@@ -58,6 +59,7 @@ def test_shadow_scan_follows_inserts_and_extremes(port, plane):
     with B.Engine(D, D) as e:
         e.insert(rows)
         e.set_option("scan.plane", plane)
+        e.set_option("nearest.umma_min_queries", 0)
         Q = synth.uniform_rows(33, 2, D)
         assert_topk_equal(e.nearest(Q, 5), oracle_topk(port, rows, D, Q, 5), 5)
         e.insert(more)
