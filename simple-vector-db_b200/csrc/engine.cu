@@ -230,7 +230,7 @@ void svdb_engine::destroy() {
     shadow_ready = false;
     shadow_n = 0;
     shadow_mapped_counted = 0;
-    for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal}) s->free_();
+    for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal, &tail_dbg}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
                        &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
@@ -620,6 +620,10 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         if (fuse) {
             ta.ticket = ticket.as<unsigned>();
             ta.fin = fa;
+            if (tail_debug) {
+                if (!tail_dbg.ensure((size_t)(8 + nlists) * 8, err)) return fail(SVDB_ERR_OOM, err);
+                ta.dbg = tail_dbg.as<unsigned long long>();
+            }
             if (x && exchanged && done == 0 && (size_t)nqp == nq) {      // the whole call is this one pass
                 exchange_fill_tail(x, ta, d_merged);
                 fused_exchange = true;
@@ -1709,6 +1713,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
         e->scan_plane = (int)value;
     }
     else if (n == "scan.fuse_tail") e->fuse_tail = value != 0;
+    else if (n == "scan.tail_debug") e->tail_debug = value != 0;
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;
@@ -1782,6 +1787,19 @@ int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches) {
     *total_ms = sum;
     *launches = e->scan_events_used;
     e->scan_events_used = 0;
+    return SVDB_OK;
+}
+
+/* Diagnostics of the fused tail (option "scan.tail_debug" = 1): the %globaltimer stamps (ns) the last fused scan launch
+ * left -- see kernels.h: TailArgs::dbg; count <= 8 + number of CTAs. */
+int svdb_debug_tail_times(svdb_engine *e, unsigned long long *out, size_t count) {
+    if (!e || !out) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->tail_dbg.p || count * 8 > e->tail_dbg.cap) return e->fail(SVDB_ERR_ARG, "no tail debug capture (set scan.tail_debug before the call)");
+    cudaSetDevice(e->device);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, e->tail_dbg.p, count * 8, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) return e->fail_cuda("debug_tail_times", ce);
     return SVDB_OK;
 }
 

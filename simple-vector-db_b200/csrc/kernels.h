@@ -69,6 +69,9 @@ struct TailArgs {
     PeerPtrs peers;         // exchange.cu: every rank's gather buffer
     size_t max_rec;
     svdb_candidate *xout;   // merged answers [nq][k]
+    unsigned long long *dbg; // NULL, or 8 + gridDim.x words of %globaltimer stamps (option "scan.tail_debug"):
+                            // [0] last CTA took its ticket, [1] lists merged, [2] re-rank done (finalize end), [3] pushed to
+                            // the peers, [4] every peer's data has landed, [5] merged; [8 + b] CTA b took its ticket
 };
 
 struct ScanArgs {

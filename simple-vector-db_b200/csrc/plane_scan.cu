@@ -47,6 +47,7 @@ template <int NQ, int TRIPS, int LPR, int TR>
 __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constant__ PlaneScanArgs p, int nstages, int smem_bytes) {
     static_assert(LPR == 32 || (TRIPS == 1 && NQ == 1 && TR == 32), "packed rows: one trip, one query, 32-row tiles");
     extern __shared__ __align__(128) unsigned char smem[];
+    if (p.tail.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Kp = p.Kp;
@@ -192,6 +193,8 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
         cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    if (threadIdx.x == 0)                                // the tail reuses this memory (and brings its own barrier)
+        for (int i = 0; i < W * nstages; i++) mbar_inval(smem_u32(bars + i));
     scan_tail(p.tail, smem, smem_bytes);
 }
 

@@ -38,6 +38,7 @@ template <int TR, int NQ, int LPR = 32>
 __global__ void __launch_bounds__(512, 1) scan_wide_kernel(const __grid_constant__ ScanArgs p, int nstages, int smem_bytes) {
     static_assert(LPR == 32 || (TR == 32 && NQ == 1), "packed rows: 32-row tiles, one query");
     extern __shared__ __align__(128) unsigned char smem[];
+    if (p.tail.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpad = p.stride;
@@ -205,6 +206,8 @@ __global__ void __launch_bounds__(512, 1) scan_wide_kernel(const __grid_constant
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
         cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    if (threadIdx.x == 0)                                // the tail reuses this memory (and brings its own barrier)
+        for (int i = 0; i <= W * nstages; i++) mbar_inval(smem_u32(bars + i));
     scan_tail(p.tail, smem, smem_bytes);
 }
 
@@ -341,6 +344,8 @@ __global__ void __launch_bounds__(512, 1) scan_shadow_kernel(const __grid_consta
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
         cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < W * nstages; i++) mbar_inval(smem_u32(bars + i));
     scan_tail(p.tail, smem, smem_bytes);
 }
 
@@ -495,9 +500,12 @@ __global__ void __launch_bounds__(512, 1) scan_exact_kernel(ScanArgs p) {
 constexpr int FIN_WARPS = 8;
 constexpr size_t FIN_SMEM = fin_head_bytes(FIN_WARPS) + (size_t)32 * 257 * 8;
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(FinalArgs p) {
-    extern __shared__ __align__(16) unsigned char fsm[];
-    finalize_query(p, blockIdx.x, fsm, (int)FIN_SMEM);
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const __grid_constant__ FinalArgs p) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    if (threadIdx.x == 0) fin_bar_init(fsm, FIN_WARPS);
+    __syncthreads();
+    uint32_t phase = 0;
+    finalize_query(p, blockIdx.x, fsm, (int)FIN_SMEM, phase);
 }
 
 // =====================================================================================
