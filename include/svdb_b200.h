@@ -300,7 +300,7 @@ int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches);
 int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count);
 /* Diagnostics of the fused scan tail: with option "scan.tail_debug" = 1 the last fused scan launch leaves %globaltimer
  * stamps (ns): [0] the last CTA took its ticket, [1] CTA lists merged, [2] re-rank done, [3] answers stored to the peers,
- * [4] every peer's answers have landed, [5] merged; [8 + b] CTA b finished its part of the scan.  count <= 8 + CTAs. */
+ * [4] every peer's answers have landed, [5] merged; [32 + b] CTA b finished its part of the scan ([9..14]: phases inside the re-rank).  count <= 32 + CTAs. */
 int svdb_debug_tail_times(svdb_engine *e, unsigned long long *out, size_t count);
 
 #ifdef __cplusplus

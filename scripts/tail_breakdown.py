@@ -42,11 +42,15 @@ def main():
             t = e.debug_tail_times(296).astype(np.int64)
             if i < 8:
                 continue                                   # warm-up (shadow build, clocks)
-            start, ctas = t[6], t[8:]
+            start, ctas = t[6], t[32:]
             recs.append({"event_us": ev0.elapsed_time(ev1) * 1e3, "first_cta_done_us": (ctas.min() - start) / 1e3,
                          "median_cta_done_us": (np.median(ctas) - start) / 1e3, "p90_cta_done_us": (np.percentile(ctas, 90) - start) / 1e3,
                          "last_cta_done_us": (t[0] - start) / 1e3, "lists_merged_us": (t[1] - t[0]) / 1e3,
-                         "rerank_us": (t[2] - t[1]) / 1e3, "kernel_span_us": (t[2] - start) / 1e3})
+                         "rerank_us": (t[2] - t[1]) / 1e3, "kernel_span_us": (t[2] - start) / 1e3,
+                         "a_ticket_to_finalize_entry_us": (t[9] - t[0]) / 1e3, "b_lists_in_smem_us": (t[10] - t[9]) / 1e3,
+                         "c_lists_merged_per_warp_us": (t[11] - t[10]) / 1e3, "d_query_norms_us": (t[12] - t[11]) / 1e3,
+                         "e_cross_warp_merge_us": (t[1] - t[12]) / 1e3, "f_window_us": (t[13] - t[1]) / 1e3,
+                         "g_rows_fetched_squared_us": (t[14] - t[13]) / 1e3, "h_serial_chain_rank_emit_us": (t[2] - t[14]) / 1e3})
         keys = recs[0].keys()
         print(json.dumps({"rows": n, "dim": D, "plane": plane, "k": k, "calls": len(recs),
                           **{kk: float(np.median([r[kk] for r in recs])) for kk in keys}}), flush=True)

@@ -69,9 +69,9 @@ struct TailArgs {
     PeerPtrs peers;         // exchange.cu: every rank's gather buffer
     size_t max_rec;
     svdb_candidate *xout;   // merged answers [nq][k]
-    unsigned long long *dbg; // NULL, or 8 + gridDim.x words of %globaltimer stamps (option "scan.tail_debug"):
+    unsigned long long *dbg; // NULL, or 32 + gridDim.x words of %globaltimer stamps (option "scan.tail_debug"):
                             // [0] last CTA took its ticket, [1] lists merged, [2] re-rank done (finalize end), [3] pushed to
-                            // the peers, [4] every peer's data has landed, [5] merged; [8 + b] CTA b took its ticket
+                            // the peers, [4] every peer's data has landed, [5] merged; [32 + b] CTA b took its ticket; [9..14] phases inside finalize
 };
 
 struct ScanArgs {

@@ -74,14 +74,18 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
 
     // ---- 1. merge ----
     // The lists (nlists x cap x 16 bytes, written by other CTAs or by the launch before) come into shared memory with ONE bulk
-    // async copy per chunk of whole lists that fits the buffer -- one trip to L2 instead of a chain of dependent loads
-    // (measured: 18 of the 27 us a single-query tail took went into walking 296 lists with 4 loads in flight per lane).
-    WarpList wl;
+    // async copy per chunk of whole lists that fits the buffer.  Every list is sorted, so the cap-th smallest of the list
+    // HEADS, tau, is an upper bound of the cap-th smallest key overall: a first pass over the heads finds tau, a second
+    // pass over all entries inserts only those <= tau (about cap + a few) -- serial inserts are what a merge costs
+    // (measured: walking 296 lists by insertion took 11 of the 27 us of a single-query tail).
+    WarpList wl, wh;                                     // the smallest entries <= tau / the smallest heads, per warp
     wl.reset();
+    wh.reset();
     double bound = CUDART_INF;
     const uint32_t bar = fin_bar_addr(fsm, NW);
     const Cand *sl = reinterpret_cast<const Cand *>(tbuf);
     const int per_chunk = max(1, (int)(((size_t)tcap * 8) / ((size_t)p.cap * sizeof(Cand))));
+    double eq2 = 0.0, qn2 = 0.0;
     for (int l0 = 0; l0 < p.nlists; l0 += per_chunk) {
         const int nl = min(per_chunk, p.nlists - l0);
         if (threadIdx.x == 0) {
@@ -91,55 +95,70 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s(smem_u32(tbuf), L + (size_t)l0 * p.cap, bytes, bar);
         }
+        if (l0 == 0 && p.sq_mode) {
+            // sqrt-form keys: |q - fl32(q)|^2 and |q|^2 of this query, formed here (no prep launch in front of the scan),
+            // while the copy is in flight
+            for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+                const double v = __ldg(qv + i);
+                const double r = v - (double)__double2float_rn(v);
+                eq2 = fma(r, r, eq2);
+                qn2 = fma(v, v, qn2);
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                eq2 += shfl_xor_f64(eq2, m);
+                qn2 += shfl_xor_f64(qn2, m);
+            }
+        }
         mbar_wait(bar, phase);
         phase ^= 1;
-        if (p.cap >= 16) {
-            // long lists (k >= 8): most keys of a list qualify while the running list fills up, and every one of them
-            // would be a serial insert -- merge list by list with the fixed-cost bitonic network instead
-            for (int l = warp; l < nl; l += NW) {
-                Cand c = Cand{CUDART_INF, SEQ_NONE};
-                if (lane < p.cap) c = sl[(size_t)l * p.cap + lane];
-                if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);   // that list was full
-                wl.merge_sorted(c.d, c.seq, lane);
+        if (dbg && threadIdx.x == 0 && l0 == 0) dbg[10] = global_timer_ns();
+        // pass 1: the heads of this chunk's lists join the warp's smallest heads seen so far
+        for (int base = warp * 32; base < nl; base += NW * 32) {
+            const int l = base + lane;
+            Cand c = Cand{CUDART_INF, SEQ_NONE};
+            if (l < nl) c = sl[(size_t)l * p.cap];
+            wh.offer(c.seq != SEQ_NONE, c.d, c.seq, lane, p.cap);
+        }
+        mrg[warp * 32 + lane] = Cand{wh.d, wh.seq};
+        __syncthreads();
+        // tau = the cap-th smallest head so far: every warp merges the others' sorted head lists into a copy of its own
+        // (NW - 1 fixed-cost bitonic merges; no second barrier, no broadcast)
+        double td;
+        u64 ts;
+        {
+            WarpList t = wh;
+            for (int w = 1; w < NW; w++) {
+                const Cand c = mrg[((warp + w) % NW) * 32 + lane];
+                t.merge_sorted(c.d, c.seq, lane);
             }
-        } else {
-            const int total_c = nl * p.cap;
-            for (int base = warp * 32; base < total_c; base += NW * 32) {
-                const int i = base + lane;
-                Cand c = Cand{CUDART_INF, SEQ_NONE};
-                if (i < total_c) c = sl[i];
-                const bool has = c.seq != SEQ_NONE;
-                if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);       // that list was full
-                wl.offer(has, c.d, c.seq, lane, p.cap);
-            }
+            t.key_at(p.cap - 1, td, ts);
+        }
+        // pass 2: entries of this chunk that are <= tau (all of them while fewer than cap heads exist)
+        const int total_c = nl * p.cap;
+        for (int base = warp * 32; base < total_c; base += NW * 32) {
+            const int i = base + lane;
+            Cand c = Cand{CUDART_INF, SEQ_NONE};
+            if (i < total_c) c = sl[i];
+            const bool has = c.seq != SEQ_NONE;
+            if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);           // that list was full
+            wl.offer(has && !key_less(td, ts, c.d, c.seq), c.d, c.seq, lane, p.cap);
         }
         __syncthreads();                                 // the buffer is refilled (or reused by the re-rank) next
     }
+    if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
     mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
-    if (lane == 0) wbound[warp] = bound;
-
-    // sqrt-form keys: |q - fl32(q)| and |q|^2 of this query, formed here (no prep launch in front of the scan)
-    double eq2 = 0.0, qn2 = 0.0;
-    if (p.sq_mode) {
-        for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
-            const double v = __ldg(qv + i);
-            const double r = v - (double)__double2float_rn(v);
-            eq2 = fma(r, r, eq2);
-            qn2 = fma(v, v, qn2);
-        }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            eq2 += shfl_xor_f64(eq2, m);
-            qn2 += shfl_xor_f64(qn2, m);
-        }
-        if (lane == 0) {
+    if (lane == 0) {
+        wbound[warp] = bound;
+        if (p.sq_mode) {
             tbuf[2 * warp] = eq2;
             tbuf[2 * warp + 1] = qn2;
         }
     }
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[12] = global_timer_ns();
     if (p.sq_mode && threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
         for (int w = 0; w < NW; w++) {
@@ -206,6 +225,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     }
     __syncthreads();
     nneed = (int)cseq[32];
+    if (dbg && threadIdx.x == 0) dbg[13] = global_timer_ns();
 
     const bool approx = p.sq_mode || p.eps >= 0.0;
     double dex = CUDART_INF;
@@ -256,6 +276,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
                 }
             }
             __syncthreads();
+            if (dbg && threadIdx.x == 0 && c0 == 0) dbg[14] = global_timer_ns();
             if (warp == 0 && lane < nneed) {
                 const double *t = tbuf + lane * ld;
 #pragma unroll 8
@@ -473,7 +494,7 @@ __device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem
     __syncthreads();
     if (threadIdx.x == 0) {
         s_last = atomicAdd(t.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;                     // ... before its ticket is
-        if (t.dbg) t.dbg[8 + blockIdx.x] = global_timer_ns();
+        if (t.dbg) t.dbg[32 + blockIdx.x] = global_timer_ns();
     }
     __syncthreads();
     if (!s_last) return;
@@ -484,6 +505,7 @@ __device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem
     }
     if (threadIdx.x == 0) fin_bar_init(smem, blockDim.x >> 5);
     __syncthreads();
+    if (t.dbg && threadIdx.x == 0) t.dbg[9] = global_timer_ns();
     uint32_t phase = 0;
     for (int qi = 0; qi < t.fin.nq; qi++) finalize_query(t.fin, qi, smem, smem_bytes, phase, qi == 0 ? t.dbg : nullptr);
     if (t.dbg && threadIdx.x == 0) t.dbg[2] = global_timer_ns();

@@ -349,7 +349,7 @@ class Engine:
         return out
 
     def debug_tail_times(self, n_ctas: int = 296) -> np.ndarray:
-        out = np.zeros(8 + n_ctas, dtype=np.uint64)
+        out = np.zeros(32 + n_ctas, dtype=np.uint64)
         _check(self.L.svdb_debug_tail_times(self.h, C.c_void_p(out.ctypes.data), out.size), "svdb_debug_tail_times")
         return out
 
