@@ -32,7 +32,8 @@ __device__ __forceinline__ Cand ldcg_cand(const Cand *p) {
 
 // shared memory finalize_query needs besides the staging / re-rank buffer: [nw][32] Cand, [nw] bounds, 40 words, and the
 // mbarrier its bulk copies complete on (the caller initialises it: fin_bar_init)
-__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)nw * 8 + 40 * 8 + 16; }
+// (every part a multiple of 16 bytes: the buffer behind it is the destination of bulk copies)
+__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)((nw + 1) & ~1) * 8 + 40 * 8 + 16; }
 __device__ __forceinline__ uint32_t fin_bar_addr(unsigned char *fsm, int nw) { return smem_u32(fsm + fin_head_bytes(nw) - 16); }
 // one thread, followed by a __syncthreads() before the first finalize_query
 __device__ __forceinline__ void fin_bar_init(unsigned char *fsm, int nw) {
@@ -64,7 +65,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     const int NW = blockDim.x >> 5;
     Cand *mrg = reinterpret_cast<Cand *>(fsm);                                        // [NW][32]
     double *wbound = reinterpret_cast<double *>(fsm + (size_t)NW * 32 * sizeof(Cand)); // [NW]
-    u64 *cseq = reinterpret_cast<u64 *>(wbound + NW);                                 // [33] + 4 words of block reductions
+    u64 *cseq = reinterpret_cast<u64 *>(wbound + ((NW + 1) & ~1));                    // [33] + 4 words of block reductions + tau
     double *red = reinterpret_cast<double *>(cseq + 34);                              // [4]
     double *tbuf = reinterpret_cast<double *>(fsm + fin_head_bytes(NW));
     const int tcap = (fsm_bytes - (int)fin_head_bytes(NW)) / 8;                       // doubles in tbuf
@@ -78,14 +79,16 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     // HEADS, tau, is an upper bound of the cap-th smallest key overall: a first pass over the heads finds tau, a second
     // pass over all entries inserts only those <= tau (about cap + a few) -- serial inserts are what a merge costs
     // (measured: walking 296 lists by insertion took 11 of the 27 us of a single-query tail).
-    WarpList wl, wh;                                     // the smallest entries <= tau / the smallest heads, per warp
+    WarpList wl;                                         // the smallest entries <= tau, per warp
     wl.reset();
-    wh.reset();
     double bound = CUDART_INF;
     const uint32_t bar = fin_bar_addr(fsm, NW);
     const Cand *sl = reinterpret_cast<const Cand *>(tbuf);
+    Cand *tau_slot = reinterpret_cast<Cand *>(cseq + 38);    // the chunk's tau, published by whoever holds it
     const int per_chunk = max(1, (int)(((size_t)tcap * 8) / ((size_t)p.cap * sizeof(Cand))));
     double eq2 = 0.0, qn2 = 0.0;
+    double td = CUDART_INF;                               // tau so far = (td, ts)
+    u64 ts = SEQ_NONE;
     for (int l0 = 0; l0 < p.nlists; l0 += per_chunk) {
         const int nl = min(per_chunk, p.nlists - l0);
         if (threadIdx.x == 0) {
@@ -94,15 +97,24 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             const uint32_t bytes = (uint32_t)nl * p.cap * sizeof(Cand);
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s(smem_u32(tbuf), L + (size_t)l0 * p.cap, bytes, bar);
+            *tau_slot = Cand{CUDART_INF, SEQ_NONE};
         }
         if (l0 == 0 && p.sq_mode) {
             // sqrt-form keys: |q - fl32(q)|^2 and |q|^2 of this query, formed here (no prep launch in front of the scan),
-            // while the copy is in flight
-            for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
-                const double v = __ldg(qv + i);
-                const double r = v - (double)__double2float_rn(v);
-                eq2 = fma(r, r, eq2);
-                qn2 = fma(v, v, qn2);
+            // while the copy is in flight; eight loads in flight per thread
+            for (int i0 = 0; i0 < p.K; i0 += 8 * (int)blockDim.x) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+                    v[u] = i < p.K ? __ldg(qv + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double r = v[u] - (double)__double2float_rn(v[u]);
+                    eq2 = fma(r, r, eq2);
+                    qn2 = fma(v[u], v[u], qn2);
+                }
             }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
@@ -112,27 +124,38 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
         }
         mbar_wait(bar, phase);
         phase ^= 1;
+        __syncthreads();                                 // tau_slot is initialised for everybody
         if (dbg && threadIdx.x == 0 && l0 == 0) dbg[10] = global_timer_ns();
-        // pass 1: the heads of this chunk's lists join the warp's smallest heads seen so far
-        for (int base = warp * 32; base < nl; base += NW * 32) {
-            const int l = base + lane;
-            Cand c = Cand{CUDART_INF, SEQ_NONE};
-            if (l < nl) c = sl[(size_t)l * p.cap];
-            wh.offer(c.seq != SEQ_NONE, c.d, c.seq, lane, p.cap);
-        }
-        mrg[warp * 32 + lane] = Cand{wh.d, wh.seq};
-        __syncthreads();
-        // tau = the cap-th smallest head so far: every warp merges the others' sorted head lists into a copy of its own
-        // (NW - 1 fixed-cost bitonic merges; no second barrier, no broadcast)
-        double td;
-        u64 ts;
-        {
-            WarpList t = wh;
-            for (int w = 1; w < NW; w++) {
-                const Cand c = mrg[((warp + w) % NW) * 32 + lane];
-                t.merge_sorted(c.d, c.seq, lane);
+        // pass 1: tau of this chunk = the head of rank cap - 1 among its nl heads.  Ranks by counting: every thread
+        // owns up to four heads and walks all heads once (broadcast reads, no dependent chain, no serial inserts).
+        for (int g0 = 0; g0 < nl; g0 += 4 * (int)blockDim.x) {
+            Cand mine[4];
+            int rank[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int l = g0 + u * (int)blockDim.x + (int)threadIdx.x;
+                mine[u] = l < nl ? sl[(size_t)l * p.cap] : Cand{CUDART_INF, SEQ_NONE};
+                rank[u] = 0;
             }
-            t.key_at(p.cap - 1, td, ts);
+            if (g0 < nl) {
+                for (int j = 0; j < nl; j++) {
+                    const Cand o = sl[(size_t)j * p.cap];
+                    const bool ov = o.seq != SEQ_NONE;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) rank[u] += (ov && key_less(o.d, o.seq, mine[u].d, mine[u].seq)) ? 1 : 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (mine[u].seq != SEQ_NONE && rank[u] == p.cap - 1) *tau_slot = mine[u];   // keys are distinct: one writer
+        }
+        __syncthreads();
+        {
+            const Cand t = *tau_slot;
+            if (key_less(t.d, t.seq, td, ts)) {           // every chunk's tau bounds the cap-th smallest key overall
+                td = t.d;
+                ts = t.seq;
+            }
         }
         // pass 2: entries of this chunk that are <= tau (all of them while fewer than cap heads exist)
         const int total_c = nl * p.cap;
