@@ -30,10 +30,10 @@ __device__ __forceinline__ Cand ldcg_cand(const Cand *p) {
     return c;
 }
 
-// shared memory finalize_query needs besides the staging / re-rank buffer: [nw][32] Cand, [nw] bounds, 40 words, and the
-// mbarrier its bulk copies complete on (the caller initialises it: fin_bar_init)
+// shared memory finalize_query needs besides the staging / re-rank buffer: [nw][32] Cand, [nw] bounds, 40 words, 32 candidates,
+// and the mbarrier its bulk copies complete on (the caller initialises it: fin_bar_init)
 // (every part a multiple of 16 bytes: the buffer behind it is the destination of bulk copies)
-__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)((nw + 1) & ~1) * 8 + 40 * 8 + 16; }
+__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)((nw + 1) & ~1) * 8 + 40 * 8 + 32 * 16 + 16; }
 __device__ __forceinline__ uint32_t fin_bar_addr(unsigned char *fsm, int nw) { return smem_u32(fsm + fin_head_bytes(nw) - 16); }
 // one thread, followed by a __syncthreads() before the first finalize_query
 __device__ __forceinline__ void fin_bar_init(unsigned char *fsm, int nw) {
@@ -67,193 +67,292 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     double *wbound = reinterpret_cast<double *>(fsm + (size_t)NW * 32 * sizeof(Cand)); // [NW]
     u64 *cseq = reinterpret_cast<u64 *>(wbound + ((NW + 1) & ~1));                    // [33] + 4 words of block reductions + tau
     double *red = reinterpret_cast<double *>(cseq + 34);                              // [4]
+    Cand *cand = reinterpret_cast<Cand *>(cseq + 40);                                 // [32] (selection path)
     double *tbuf = reinterpret_cast<double *>(fsm + fin_head_bytes(NW));
     const int tcap = (fsm_bytes - (int)fin_head_bytes(NW)) / 8;                       // doubles in tbuf
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Cand *L = p.lists + (size_t)qi * p.nlists * p.cap;
     const double *qv = p.q + (size_t)qi * p.ldq;
 
-    // ---- 1. merge ----
-    // The lists (nlists x cap x 16 bytes, written by other CTAs or by the launch before) come into shared memory with ONE bulk
-    // async copy per chunk of whole lists that fits the buffer.  Every list is sorted, so the cap-th smallest of the list
-    // HEADS, tau, is an upper bound of the cap-th smallest key overall: a first pass over the heads finds tau, a second
-    // pass over all entries inserts only those <= tau (about cap + a few) -- serial inserts are what a merge costs
-    // (measured: walking 296 lists by insertion took 11 of the 27 us of a single-query tail).
-    WarpList wl;                                         // the smallest entries <= tau, per warp
-    wl.reset();
-    double bound = CUDART_INF;
+    const bool approx = p.sq_mode || p.eps >= 0.0;
+    const double eps64 = 4.0 * (double)(p.K + 2) * 1.1102230246251565e-16;    // reference-order sum vs the real-number sum
     const uint32_t bar = fin_bar_addr(fsm, NW);
     const Cand *sl = reinterpret_cast<const Cand *>(tbuf);
-    Cand *tau_slot = reinterpret_cast<Cand *>(cseq + 38);    // the chunk's tau, published by whoever holds it
-    const int per_chunk = max(1, (int)(((size_t)tcap * 8) / ((size_t)p.cap * sizeof(Cand))));
-    double eq2 = 0.0, qn2 = 0.0;
-    double td = CUDART_INF;                               // tau so far = (td, ts)
-    u64 ts = SEQ_NONE;
-    for (int l0 = 0; l0 < p.nlists; l0 += per_chunk) {
-        const int nl = min(per_chunk, p.nlists - l0);
+    const int T = blockDim.x;
+    double bound = CUDART_INF;                           // the smallest approximate key any scan list may have dropped
+    double eq2 = 0.0, qn2 = 0.0, eabs = 0.0, E = 0.0, scale = 0.0;
+    double cd = CUDART_INF;                              // warp 0, lane j < nneed: approximate key and entry of candidate j
+    u64 cs = SEQ_NONE;
+    int nneed = 0;
+    bool overflow = false;
+
+    // |key - d| bounds -> the largest approximate key a member of the true top-k can have, given the k-th smallest key dk
+    auto window = [&](double dk) -> double {
+        if (p.sq_mode) {
+            // the k rows with the smallest keys have sqrt(d) <= U; a row with sqrt(d) <= U has sqrt(key) <= (U + E)(1 + gamma)
+            const double U = sqrt(dk) / (1.0 - p.sq_gamma) + E;
+            const double lim = (U * (1.0 + eps64) + E) * (1.0 + p.sq_gamma);
+            return lim * lim * (1.0 + 1e-12);
+        }
+        // |key - d| <= eps d + eabs: a member of the true top-k has key <= (dk + eabs)(1 + eps)/(1 - eps) + eabs
+        return (dk + eabs) * ((1.0 + p.eps) / (1.0 - p.eps)) * (1.0 + 1e-15) + eabs;
+    };
+    // sqrt-form keys: |q - fl32(q)|^2 and |q|^2 of this query are formed here (no prep launch in front of the scan), while
+    // the first copy of lists is in flight; eight loads in flight per thread.  Per-warp sums.
+    auto query_norms = [&]() {
+        for (int i0 = 0; i0 < p.K; i0 += 8 * T) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * T + (int)threadIdx.x;
+                v[u] = i < p.K ? __ldg(qv + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double r = v[u] - (double)__double2float_rn(v[u]);
+                eq2 = fma(r, r, eq2);
+                qn2 = fma(v[u], v[u], qn2);
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            eq2 += shfl_xor_f64(eq2, m);
+            qn2 += shfl_xor_f64(qn2, m);
+        }
+    };
+    auto error_terms = [&]() {                           // after red[] is complete
+        if (p.sq_mode) {
+            // E bounds |x - x^| + |q - q^| (2-norms) plus what squares of tiny differences lose to fp32 underflow
+            E = __longlong_as_double((long long)*p.plane_err_bits) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
+            scale = __longlong_as_double((long long)*p.xn_max_bits) + red[1];
+        } else if (p.eabs_coef > 0.0) {
+            // GEMM-form keys (K2, K10) carry an absolute error
+            scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
+            eabs = p.eabs_coef * scale;
+        }
+    };
+
+    const int total_c = p.nlists * p.cap;
+    const bool select_path = approx && p.cap < 16 && total_c > 0 && (size_t)total_c * sizeof(Cand) <= (size_t)tcap * 8;
+    if (select_path) {
+        // ---- 1+2 (approximate keys, k <= 7, all lists fit the buffer -- the single-query tail): SELECTION, not a merge.
+        // One bulk async copy brings every list into shared memory.  k rounds of "smallest key above the previous one"
+        // over all entries (a strided pass + a min-reduction each: no serial inserts) give the k-th smallest key dk; the
+        // candidates are the entries <= window(dk), compacted with one ballot per 32 entries.  Measured before: walking
+        // the 296 lists of a single-query scan by warp-list insertion cost 11-18 of the tail's 27 us.
         if (threadIdx.x == 0) {
             // the lists were written through the generic proxy (by other SMs), the bulk copy reads through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
-            const uint32_t bytes = (uint32_t)nl * p.cap * sizeof(Cand);
+            const uint32_t bytes = (uint32_t)total_c * sizeof(Cand);
             mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(smem_u32(tbuf), L + (size_t)l0 * p.cap, bytes, bar);
-            *tau_slot = Cand{CUDART_INF, SEQ_NONE};
+            bulk_g2s(smem_u32(tbuf), L, bytes, bar);
+            cseq[32] = 0;                                // candidate counter
         }
-        if (l0 == 0 && p.sq_mode) {
-            // sqrt-form keys: |q - fl32(q)|^2 and |q|^2 of this query, formed here (no prep launch in front of the scan),
-            // while the copy is in flight; eight loads in flight per thread
-            for (int i0 = 0; i0 < p.K; i0 += 8 * (int)blockDim.x) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
-                    v[u] = i < p.K ? __ldg(qv + i) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const double r = v[u] - (double)__double2float_rn(v[u]);
-                    eq2 = fma(r, r, eq2);
-                    qn2 = fma(v[u], v[u], qn2);
+        if (p.sq_mode) query_norms();
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (dbg && threadIdx.x == 0) dbg[10] = global_timer_ns();
+        double pd = 0.0, dk = CUDART_INF;
+        u64 ps = 0, sk = SEQ_NONE;
+        for (int r = 0; r < p.k; r++) {
+            double bd = CUDART_INF;
+            u64 bs = SEQ_NONE;
+            for (int i = threadIdx.x; i < total_c; i += T) {
+                const Cand c = sl[i];
+                if (c.seq == SEQ_NONE) continue;
+                if (r == 0 && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);      // that list was full
+                if ((r == 0 || key_less(pd, ps, c.d, c.seq)) && key_less(c.d, c.seq, bd, bs)) {
+                    bd = c.d;
+                    bs = c.seq;
                 }
             }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
-                eq2 += shfl_xor_f64(eq2, m);
-                qn2 += shfl_xor_f64(qn2, m);
+                const double od = shfl_xor_f64(bd, m);
+                const u64 os = __shfl_xor_sync(FULL, bs, m);
+                if (key_less(od, os, bd, bs)) {
+                    bd = od;
+                    bs = os;
+                }
+                if (r == 0) bound = fmin(bound, shfl_xor_f64(bound, m));
             }
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        __syncthreads();                                 // tau_slot is initialised for everybody
-        if (dbg && threadIdx.x == 0 && l0 == 0) dbg[10] = global_timer_ns();
-        // pass 1: tau of this chunk = the head of rank cap - 1 among its nl heads.  Ranks by counting: every thread
-        // owns up to four heads and walks all heads once (broadcast reads, no dependent chain, no serial inserts).
-        for (int g0 = 0; g0 < nl; g0 += 4 * (int)blockDim.x) {
-            Cand mine[4];
-            int rank[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int l = g0 + u * (int)blockDim.x + (int)threadIdx.x;
-                mine[u] = l < nl ? sl[(size_t)l * p.cap] : Cand{CUDART_INF, SEQ_NONE};
-                rank[u] = 0;
-            }
-            if (g0 < nl) {
-                for (int j = 0; j < nl; j++) {
-                    const Cand o = sl[(size_t)j * p.cap];
-                    const bool ov = o.seq != SEQ_NONE;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) rank[u] += (ov && key_less(o.d, o.seq, mine[u].d, mine[u].seq)) ? 1 : 0;
+            if (lane == 0) {
+                mrg[warp] = Cand{bd, bs};
+                if (r == 0) {
+                    wbound[warp] = bound;
+                    cand[warp] = Cand{eq2, (u64)__double_as_longlong(qn2)};
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (mine[u].seq != SEQ_NONE && rank[u] == p.cap - 1) *tau_slot = mine[u];   // keys are distinct: one writer
-        }
-        __syncthreads();
-        {
-            const Cand t = *tau_slot;
-            if (key_less(t.d, t.seq, td, ts)) {           // every chunk's tau bounds the cap-th smallest key overall
-                td = t.d;
-                ts = t.seq;
+            __syncthreads();
+            bd = CUDART_INF;
+            bs = SEQ_NONE;
+            for (int w = 0; w < NW; w++) {
+                const Cand c = mrg[w];
+                if (key_less(c.d, c.seq, bd, bs)) {
+                    bd = c.d;
+                    bs = c.seq;
+                }
+            }
+            if (r == 0) {
+                double a = 0.0, b2 = 0.0;
+                bound = CUDART_INF;
+                for (int w = 0; w < NW; w++) {
+                    bound = fmin(bound, wbound[w]);
+                    a += cand[w].d;
+                    b2 += __longlong_as_double((long long)cand[w].seq);
+                }
+                if (threadIdx.x == 0) {
+                    red[0] = a;
+                    red[1] = b2;
+                }
+            }
+            __syncthreads();                             // mrg is rewritten by the next round
+            if (bs == SEQ_NONE) break;                   // fewer than r + 1 entries in all
+            pd = bd;
+            ps = bs;
+            if (r == p.k - 1) {
+                dk = bd;
+                sk = bs;
             }
         }
-        // pass 2: entries of this chunk that are <= tau (all of them while fewer than cap heads exist)
-        const int total_c = nl * p.cap;
+        if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
+        error_terms();
+        // with fewer than k entries every entry is a candidate
+        const double lim = sk != SEQ_NONE ? window(dk) : CUDART_INF;
+        const unsigned below = (1u << lane) - 1u;
         for (int base = warp * 32; base < total_c; base += NW * 32) {
             const int i = base + lane;
             Cand c = Cand{CUDART_INF, SEQ_NONE};
             if (i < total_c) c = sl[i];
-            const bool has = c.seq != SEQ_NONE;
-            if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);           // that list was full
-            wl.offer(has && !key_less(td, ts, c.d, c.seq), c.d, c.seq, lane, p.cap);
+            const bool in = c.seq != SEQ_NONE && !(c.d > lim);
+            const unsigned m = __ballot_sync(FULL, in);
+            if (m) {
+                unsigned at = 0;
+                if (lane == 0) at = (unsigned)atomicAdd(reinterpret_cast<unsigned long long *>(cseq + 32), (unsigned long long)__popc(m));
+                at = __shfl_sync(FULL, at, 0) + __popc(m & below);
+                if (in && at < 32u) {
+                    cand[at] = c;
+                    cseq[at] = c.seq;
+                }
+            }
         }
-        __syncthreads();                                 // the buffer is refilled (or reused by the re-rank) next
-    }
-    if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-    mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
-    if (lane == 0) {
-        wbound[warp] = bound;
-        if (p.sq_mode) {
-            tbuf[2 * warp] = eq2;
-            tbuf[2 * warp + 1] = qn2;
+        __syncthreads();
+        const unsigned found = (unsigned)cseq[32];
+        overflow = found > 32u;                          // more near-ties than lanes: not provable here (-> fp64 / exact rerun)
+        nneed = (int)min(found, 32u);
+        if (warp == 0 && lane < nneed) {
+            cd = cand[lane].d;
+            cs = cand[lane].seq;
         }
-    }
-    __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[12] = global_timer_ns();
-    if (p.sq_mode && threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < NW; w++) {
-            a += tbuf[2 * w];
-            b += tbuf[2 * w + 1];
+        if (dbg && threadIdx.x == 0) dbg[1] = dbg[12] = dbg[13] = global_timer_ns();
+    } else {
+        // ---- 1. merge (long lists, exact keys, or lists larger than the buffer) ----
+        // The lists come into shared memory with one bulk async copy per chunk of whole lists that fits the buffer; every
+        // warp merges a slice into its register list, the slices are merged through shared memory -> the 32 best
+        // approximate keys, plus `bound`.
+        WarpList wl;
+        wl.reset();
+        const int per_chunk = max(1, (int)(((size_t)tcap * 8) / ((size_t)p.cap * sizeof(Cand))));
+        for (int l0 = 0; l0 < p.nlists; l0 += per_chunk) {
+            const int nl = min(per_chunk, p.nlists - l0);
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                const uint32_t bytes = (uint32_t)nl * p.cap * sizeof(Cand);
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(smem_u32(tbuf), L + (size_t)l0 * p.cap, bytes, bar);
+            }
+            if (l0 == 0 && p.sq_mode) query_norms();
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            if (dbg && threadIdx.x == 0 && l0 == 0) dbg[10] = global_timer_ns();
+            if (p.cap >= 16) {
+                // long lists (k >= 8): most keys of a list qualify while the running list fills up, and every one of them
+                // would be a serial insert -- merge list by list with the fixed-cost bitonic network instead
+                for (int l = warp; l < nl; l += NW) {
+                    Cand c = Cand{CUDART_INF, SEQ_NONE};
+                    if (lane < p.cap) c = sl[(size_t)l * p.cap + lane];
+                    if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);   // that list was full
+                    wl.merge_sorted(c.d, c.seq, lane);
+                }
+            } else {
+                const int tc = nl * p.cap;
+                for (int base = warp * 32; base < tc; base += NW * 32) {
+                    const int i = base + lane;
+                    Cand c = Cand{CUDART_INF, SEQ_NONE};
+                    if (i < tc) c = sl[i];
+                    const bool has = c.seq != SEQ_NONE;
+                    if (has && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);       // that list was full
+                    wl.offer(has, c.d, c.seq, lane, p.cap);
+                }
+            }
+            __syncthreads();                             // the buffer is refilled (or reused by the re-rank) next
         }
-        red[0] = a;
-        red[1] = b;
-    }
-    if (warp == 0) {
-        // only the best `cap` keys of a slice list are meaningful; the slice lists are sorted: bitonic merges
-        if (lane >= p.cap) wl.reset();
-        for (int w = 1; w < NW; w++) {
-            Cand c = mrg[w * 32 + lane];
-            // a slice list that is full may itself have dropped keys >= its last one
-            if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
-            if (lane >= p.cap) c = Cand{CUDART_INF, SEQ_NONE};
-            wl.merge_sorted(c.d, c.seq, lane);
-            bound = fmin(bound, wbound[w]);
-        }
+        if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
-        double dl;
-        u64 sl;
-        wl.key_at(p.cap - 1, dl, sl);
-        if (sl != SEQ_NONE) bound = fmin(bound, dl);     // the final list is full too
-    }
-    __syncthreads();                                     // red[] is complete; tbuf may be reused
-    if (dbg && threadIdx.x == 0) dbg[1] = global_timer_ns();
-
-    // ---- 2. which candidates can still belong to the exact top-k ----
-    const double eps64 = 4.0 * (double)(p.K + 2) * 1.1102230246251565e-16;    // reference-order sum vs the real-number sum
-    // GEMM-form keys (K2) carry an absolute error on top of the relative one
-    double eabs = 0.0, E = 0.0, scale = 0.0;
-    if (p.sq_mode) {
-        // E bounds |x - x^| + |q - q^| (2-norms) plus what squares of tiny differences lose to fp32 underflow
-        E = __longlong_as_double((long long)*p.plane_err_bits) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
-        scale = __longlong_as_double((long long)*p.xn_max_bits) + red[1];
-    } else if (p.eabs_coef > 0.0) {
-        scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
-        eabs = p.eabs_coef * scale;
-    }
-    int nneed = 0;
-    if (warp == 0) {
-        const bool valid = wl.seq != SEQ_NONE && lane < p.cap;
-        bool need = valid;
-        double dk;
-        u64 sk;
-        wl.key_at(p.k - 1, dk, sk);
-        if (p.sq_mode) {
-            // the k rows with the smallest keys have sqrt(d) <= U; a row with sqrt(d) <= U has sqrt(key) <= (U + E)(1 + gamma)
-            if (sk != SEQ_NONE) {
-                const double U = sqrt(dk) / (1.0 - p.sq_gamma) + E;
-                const double lim = (U * (1.0 + eps64) + E) * (1.0 + p.sq_gamma);
-                need = valid && !(wl.d > lim * lim * (1.0 + 1e-12));
+        mrg[warp * 32 + lane] = Cand{wl.d, wl.seq};
+        if (lane == 0) {
+            wbound[warp] = bound;
+            if (p.sq_mode) {
+                tbuf[2 * warp] = eq2;
+                tbuf[2 * warp + 1] = qn2;
             }
-        } else if (p.eps >= 0.0) {
-            // |key - d| <= eps d + eabs: a member of the true top-k has key <= (dk + eabs)(1 + eps)/(1 - eps) + eabs
-            if (sk != SEQ_NONE) need = valid && wl.d <= (dk + eabs) * ((1.0 + p.eps) / (1.0 - p.eps)) * (1.0 + 1e-15) + eabs;
         }
-        nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
-        cseq[lane] = wl.seq;
-        if (lane == 0) cseq[32] = (u64)nneed;
-    }
-    __syncthreads();
-    nneed = (int)cseq[32];
-    if (dbg && threadIdx.x == 0) dbg[13] = global_timer_ns();
+        __syncthreads();
+        if (dbg && threadIdx.x == 0) dbg[12] = global_timer_ns();
+        if (p.sq_mode && threadIdx.x == 0) {
+            double a = 0.0, b2 = 0.0;
+            for (int w = 0; w < NW; w++) {
+                a += tbuf[2 * w];
+                b2 += tbuf[2 * w + 1];
+            }
+            red[0] = a;
+            red[1] = b2;
+        }
+        if (warp == 0) {
+            // only the best `cap` keys of a slice list are meaningful; the slice lists are sorted: bitonic merges
+            if (lane >= p.cap) wl.reset();
+            for (int w = 1; w < NW; w++) {
+                Cand c = mrg[w * 32 + lane];
+                // a slice list that is full may itself have dropped keys >= its last one
+                if (lane == p.cap - 1 && c.seq != SEQ_NONE) bound = fmin(bound, c.d);
+                if (lane >= p.cap) c = Cand{CUDART_INF, SEQ_NONE};
+                wl.merge_sorted(c.d, c.seq, lane);
+                bound = fmin(bound, wbound[w]);
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
+            double dl;
+            u64 sl2;
+            wl.key_at(p.cap - 1, dl, sl2);
+            if (sl2 != SEQ_NONE) bound = fmin(bound, dl);     // the final list is full too
+        }
+        __syncthreads();                                     // red[] is complete; tbuf may be reused
+        if (dbg && threadIdx.x == 0) dbg[1] = global_timer_ns();
 
-    const bool approx = p.sq_mode || p.eps >= 0.0;
+        // ---- 2. which candidates can still belong to the exact top-k ----
+        error_terms();
+        if (warp == 0) {
+            const bool valid = wl.seq != SEQ_NONE && lane < p.cap;
+            bool need = valid;
+            double dk;
+            u64 sk;
+            wl.key_at(p.k - 1, dk, sk);
+            if (approx && sk != SEQ_NONE) need = valid && !(wl.d > window(dk));
+            nneed = __popc(__ballot_sync(FULL, need));      // the list is sorted: a prefix of the lanes
+            cd = wl.d;
+            cs = wl.seq;
+            cseq[lane] = wl.seq;
+            if (lane == 0) cseq[32] = (u64)nneed;
+        }
+        __syncthreads();
+        nneed = (int)cseq[32];
+        if (dbg && threadIdx.x == 0) dbg[13] = global_timer_ns();
+    }
+
     double dex = CUDART_INF;
     if (!approx) {
-        dex = wl.d;                                     // keys are reference-order already
+        dex = cd;                                       // keys are reference-order already
     } else {
         dex = 0.0;
         // as many coordinates per round as the buffer holds for `nneed` candidates (usually all K)
@@ -311,8 +410,8 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
 
     if (warp == 0) {
         // ---- 3. rank and emit ----
-        bool valid = lane < nneed && wl.seq != SEQ_NONE;
-        u64 seq = wl.seq;
+        bool valid = lane < nneed && cs != SEQ_NONE;
+        u64 seq = cs;
         if (valid && !(dex < CUDART_INF)) valid = false;    // kdtree.c:139 strict <: non-finite never wins
         if (!valid) {
             dex = CUDART_INF;
@@ -329,7 +428,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
         const unsigned mk = __ballot_sync(FULL, valid && rank == p.k - 1);
         const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
 
-        bool unsafe = false;
+        bool unsafe = overflow;
         if (approx && bound < CUDART_INF) {
             if (p.sq_mode) {
                 // entries outside the candidate set have key >= bound, hence sqrt(d) >= sqrt(bound)/(1 + gamma) - E
