@@ -152,44 +152,55 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
         mbar_wait(bar, phase);
         phase ^= 1;
         if (dbg && threadIdx.x == 0) dbg[10] = global_timer_ns();
-        double pd = 0.0, dk = CUDART_INF;
-        u64 ps = 0, sk = SEQ_NONE;
+        // keys are compared as integers: ord() maps a double's bits to an unsigned with the same order (negative keys
+        // happen with GEMM-form keys), so a round costs integer compares only -- this CTA runs alone on its SM with one warp
+        // per scheduler, every instruction's latency shows
+        auto ord = [](u64 bits) -> u64 { return bits ^ ((u64)((long long)bits >> 63) | 0x8000000000000000ull); };
+        const ulonglong2 *se = reinterpret_cast<const ulonglong2 *>(sl);       // .x = key bits, .y = entry
+        const int slot0 = (int)threadIdx.x % p.cap, slot_step = T % p.cap;
+        u64 po = 0, ps = 0, ko = 0, sk = SEQ_NONE;                             // previous round's key; the k-th smallest
         for (int r = 0; r < p.k; r++) {
-            double bd = CUDART_INF;
-            u64 bs = SEQ_NONE;
+            u64 bo = ~0ull, bs = SEQ_NONE;
+            int slot = slot0;
+#pragma unroll 4
             for (int i = threadIdx.x; i < total_c; i += T) {
-                const Cand c = sl[i];
-                if (c.seq == SEQ_NONE) continue;
-                if (r == 0 && (i % p.cap) == p.cap - 1) bound = fmin(bound, c.d);      // that list was full
-                if ((r == 0 || key_less(pd, ps, c.d, c.seq)) && key_less(c.d, c.seq, bd, bs)) {
-                    bd = c.d;
-                    bs = c.seq;
+                const ulonglong2 c = se[i];
+                const u64 o = ord(c.x);
+                const bool valid = c.y != SEQ_NONE;
+                if (r == 0 && valid && slot == p.cap - 1) bound = fmin(bound, __longlong_as_double((long long)c.x));   // that list was full
+                const bool above = r == 0 || o > po || (o == po && c.y > ps);
+                const bool better = o < bo || (o == bo && c.y < bs);
+                if (valid && above && better) {
+                    bo = o;
+                    bs = c.y;
                 }
+                slot += slot_step;
+                if (slot >= p.cap) slot -= p.cap;
             }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
-                const double od = shfl_xor_f64(bd, m);
-                const u64 os = __shfl_xor_sync(FULL, bs, m);
-                if (key_less(od, os, bd, bs)) {
-                    bd = od;
+                const u64 oo = __shfl_xor_sync(FULL, bo, m), os = __shfl_xor_sync(FULL, bs, m);
+                if (oo < bo || (oo == bo && os < bs)) {
+                    bo = oo;
                     bs = os;
                 }
                 if (r == 0) bound = fmin(bound, shfl_xor_f64(bound, m));
             }
             if (lane == 0) {
-                mrg[warp] = Cand{bd, bs};
+                mrg[warp] = Cand{__longlong_as_double((long long)bo), bs};     // (ord, entry), not a distance
                 if (r == 0) {
                     wbound[warp] = bound;
                     cand[warp] = Cand{eq2, (u64)__double_as_longlong(qn2)};
                 }
             }
             __syncthreads();
-            bd = CUDART_INF;
+            bo = ~0ull;
             bs = SEQ_NONE;
             for (int w = 0; w < NW; w++) {
                 const Cand c = mrg[w];
-                if (key_less(c.d, c.seq, bd, bs)) {
-                    bd = c.d;
+                const u64 oo = (u64)__double_as_longlong(c.d);
+                if (oo < bo || (oo == bo && c.seq < bs)) {
+                    bo = oo;
                     bs = c.seq;
                 }
             }
@@ -208,13 +219,16 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             }
             __syncthreads();                             // mrg is rewritten by the next round
             if (bs == SEQ_NONE) break;                   // fewer than r + 1 entries in all
-            pd = bd;
+            po = bo;
             ps = bs;
             if (r == p.k - 1) {
-                dk = bd;
+                ko = bo;
                 sk = bs;
             }
         }
+        // the k-th smallest key as a distance again (ord is an involution up to the sign test)
+        const u64 kbits = (ko >> 63) ? (ko ^ 0x8000000000000000ull) : ~ko;
+        const double dk = __longlong_as_double((long long)kbits);
         if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
         error_terms();
         // with fewer than k entries every entry is a candidate
