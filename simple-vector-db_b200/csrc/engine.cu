@@ -228,7 +228,7 @@ void svdb_engine::destroy() {
     shadow_hi.release();
     shadow_lo.release();
     shadow_ready = false;
-    shadow_n = 0;
+    shadow_n = shadow_lo_n = 0;
     shadow_mapped_counted = 0;
     for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal, &tail_dbg}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
@@ -545,9 +545,11 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         // never build or extend the shadow under stream capture (see nearest_host): fall back to the fp64 rows there
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
-        if (cs == cudaStreamCaptureStatusNone || (shadow_ready && shadow_n == n_versions)) {
-            const int sr = ensure_shadow();
-            if (sr == SVDB_OK) plane = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
+        const int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
+        const bool have = shadow_ready && shadow_n == n_versions && (want == 2 || shadow_lo_n == n_versions);
+        if (cs == cudaStreamCaptureStatusNone || have) {
+            const int sr = ensure_shadow(want == 1);
+            if (sr == SVDB_OK) plane = want;
             else if (sr != -1000) return sr;
         }
     }
@@ -700,7 +702,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
 
 // The split-bf16 shadow of the kd log (two planes of [versions][Kp] bf16; K10, K11 and K12 read it): created on first use, extended by
 // the entries appended since.  -1000: no HBM for it (or no address space) -- the fp64 paths keep serving.
-int svdb_engine::ensure_shadow() {
+int svdb_engine::ensure_shadow(bool need_lo) {
     std::string err;
     const int Kp = umma_kpad(K);
     const size_t plane_row = (size_t)Kp * 2;
@@ -713,19 +715,34 @@ int svdb_engine::ensure_shadow() {
         }
         shadow_ready = true;
     }
+    bool grown = false;
     if (shadow_n < n_versions) {
-        if (!shadow_hi.ensure(n_versions * plane_row, stream, err) || !shadow_lo.ensure(n_versions * plane_row, stream, err)) {
+        if (!shadow_hi.ensure(n_versions * plane_row, stream, err)) {
             umma_ok = false;                 // not enough HBM next to the store: nothing is lost
             cudaGetLastError();
             return -1000;
         }
-        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow_hi.as<uint16_t>(),
-                             shadow_lo.as<uint16_t>(), plane_err.as<unsigned long long>(), tune.num_sms, stream));
+        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_n, n_versions - shadow_n, shadow_hi.as<uint16_t>(), nullptr,
+                             plane_err.as<unsigned long long>(), tune.num_sms, stream));
         stats.kernels_launched++;
+        shadow_n = n_versions;
+        grown = true;
+    }
+    if (need_lo && shadow_lo_n < n_versions) {
+        if (!shadow_lo.ensure(n_versions * plane_row, stream, err)) {
+            cudaGetLastError();
+            return -1000;                    // K12 keeps its hi plane; K10 / K11 are not available (K2 / K12 serve)
+        }
+        CK(launch_split_bf16(kd_ptr(), kstride, K, Kp, shadow_lo_n, n_versions - shadow_lo_n, nullptr, shadow_lo.as<uint16_t>(),
+                             nullptr, tune.num_sms, stream));
+        stats.kernels_launched++;
+        shadow_lo_n = n_versions;
+        grown = true;
+    }
+    if (grown) {
         const size_t mapped = shadow_hi.mapped() + shadow_lo.mapped();
         stats.hbm_bytes_mapped += mapped - shadow_mapped_counted;
         shadow_mapped_counted = mapped;
-        shadow_n = n_versions;
     }
     return SVDB_OK;
 }
@@ -739,8 +756,8 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
     // never build or extend the shadow under stream capture (see nearest_host): K2 serves that call
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
-    if (cs != cudaStreamCaptureStatusNone && !(shadow_ready && shadow_n == n_versions)) return -1000;
-    const int sr = ensure_shadow();
+    if (cs != cudaStreamCaptureStatusNone && !(shadow_ready && shadow_n == n_versions && shadow_lo_n == n_versions)) return -1000;
+    const int sr = ensure_shadow(true);
     if (sr) return sr;
     const int bn = umma_group_size(nq);
     const int cap = (int)std::min<size_t>(32, k + 14);
@@ -855,7 +872,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        rc = ensure_shadow();
+        rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1));
         if (rc && rc != -1000) return rc;
     }
     stats.h2d_bytes += nq * (size_t)K * 8;

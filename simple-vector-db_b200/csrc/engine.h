@@ -79,7 +79,8 @@ struct svdb_engine {
     // shorter rows its per-tile epilogue dominates and K2 stays ahead up to 16 queries (set in init(); -1 = not chosen yet).
     int umma_min_q = -1, umma_min_k = 32;
     bool umma_ok = true, shadow_ready = false;
-    size_t shadow_n = 0;                 // log entries present in the shadow
+    size_t shadow_n = 0;                 // log entries present in the hi plane ...
+    size_t shadow_lo_n = 0;              // ... and in the lo plane (built when K10 / K11 first ask for it: K12 reads hi only)
     size_t shadow_mapped_counted = 0;    // part of the shadow's mapped bytes already included in stats.hbm_bytes_mapped
     svdb::DeviceBuffer shadow_hi, shadow_lo;   // [versions][Kp] bf16 each: x ~ hi + lo (split_bf16_kernel)
     svdb::Scratch qsplit, ubuf, udbg, plane_err, ticket, xlocal;
@@ -91,7 +92,7 @@ struct svdb_engine {
     bool tail_debug = false;             // option "scan.tail_debug": fused tails leave %globaltimer stamps in tail_dbg
     svdb::Scratch tail_dbg;
     int last_scan_plane = 0;             // what the last scan pass of nearest_device read (escalation: skip a redundant K1 rerun)
-    int ensure_shadow();                 // SVDB_OK, an error, or -1000: not available
+    int ensure_shadow(bool need_lo);     // SVDB_OK, an error, or -1000: not available
     bool umma_debug = false;             // next K10 launch dumps the keys of its first tile into udbg
     int nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out);   // SVDB_OK, an error, or -1000: not available
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped

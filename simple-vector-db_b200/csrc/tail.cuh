@@ -414,9 +414,19 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             __syncthreads();
             if (dbg && threadIdx.x == 0 && c0 == 0) dbg[14] = global_timer_ns();
             if (warp == 0 && lane < nneed) {
-                const double *t = tbuf + lane * ld;
-#pragma unroll 8
-                for (int i = 0; i < len; i++) dex = __dadd_rn(dex, t[i]);   // kdtree.c:136, in index order
+                // kdtree.c:136, strictly in index order: a chain of `len` dependent rounded adds (the one part of the
+                // reference's loop that cannot be parallelised).  Sixteen squares are fetched ahead of the chain.
+                const uint32_t ta = smem_u32(tbuf + lane * ld);
+                int i = 0;
+                for (; i + 16 <= len; i += 16) {
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[u]) : "r"(ta + (uint32_t)(i + u) * 8u));
+#pragma unroll
+                    for (int u = 0; u < 16; u++) dex = __dadd_rn(dex, v[u]);
+                }
+                for (; i < len; i++) dex = __dadd_rn(dex, tbuf[lane * ld + i]);
             }
             __syncthreads();
         }

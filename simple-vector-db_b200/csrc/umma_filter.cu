@@ -351,7 +351,8 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 }
 
 // ---- fp64 rows -> the two bf16 planes of the shadow, [n][Kp] each (zeros beyond K): hi = bf16(fl32(x)),
-// lo = bf16(fl32(x) - hi).  One warp per row.  err_bits (may be NULL): running maximum over the rows of |x - hi|_2, the
+// lo = bf16(fl32(x) - hi); either destination may be NULL (the lo plane is only built once K10 / K11 ask for it).
+// One warp per row.  err_bits (may be NULL): running maximum over the rows of |x - hi|_2, the
 // error of the HI plane alone, formed in fp64 and rounded up -- what K12's completeness proof needs (plane_scan.cu).
 // Rows with a non-finite coordinate are left out of it: their distance is never finite, so they can never win
 // (kdtree.c:139) and no bound on them is needed. ----
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const double *__restric
             const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
             const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
             const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-            *reinterpret_cast<__nv_bfloat162 *>(dst_hi + r * (u64)Kp + c) = __nv_bfloat162(h0, h1);
-            *reinterpret_cast<__nv_bfloat162 *>(dst_lo + r * (u64)Kp + c) = __nv_bfloat162(l0, l1);
+            if (dst_hi) *reinterpret_cast<__nv_bfloat162 *>(dst_hi + r * (u64)Kp + c) = __nv_bfloat162(h0, h1);
+            if (dst_lo) *reinterpret_cast<__nv_bfloat162 *>(dst_lo + r * (u64)Kp + c) = __nv_bfloat162(l0, l1);
             const double d0 = v0 - (double)__bfloat162float(h0), d1 = v1 - (double)__bfloat162float(h1);
             e2 = fma(d0, d0, e2);
             e2 = fma(d1, d1, e2);

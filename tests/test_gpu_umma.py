@@ -40,7 +40,7 @@ def test_umma_path_vs_oracle(port, n, D, K, nq, k, seed):
         l0 = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q, k), want, k)
         assert e.stats()["exact_reruns"] == 0
-        assert e.stats()["kernels_launched"] - l0 == 5          # shadow split + (prep, query split, filter, finalize)
+        assert e.stats()["kernels_launched"] - l0 == 6          # shadow split (hi plane, lo plane) + (prep, query split, filter, finalize)
         l0 = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q, k), want, k)             # shadow is kept
         assert e.stats()["kernels_launched"] - l0 == 4
