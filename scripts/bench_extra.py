@@ -31,19 +31,47 @@ except Exception:
     pass
 
 
-def fill(e: B.Engine, n: int, D: int, seed: int, chunk: int = 250_000):
+def chunks(n: int, D: int, seed: int, chunk: int = 250_000):
+    """The synthetic rows, regenerable from (seed, chunk number): the parity checks below never read rows back from the
+    engine, they regenerate them."""
     done = 0
     c = 0
     while done < n:
         m = min(chunk, n - done)
         g = torch.Generator(device=DEV).manual_seed(seed * 1_000_003 + c)
-        t = torch.rand((m, D), dtype=torch.float64, device=DEV, generator=g)
-        e.insert_device(t.data_ptr(), m, D)
-        torch.cuda.synchronize()
-        del t
+        yield done, torch.rand((m, D), dtype=torch.float64, device=DEV, generator=g)
         done += m
         c += 1
+
+
+def fill(e: B.Engine, n: int, D: int, seed: int, chunk: int = 250_000):
+    for _, t in chunks(n, D, seed, chunk):
+        e.insert_device(t.data_ptr(), t.shape[0], D)
+        torch.cuda.synchronize()
+        del t
     torch.cuda.empty_cache()
+
+
+PLANE_BYTES = {0: 8, 1: 4, 2: 2}      # bytes per coordinate of the copy of the log a single-query scan streams (engine stat scan_plane_last)
+
+
+def nearest_parity(e: B.Engine, n: int, D: int, K: int, seed: int, k: int, nq: int = 8):
+    """ids + fp64 distance bits of the engine's top-k == the CPU oracle's on an independent brute force over the WHOLE
+    store (oracle/bigcheck.py), for nq single queries and for the same queries as one batch call."""
+    from oracle import bigcheck
+    g = torch.Generator(device=DEV).manual_seed(seed + 4242)
+    Q = torch.rand((nq, D), dtype=torch.float64, device=DEV, generator=g)
+    Qh = Q.cpu().numpy()
+    one = [e.nearest(Qh[i], k) for i in range(nq)]
+    ids = np.stack([o[0][0] for o in one])
+    dist = np.stack([o[1][0] for o in one])
+    bi, bd, _ = e.nearest(Qh, k)
+    cand = bigcheck.brute_candidates(chunks(n, D, seed), Q[:, :K].contiguous(), 64)
+    v = bigcheck.verdict([cand], Qh[:, :K], ids, dist, k, n)
+    vb = bigcheck.verdict([cand], Qh[:, :K], bi, bd, k, n)
+    v["batch_call_ok"] = vb["ok"]
+    v["ok"] = v["ok"] and vb["ok"]
+    return v
 
 
 def timed(fn, iters: int, warm: int = 3) -> float:
@@ -59,21 +87,35 @@ def timed(fn, iters: int, warm: int = 3) -> float:
     return a.elapsed_time(b) / iters
 
 
-def nearest_case(name, n, D, K, k, nqs, iters=20, extra_opts=()):
+def nearest_case(name, n, D, K, k, nqs, iters=20, extra_opts=(), parity=False):
     out = []
+    seed = hash(name) % 1000 if not parity else sum(map(ord, name)) % 1000      # str hashes are salted per process
     with B.Engine(D, K, reserve_rows=n) as e:
         e.set_stream(torch.cuda.current_stream().cuda_stream)
-        fill(e, n, D, seed=hash(name) % 1000)
+        t0 = time.perf_counter()
+        fill(e, n, D, seed=seed)
+        e.flush()
+        torch.cuda.synchronize()
+        ingest_s = time.perf_counter() - t0
         for o, v in extra_opts:
             e.set_option(o, v)
         for nq in nqs:
             q = torch.rand((nq, D), dtype=torch.float64, device=DEV)
             res = torch.zeros((nq, k, 4), dtype=torch.int64, device=DEV)
-            e.set_option("scan.nq_per_pass", min(8, nq))
             ms = timed(lambda: e.nearest_device(q.data_ptr(), nq, D, k, res.data_ptr()), iters)
-            passes = -(-nq // min(8, nq))
-            scan_ms = e.time_scan(q.data_ptr(), nq, D, k, 10)
-            algo = n * K * 8
+            # the scan launches of one call, timed by CUDA events on the engine's stream
+            e.set_option("profile.scan_events", 1)
+            e.take_scan_time()
+            for _ in range(5):
+                e.nearest_device(q.data_ptr(), nq, D, k, res.data_ptr())
+            scan_total, launches = e.take_scan_time()
+            e.set_option("profile.scan_events", 0)
+            st = e.stats()
+            plane = int(st["scan_plane_last"])
+            passes = max(1, int(launches) // 5)
+            scan_ms = scan_total / max(1, launches)
+            kp = -(-K // 64) * 64
+            algo = n * K * 8 if plane == 0 else n * kp * PLANE_BYTES[plane]
             qh = q.cpu().numpy()
             t0 = time.perf_counter()
             for _ in range(5):
@@ -81,13 +123,52 @@ def nearest_case(name, n, D, K, k, nqs, iters=20, extra_opts=()):
             e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
             out.append({"config": name, "rows": n, "dim": D, "kd_dim": K, "k": k, "queries_per_call": nq,
                         "ms_per_call": ms, "queries_per_s": nq / ms * 1e3, "e2e_queries_per_s": nq / e2e_ms * 1e3,
-                        "scan_ms_per_pass": scan_ms, "scan_passes": passes,
-                        "scan_GBps_algorithmic": algo / scan_ms / 1e6, "frac_of_measured_peak": algo / scan_ms / 1e6 / PEAK})
+                        "scan_launches_per_call": passes, "scan_ms_per_launch": scan_ms,
+                        "scan_reads": {0: "fp64 rows (or a tree / tensor-core path)", 1: "hi + lo bf16 planes", 2: "bf16 hi plane"}[plane],
+                        "scan_GBps_algorithmic": algo / scan_ms / 1e6 if scan_ms > 0 else None,
+                        "frac_of_measured_peak": algo / scan_ms / 1e6 / PEAK if scan_ms > 0 else None,
+                        "fp64_pass_ms_at_peak": n * K * 8 / PEAK / 1e6, "ingest_s": ingest_s,
+                        "hbm_gib_mapped": st["hbm_bytes_mapped"] / 2**30, "tree_rounds": st["tree_rounds"],
+                        "mtree_builds": st["mtree_builds"]})
             print(json.dumps(out[-1]), flush=True)
+        if parity:
+            torch.cuda.empty_cache()
+            v = nearest_parity(e, n, D, K, seed, k)
+            v["config"] = name + "_parity_check"
+            st = e.stats()
+            v["exact_reruns"], v["fp64_reruns"] = st["exact_reruns"], st["fp64_reruns"]
+            out.append(v)
+            print(json.dumps(v), flush=True)
     return out
 
 
-def compare_case(name, n, D, npairs, iters=5):
+def compare_parity(e: B.Engine, n: int, D: int, seed: int, i1, i2, got, npick: int = 2000):
+    """fp32 BIT patterns of the three metrics for `npick` of the benchmarked pairs == the reference's own functions
+    (oracle/_ref when present, else the port) on rows regenerated from their seeds."""
+    from oracle import binding as OB
+    ref = OB.load_ref() if OB.have_ref() else None
+    port = OB.load_port()
+    pick = np.random.default_rng(11).choice(len(i1), npick, replace=False)
+    a_idx, b_idx = i1[pick], i2[pick]
+    need = np.unique(np.concatenate([a_idx, b_idx]))
+    rows = {}
+    for first, t in chunks(n, D, seed):
+        m = need[(need >= first) & (need < first + t.shape[0])]
+        if len(m):
+            sub = t[torch.from_numpy((m - first).astype(np.int64)).to(DEV)].cpu().numpy()
+            rows.update({int(r): sub[j] for j, r in enumerate(m)})
+        del t
+    bad = 0
+    for j, (a, b) in enumerate(zip(a_idx, b_idx)):
+        for metric in range(3):
+            want = (ref or port).metric(metric, rows[int(a)], rows[int(b)])
+            bad += int(np.float32(want).view(np.uint32) != got[pick[j], metric].view(np.uint32))
+    return {"pairs_checked": int(npick), "metrics": 3, "mismatching_bit_patterns": int(bad), "ok": bad == 0,
+            "oracle": ("the reference's own cosine_similarity / euclidean_distance / dot_product (oracle/_ref)" if ref
+                       else "oracle/svdb_oracle.c port") + " on rows regenerated from their seeds; fp32 bit patterns compared with =="}
+
+
+def compare_case(name, n, D, npairs, iters=5, parity=False):
     out = []
     with B.Engine(D, 1, reserve_rows=n, flags=B.FLAG_NO_LOG) as e:
         e.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -104,6 +185,14 @@ def compare_case(name, n, D, npairs, iters=5):
                         "pairs_per_s": npairs / ms * 1e3, "GBps_algorithmic": algo / ms / 1e6,
                         "frac_of_measured_peak": algo / ms / 1e6 / PEAK})
             print(json.dumps(out[-1]), flush=True)
+        if parity:
+            e.compare_device(3, i1.data_ptr(), i2.data_ptr(), npairs, res.data_ptr())
+            torch.cuda.synchronize()
+            v = compare_parity(e, n, D, 7, i1.cpu().numpy(), i2.cpu().numpy(), res.cpu().numpy())
+            v["config"] = name + "_parity_check"
+            v["store_gb"] = n * D * 8 / 1e9
+            out.append(v)
+            print(json.dumps(v), flush=True)
         # single pair latency through the host call
         a = np.random.rand(D)
         b = np.random.rand(D)
@@ -189,12 +278,12 @@ def main():
             n = int(3e9 / (max(D, 16) * 8))
             res += compare_case(f"dsweep_d{D}", n, D, 2_000_000 if D <= 768 else 1_000_000, iters=5)
     if "c2" in which:
-        res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50)
+        res += nearest_case("c2_1M_x128", 1_000_000, 128, 128, 1, (1, 8, 64), iters=50, parity=True)
         res += compare_case("c2_compare_1M_x128", 1_000_000, 128, 100_000)
     if "c4" in which:
-        res += compare_case("c4_compare_1M_x1536", 1_000_000, 1536, 1_000_000)
+        res += compare_case("c4_compare_1M_x1536", 1_000_000, 1536, 1_000_000, parity=True)
     if "c5" in which:
-        res += nearest_case("c5_100M_x128_k128", 100_000_000, 128, 128, 1, (1, 8), iters=5)
+        res += nearest_case("c5_100M_x128_k128", 100_000_000, 128, 128, 1, (1, 8), iters=5, parity=True)
     if "c5k3" in which:
         res += nearest_case("c5_100M_x128_k3", 100_000_000, 128, 3, 1, (1, 1024), iters=5)
     out = "gpurun_out/extra.jsonl"

@@ -76,6 +76,10 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
 
     const bool approx = p.sq_mode || p.eps >= 0.0;
     const double eps64 = 4.0 * (double)(p.K + 2) * 1.1102230246251565e-16;    // reference-order sum vs the real-number sum
+    // the store-wide terms of the error bounds: fetched now, needed once the k-th smallest key is known
+    const unsigned long long plane_err_b = p.plane_err_bits ? __ldg(p.plane_err_bits) : 0ull;
+    const unsigned long long xn_max_b = p.xn_max_bits ? __ldg(p.xn_max_bits) : 0ull;
+    const double qnorm_in = (!p.sq_mode && p.eabs_coef > 0.0) ? __ldg(p.qnorm + qi) : 0.0;
     const uint32_t bar = fin_bar_addr(fsm, NW);
     const Cand *sl = reinterpret_cast<const Cand *>(tbuf);
     const int T = blockDim.x;
@@ -123,11 +127,11 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     auto error_terms = [&]() {                           // after red[] is complete
         if (p.sq_mode) {
             // E bounds |x - x^| + |q - q^| (2-norms) plus what squares of tiny differences lose to fp32 underflow
-            E = __longlong_as_double((long long)*p.plane_err_bits) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
-            scale = __longlong_as_double((long long)*p.xn_max_bits) + red[1];
+            E = __longlong_as_double((long long)plane_err_b) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
+            scale = __longlong_as_double((long long)xn_max_b) + red[1];
         } else if (p.eabs_coef > 0.0) {
             // GEMM-form keys (K2, K10) carry an absolute error
-            scale = __longlong_as_double((long long)*p.xn_max_bits) + p.qnorm[qi];
+            scale = __longlong_as_double((long long)xn_max_b) + qnorm_in;
             eabs = p.eabs_coef * scale;
         }
     };
