@@ -56,7 +56,7 @@ def main():
         d_true = ((X[:, None, :] - QQ[None, :, :]) ** 2).sum(-1)
         err = np.abs(keys[:nr, :ncol].astype(np.float64) - d_true)
         scale = (rows[:, :K] ** 2).sum(1).max() + (QQ ** 2).sum(1)[None, :]
-        coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0 + 8.0) * 2.0 ** -20
+        coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0) * 2.0 ** -21 + 8.0 * 2.0 ** -20
         out["key_err_max"] = float(err.max())
         out["key_err_over_scale_max"] = float((err / scale).max())
         out["bound_coef"] = coef

@@ -9,9 +9,16 @@
 //   <x, q> ~ <xh, qh> + <xh, ql> + <xl, qh>            three kind::f16 UMMAs per 16 coordinates, fp32 accumulators in TMEM
 //   d~(r, q) = |x_r|^2 + |q|^2 - 2 <x_r, q>            |x|^2, |q|^2 from the fp64 rows (precomputed, rounded to fp32 once)
 //
-// Error: the dropped terms are bounded by 3.1 * 2^-16 sum|x_i q_i|, the fp32 accumulation of 3K exact bf16 products in
-// K/16 chained instructions by (3K/16) 2^-21 sum|x_i q_i| (a deliberately loose model of the tensor core's aligned
-// adder; umma_eabs_coef doubles it again), the three fp32 roundings of the key by 2^-21 (|x|^2 + |q|^2).  With
+// Error: the dropped terms are bounded by 3.1 * 2^-16 sum|x_i q_i|.  The fp32 accumulation of the 3K exact bf16 products in
+// K/16 steps of three chained instructions was MEASURED, not modelled (scripts/umma_accumulator_probe.py,
+// profiles/r02_umma_accumulator_probe.jsonl, pinned by tests/test_gpu_umma.py): rows and queries made of +-powers of two
+// (no lo plane, exact products) in truncation-adversarial patterns -- one product of magnitude 1 and K-1 same-sign
+// products of 2^-30 .. 2^-16, big products at the head of every instruction, alternating signs, ramps -- lose at most
+// 1.5 * 2^-24 sum|x_i q_i| per chained instruction (K = 64: nothing at all; the loss appears once the running sum dwarfs the
+// addends, as for an adder that aligns the 16 products and the accumulator to the largest exponent, keeps a few guard
+// bits and truncates: <= 1 ulp = 2 * 2^-24 of the running sum per instruction).  The budget is FOUR times that model,
+// 8 * 2^-24 = 2^-21 per instruction, i.e. (3K/16) 2^-21 sum|x_i q_i| per key (5.3 x the measured worst case); the three
+// fp32 roundings of the key add 2^-21 (|x|^2 + |q|^2).  With
 // sum|x_i q_i| <= |x||q| <= (|x|^2 + |q|^2)/2 the key error is ABSOLUTE, E = coef (max|x|^2 + |q|^2) like K2's, and
 // finalize_kernel widens its re-rank window and its proof by it.  Non-finite keys (overflow of bf16/fp32 on huge
 // values) are kept as candidates, never dropped, so extreme data ends in the exact fallback instead of a wrong answer.
@@ -57,7 +64,7 @@ constexpr int UF_SMEM = UF_STAGES * UF_STAGE_BYTES + UF_TAIL + 1024; // + slack 
 int umma_kpad(int K) { return (K + UF_KC - 1) / UF_KC * UF_KC; }
 int umma_group_size(size_t nq) { return nq <= 64 ? 64 : (nq <= 128 ? 128 : 256); }
 size_t umma_buf_bytes(int ngroups, int nstreams, int bn) { return (size_t)ngroups * nstreams * bn * UF_BUF * 8; }
-double umma_eabs_coef(int K) { return 3.2 * ldexp(1.0, -16) + (3.0 * K / 16.0 + 8.0) * ldexp(1.0, -20); }
+double umma_eabs_coef(int K) { return 3.2 * ldexp(1.0, -16) + (3.0 * K / 16.0) * ldexp(1.0, -21) + 8.0 * ldexp(1.0, -20); }
 
 // ---- PTX wrappers (tcgen05 / TMA); the mbarrier ones live in common.cuh ----
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {

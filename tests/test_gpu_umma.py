@@ -1,8 +1,12 @@
 """GPU parity of K10 (csrc/umma_filter.cu): batched /nearest on the tcgen05 tensor cores with split-bf16 keys.
 The keys are approximate by design; the answers, after finalize's reference-order re-rank (kdtree.c:134-137),
 must be bit-identical to the oracle's -- and the measured key error must stay inside the bound the proof uses."""
+import os
+
 import numpy as np
 import pytest
+
+from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -58,9 +62,25 @@ def test_umma_key_error_is_inside_the_bound():
         keys = e.debug_filter_keys(256).astype(np.float64)
     d = ((rows[:128, None, :] - Q[None, :, :]) ** 2).sum(-1)
     scale = (rows ** 2).sum(1).max() + (Q ** 2).sum(1)[None, :]
-    coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0 + 8.0) * 2.0 ** -20
+    coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0) * 2.0 ** -21 + 8.0 * 2.0 ** -20
     rel = np.abs(keys - d) / scale
     assert rel.max() < coef / 4, (rel.max(), coef)              # the proof's bound with a margin of at least 4
+
+
+@pytest.mark.parametrize("K", [64, 256, 768, 1024])
+def test_tcgen05_accumulator_loss_is_inside_the_budget(K):
+    """What the fp32 accumulation inside and between the chained tcgen05.mma instructions loses, MEASURED on
+    truncation-adversarial tiles of +-powers of two (scripts/umma_accumulator_probe.py: no lo plane, exact products, the
+    kernel's own keys dumped through umma.debug_keys and compared with exact arithmetic): at most 1 ulp of the running sum
+    (2 * 2^-24 sum|x_i q_i|) per instruction -- umma_eabs_coef budgets 2^-21 = four times that -- and the whole key error
+    at most a quarter of coef * (max|x|^2 + |q|^2)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from umma_accumulator_probe import probe
+    r = probe(K)
+    assert r["in_units_of_2^-24_per_mma"] <= 2.0, r
+    coef = 3.2 * 2.0 ** -16 + (3.0 * K / 16.0) * 2.0 ** -21 + 8.0 * 2.0 ** -20
+    assert r["key_err_over_scale_max"] <= coef / 4, (r["key_err_over_scale_max"], coef)
 
 
 def test_umma_shadow_follows_inserts_and_updates(port):
