@@ -229,7 +229,8 @@ def plane_bytes(plane: int, rows: int, K: int) -> int:
 
 
 def workload_config(args):
-    return {"workload": f"config3: {args.rows}x{args.dim} fp64 store, kd_dim={args.kd_dim}, single-query nearest top-1 "
+    cfg = {(10_000_000, 768): "config3", (100_000_000, 128): "config5", (1_000_000, 128): "config2"}.get((args.rows, args.dim), "custom")
+    return {"workload": f"{cfg}: {args.rows}x{args.dim} fp64 store, kd_dim={args.kd_dim}, single-query nearest top-1 "
                         f"per step, row-sharded over n_gpus",
             "rows": args.rows, "dim": args.dim, "kd_dim": args.kd_dim, "k": 1, "queries_per_step": 1,
             "parallelism": f"row-shards x{args.gpus}", "exchange": os.environ.get("SVDB_EXCHANGE", "p2p") if args.gpus > 1 else None,
