@@ -795,6 +795,7 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         ua.gtau = reinterpret_cast<uint32_t *>(static_cast<char *>(ubuf.p) + umma_buf_bytes(ngroups, nstreams, bn));
         CK(cudaMemsetAsync(ua.gtau, 0xff, nq_pad * 4, stream));
         ua.dbg_keys = (umma_debug && done == 0) ? udbg.as<float>() : nullptr;
+        ua.qres = umma_resident ? umma_resident_stages(bn, Kp) : 0;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (profile_scan) {
             if (scan_events_used == scan_events.size()) {
@@ -1724,6 +1725,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "umma.debug_keys") e->umma_debug = value != 0;
+    else if (n == "umma.resident_queries") e->umma_resident = value != 0;
     else if (n == "scan.shadow") e->scan_plane = value != 0 ? 1 : 0;      // round-1 name: 1 = K11 (hi + lo planes), 0 = fp64 rows
     else if (n == "scan.plane") {
         if (value < 0 || value > 2) return e->fail(SVDB_ERR_ARG, "scan.plane must be 0 (fp64 rows), 1 (hi + lo planes) or 2 (hi plane)");

@@ -94,6 +94,7 @@ struct svdb_engine {
     int last_scan_plane = 0;             // what the last scan pass of nearest_device read (escalation: skip a redundant K1 rerun)
     int ensure_shadow(bool need_lo);     // SVDB_OK, an error, or -1000: not available
     bool umma_debug = false;             // next K10 launch dumps the keys of its first tile into udbg
+    bool umma_resident = true;           // K10 keeps the query planes in shared memory when they fit (option umma.resident_queries)
     int nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k, svdb_candidate *d_out);   // SVDB_OK, an error, or -1000: not available
     int tree_max_depth = 8192;           // deeper than this (degenerate insertion order): the tree is dropped
     int tree_max_k = 8;                  // K <= this and k == 1: answer by tree traversal (K6)

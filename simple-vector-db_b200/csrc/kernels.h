@@ -169,7 +169,10 @@ struct UmmaArgs {
     void *bufs;             // umma_buf_bytes(ngroups, nstreams, bn) of scratch
     uint32_t *gtau;         // [ngroups*bn] words, all 0xffffffff at launch: per query the smallest cap-th key published so far
     float *dbg_keys;        // NULL, or [128][bn]: the keys of rows 0..127 against the first query group (diagnostics)
+    int qres;               // 0: query planes streamed next to the rows; else umma_resident_stages(bn, Kp): they stay in shared
+                            // memory and the ring carries rows only, that many stages deep
 };
+int umma_resident_stages(int bn, int Kp);
 int umma_kpad(int K);
 int umma_group_size(size_t nq);
 size_t umma_buf_bytes(int ngroups, int nstreams, int bn);

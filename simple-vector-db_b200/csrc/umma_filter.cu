@@ -53,16 +53,32 @@ namespace svdb {
 constexpr int UF_M = 128;                       // rows per tile = TMEM lanes
 constexpr int UF_NMAX = 256;                    // queries per CTA group, at most
 constexpr int UF_KC = 64;                       // bf16 coordinates per stage row = one 128-byte swizzle row
-constexpr int UF_STAGES = 2;
+constexpr int UF_STAGES = 2;                     // ring depth when the queries are streamed with the rows
+constexpr int UF_MAX_STAGES = 6;                 // ... and at most when they are resident (rows only in the ring)
 constexpr int UF_A_BYTES = UF_M * 128;          // one plane of a row tile
 constexpr int UF_B_BYTES = UF_NMAX * 128;       // one plane of a query tile
-constexpr int UF_STAGE_BYTES = 2 * UF_A_BYTES + 2 * UF_B_BYTES;     // 96 KB
+constexpr int UF_STAGE_BYTES = 2 * UF_A_BYTES + 2 * UF_B_BYTES;     // 96 KB: row hi/lo + query hi/lo of one 64-coordinate chunk
+constexpr int UF_RING_BYTES = UF_STAGES * UF_STAGE_BYTES;           // 192 KB of operand staging either way
 constexpr int UF_THREADS = 384;                  // TMA warp, MMA warp, two idle, eight epilogue warps
-constexpr int UF_TAIL = 64 + 64 + 3 * UF_NMAX * 4;                   // barriers, tmem pointer, cnt / tau / qn
-constexpr int UF_SMEM = UF_STAGES * UF_STAGE_BYTES + UF_TAIL + 1024; // + slack to align the stages to 1024 bytes
+constexpr int UF_TAIL = 256 + 3 * UF_NMAX * 4;                      // barriers + tmem pointer, cnt / tau / qn
+constexpr int UF_SMEM = UF_RING_BYTES + UF_TAIL + 1024;             // + slack to align the stages to 1024 bytes
+
+// Short kd-points (config 2 / 5 rows: K = 128): a row tile is only one or two 64-coordinate chunks, so with the queries
+// streamed next to the rows (96 KB per chunk, two stages) the ring is ONE tile deep and every tile waits out a TMA round
+// trip -- measured 6 us per 128-row tile at 1M x 128 where the tensor work needs 0.4 and HBM 1.4.  When the query planes
+// of the CTA's group fit next to at least two row stages they are loaded ONCE and stay resident: the ring then carries
+// rows only (32 KB per chunk, up to six stages deep) and the query planes are no longer re-read from L2 for every tile.
+__host__ __device__ inline int uf_resident_stages(int bn, int Kp) {
+    const int qbytes = (Kp / UF_KC) * 2 * bn * 128;
+    const int left = UF_RING_BYTES - qbytes;
+    if (left < 2 * 2 * UF_A_BYTES) return 0;                        // not resident: stream the queries (UF_STAGES stages)
+    const int st = left / (2 * UF_A_BYTES);
+    return st > UF_MAX_STAGES ? UF_MAX_STAGES : st;
+}
 
 int umma_kpad(int K) { return (K + UF_KC - 1) / UF_KC * UF_KC; }
 int umma_group_size(size_t nq) { return nq <= 64 ? 64 : (nq <= 128 ? 128 : 256); }
+int umma_resident_stages(int bn, int Kp) { return uf_resident_stages(bn, Kp); }
 size_t umma_buf_bytes(int ngroups, int nstreams, int bn) { return (size_t)ngroups * nstreams * bn * UF_BUF * 8; }
 double umma_eabs_coef(int K) { return 3.2 * ldexp(1.0, -16) + (3.0 * K / 16.0) * ldexp(1.0, -21) + 8.0 * ldexp(1.0, -20); }
 
@@ -124,14 +140,14 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     const uint32_t raw = smem_u32(uf_smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B tiles want 1024-byte alignment
     unsigned char *sgen = uf_smem_raw + (sbase - raw);
-    unsigned char *tail = sgen + UF_STAGES * UF_STAGE_BYTES;
-    const uint32_t tail_u = sbase + UF_STAGES * UF_STAGE_BYTES;
-    // barriers: full[2] (TMA -> MMA), empty[2] (MMA -> TMA), tfull[2] (MMA -> epilogue), tempty[2] (epilogue -> MMA)
-    const uint32_t bar_full = tail_u, bar_empty = tail_u + 16, bar_tfull = tail_u + 32, bar_tempty = tail_u + 48;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 64);
-    unsigned *cnt_s = reinterpret_cast<unsigned *>(tail + 128);
-    float *thr_s = reinterpret_cast<float *>(tail + 128 + UF_NMAX * 4);   // per query: tau - |q|^2, tau = cap-th smallest key so far
-    float *qn_s = reinterpret_cast<float *>(tail + 128 + 2 * UF_NMAX * 4);
+    unsigned char *tail = sgen + UF_RING_BYTES;
+    const uint32_t tail_u = sbase + UF_RING_BYTES;
+    // barriers: full[S] (TMA -> MMA), empty[S] (MMA -> TMA), tfull[2] (MMA -> epilogue), tempty[2] (epilogue -> MMA), qfull
+    const uint32_t bar_full = tail_u, bar_empty = tail_u + 64, bar_tfull = tail_u + 128, bar_tempty = tail_u + 144, bar_q = tail_u + 160;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 176);
+    unsigned *cnt_s = reinterpret_cast<unsigned *>(tail + 256);
+    float *thr_s = reinterpret_cast<float *>(tail + 256 + UF_NMAX * 4);   // per query: tau - |q|^2, tau = cap-th smallest key so far
+    float *qn_s = reinterpret_cast<float *>(tail + 256 + 2 * UF_NMAX * 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bn = p.bn;
@@ -139,14 +155,22 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     const int q0 = group * bn;
     const int nchunks = p.Kp / UF_KC;
     const u64 ntiles = (p.n + UF_M - 1) / UF_M;
+    // resident queries (p.qres stages of rows behind nchunks x [hi | lo] query tiles) or queries streamed with the rows
+    const int nst = p.qres > 0 ? p.qres : UF_STAGES;
+    const uint32_t qchunk_bytes = 2u * (uint32_t)bn * 128u;
+    const uint32_t ring0 = p.qres > 0 ? sbase + (uint32_t)nchunks * qchunk_bytes : sbase;
+    const uint32_t stage_bytes = p.qres > 0 ? 2u * UF_A_BYTES : (uint32_t)UF_STAGE_BYTES;
 
     if (tid == 0) {
-        for (int s = 0; s < UF_STAGES; s++) {
+        for (int s = 0; s < nst; s++) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
             mbar_init(bar_tempty + 8 * s, 8);            // one arrival per epilogue warp
         }
+        mbar_init(bar_q, 1);
         mbar_fence_init();
     }
     if (warp == 1) {                                     // the whole warp allocates all 512 TMEM columns (one CTA per SM)
@@ -167,7 +191,14 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t stage_tx = 2 * UF_A_BYTES + 2 * (uint32_t)bn * 128u;
+            if (p.qres > 0) {                            // the group's query planes, once
+                mbar_arrive_expect_tx(bar_q, (uint32_t)nchunks * qchunk_bytes);
+                for (int kc = 0; kc < nchunks; kc++) {
+                    tma_load_2d(sbase + kc * qchunk_bytes, &map_qh, kc * UF_KC, q0, bar_q);
+                    tma_load_2d(sbase + kc * qchunk_bytes + (uint32_t)bn * 128u, &map_ql, kc * UF_KC, q0, bar_q);
+                }
+            }
+            const uint32_t stage_tx = p.qres > 0 ? 2u * UF_A_BYTES : 2 * UF_A_BYTES + 2 * (uint32_t)bn * 128u;
             int stage = 0;
             uint32_t phase = 0;
             for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
@@ -175,13 +206,15 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 for (int kc = 0; kc < nchunks; kc++) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    const uint32_t st = sbase + stage * UF_STAGE_BYTES;
+                    const uint32_t st = ring0 + stage * stage_bytes;
                     mbar_arrive_expect_tx(full, stage_tx);
                     tma_load_2d(st, &map_xh, kc * UF_KC, row0, full);                                  // row tile, hi plane
                     tma_load_2d(st + UF_A_BYTES, &map_xl, kc * UF_KC, row0, full);                     //           lo plane
-                    tma_load_2d(st + 2 * UF_A_BYTES, &map_qh, kc * UF_KC, q0, full);                   // queries, hi plane
-                    tma_load_2d(st + 2 * UF_A_BYTES + UF_B_BYTES, &map_ql, kc * UF_KC, q0, full);      //          lo plane
-                    if (++stage == UF_STAGES) {
+                    if (p.qres == 0) {
+                        tma_load_2d(st + 2 * UF_A_BYTES, &map_qh, kc * UF_KC, q0, full);               // queries, hi plane
+                        tma_load_2d(st + 2 * UF_A_BYTES + UF_B_BYTES, &map_ql, kc * UF_KC, q0, full);  //          lo plane
+                    }
+                    if (++stage == nst) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -194,6 +227,10 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             const uint32_t idesc = umma_idesc(bn);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
+            if (p.qres > 0) {
+                mbar_wait(bar_q, 0);
+                tc_fence_after();
+            }
             for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);      // the epilogue has drained this accumulator stage
                 tc_fence_after();
@@ -201,18 +238,20 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 for (int kc = 0; kc < nchunks; kc++) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t st = sbase + stage * UF_STAGE_BYTES;
+                    const uint32_t st = ring0 + stage * stage_bytes;
+                    const uint32_t qb = p.qres > 0 ? sbase + kc * qchunk_bytes : st + 2 * UF_A_BYTES;
+                    const uint32_t qlo_off = p.qres > 0 ? (uint32_t)bn * 128u : (uint32_t)UF_B_BYTES;
 #pragma unroll
                     for (int j = 0; j < UF_KC / 16; j++) {
                         const uint64_t xh = umma_desc(st + j * 32), xl = umma_desc(st + UF_A_BYTES + j * 32);
-                        const uint64_t qh = umma_desc(st + 2 * UF_A_BYTES + j * 32);
-                        const uint64_t ql = umma_desc(st + 2 * UF_A_BYTES + UF_B_BYTES + j * 32);
+                        const uint64_t qh = umma_desc(qb + j * 32);
+                        const uint64_t ql = umma_desc(qb + qlo_off + j * 32);
                         tc_mma(acc, xh, ql, idesc, (kc | j) != 0);      // the small products first
                         tc_mma(acc, xl, qh, idesc, 1);
                         tc_mma(acc, xh, qh, idesc, 1);
                     }
                     tc_commit(bar_empty + 8 * stage);            // smem stage free once these MMAs have read it
-                    if (++stage == UF_STAGES) {
+                    if (++stage == nst) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -447,6 +486,10 @@ bool make_map(CUtensorMap *m, const void *base, u64 rows, int Kp, int box_rows, 
 
 cudaError_t launch_umma_filter(const UmmaArgs &a, cudaStream_t st, std::string *why) {
     std::string err;
+    if (a.qres != 0 && a.qres != uf_resident_stages(a.bn, a.Kp)) {
+        if (why) *why = "umma filter: bad resident-query setting";
+        return cudaErrorInvalidValue;
+    }
     if ((a.bn != 64 && a.bn != 128 && a.bn != 256) || a.ngroups < 1 || a.nstreams < 1 || a.Kp % UF_KC || a.Kp < a.K || a.cap < 1 ||
         a.cap > 32 || a.n == 0 || a.n >= (1ull << 31)) {
         if (why) *why = "umma filter: bad launch shape";
