@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     const uint32_t tile_bytes = (uint32_t)TR * row_bytes;
     Cand *mrg = reinterpret_cast<Cand *>(smem + (size_t)W * nstages * tile_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(mrg) + (size_t)W * 32 * sizeof(Cand));
+    uint32_t *tile_of = reinterpret_cast<uint32_t *>(bars + W * nstages) + warp * 4;   // which tile sits in each of this warp's stages
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < W * nstages; i++) mbar_init(smem_u32(bars + i), 1);
@@ -62,8 +63,14 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     }
     __syncthreads();
 
+    // Tiles are handed out DYNAMICALLY when the launch has a fused tail (a device counter next to the tail's ticket, re-armed
+    // by the last CTA): with a static round-robin the CTAs of a 1.25M-row shard finished 11 us apart (4 % of the scan,
+    // HBM channel luck), and the step ends with the slowest.  A warp asks for its next tile BEFORE it waits for the current
+    // one, so the atomic's round trip hides behind the wait and the arithmetic.
     const u64 ntiles = (p.n + TR - 1) / TR;
     const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    unsigned *next_tile = p.tail.ticket ? p.tail.ticket + 2 : nullptr;
+    constexpr uint32_t NO_TILE = 0xffffffffu;
     const uint32_t my_stage = smem_u32(smem) + (uint32_t)warp * nstages * tile_bytes;
     const uint32_t my_bar = smem_u32(bars + warp * nstages);
     auto issue = [&](u64 t, int s) {
@@ -77,10 +84,12 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     };
     if (lane == 0) {
         for (int s = 0; s < nstages; s++) {
-            const u64 t = gw + (u64)s * GW;
+            const u64 t = next_tile ? (u64)atomicAdd(next_tile, 1u) : gw + (u64)s * GW;
             if (t < ntiles) issue(t, s);
+            tile_of[s] = t < ntiles ? (uint32_t)t : NO_TILE;
         }
     }
+    __syncwarp();
 
     // the query, fp32, in registers: lane (j = lane % LPR) owns coordinates trip * 256 + j * 8 .. + 7; zeros beyond K
     // match the zero padding of the plane
@@ -104,7 +113,13 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
 
     int s = 0;
     uint32_t phase = 0;
-    for (u64 t = gw; t < ntiles; t += GW) {
+    for (u64 tstat = gw;; tstat += GW) {
+        const uint32_t t32 = tile_of[s];
+        if (t32 == NO_TILE) break;                     // tiles are handed out in order: nothing follows an empty stage
+        const u64 t = t32;
+        // the tile that will refill this stage: asked for now, needed after the arithmetic
+        u64 tn = tstat + (u64)nstages * GW;
+        if (next_tile && lane == 0) tn = (u64)atomicAdd(next_tile, 1u);
         mbar_wait(my_bar + 8 * s, phase);
         float key[NQ];
         int my_row;
@@ -177,8 +192,11 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
         }
         __syncwarp();
         // the stage is consumed: refill it before the (rare) list maintenance
-        const u64 tn = t + (u64)nstages * GW;
-        if (lane == 0 && tn < ntiles) issue(tn, s);
+        if (lane == 0) {
+            if (tn < ntiles) issue(tn, s);
+            tile_of[s] = tn < ntiles ? (uint32_t)tn : NO_TILE;
+        }
+        __syncwarp();
         if (++s == nstages) {
             s = 0;
             phase ^= 1;
@@ -209,7 +227,7 @@ static cudaError_t launch_plane_inst(const ScanTuning &t, const PlaneScanArgs &a
     int NS = t.stages < 2 ? 2 : t.stages;
     while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
     const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
-    auto need = [&](int w, int ns) { return (size_t)w * ns * TR * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)w * ns * 8; };
+    auto need = [&](int w, int ns) { return (size_t)w * ns * TR * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)w * ns * 8 + (size_t)w * 16; };
     const size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
     while (need(W, NS) > budget && NS > 2) NS--;
     while (need(W, NS) > budget && W > 1) W--;

@@ -650,7 +650,8 @@ __device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) {
-        *t.ticket = 0;                                 // re-armed for the next launch on the stream
+        t.ticket[0] = 0;                               // re-armed for the next launch on the stream ...
+        t.ticket[2] = 0;                               // ... and so is the tile counter of the scans that hand tiles out dynamically
         if (t.dbg) t.dbg[0] = global_timer_ns();
     }
     if (threadIdx.x == 0) fin_bar_init(smem, blockDim.x >> 5);
