@@ -63,13 +63,18 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     }
     __syncthreads();
 
-    // Tiles are handed out DYNAMICALLY when the launch has a fused tail (a device counter next to the tail's ticket, re-armed
-    // by the last CTA): with a static round-robin the CTAs of a 1.25M-row shard finished 11 us apart (4 % of the scan,
-    // HBM channel luck), and the step ends with the slowest.  A warp asks for its next tile BEFORE it waits for the current
-    // one, so the atomic's round trip hides behind the wait and the arithmetic.
+    // Load balance.  With a static round-robin the CTAs of a 1.25M-row shard finished 11 us apart (4 % of the scan: HBM
+    // channel luck), and the step ends with the slowest.  Handing out EVERY tile through one device counter fixes the spread
+    // but costs 25 % of the bandwidth (1.2 G atomics/s on one address).  So: the first 7/8 of a warp's share is static, the
+    // rest of the log is handed out dynamically (a counter next to the tail's ticket, re-armed by the last CTA; launches
+    // without a fused tail stay static).  A warp asks for its next tile BEFORE it waits for the current one, so the atomic's
+    // round trip hides behind the wait and the arithmetic.
     const u64 ntiles = (p.n + TR - 1) / TR;
     const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
     unsigned *next_tile = p.tail.ticket ? p.tail.ticket + 2 : nullptr;
+    const u64 n_static = next_tile ? (ntiles / GW) * 7 / 8 : ~0ull;          // static tiles per warp
+    const u64 t_static = next_tile ? n_static * GW : 0;                       // tiles [0, t_static) are static
+    u64 my_i = 0;                                                              // tiles this warp has asked for so far
     constexpr uint32_t NO_TILE = 0xffffffffu;
     const uint32_t my_stage = smem_u32(smem) + (uint32_t)warp * nstages * tile_bytes;
     const uint32_t my_bar = smem_u32(bars + warp * nstages);
@@ -82,9 +87,13 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
         bulk_g2s(my_stage + s * tile_bytes, reinterpret_cast<const unsigned char *>(p.xhi) + row0 * (u64)row_bytes, bytes,
                  my_bar + 8 * s);
     };
+    auto next = [&]() -> u64 {                            // lane 0 only
+        if (my_i < n_static) return gw + (my_i++) * GW;
+        return t_static + (u64)atomicAdd(next_tile, 1u);
+    };
     if (lane == 0) {
         for (int s = 0; s < nstages; s++) {
-            const u64 t = next_tile ? (u64)atomicAdd(next_tile, 1u) : gw + (u64)s * GW;
+            const u64 t = next();
             if (t < ntiles) issue(t, s);
             tile_of[s] = t < ntiles ? (uint32_t)t : NO_TILE;
         }
@@ -113,13 +122,13 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
 
     int s = 0;
     uint32_t phase = 0;
-    for (u64 tstat = gw;; tstat += GW) {
+    for (;;) {
         const uint32_t t32 = tile_of[s];
         if (t32 == NO_TILE) break;                     // tiles are handed out in order: nothing follows an empty stage
         const u64 t = t32;
         // the tile that will refill this stage: asked for now, needed after the arithmetic
-        u64 tn = tstat + (u64)nstages * GW;
-        if (next_tile && lane == 0) tn = (u64)atomicAdd(next_tile, 1u);
+        u64 tn = ~0ull;
+        if (lane == 0) tn = next();
         mbar_wait(my_bar + 8 * s, phase);
         float key[NQ];
         int my_row;

@@ -273,12 +273,30 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         const int c_lo = half * (bn / 64), c_hi = c_lo + bn / 64;  // 32-column chunks of this warp
         int as = 0, it = 0;
         uint32_t aphase = 0;
+        // |x|^2 of this lane's row of the NEXT tile and the group's shared thresholds are fetched before the wait for the
+        // accumulator, not after it: two global round trips per tile came off the epilogue's critical path
+        // (profiles/r02_ncu_umma_filter_1Mx128_q64_*: the F2F behind the norm load and the threshold load were the top
+        // long-scoreboard stalls, and the eight warps wait for each other twice per tile)
+        const int jmine = wi + 8 * lane;                  // bn / 8 <= 32 queries per warp: lane t looks after query wi + 8 t
+        const bool mineok = lane < bn / 8;
+        double xn_next = 0.0;
+        {
+            const u64 r0 = (u64)stream * UF_M + ew * 32 + lane;
+            if (stream < ntiles && r0 < p.n) xn_next = __ldg(p.xnorm + r0);
+        }
         for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
-            mbar_wait(bar_tfull + 8 * as, aphase);
-            tc_fence_after();
+            const bool refresh = it < 16 || (it & 3) == 0;
+            uint32_t g = 0xffffffffu;
+            if (refresh && mineok) g = __ldcg(p.gtau + q0 + jmine);
             const u64 row = tile * UF_M + ew * 32 + lane;
             const bool ok = row < p.n;
-            const float xn = ok ? (float)__ldg(p.xnorm + row) : 0.f;
+            const float xn = ok ? (float)xn_next : 0.f;
+            {
+                const u64 rn = row + (u64)p.nstreams * UF_M;
+                xn_next = (tile + p.nstreams < ntiles && rn < p.n) ? __ldg(p.xnorm + rn) : 0.0;
+            }
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
             const bool dbg = p.dbg_keys != nullptr && blockIdx.x == 0 && tile == (u64)stream;
             for (int c = c_lo; c < c_hi; c++) {
                 uint32_t v[32];
@@ -335,14 +353,8 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             // ---- prune the buffers that could overflow during the next tile (warp wi owns queries wi, wi+8, ...) ----
             asm volatile("bar.sync 1, 256;" ::: "memory");
             {
-                // bn / 8 <= 32 queries per warp: lane t looks after query wi + 8 t
-                const int jmine = wi + 8 * lane;
-                const bool mineok = lane < bn / 8;
-                // the smallest cap-th key any CTA of this query group has published so far: an upper bound of the
-                // group's cap-th smallest key, so keys above it are nobody's candidates (37 CTAs converge as one)
-                const bool refresh = it < 16 || (it & 3) == 0;
-                uint32_t g = 0xffffffffu;
-                if (refresh && mineok) g = __ldcg(p.gtau + q0 + jmine);
+                // g: the smallest cap-th key any CTA of this query group had published when this tile began: an upper bound
+                // of the group's cap-th smallest key, so keys above it are nobody's candidates (the CTAs converge as one)
                 unsigned m = __ballot_sync(FULL, mineok && cnt_s[jmine] > (unsigned)(UF_BUF - UF_M));
                 while (m) {
                     const int j = wi + 8 * (__ffs(m) - 1);
