@@ -657,6 +657,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 pa.cap = cap;
                 pa.lists = lists.as<Cand>();
                 pa.tail = ta;
+                pa.dyn_eighths = dyn_tiles;
                 CK(launch_scan_plane(tune, pa, stream));
             } else if (plane == 1) {
                 ShadowScanArgs ha{};
@@ -1733,6 +1734,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     }
     else if (n == "scan.fuse_tail") e->fuse_tail = value != 0;
     else if (n == "scan.tail_debug") e->tail_debug = value != 0;
+    else if (n == "scan.dynamic_tiles") e->dyn_tiles = (int)std::min(8l, std::max(0l, value));
     else if (n == "profile.scan_events") e->profile_scan = value != 0;
     else return e->fail(SVDB_ERR_ARG, "unknown option " + n);
     return SVDB_OK;

@@ -89,6 +89,7 @@ struct svdb_engine {
     // whatever the re-rank cannot prove complete is re-answered from the fp64 rows.
     int scan_plane = 2;
     bool fuse_tail = true;               // the scan's last CTA runs finalize (and the cross-shard exchange) itself
+    int dyn_tiles = 0;                   // option "scan.dynamic_tiles": eighths of the log K12 hands out dynamically (A/B; slower)
     bool tail_debug = false;             // option "scan.tail_debug": fused tails leave %globaltimer stamps in tail_dbg
     svdb::Scratch tail_dbg;
     int last_scan_plane = 0;             // what the last scan pass of nearest_device read (escalation: skip a redundant K1 rerun)

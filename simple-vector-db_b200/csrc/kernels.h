@@ -119,6 +119,7 @@ struct PlaneScanArgs {
     const double *q;        // device queries (fp64), query i at q + i * ldq; K coordinates each are read
     int ldq;
     int nq;                 // 1 or 2 queries share the pass (plane_scan_supports)
+    int dyn_eighths;        // 0: tiles dealt round-robin (default); 1..8: that many eighths of the log handed out dynamically
     int cap;
     Cand *lists;            // [nq][nlists][cap]
     TailArgs tail;

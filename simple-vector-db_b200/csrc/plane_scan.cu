@@ -63,16 +63,16 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     }
     __syncthreads();
 
-    // Load balance.  With a static round-robin the CTAs of a 1.25M-row shard finished 11 us apart (4 % of the scan: HBM
-    // channel luck), and the step ends with the slowest.  Handing out EVERY tile through one device counter fixes the spread
-    // but costs 25 % of the bandwidth (1.2 G atomics/s on one address).  So: the first 7/8 of a warp's share is static, the
-    // rest of the log is handed out dynamically (a counter next to the tail's ticket, re-armed by the last CTA; launches
-    // without a fused tail stay static).  A warp asks for its next tile BEFORE it waits for the current one, so the atomic's
-    // round trip hides behind the wait and the arithmetic.
+    // Load balance (option "scan.dynamic_tiles", off by default).  With the static round-robin the CTAs of a 1.25M-row
+    // shard finish 11 us apart (4 % of the scan: HBM channel luck), and the step ends with the slowest.  Handing tiles out
+    // through a device counter (next to the tail's ticket, re-armed by the last CTA) closes the spread to 3 us -- but one
+    // address takes ~1 G atomics/s: with every tile dynamic the scan ran 33 % SLOWER, with the last eighth dynamic still
+    // 2.6 % slower than static (profiles/r02_K12_dynamic_tiles_ab.txt).  Kept as an A/B: p.dyn_eighths of a warp's
+    // share are dynamic.  A warp asks for its next tile BEFORE it waits for the current one.
     const u64 ntiles = (p.n + TR - 1) / TR;
     const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
-    unsigned *next_tile = p.tail.ticket ? p.tail.ticket + 2 : nullptr;
-    const u64 n_static = next_tile ? (ntiles / GW) * 7 / 8 : ~0ull;          // static tiles per warp
+    unsigned *next_tile = (p.tail.ticket && p.dyn_eighths > 0) ? p.tail.ticket + 2 : nullptr;
+    const u64 n_static = next_tile ? (ntiles / GW) * (u64)(8 - p.dyn_eighths) / 8 : ~0ull;   // static tiles per warp
     const u64 t_static = next_tile ? n_static * GW : 0;                       // tiles [0, t_static) are static
     u64 my_i = 0;                                                              // tiles this warp has asked for so far
     constexpr uint32_t NO_TILE = 0xffffffffu;
