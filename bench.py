@@ -219,13 +219,14 @@ def store_chunks(dev, lo: int, hi: int, N: int, D: int):
 
 
 PLANE_KERNEL = {0: "scan_wide_kernel<TR,1> (K1, fp64 rows)", 1: "scan_shadow_kernel<1> (K11, hi + lo bf16 planes of the shadow)",
-                2: "scan_plane_kernel<1,TRIPS,32,TR> (K12, bf16 hi plane of the shadow)"}
+                2: "scan_plane_kernel<1,TRIPS,32,TR> (K12, bf16 hi plane of the shadow)",
+                3: "scan_plane8_kernel<TRIPS,TR> (K13, one-byte plane, exact integer keys)"}
 
 
 def plane_bytes(plane: int, rows: int, K: int) -> int:
     """Algorithmic bytes one scan launch reads: the copy of the log the kernel streams, once."""
     kp = -(-K // 64) * 64
-    return rows * K * 8 if plane == 0 else rows * kp * (4 if plane == 1 else 2)
+    return rows * K * 8 if plane == 0 else rows * kp * {1: 4, 2: 2, 3: 1}[plane]
 
 
 def workload_config(args):
@@ -235,7 +236,7 @@ def workload_config(args):
             "rows": args.rows, "dim": args.dim, "kd_dim": args.kd_dim, "k": 1, "queries_per_step": 1,
             "parallelism": f"row-shards x{args.gpus}", "exchange": os.environ.get("SVDB_EXCHANGE", "p2p") if args.gpus > 1 else None,
             "l2": "bytes streamed per GPU and step >> 126 MB L2 (no flush needed)"
-                  if plane_bytes(2, args.rows // max(1, args.gpus), args.kd_dim) > 4 * L2_BYTES else "store fits L2: flushed between steps"}
+                  if plane_bytes(3, args.rows // max(1, args.gpus), args.kd_dim) > 4 * L2_BYTES else "store fits L2: flushed between steps"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -280,7 +281,7 @@ def ours(args):
         log(f"[bench] store built: {hi - lo} rows/rank in {build_s:.1f}s, {e.stats()['hbm_bytes_mapped'] / 2**30:.1f} GiB mapped")
 
     flush_buf = None
-    if plane_bytes(2, hi - lo, K) <= 4 * L2_BYTES:      # the smallest copy of the log a scan may stream
+    if plane_bytes(3, hi - lo, K) <= 4 * L2_BYTES:      # the smallest copy of the log a scan may stream
         flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
 
     # ---- queries: a pool of distinct ones, in pinned host memory and in HBM --------------
@@ -564,12 +565,14 @@ def ours(args):
     peak, peak_src = measured_peak_gbs()
     achieved = algo_bytes / (scan_ms_avg / 1e3) / 1e9 if scan_ms_avg > 0 else 0.0
     traffic = profile_traffic()
-    tr = (traffic or {}).get({0: "scan_wide", 1: "scan_shadow", 2: "scan_plane"}[plane_used])
+    tr = (traffic or {}).get({0: "scan_wide", 1: "scan_shadow", 2: "scan_plane", 3: "scan_plane8"}[plane_used])
     qps = args.steps / (dev_ms / 1e3)
     dtype = {0: "f64",
              1: "answers f64 (reference operation order, bit-identical to the reference); scan keys fp32 from the hi + lo bf16 planes",
              2: "answers f64 (reference operation order, bit-identical to the reference); scan keys fp32 from the bf16 hi plane of "
-                "the log's split-bf16 shadow, completeness proven per query, unproven queries re-answered from the fp64 rows"}[plane_used]
+                "the log's split-bf16 shadow, completeness proven per query, unproven queries re-answered from the fp64 rows",
+             3: "answers f64 (reference operation order, bit-identical to the reference); scan keys exact integers (u8 x u16 dot "
+                "products) from a one-byte plane of the log, completeness proven per query, unproven queries re-answered from the fp64 rows"}[plane_used]
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -72,6 +72,17 @@ __device__ __forceinline__ double2 ldg128_stream(const double *p) {
 }
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
 
+// ---- K13's one-byte plane (plane_scan.cu): x^ = lo + step * u, u in 0..255; queries on a 16-bit grid, q^ = lo + step * Q / 256.
+// The SAME expressions quantise rows (build), queries (scan) and form |q - q^| (finalize): the bound needs them identical.
+__device__ __forceinline__ unsigned p8_quant_x(double v, double lo, double step) {
+    const double t = rint((v - lo) / step);
+    return t >= 255.0 ? 255u : (t > 0.0 ? (unsigned)t : 0u);          // NaN -> 0
+}
+__device__ __forceinline__ unsigned p8_quant_q(double v, double lo, double step) {
+    const double t = rint(256.0 * ((v - lo) / step));
+    return t >= 65535.0 ? 65535u : (t > 0.0 ? (unsigned)t : 0u);
+}
+
 // ---- reference-order arithmetic (kdtree.c:134-137): rounded sub, mul, add; never fused ----
 __device__ __forceinline__ double exact_sqdist(const double *__restrict__ p, const double *__restrict__ q, int K) {
     double d = 0.0;

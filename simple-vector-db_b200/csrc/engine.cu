@@ -227,10 +227,13 @@ void svdb_engine::destroy() {
     xnorm.release();
     shadow_hi.release();
     shadow_lo.release();
+    plane8.release();
+    plane8_ready = false;
+    plane8_n = 0;
     shadow_ready = false;
     shadow_n = shadow_lo_n = 0;
     shadow_mapped_counted = 0;
-    for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal, &tail_dbg}) s->free_();
+    for (Scratch *s : {&qsplit, &ubuf, &udbg, &plane_err, &ticket, &xlocal, &tail_dbg, &plane8_par}) s->free_();
     for (Scratch *s : {&qpad, &qraw, &lists, &outc, &idx1, &idx2, &fout, &tree_pn, &tree_pds, &tree_flag, &qnorm, &xnmax,
                        &mt_split, &mt_pts, &mt_seq, &mt_marks}) s->free_();
     for (PinnedScratch *s : {&stage_rows, &stage_idx, &hq, &hout, &hidx, &hf, &tree_hflag}) s->free_();
@@ -356,8 +359,9 @@ int svdb_engine::flush() {
     CK(cudaStreamSynchronize(stream));   // staging buffers are reused by the caller
     n_versions = n1;
     stage_n = 0;
-    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped() + shadow_hi.mapped() + shadow_lo.mapped();
+    stats.hbm_bytes_mapped = rows.mapped() + kdpts.mapped() + log_idx.mapped() + norms.mapped() + cur.mapped() + child.mapped() + xnorm.mapped() + shadow_hi.mapped() + shadow_lo.mapped() + plane8.mapped();
     shadow_mapped_counted = shadow_hi.mapped() + shadow_lo.mapped();
+    plane8_mapped_counted = plane8.mapped();
     return SVDB_OK;
 }
 
@@ -545,9 +549,19 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         // never build or extend the shadow under stream capture (see nearest_host): fall back to the fp64 rows there
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
-        const int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
+        int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
+        if (scan_plane >= 3 && plane8_ok && plane8_scan_supports(Kp) && nq <= 2) want = 3;
+        if (want == 3) {
+            const bool have8 = plane8_ready && plane8_n == n_versions;
+            if (cs == cudaStreamCaptureStatusNone || have8) {
+                const int sr = ensure_plane8();
+                if (sr == SVDB_OK) plane = 3;
+                else if (sr != -1000) return sr;
+            }
+            if (plane != 3) want = 2;
+        }
         const bool have = shadow_ready && shadow_n == n_versions && (want == 2 || shadow_lo_n == n_versions);
-        if (cs == cudaStreamCaptureStatusNone || have) {
+        if (plane != 3 && (cs == cudaStreamCaptureStatusNone || have)) {
             const int sr = ensure_shadow(want == 1);
             if (sr == SVDB_OK) plane = want;
             else if (sr != -1000) return sr;
@@ -578,6 +592,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
     }
     int limit = std::max(1, tune.nq_per_pass);
     if (plane == 2) limit = plane_scan_supports(Kp, 2) ? std::min(limit, 2) : 1;
+    if (plane == 3) limit = 1;
     if (nlists && !lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return fail(SVDB_ERR_OOM, err);
     // the scan's last CTA finalizes (and exchanges) itself -- every wide scan but the LDG variant and the exact kernel
     const bool fuse = fuse_tail && ticket.p && nlists && !use_exact && (plane > 0 || tune.variant == 0);
@@ -606,6 +621,12 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
             fa.xn_max_bits = xnmax.as<unsigned long long>();
             fa.scale_lo = 1e-24;               // fp32 keys: see nearest_umma
             fa.scale_hi = 1e30;
+        } else if (plane == 3) {
+            fa.sq_mode = 2;
+            fa.sq_gamma = ldexp(1.0, -50);     // the keys are exact integers times one rounded constant
+            fa.plane8 = plane8_par.as<Plane8Par>();
+            fa.plane_err_bits = reinterpret_cast<const unsigned long long *>(plane8_par.as<unsigned char>() + sizeof(Plane8Par));
+            fa.xn_max_bits = xnmax.as<unsigned long long>();
         } else if (plane == 2) {
             fa.sq_mode = 1;
             fa.sq_gamma = plane_gamma(Kp);
@@ -645,7 +666,19 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 scan_events_used++;
                 CK(cudaEventRecord(ev0, stream));
             }
-            if (plane == 2) {
+            if (plane == 3) {
+                Plane8ScanArgs pa{};
+                pa.x8 = plane8.as<unsigned char>();
+                pa.par = plane8_par.as<Plane8Par>();
+                pa.n = n_versions;
+                pa.K = K;
+                pa.Kp = Kp;
+                pa.q = fa.q;
+                pa.cap = cap;
+                pa.lists = lists.as<Cand>();
+                pa.tail = ta;
+                CK(launch_scan_plane8(tune, pa, stream));
+            } else if (plane == 2) {
                 PlaneScanArgs pa{};
                 pa.xhi = shadow_hi.as<uint16_t>();
                 pa.n = n_versions;
@@ -744,6 +777,37 @@ int svdb_engine::ensure_shadow(bool need_lo) {
         const size_t mapped = shadow_hi.mapped() + shadow_lo.mapped();
         stats.hbm_bytes_mapped += mapped - shadow_mapped_counted;
         shadow_mapped_counted = mapped;
+    }
+    return SVDB_OK;
+}
+
+// K13's one-byte plane: created (grid chosen from the rows present) on first use, extended by the entries appended since.
+// -1000: no HBM for it -- K12 keeps serving.
+int svdb_engine::ensure_plane8() {
+    std::string err;
+    const int Kp = umma_kpad(K);
+    if (!plane8_ready) {
+        if (!plane8_par.ensure(sizeof(Plane8Par) + 16, err)) return fail(SVDB_ERR_OOM, err);
+        CK(cudaMemsetAsync(plane8_par.p, 0, sizeof(Plane8Par) + 16, stream));
+        if (!plane8.init(device, max_versions * (size_t)Kp, err)) {
+            plane8_ok = false;
+            return -1000;
+        }
+        plane8_ready = true;
+    }
+    if (plane8_n < n_versions) {
+        if (!plane8.ensure(n_versions * (size_t)Kp, stream, err)) {
+            plane8_ok = false;
+            cudaGetLastError();
+            return -1000;
+        }
+        unsigned long long *errw = reinterpret_cast<unsigned long long *>(plane8_par.as<unsigned char>() + sizeof(Plane8Par));
+        CK(launch_plane8_build(kd_ptr(), kstride, K, Kp, plane8_n, n_versions - plane8_n, plane8_par.as<Plane8Par>(), plane8_n == 0,
+                               plane8.as<unsigned char>(), errw, tune.num_sms, stream));
+        stats.kernels_launched += plane8_n == 0 ? 4 : 1;
+        stats.hbm_bytes_mapped += plane8.mapped() - plane8_mapped_counted;
+        plane8_mapped_counted = plane8.mapped();
+        plane8_n = n_versions;
     }
     return SVDB_OK;
 }
@@ -874,8 +938,14 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1));
-        if (rc && rc != -1000) return rc;
+        if (few && scan_plane >= 3 && plane8_ok && plane8_scan_supports(umma_kpad(K)) && nq <= 2) {
+            rc = ensure_plane8();
+            if (rc && rc != -1000) return rc;
+        }
+        if (!(few && scan_plane >= 3 && plane8_ready && plane8_n == n_versions) || to_umma) {
+            rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1));
+            if (rc && rc != -1000) return rc;
+        }
     }
     stats.h2d_bytes += nq * (size_t)K * 8;
     stats.d2h_bytes += nq * k * sizeof(svdb_candidate);
@@ -966,6 +1036,16 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
             rc = resolve_ties_engine(this, x, exchange_rank(x), exchange_world(x), nullptr, nullptr, hq.as<double>(), nq,
                                      (size_t)K, res, k);
             if (rc) return rc;
+        }
+    }
+    if (last_scan_plane == 3) {
+        // a store-wide uniform grid resolves some data badly (heavy tails, a few huge coordinates): the measured plane error
+        // then makes most proofs fail and every query pays for two scans.  Stop using the plane when that shows.
+        p8_calls += nq;
+        for (size_t i = 0; i < nq; i++) p8_unsafe += (res[i * k].flags & SVDB_CAND_UNSAFE) ? 1 : 0;
+        if (p8_calls >= 8 && p8_unsafe * 4 > p8_calls) {
+            plane8_ok = false;
+            opt_gen++;                       // captured graphs baked the plane's scan in
         }
     }
     const bool low_precision_first = wide && (last_scan_plane > 0 || nq >= (size_t)std::max(1, mma_min_q));
@@ -1173,8 +1253,9 @@ int svdb_engine::ingest_device_rows(const double *d_rows, size_t n, size_t ld, s
     e->uuids.resize(e->cur_host.size(), std::array<char, 37>{});
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped() + e->plane8.mapped();
     e->shadow_mapped_counted = e->shadow_hi.mapped() + e->shadow_lo.mapped();
+    e->plane8_mapped_counted = e->plane8.mapped();
     return SVDB_OK;
 }
 
@@ -1315,8 +1396,9 @@ int svdb_append_kdpoints_device(svdb_engine *e, const double *d_pts, size_t firs
     if (rc) return rc;
     e->n_versions = n1;
     e->stats.hbm_bytes_mapped = e->rows.mapped() + e->kdpts.mapped() + e->log_idx.mapped() + e->norms.mapped() +
-                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped();
+                                e->cur.mapped() + e->child.mapped() + e->xnorm.mapped() + e->shadow_hi.mapped() + e->shadow_lo.mapped() + e->plane8.mapped();
     e->shadow_mapped_counted = e->shadow_hi.mapped() + e->shadow_lo.mapped();
+    e->plane8_mapped_counted = e->plane8.mapped();
     return SVDB_OK;
 }
 
@@ -1729,7 +1811,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "umma.resident_queries") e->umma_resident = value != 0;
     else if (n == "scan.shadow") e->scan_plane = value != 0 ? 1 : 0;      // round-1 name: 1 = K11 (hi + lo planes), 0 = fp64 rows
     else if (n == "scan.plane") {
-        if (value < 0 || value > 2) return e->fail(SVDB_ERR_ARG, "scan.plane must be 0 (fp64 rows), 1 (hi + lo planes) or 2 (hi plane)");
+        if (value < 0 || value > 3) return e->fail(SVDB_ERR_ARG, "scan.plane must be 0 (fp64 rows), 1 (hi + lo planes), 2 (hi plane) or 3 (byte plane)");
         e->scan_plane = (int)value;
     }
     else if (n == "scan.fuse_tail") e->fuse_tail = value != 0;

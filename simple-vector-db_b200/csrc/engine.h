@@ -83,9 +83,19 @@ struct svdb_engine {
     size_t shadow_lo_n = 0;              // ... and in the lo plane (built when K10 / K11 first ask for it: K12 reads hi only)
     size_t shadow_mapped_counted = 0;    // part of the shadow's mapped bytes already included in stats.hbm_bytes_mapped
     svdb::DeviceBuffer shadow_hi, shadow_lo;   // [versions][Kp] bf16 each: x ~ hi + lo (split_bf16_kernel)
+    // K13: the one-byte plane ([versions][Kp] bytes on one store-wide grid), its grid + measured error (plane8_par: a
+    // svdb::Plane8Par followed by the error word)
+    svdb::DeviceBuffer plane8;
+    svdb::Scratch plane8_par;
+    bool plane8_ready = false, plane8_ok = true;
+    size_t plane8_n = 0, plane8_mapped_counted = 0;
+    uint64_t p8_calls = 0, p8_unsafe = 0;      // queries K13 answered / could not prove: the engine stops using the plane
+                                               // for data its grid resolves badly (nearest_host)
+    int ensure_plane8();                 // SVDB_OK, an error, or -1000: not available
     svdb::Scratch qsplit, ubuf, udbg, plane_err, ticket, xlocal;
     // Which copy of the log 1-2 query calls scan (option "scan.plane"): 0 the fp64 rows (K1), 1 the hi + lo shadow (K11, 4 bytes
-    // per coordinate), 2 the hi plane alone (K12, 2 bytes per coordinate; the default).  Same answers on every setting:
+    // per coordinate), 2 the hi plane alone (K12, 2 bytes per coordinate), 3 the one-byte plane (K13; kd_dim 193..1024,
+    // else 2 serves).  Same answers on every setting:
     // whatever the re-rank cannot prove complete is re-answered from the fp64 rows.
     int scan_plane = 2;
     bool fuse_tail = true;               // the scan's last CTA runs finalize (and the cross-shard exchange) itself

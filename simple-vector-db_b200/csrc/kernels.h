@@ -45,9 +45,10 @@ struct FinalArgs {
     // sqrt-form keys (K12, the scan of ONE low-precision plane of the log): key = |x^ - q^|^2 in fp32, hence
     //   |sqrt(key) - sqrt(d)| <= E + gamma (sqrt(d) + E),   E = max_r |x_r - x^_r| + |q - fl32(q)| + underflow slack
     // sq_mode = 1: eps / eabs_coef / qnorm are ignored; finalize forms |q - fl32(q)| and |q|^2 itself
-    int sq_mode;
+    int sq_mode;            // 1: K12 (q^ = fl32(q)); 2: K13 (q^ on the byte plane's query grid, plane8 != NULL)
     double sq_gamma;
     const unsigned long long *plane_err_bits;   // max_r |x_r - x^_r| over the log, as double bits
+    const struct Plane8Par *plane8;             // K13: the grid the queries are quantised on
     const uint32_t *child;  // reference-shaped tree links (tree.cuh) for exact tie order; NULL: ties -> lowest seq
     int mark_ties;          // shards (child == NULL): flag SVDB_CAND_TIE when distinct kd-points may tie at the minimum
     svdb_candidate *out;    // [nq][k]
@@ -127,6 +128,29 @@ struct PlaneScanArgs {
 bool plane_scan_supports(int Kp, int nq);
 double plane_gamma(int Kp);
 cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaStream_t st);
+
+// K13: the single-query scan over a ONE-BYTE plane of the log (x^ = lo + step * u on one store-wide grid; 1 byte per
+// coordinate).  Keys |x^ - q^|^2 are formed EXACTLY from integer dot products (dp4a); sqrt-form bound, FinalArgs::sq_mode = 2.
+struct Plane8Par {          // device-resident parameters of the grid
+    double lo, step;        // fixed when the plane is first built (rows appended later are clamped; their error is measured)
+    unsigned long long min_ord, max_ord;   // running range of the log while the grid is being chosen (order-preserving bit patterns)
+};
+struct Plane8ScanArgs {
+    const unsigned char *x8; // [n][Kp] bytes
+    const Plane8Par *par;
+    u64 n;
+    int K, Kp;
+    const double *q;        // one device query (fp64), K coordinates
+    int cap;
+    Cand *lists;            // [nlists][cap]
+    TailArgs tail;
+};
+bool plane8_scan_supports(int Kp);
+cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st);
+// rows [first, first+n) of the log -> the byte plane; choose_grid: first take lo / step from the range of those rows.
+// err_bits: running max over the rows of |x - x^|_2 (double bits).
+cudaError_t launch_plane8_build(const double *src, int ld, int K, int Kp, u64 first, u64 n, Plane8Par *par, bool choose_grid,
+                                unsigned char *dst, unsigned long long *err_bits, int num_sms, cudaStream_t st);
 
 
 

@@ -241,7 +241,9 @@ static cudaError_t launch_plane_inst(const ScanTuning &t, const PlaneScanArgs &a
     while (need(W, NS) > budget && NS > 2) NS--;
     while (need(W, NS) > budget && W > 1) W--;
     if (need(W, NS) > budget) return cudaErrorInvalidValue;
-    const size_t smem = std::max(need(W, NS), a.tail.ticket ? fin_head_bytes(W) + FIN_MIN_TBUF : (size_t)0);
+    // the tail wants every CTA's list in shared memory at once (selection path): nlists x cap x 16 bytes per query
+    const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
+    const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(scan_plane_kernel<NQ, TRIPS, LPR, TR>, smem);
     if (e != cudaSuccess) return e;
@@ -265,6 +267,254 @@ cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaS
     }
     if (Kp <= 256) return launch_plane_inst<2, 1, 32, 16>(t, a, st);
     return launch_plane_inst<2, 2, 32, 8>(t, a, st);
+}
+
+// =====================================================================================================================
+// K13: the same scan over a ONE-BYTE plane.  x^_i = lo + step * u_i with u_i = round((x_i - lo) / step) in 0..255 on ONE
+// store-wide grid (lo, step from the range of the rows present when the plane is first built; rows appended later are
+// clamped).  The query goes onto a grid 256 times finer, Q_i = round(256 (q_i - lo) / step) in 0..65535 = 256 a_i + b_i, and
+//     sum_i (256 u_i - Q_i)^2 = 65536 sum u_i^2 - 512 (256 sum u_i a_i + sum u_i b_i) + sum Q_i^2
+// is formed EXACTLY from three byte dot products (dp4a, 4 coordinates per instruction, the query's digits in registers):
+// key = (step / 256)^2 * that = |x^ - q^|^2 with one rounding.  Nothing about the arithmetic is approximate; the only error
+// is the quantisation itself, measured when the plane is written (max_r |x_r - x^_r|_2) and, for the query, formed by
+// finalize from the same expression: the sqrt-form bound of K12 with gamma = 2^-50.  A quarter of K12's bytes again
+// (an eighth of the fp64 rows): algorithmic bytes per launch = n * Kp.  HBM-bound; one launch per query (fused tail).
+// Data a uniform grid resolves badly (heavy tails, a few huge coordinates) shows up as a large measured error: the
+// proof fails, the query is re-answered from the fp64 rows, and the engine stops using the plane (engine.cu).
+// =====================================================================================================================
+template <int TRIPS, int TR>
+__global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_constant__ Plane8ScanArgs p, int nstages, int smem_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (p.tail.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = p.Kp;
+    const uint32_t row_bytes = (uint32_t)Kp;
+    const uint32_t tile_bytes = (uint32_t)TR * row_bytes;
+    Cand *mrg = reinterpret_cast<Cand *>(smem + (size_t)W * nstages * tile_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(mrg) + (size_t)W * 32 * sizeof(Cand));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W * nstages; i++) mbar_init(smem_u32(bars + i), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const u64 ntiles = (p.n + TR - 1) / TR;
+    const u64 gw = (u64)blockIdx.x * W + warp, GW = (u64)gridDim.x * W;
+    const uint32_t my_stage = smem_u32(smem) + (uint32_t)warp * nstages * tile_bytes;
+    const uint32_t my_bar = smem_u32(bars + warp * nstages);
+    auto issue = [&](u64 t, int s) {
+        const u64 row0 = t * TR;
+        const u64 left = p.n - row0;
+        const uint32_t rows = left < (u64)TR ? (uint32_t)left : (uint32_t)TR;
+        const uint32_t bytes = rows * row_bytes;
+        mbar_arrive_expect_tx(my_bar + 8 * s, bytes);
+        bulk_g2s(my_stage + s * tile_bytes, p.x8 + row0 * (u64)row_bytes, bytes, my_bar + 8 * s);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < nstages; s++) {
+            const u64 t = gw + (u64)s * GW;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    // the query's digits, packed like the plane's bytes: lane l owns coordinates trip * 256 + l * 8 .. + 7
+    const double lo = p.par->lo, step = p.par->step;
+    uint32_t qa[TRIPS][2], qb[TRIPS][2];
+    bool act[TRIPS];
+    long long qq = 0;                                   // sum Q_i^2 over the lane's coordinates
+#pragma unroll
+    for (int t = 0; t < TRIPS; t++) {
+        const int c0 = t * 256 + lane * 8;
+        act[t] = c0 < Kp;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t wa = 0, wb = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = c0 + h * 4 + j;
+                const unsigned Q = c < p.K ? p8_quant_q(__ldg(p.q + c), lo, step) : 0u;
+                wa |= (Q >> 8) << (8 * j);
+                wb |= (Q & 255u) << (8 * j);
+                qq += (long long)Q * Q;
+            }
+            qa[t][h] = wa;
+            qb[t][h] = wb;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) qq += __shfl_xor_sync(FULL, qq, m);
+    const double c2 = (step / 256.0) * (step / 256.0);
+
+    WarpList wl;
+    wl.reset();
+    int s = 0;
+    uint32_t phase = 0;
+    for (u64 t = gw; t < ntiles; t += GW) {
+        mbar_wait(my_bar + 8 * s, phase);
+        long long v[TR];
+        const uint32_t sa = my_stage + s * tile_bytes + lane * 8;
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+            uint32_t s2 = 0, A = 0, B = 0;
+#pragma unroll
+            for (int tr = 0; tr < TRIPS; tr++) {
+                uint32_t w0 = 0, w1 = 0;
+                if (act[tr]) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + r * row_bytes + tr * 256));
+                s2 = __dp4a(w0, w0, s2);
+                s2 = __dp4a(w1, w1, s2);
+                A = __dp4a(w0, qa[tr][0], A);
+                A = __dp4a(w1, qa[tr][1], A);
+                B = __dp4a(w0, qb[tr][0], B);
+                B = __dp4a(w1, qb[tr][1], B);
+            }
+            v[r] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)B;
+        }
+        reduce_rows<TR>(v, lane);
+        __syncwarp();
+        // the stage is consumed: refill it before the (rare) list maintenance
+        const u64 tn = t + (u64)nstages * GW;
+        if (lane == 0 && tn < ntiles) issue(tn, s);
+        if (++s == nstages) {
+            s = 0;
+            phase ^= 1;
+        }
+        const u64 row = t * TR + RowLane<TR>::row(lane);
+        const bool has = RowLane<TR>::owner(lane) && row < p.n;
+        wl.offer(has, (double)(v[0] + qq) * c2, row, lane, p.cap);
+    }
+
+    cta_merge_emit(wl, mrg, W, warp, lane, p.cap, p.lists + (size_t)blockIdx.x * p.cap);
+    if (threadIdx.x == 0)                                // the tail reuses this memory (and brings its own barrier)
+        for (int i = 0; i < W * nstages; i++) mbar_inval(smem_u32(bars + i));
+    scan_tail(p.tail, smem, smem_bytes);
+}
+
+// ---- the plane's grid and its rows ----
+__device__ __forceinline__ u64 p8_ord(double d) {
+    const u64 b = (u64)__double_as_longlong(d);
+    return b ^ ((u64)((long long)b >> 63) | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double p8_unord(u64 k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k ^ 0x8000000000000000ull) : ~k));
+}
+__global__ void plane8_range_init_kernel(Plane8Par *par) {
+    par->min_ord = ~0ull;
+    par->max_ord = 0ull;
+}
+__global__ void __launch_bounds__(256) plane8_range_kernel(const double *__restrict__ src, int ld, int K, u64 first, u64 n, Plane8Par *par) {
+    u64 mn = ~0ull, mx = 0ull;
+    const u64 total = n * (u64)K;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const double v = src[(first + i / K) * (u64)ld + i % K];
+        if (v - v == 0.0) {                              // finite
+            const u64 o = p8_ord(v);
+            mn = o < mn ? o : mn;
+            mx = o > mx ? o : mx;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const u64 a = __shfl_xor_sync(FULL, mn, m), b = __shfl_xor_sync(FULL, mx, m);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(&par->min_ord, mn);
+        atomicMax(&par->max_ord, mx);
+    }
+}
+__global__ void plane8_grid_kernel(Plane8Par *par) {
+    double lo = 0.0, hi = 0.0;
+    if (par->min_ord <= par->max_ord) {
+        lo = p8_unord(par->min_ord);
+        hi = p8_unord(par->max_ord);
+    }
+    par->lo = lo;
+    par->step = hi > lo ? (hi - lo) / 255.0 : 1.0;
+}
+// one warp per row, four coordinates (one 32-bit word of the plane) per lane and step
+__global__ void __launch_bounds__(256) plane8_build_kernel(const double *__restrict__ src, int ld, int K, int Kp, u64 first, u64 n,
+                                                           const Plane8Par *__restrict__ par, unsigned char *__restrict__ dst,
+                                                           unsigned long long *__restrict__ err_bits) {
+    const int lane = threadIdx.x & 31;
+    const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, GW = ((u64)gridDim.x * blockDim.x) >> 5;
+    const double lo = par->lo, step = par->step;
+    double emax = 0.0;
+    for (u64 i = gw; i < n; i += GW) {
+        const u64 r = first + i;
+        const double *row = src + r * (u64)ld;
+        double e2 = 0.0;
+        for (int c = lane * 4; c < Kp; c += 128) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (c + j < K) {
+                    const double v = row[c + j];
+                    const unsigned u = p8_quant_x(v, lo, step);
+                    w |= u << (8 * j);
+                    const double d = v - (lo + step * (double)u);
+                    e2 = fma(d, d, e2);
+                }
+            }
+            *reinterpret_cast<uint32_t *>(dst + r * (u64)Kp + c) = w;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) e2 += __shfl_xor_sync(FULL, e2, m);
+        if (e2 == e2 && e2 < CUDART_INF) emax = fmax(emax, e2);    // rows with a non-finite coordinate never win (kdtree.c:139)
+    }
+    if (err_bits != nullptr && lane == 0 && emax > 0.0)
+        atomicMax(err_bits, (unsigned long long)__double_as_longlong(sqrt(emax) * (1.0 + 1e-12)));
+}
+
+cudaError_t launch_plane8_build(const double *src, int ld, int K, int Kp, u64 first, u64 n, Plane8Par *par, bool choose_grid,
+                                unsigned char *dst, unsigned long long *err_bits, int num_sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    if (choose_grid) {
+        plane8_range_init_kernel<<<1, 1, 0, st>>>(par);
+        u64 g = (n * (u64)K + 255) / 256;
+        if (g > (u64)num_sms * 16) g = (u64)num_sms * 16;
+        plane8_range_kernel<<<(unsigned)g, 256, 0, st>>>(src, ld, K, first, n, par);
+        plane8_grid_kernel<<<1, 1, 0, st>>>(par);
+    }
+    u64 grid = (n + 7) / 8;
+    if (grid > (u64)num_sms * 16) grid = (u64)num_sms * 16;
+    plane8_build_kernel<<<(unsigned)grid, 256, 0, st>>>(src, ld, K, Kp, first, n, par, dst, err_bits);
+    return cudaGetLastError();
+}
+
+bool plane8_scan_supports(int Kp) { return Kp >= 256 && Kp % 64 == 0 && Kp <= 1024; }
+
+template <int TRIPS, int TR>
+static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
+    const size_t row_bytes = (size_t)a.Kp;
+    const int grid = scan_num_lists(t, true);
+    int W = t.warps < 1 ? 1 : (t.warps > 8 ? 8 : t.warps);
+    int NS = t.stages < 2 ? 2 : t.stages;
+    while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
+    const int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
+    auto need = [&](int w, int ns) { return (size_t)w * ns * TR * row_bytes + (size_t)w * 32 * sizeof(Cand) + (size_t)w * ns * 8; };
+    const size_t budget = (size_t)MAX_SMEM / cps - (cps > 1 ? 1024 : 0);
+    while (need(W, NS) > budget && NS > 2) NS--;
+    while (need(W, NS) > budget && W > 1) W--;
+    if (need(W, NS) > budget) return cudaErrorInvalidValue;
+    // the tail wants every CTA's list in shared memory at once (selection path): 296 lists x cap x 16 bytes
+    const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
+    const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
+    static SmemOptIn optin;
+    cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR>, smem);
+    if (e != cudaSuccess) return e;
+    scan_plane8_kernel<TRIPS, TR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
+    if (!plane8_scan_supports(a.Kp) || a.Kp < a.K || !a.x8 || !a.par || a.n == 0) return cudaErrorInvalidValue;
+    if (a.Kp <= 256) return launch_plane8_inst<1, 16>(t, a, st);
+    if (a.Kp <= 512) return launch_plane8_inst<2, 16>(t, a, st);
+    if (a.Kp <= 768) return launch_plane8_inst<3, 8>(t, a, st);
+    return launch_plane8_inst<4, 8>(t, a, st);
 }
 
 }  // namespace svdb

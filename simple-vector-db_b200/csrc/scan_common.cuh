@@ -33,6 +33,7 @@ __device__ __forceinline__ void cta_merge_emit(WarpList &mine, Cand *mrg, int W,
 // On return the total of row r is in v[0] of the lanes with (lane >> (5 - log2 TR)) == r.
 __device__ __forceinline__ double shfl_xor_t(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
 __device__ __forceinline__ float shfl_xor_t(float v, int m) { return __shfl_xor_sync(FULL, v, m); }
+__device__ __forceinline__ long long shfl_xor_t(long long v, int m) { return __shfl_xor_sync(FULL, v, m); }
 template <int TR, typename T>
 __device__ __forceinline__ void reduce_rows(T (&v)[TR], int lane) {
     constexpr int L = TR == 32 ? 5 : TR == 16 ? 4 : TR == 8 ? 3 : TR == 4 ? 2 : TR == 2 ? 1 : 0;

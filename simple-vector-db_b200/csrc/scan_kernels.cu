@@ -649,7 +649,8 @@ static cudaError_t launch_wide_inst(const ScanTuning &t, const ScanArgs &a, cuda
         if (need(W, NS) > budget) return cudaErrorInvalidValue;
     }
     // the fused tail (finalize in the last CTA) reuses the ring's shared memory
-    const size_t smem = std::max(need(W, NS), a.tail.ticket ? fin_head_bytes(W) + FIN_MIN_TBUF : (size_t)0);
+    const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
+    const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(scan_wide_kernel<TR, NQ, LPR>, smem);
     if (e != cudaSuccess) return e;

@@ -80,6 +80,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     const unsigned long long plane_err_b = p.plane_err_bits ? __ldg(p.plane_err_bits) : 0ull;
     const unsigned long long xn_max_b = p.xn_max_bits ? __ldg(p.xn_max_bits) : 0ull;
     const double qnorm_in = (!p.sq_mode && p.eabs_coef > 0.0) ? __ldg(p.qnorm + qi) : 0.0;
+    const double p8_lo = p.sq_mode == 2 ? __ldg(&p.plane8->lo) : 0.0, p8_step = p.sq_mode == 2 ? __ldg(&p.plane8->step) : 1.0;
     const uint32_t bar = fin_bar_addr(fsm, NW);
     const Cand *sl = reinterpret_cast<const Cand *>(tbuf);
     const int T = blockDim.x;
@@ -113,7 +114,10 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const double r = v[u] - (double)__double2float_rn(v[u]);
+                // q^: K12 scans against fl32(q); K13 against q on the byte plane's query grid (the scan's own expression)
+                const double qh = p.sq_mode == 2 ? p8_lo + p8_step * ((double)p8_quant_q(v[u], p8_lo, p8_step) / 256.0)
+                                                 : (double)__double2float_rn(v[u]);
+                const double r = v[u] - qh;
                 eq2 = fma(r, r, eq2);
                 qn2 = fma(v[u], v[u], qn2);
             }
@@ -129,6 +133,9 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             // E bounds |x - x^| + |q - q^| (2-norms) plus what squares of tiny differences lose to fp32 underflow
             E = __longlong_as_double((long long)plane_err_b) + sqrt(red[0]) * (1.0 + 1e-9) + sqrt((double)p.K) * 1e-22;
             scale = __longlong_as_double((long long)xn_max_b) + red[1];
+            // K13: x^ and q^ are real numbers lo + step * (integer); their fp64 evaluations (plane build, above) are off by
+            // 2^-52 of their size -- far below anything the window notices, but it belongs to E
+            if (p.sq_mode == 2) E += 1e-14 * sqrt(scale);
         } else if (p.eabs_coef > 0.0) {
             // GEMM-form keys (K2, K10) carry an absolute error
             scale = __longlong_as_double((long long)xn_max_b) + qnorm_in;

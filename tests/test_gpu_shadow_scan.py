@@ -1,5 +1,5 @@
-"""GPU parity of K11 (scan_shadow_kernel, csrc/scan_kernels.cu: hi + lo bf16 planes) and K12 (scan_plane_kernel,
-csrc/plane_scan.cu: the hi plane alone, the default): the single-query / small-batch scans over the split-bf16 shadow of
+"""GPU parity of K11 (scan_shadow_kernel, csrc/scan_kernels.cu: hi + lo bf16 planes), K12 (scan_plane_kernel,
+csrc/plane_scan.cu: the hi plane alone) and K13 (scan_plane8_kernel: the one-byte plane, exact integer keys): the single-query / small-batch scans over the split-bf16 shadow of
 the log instead of the fp64 rows (option scan.plane).  Approximate fp32 keys, answers after the reference-order re-rank
 (kdtree.c:134-137) bit-identical to the oracle's; with and without the fused tail (option scan.fuse_tail)."""
 import numpy as np
@@ -16,7 +16,7 @@ from svdb import synth  # noqa: E402
 from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
 
 
-@pytest.mark.parametrize("plane,fuse", [(1, 1), (2, 1), (1, 0), (2, 0)])
+@pytest.mark.parametrize("plane,fuse", [(1, 1), (2, 1), (3, 1), (1, 0), (2, 0), (3, 0)])
 @pytest.mark.parametrize("n,D,K,nq,k,seed", [
     (20000, 128, 128, 1, 1, 1),        # the headline shape in small: one query, top-1
     (9000, 768, 768, 3, 10, 2),        # config-3 rows; passes of 2 + 1 queries
@@ -45,12 +45,55 @@ def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed, plane, fuse):
         for _ in range(3):                                      # the shadow is built before the capture, never inside it
             assert_topk_equal(e.nearest(Q, k), want, k)
         st = e.stats()
-        assert st["exact_reruns"] == 0 and (plane == 2 or st["fp64_reruns"] == 0)
+        assert st["exact_reruns"] == 0 and (plane >= 2 or st["fp64_reruns"] == 0)
+        if plane == 3 and 192 < K <= 1024 and nq <= 2:
+            assert st["scan_plane_last"] == 3            # K13 really ran (kd_dim it supports, one or two queries)
         e.set_option("scan.plane", 0)
         assert_topk_equal(e.nearest(Q, k), want, k)
 
 
-@pytest.mark.parametrize("plane", [1, 2])
+@pytest.mark.parametrize("plane", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["uniform", "normal", "offset", "heavy_tail", "constant_columns"])
+@pytest.mark.parametrize("K", [256, 768, 1000])
+def test_byte_plane_scan_on_distributions(port, kind, K):
+    """K13 on data a store-wide uniform grid resolves well and badly: answers identical to the oracle either way (what the
+    plane cannot prove is re-answered from the fp64 rows); on heavy tails the engine stops using the plane."""
+    rng = np.random.Generator(np.random.PCG64(K + len(kind)))
+    n = 6000
+    if kind == "uniform":
+        rows, Q = rng.random((n, K)), rng.random((12, K))
+    elif kind == "normal":
+        rows, Q = rng.standard_normal((n, K)), rng.standard_normal((12, K))
+    elif kind == "offset":
+        rows, Q = 1000.0 + rng.random((n, K)), 1000.0 + rng.random((12, K))
+    elif kind == "heavy_tail":
+        rows, Q = rng.standard_cauchy((n, K)).clip(-1e6, 1e6), rng.standard_cauchy((12, K)).clip(-1e6, 1e6)
+    else:
+        rows, Q = rng.random((n, K)), rng.random((12, K))
+        rows[:, ::3] = 0.5
+        Q[:, ::3] = 0.5
+    want = oracle_topk(port, rows, K, Q, 5)
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        e.set_option("scan.plane", 3)
+        e.set_option("nearest.umma_min_queries", 0)
+        for i in range(12):
+            assert_topk_equal(e.nearest(Q[i:i + 1], 5), want[i:i + 1], 5)
+        st = e.stats()
+        assert st["exact_reruns"] == 0
+        if kind in ("uniform", "offset", "constant_columns"):
+            assert st["scan_plane_last"] == 3 and st["fp64_reruns"] <= 2
+        # queries far outside the grid: the query's own quantisation error makes the proof fail, K1 answers
+        far = Q[:2] * 50.0 + 7.0
+        assert_topk_equal(e.nearest(far[:1], 5), oracle_topk(port, rows, K, far[:1], 5), 5)
+        # rows appended after the grid was fixed, outside its range: clamped, measured, still exact answers
+        more = rows[:40] * 3.0 + 2.0
+        e.insert(more)
+        allrows = np.vstack([rows, more])
+        for q in (Q[0:1], more[7:8]):
+            assert_topk_equal(e.nearest(q, 5), oracle_topk(port, allrows, K, q, 5), 5)
+
+
 def test_shadow_scan_follows_inserts_and_extremes(port, plane):
     D = 64
     rng = np.random.Generator(np.random.PCG64(7))

@@ -1,0 +1,153 @@
+"""The square-root-form key error bound of the single-plane scans (csrc/plane_scan.cu, csrc/tail.cuh: FinalArgs::sq_mode),
+checked in numpy.  K12 forms key = |x^ - fl32(q)|^2 in fp32 from the bf16 hi plane x^ = bf16(fl32(x)); K13 forms
+key = |x^ - q^|^2 EXACTLY (integer dot products) from a one-byte plane x^ = lo + step * u and a 16-bit query grid.  Both hand
+finalize   | sqrt(key) - sqrt(d) | <= E + gamma (sqrt(d) + E),   E = max_r |x_r - x^_r|_2 + |q - q^|_2,
+from which it derives the re-rank window and the completeness proof.  A bound that were too small would mean silently
+wrong answers, so the inequality AND the two decisions finalize takes from it are pinned here, on benign and on
+adversarial inputs (the CUDA paths are pinned against the oracle in tests/test_gpu_shadow_scan.py)."""
+import numpy as np
+import pytest
+
+from test_umma_bound import split
+
+
+def make(kind, n, nq, K, rng):
+    if kind == "uniform":
+        return rng.random((n, K)), rng.random((nq, K))
+    if kind == "normal":
+        return rng.standard_normal((n, K)), rng.standard_normal((nq, K))
+    if kind == "near_query":
+        q = rng.random((nq, K))
+        return np.repeat(q, n // nq, axis=0) + 1e-3 * rng.standard_normal((n, K)), q
+    if kind == "offset":
+        return 1000.0 + rng.random((n, K)), 1000.0 + rng.random((nq, K))
+    if kind == "cauchy":
+        return rng.standard_cauchy((n, K)).clip(-1e3, 1e3), rng.standard_cauchy((nq, K)).clip(-1e3, 1e3)
+    if kind == "sparse":
+        return (np.where(rng.random((n, K)) < 0.05, rng.standard_normal((n, K)) * 100, 0.0),
+                np.where(rng.random((nq, K)) < 0.05, rng.standard_normal((nq, K)) * 100, 0.0))
+    if kind == "small_integers":
+        return rng.integers(-3, 4, (n, K)).astype(float), rng.integers(-3, 4, (nq, K)).astype(float)
+    if kind == "query_outside":      # queries far outside the range the plane's grid covers
+        return rng.random((n, K)), 3.0 + 5.0 * rng.random((nq, K))
+    mag = 10.0 ** rng.integers(-3, 3, size=K).astype(float)
+    return rng.standard_normal((n, K)) * mag, rng.standard_normal((nq, K)) * mag
+
+
+KINDS = ["uniform", "normal", "near_query", "offset", "cauchy", "sparse", "small_integers", "query_outside", "mixed_magnitudes"]
+
+
+# ---- K12: bf16 hi plane, fp32 arithmetic ---------------------------------------------------------------------------
+def k12_keys(x, q):
+    """fp32 emulation of scan_plane_kernel: lane l owns coordinates trip * 256 + l * 8 .. + 7, two FMA chains per slice."""
+    n, K = x.shape
+    Kp = -(-K // 64) * 64
+    trips = -(-Kp // 256)
+    xh = np.zeros((n, trips * 256), np.float32)
+    xh[:, :K] = split(x)[0].astype(np.float32)
+    out = np.empty((n, q.shape[0]))
+    for j in range(q.shape[0]):
+        qf = np.zeros(trips * 256, np.float32)
+        qf[:K] = q[j].astype(np.float32)
+        d = (xh - qf).astype(np.float32).reshape(n, trips, 32, 8)
+        acc = np.zeros((n, 32), np.float32)
+        for t in range(trips):
+            a0, a1 = acc.copy(), np.zeros((n, 32), np.float32)
+            for c in range(0, 8, 2):
+                a0 = (d[:, t, :, c].astype(np.float64) ** 2 + a0).astype(np.float32)         # fmaf
+                a1 = (d[:, t, :, c + 1].astype(np.float64) ** 2 + a1).astype(np.float32)
+            acc = (a0 + a1).astype(np.float32)
+        m = 16
+        while m >= 1:
+            acc = (acc + acc[:, np.arange(32) ^ m]).astype(np.float32)
+            m >>= 1
+        out[:, j] = acc[:, 0]
+    return out, Kp
+
+
+def k12_terms(x, q, Kp):
+    xh = split(x)[0].astype(np.float64)
+    ex = np.sqrt(((x - xh) ** 2).sum(1)).max() * (1 + 1e-12)
+    eq = np.sqrt(((q - q.astype(np.float32)) ** 2).sum(1)) * (1 + 1e-9)
+    return ex + eq + np.sqrt(x.shape[1]) * 1e-22, (Kp / 32.0 + 12.0) * 2.0 ** -24
+
+
+# ---- K13: one-byte plane, exact integer keys ------------------------------------------------------------------------
+def k13_grid(x):
+    lo, hi = float(x.min()), float(x.max())
+    step = (hi - lo) / 255.0 if hi > lo else 1.0
+    return lo, step
+
+
+def k13_keys(x, q, lo, step):
+    u = np.clip(np.rint((x - lo) / step), 0, 255).astype(np.int64)
+    Q = np.clip(np.rint(256.0 * ((q - lo) / step)), 0, 65535).astype(np.int64)
+    out = np.empty((x.shape[0], q.shape[0]))
+    for j in range(q.shape[0]):
+        a, b = Q[j] >> 8, Q[j] & 255
+        key_int = 65536 * (u * u).sum(1) - 512 * (256 * (u * a).sum(1) + (u * b).sum(1)) + (Q[j] * Q[j]).sum()
+        assert np.all(key_int == ((256 * u - Q[j]) ** 2).sum(1))                              # the kernel's decomposition is exact
+        out[:, j] = key_int.astype(np.float64) * (step / 256.0) ** 2
+    xhat = lo + step * u
+    qhat = lo + step * (Q / 256.0)
+    ex = np.sqrt(((x - xhat) ** 2).sum(1)).max() * (1 + 1e-12)
+    eq = np.sqrt(((q - qhat) ** 2).sum(1)) * (1 + 1e-9)
+    return out, ex + eq, 2.0 ** -50
+
+
+def check_sqrt_form(key, d, E, gamma):
+    lhs = np.abs(np.sqrt(key) - np.sqrt(d))
+    rhs = E[None, :] + gamma * (np.sqrt(d) + E[None, :])
+    assert np.all(lhs <= rhs * (1 + 1e-9) + 1e-300), float((lhs / rhs).max())
+
+
+def check_finalize_decisions(key, d, E, gamma, k, K, rng):
+    """What tail.cuh does with the bound: (1) the candidates are the entries with key <= window(dk), dk = k-th smallest key
+    -- every member of the TRUE top-k must be among them; (2) entries whose key is >= `bound` have d >= lb^2."""
+    eps64 = 4.0 * (K + 2) * 2.0 ** -53
+    for j in range(key.shape[1]):
+        dk = np.sort(key[:, j])[k - 1]
+        U = np.sqrt(dk) / (1.0 - gamma) + E[j]
+        lim = ((U * (1.0 + eps64) + E[j]) * (1.0 + gamma)) ** 2 * (1.0 + 1e-12)
+        cand = key[:, j] <= lim
+        true_topk = np.argsort(d[:, j], kind="stable")[:k]
+        assert np.all(cand[true_topk]), "a true top-k row fell outside the re-rank window"
+        bound = np.quantile(key[:, j], rng.random())                                           # any cut: the proof is per entry
+        lb = np.sqrt(bound) / (1.0 + gamma) - E[j]
+        if lb > 0:
+            assert np.all(d[key[:, j] >= bound, j] >= lb * lb * (1.0 - eps64 - 1e-12))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("K,seed", [(768, 1), (100, 2), (320, 3)])
+def test_k12_hi_plane_key_bound(kind, K, seed):
+    rng = np.random.default_rng(seed + 17 * KINDS.index(kind))
+    x, q = make(kind, 200, 4, K, rng)
+    d = ((x[:, None, :] - q[None, :, :]) ** 2).sum(-1)
+    key, Kp = k12_keys(x, q)
+    E, gamma = k12_terms(x, q, Kp)
+    check_sqrt_form(key, d, E, gamma)
+    for k in (1, 5):
+        check_finalize_decisions(key, d, E, gamma, k, K, rng)
+    if kind == "uniform" and K == 768:      # not vacuous: the window around a distance of ~100 is a fraction of a unit wide
+        assert E.max() < 0.03
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("K,seed", [(768, 1), (256, 2), (300, 3)])
+def test_k13_byte_plane_key_bound(kind, K, seed):
+    rng = np.random.default_rng(seed + 31 * KINDS.index(kind))
+    x, q = make(kind, 200, 4, K, rng)
+    d = ((x[:, None, :] - q[None, :, :]) ** 2).sum(-1)
+    lo, step = k13_grid(x)
+    key, E, gamma = k13_keys(x, q, lo, step)
+    check_sqrt_form(key, d, E, gamma)
+    for k in (1, 5):
+        check_finalize_decisions(key, d, E, gamma, k, K, rng)
+    if kind == "uniform" and K == 768:
+        assert E.max() < 0.04
+    # rows appended AFTER the grid was fixed may lie outside it: they are clamped and the measured plane error grows
+    x2 = np.vstack([x, x[:5] * 3.0 + 1.0])
+    d2 = ((x2[:, None, :] - q[None, :, :]) ** 2).sum(-1)
+    key2, E2, _ = k13_keys(x2, q, lo, step)
+    check_sqrt_form(key2, d2, E2, gamma)
