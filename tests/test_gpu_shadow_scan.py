@@ -52,7 +52,6 @@ def test_shadow_scan_vs_oracle(port, n, D, K, nq, k, seed, plane, fuse):
         assert_topk_equal(e.nearest(Q, k), want, k)
 
 
-@pytest.mark.parametrize("plane", [1, 2, 3])
 @pytest.mark.parametrize("kind", ["uniform", "normal", "offset", "heavy_tail", "constant_columns"])
 @pytest.mark.parametrize("K", [256, 768, 1000])
 def test_byte_plane_scan_on_distributions(port, kind, K):
@@ -94,6 +93,7 @@ def test_byte_plane_scan_on_distributions(port, kind, K):
             assert_topk_equal(e.nearest(q, 5), oracle_topk(port, allrows, K, q, 5), 5)
 
 
+@pytest.mark.parametrize("plane", [1, 2, 3])
 def test_shadow_scan_follows_inserts_and_extremes(port, plane):
     D = 64
     rng = np.random.Generator(np.random.PCG64(7))
