@@ -302,6 +302,9 @@ int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count);
  * stamps (ns): [0] the last CTA took its ticket, [1] CTA lists merged, [2] re-rank done, [3] answers stored to the peers,
  * [4] every peer's answers have landed, [5] merged; [32 + b] CTA b finished its part of the scan ([9..14]: phases inside the re-rank).  count <= 32 + CTAs. */
 int svdb_debug_tail_times(svdb_engine *e, unsigned long long *out, size_t count);
+/* Diagnostics of K13 (the one-byte plane of the log): par_out = { lo, step, measured max |x - x^| }, bytes_out (may be NULL)
+ * receives the first nbytes bytes of the plane. */
+int svdb_debug_plane8(svdb_engine *e, double par_out[3], unsigned char *bytes_out, size_t nbytes);
 
 #ifdef __cplusplus
 }

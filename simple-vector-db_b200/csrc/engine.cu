@@ -567,8 +567,10 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
             else if (sr != -1000) return sr;
         }
     }
-    last_scan_plane = plane;
-    stats.scan_plane_last = (uint64_t)plane;
+    if (!fp64_only) {                    // an escalation step must not hide which copy of the log the call itself scanned
+        last_scan_plane = plane;
+        stats.scan_plane_last = (uint64_t)plane;
+    }
 
     const double *qbase = d_Q;
     int qld = (int)ldq;
@@ -1903,6 +1905,25 @@ int svdb_debug_tail_times(svdb_engine *e, unsigned long long *out, size_t count)
     cudaError_t ce = cudaStreamSynchronize(e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpy(out, e->tail_dbg.p, count * 8, cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) return e->fail_cuda("debug_tail_times", ce);
+    return SVDB_OK;
+}
+
+/* Diagnostics of K13: the byte plane's grid (lo, step), its measured error and the first `nbytes` bytes of the plane. */
+int svdb_debug_plane8(svdb_engine *e, double par_out[3], unsigned char *bytes_out, size_t nbytes) {
+    if (!e || !par_out) return SVDB_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->plane8_ready) return e->fail(SVDB_ERR_ARG, "no byte plane yet");
+    cudaSetDevice(e->device);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    Plane8Par hp;
+    unsigned long long errw = 0;
+    if (ce == cudaSuccess) ce = cudaMemcpy(&hp, e->plane8_par.p, sizeof hp, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(&errw, e->plane8_par.as<unsigned char>() + sizeof(Plane8Par), 8, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && bytes_out && nbytes) ce = cudaMemcpy(bytes_out, e->plane8.as<unsigned char>(), nbytes, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) return e->fail_cuda("debug_plane8", ce);
+    par_out[0] = hp.lo;
+    par_out[1] = hp.step;
+    memcpy(&par_out[2], &errw, 8);
     return SVDB_OK;
 }
 

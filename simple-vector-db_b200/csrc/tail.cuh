@@ -117,7 +117,7 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
                 // q^: K12 scans against fl32(q); K13 against q on the byte plane's query grid (the scan's own expression)
                 const double qh = p.sq_mode == 2 ? p8_lo + p8_step * ((double)p8_quant_q(v[u], p8_lo, p8_step) / 256.0)
                                                  : (double)__double2float_rn(v[u]);
-                const double r = v[u] - qh;
+                const double r = i0 + u * T + (int)threadIdx.x < p.K ? v[u] - qh : 0.0;     // slots beyond K are not coordinates
                 eq2 = fma(r, r, eq2);
                 qn2 = fma(v[u], v[u], qn2);
             }
@@ -262,6 +262,13 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             }
         }
         __syncthreads();
+        if (dbg && threadIdx.x == 0) {                   // diagnostics: what the selection saw
+            dbg[16] = (unsigned long long)__double_as_longlong(E);
+            dbg[17] = (unsigned long long)__double_as_longlong(lim);
+            dbg[18] = (unsigned long long)__double_as_longlong(dk);
+            dbg[19] = cseq[32];
+            dbg[20] = (unsigned long long)__double_as_longlong(bound);
+        }
         const unsigned found = (unsigned)cseq[32];
         overflow = found > 32u;                          // more near-ties than lanes: not provable here (-> fp64 / exact rerun)
         nneed = (int)min(found, 32u);

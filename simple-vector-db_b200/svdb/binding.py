@@ -75,7 +75,7 @@ NATIVE_SYMBOLS = [
     "svdb_get_stats", "svdb_set_option", "svdb_time_scan", "svdb_take_scan_time", "svdb_debug_filter_keys",
     "svdb_engine_load_file", "svdb_save_file", "svdb_get_uuid", "svdb_set_uuid",
     "svdb_exchange_create", "svdb_exchange_connect", "svdb_exchange_destroy", "svdb_exchange_merge",
-    "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded", "svdb_nearest_batch_device_sharded", "svdb_debug_tail_times",
+    "svdb_nearest_batch_sharded", "svdb_tie_resolve", "svdb_resolve_ties_sharded", "svdb_nearest_batch_device_sharded", "svdb_debug_tail_times", "svdb_debug_plane8",
 ]
 # every symbol include/svdb_dropin.h declares (the reference's L1 API + two batched extensions)
 DROPIN_SYMBOLS = [
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.svdb_take_scan_time.argtypes = [C.c_void_p, _fp, _u64p]
     L.svdb_debug_filter_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.svdb_debug_tail_times.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.svdb_debug_plane8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.svdb_engine_load_file.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
     L.svdb_save_file.argtypes = [C.c_void_p, C.c_char_p]
     L.svdb_exchange_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
@@ -347,6 +348,13 @@ class Engine:
         out = np.empty((128, bn), dtype=np.float32)
         _check(self.L.svdb_debug_filter_keys(self.h, C.c_void_p(out.ctypes.data), out.size), "svdb_debug_filter_keys")
         return out
+
+    def debug_plane8(self, nbytes: int = 0):
+        """K13's grid (lo, step), the measured plane error, and the first nbytes bytes of the plane."""
+        par = np.zeros(3, dtype=np.float64)
+        raw = np.zeros(max(1, nbytes), dtype=np.uint8)
+        _check(self.L.svdb_debug_plane8(self.h, C.c_void_p(par.ctypes.data), C.c_void_p(raw.ctypes.data), nbytes), "svdb_debug_plane8")
+        return par[0], par[1], par[2], raw[:nbytes]
 
     def debug_tail_times(self, n_ctas: int = 296) -> np.ndarray:
         out = np.zeros(32 + n_ctas, dtype=np.uint64)
