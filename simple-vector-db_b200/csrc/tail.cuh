@@ -470,16 +470,16 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
         const unsigned mk = __ballot_sync(FULL, valid && rank == p.k - 1);
         const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
 
-        bool unsafe = overflow;
+        bool unsafe = overflow;                          // more entries inside the window than candidate slots: not provable here
         if (approx && bound < CUDART_INF) {
             if (p.sq_mode) {
                 // entries outside the candidate set have key >= bound, hence sqrt(d) >= sqrt(bound)/(1 + gamma) - E
                 const double lb = sqrt(bound) / (1.0 + p.sq_gamma) - E;
-                unsafe = nvalid < p.k || !(lb > 0.0 && ek < lb * lb * (1.0 - eps64 - 1e-12));
+                unsafe = unsafe || nvalid < p.k || !(lb > 0.0 && ek < lb * lb * (1.0 - eps64 - 1e-12));
             } else {
                 // entries outside the candidate set have approximate key >= bound, hence reference
                 // distance >= bound * (1 - eps); they cannot enter the top-k iff ek is strictly below
-                unsafe = nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
+                unsafe = unsafe || nvalid < p.k || !(ek < bound * (1.0 - p.eps) - eabs);
             }
         }
         if (p.scale_hi > 0.0) {
