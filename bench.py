@@ -397,7 +397,7 @@ def ours(args):
         except Exception as ex:  # noqa: BLE001
             fp64_scan = {"error": f"{type(ex).__name__}: {ex}"}
         finally:
-            e.set_option("scan.plane", 2 if not any(kv.startswith("scan.plane=") or kv.startswith("scan.shadow=") for kv in args.opt)
+            e.set_option("scan.plane", 3 if not any(kv.startswith("scan.plane=") or kv.startswith("scan.shadow=") for kv in args.opt)
                          else plane_used)
             e.set_option("profile.scan_events", 0)
 

@@ -97,7 +97,7 @@ struct svdb_engine {
     // per coordinate), 2 the hi plane alone (K12, 2 bytes per coordinate), 3 the one-byte plane (K13; kd_dim 193..1024,
     // else 2 serves).  Same answers on every setting:
     // whatever the re-rank cannot prove complete is re-answered from the fp64 rows.
-    int scan_plane = 2;
+    int scan_plane = 3;
     bool fuse_tail = true;               // the scan's last CTA runs finalize (and the cross-shard exchange) itself
     int dyn_tiles = 0;                   // option "scan.dynamic_tiles": eighths of the log K12 hands out dynamically (A/B; slower)
     bool tail_debug = false;             // option "scan.tail_debug": fused tails leave %globaltimer stamps in tail_dbg
