@@ -550,7 +550,9 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
-        if (scan_plane >= 3 && plane8_ok && plane8_scan_supports(Kp) && nq <= 2) want = 3;
+        // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour, so top-k
+        // calls beyond k = 4 would overflow the 32 candidate slots and pay for a second scan -- they stay on K12
+        if (scan_plane >= 3 && plane8_ok && plane8_scan_supports(Kp) && nq <= 2 && k <= 4) want = 3;
         if (want == 3) {
             const bool have8 = plane8_ready && plane8_n == n_versions;
             if (cs == cudaStreamCaptureStatusNone || have8) {
@@ -940,11 +942,12 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        if (few && scan_plane >= 3 && plane8_ok && plane8_scan_supports(umma_kpad(K)) && nq <= 2) {
+        const bool byte_plane = few && scan_plane >= 3 && plane8_ok && plane8_scan_supports(umma_kpad(K)) && nq <= 2 && k <= 4;
+        if (byte_plane) {
             rc = ensure_plane8();
             if (rc && rc != -1000) return rc;
         }
-        if (!(few && scan_plane >= 3 && plane8_ready && plane8_n == n_versions) || to_umma) {
+        if (!(byte_plane && plane8_ready && plane8_n == n_versions) || to_umma) {
             rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1));
             if (rc && rc != -1000) return rc;
         }
