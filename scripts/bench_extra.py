@@ -52,7 +52,7 @@ def fill(e: B.Engine, n: int, D: int, seed: int, chunk: int = 250_000):
     torch.cuda.empty_cache()
 
 
-PLANE_BYTES = {0: 8, 1: 4, 2: 2}      # bytes per coordinate of the copy of the log a single-query scan streams (engine stat scan_plane_last)
+PLANE_BYTES = {0: 8, 1: 4, 2: 2, 3: 1}      # bytes per coordinate of the copy of the log a single-query scan streams (engine stat scan_plane_last)
 
 
 def nearest_parity(e: B.Engine, n: int, D: int, K: int, seed: int, k: int, nq: int = 8):
@@ -127,7 +127,7 @@ def nearest_case(name, n, D, K, k, nqs, iters=20, extra_opts=(), parity=False):
             out.append({"config": name, "rows": n, "dim": D, "kd_dim": K, "k": k, "queries_per_call": nq,
                         "ms_per_call": ms, "queries_per_s": nq / ms * 1e3, "e2e_queries_per_s": nq / e2e_ms * 1e3,
                         "scan_launches_per_call": passes, "scan_ms_per_launch": scan_ms,
-                        "scan_reads": {0: "fp64 rows (or a tree / tensor-core path)", 1: "hi + lo bf16 planes", 2: "bf16 hi plane"}[plane],
+                        "scan_reads": {0: "fp64 rows (or a tree / tensor-core path)", 1: "hi + lo bf16 planes", 2: "bf16 hi plane", 3: "one-byte plane"}[plane],
                         "scan_GBps_algorithmic": algo / scan_ms / 1e6 if scan_ms > 0 else None,
                         "frac_of_measured_peak": algo / scan_ms / 1e6 / PEAK if scan_ms > 0 else None,
                         "fp64_pass_ms_at_peak": n * K * 8 / PEAK / 1e6, "ingest_s": ingest_s,
