@@ -549,7 +549,11 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         // never build or extend the shadow under stream capture (see nearest_host): fall back to the fp64 rows there
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
-        int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) ? 2 : 1;
+        // The coarser the plane, the wider the re-rank window: K12's holds ~2.3 candidates per requested neighbour at
+        // 10M x 768, so top-10 calls overflow the 32 candidate slots every other time (and pay for an fp64 scan on top);
+        // from k = 7 on the hi + lo planes (K11: a window of exactly k rows) are the cheaper choice.
+        // (K11's kernel is not tuned for short rows -- 0.27 ms vs K1's 0.19 at 1M x 128 -- so those stay on the fp64 rows.)
+        int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) && k <= 6 ? 2 : (Kp >= 384 || scan_plane == 1 ? 1 : 0);
         // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour, so top-k
         // calls beyond k = 4 would overflow the 32 candidate slots and pay for a second scan -- they stay on K12
         if (scan_plane >= 3 && plane8_ok && plane8_scan_supports(Kp) && nq <= 2 && k <= 4) want = 3;
@@ -563,7 +567,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
             if (plane != 3) want = 2;
         }
         const bool have = shadow_ready && shadow_n == n_versions && (want == 2 || shadow_lo_n == n_versions);
-        if (plane != 3 && (cs == cudaStreamCaptureStatusNone || have)) {
+        if (plane != 3 && want != 0 && (cs == cudaStreamCaptureStatusNone || have)) {
             const int sr = ensure_shadow(want == 1);
             if (sr == SVDB_OK) plane = want;
             else if (sr != -1000) return sr;
@@ -948,7 +952,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
             if (rc && rc != -1000) return rc;
         }
         if (!(byte_plane && plane8_ready && plane8_n == n_versions) || to_umma) {
-            rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1));
+            rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1) || k > 6);
             if (rc && rc != -1000) return rc;
         }
     }
