@@ -92,8 +92,9 @@ def main():
                     same = same and np.array_equal(few["seq"], wseq[:3]) and np.array_equal(few["dist"].view(np.uint64), wdist[:3].view(np.uint64))
                     single = all(np.array_equal(o["seq"][0], wseq[i]) and np.array_equal(o["index"][0], widx[i]) and
                                  np.array_equal(o["dist"][0].view(np.uint64), wdist[i].view(np.uint64)) for i, o in enumerate(ones))
-                    # the device entry point leaves exact ties between distinct points to its caller (SVDB_CAND_TIE)
-                    single_dev = all((o["flags"][0, 0] & B.CAND_TIE) or
+                    # the device entry point leaves exact ties between distinct points (SVDB_CAND_TIE) and answers it could not
+                    # prove complete (SVDB_CAND_UNSAFE: rerun with SVDB_MODE_FP64 / EXACT) to its caller
+                    single_dev = all((o["flags"][0, 0] & (B.CAND_TIE | B.CAND_UNSAFE)) or
                                      (np.array_equal(o["seq"][0], wseq[i]) and np.array_equal(o["dist"][0].view(np.uint64), wdist[i].view(np.uint64)))
                                      for i, o in enumerate(ones_dev))
                     same = same and single and single_dev
