@@ -320,9 +320,8 @@ void vector_db_update(VectorDatabase *db, size_t index, Vector vec) {
             pthread_mutex_unlock(&db->mutex);
             return;
         }
-        free(db->vectors[index].data);
-        db->vectors[index] = vec;
-        if (!d->unified) kdtree_insert(db->kdtree, vec.data, index);   // :174; unified: the update below re-appends
+        // the HBM side first: the host table changes only once the engine has taken the update, so a failure (device out
+        // of memory, a CUDA error) leaves host table, kd log and rows engine consistent -- the index keeps its old row
         const bool same = d->rows && vec.dimension == d->row_dim;
         if (d->rows) {
             std::vector<double> z;
@@ -331,9 +330,17 @@ void vector_db_update(VectorDatabase *db, size_t index, Vector vec) {
                 z.assign(d->row_dim, 0.0);
                 src = z.data();
             }
-            if (svdb_update_batch(d->rows, &index, src, 1, d->row_dim) != SVDB_OK) complain("vector_db_update");
+            if (svdb_update_batch(d->rows, &index, src, 1, d->row_dim) != SVDB_OK) {
+                complain("vector_db_update");
+                free(vec.data);                       // ours since the call (vector_database.c:172 frees the OLD row; we keep it)
+                pthread_mutex_unlock(&db->mutex);
+                return;
+            }
             d->dim_ok[index] = same ? 1 : 0;
         }
+        if (!d->unified) kdtree_insert(db->kdtree, vec.data, index);   // :174; unified: the update above re-appended
+        free(db->vectors[index].data);
+        db->vectors[index] = vec;
     }
     pthread_mutex_unlock(&db->mutex);
 }
@@ -404,6 +411,18 @@ VectorDatabase *vector_db_load(const char *filename, size_t dimension) {
             fprintf(stderr, "svdb_b200: vector_db_load: short row %zu\n", i);
             free(v.data);
             break;
+        }
+        if (db->kdtree && v.dimension < db->kdtree->dimension) {
+            // a row shorter than kd_dim: the reference's tree would read past it (kdtree.c:26-28).  Keep the row's slot --
+            // later rows keep the index the file gives them -- with the missing coordinates as zeros.
+            fprintf(stderr, "svdb_b200: vector_db_load: row %zu has %zu < kd_dim values, zero-padded to kd_dim\n", i, v.dimension);
+            double *p = (double *)calloc(db->kdtree->dimension, sizeof(double));
+            if (p) {
+                memcpy(p, v.data, v.dimension * sizeof(double));
+                free(v.data);
+                v.data = p;
+                v.dimension = db->kdtree->dimension;
+            }
         }
         if (vector_db_insert(db, v) == (size_t)-1) {
             free(v.data);
