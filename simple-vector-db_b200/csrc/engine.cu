@@ -458,7 +458,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         return SVDB_OK;
     }
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
-    const int cap = (int)std::min<size_t>(32, k + 8);
+    int cap = (int)std::min<size_t>(32, k + 8);
     // K10: larger batches go to the tcgen05 tensor cores (split-bf16 keys, same exact re-rank)
     if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_min_q > 0 && nq >= (size_t)umma_min_q &&
         K >= umma_min_k && n_versions < (1ull << 31)) {
@@ -550,13 +550,13 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         // The coarser the plane, the wider the re-rank window: K12's holds ~2.3 candidates per requested neighbour at
-        // 10M x 768, so top-10 calls overflow the 32 candidate slots every other time (and pay for an fp64 scan on top);
-        // from k = 7 on the hi + lo planes (K11: a window of exactly k rows) are the cheaper choice.
+        // 10M x 768, K13's ~4; a window that overflows the tail's candidate slots costs an fp64 scan on top.  Beyond
+        // plane_max_k the hi + lo planes (K11: a window of exactly k rows) are the cheaper choice.
         // (K11's kernel is not tuned for short rows -- 0.27 ms vs K1's 0.19 at 1M x 128 -- so those stay on the fp64 rows.)
-        int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) && k <= 6 ? 2 : (Kp >= 384 || scan_plane == 1 ? 1 : 0);
-        // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour, so top-k
-        // calls beyond k = 4 would overflow the 32 candidate slots and pay for a second scan -- they stay on K12
-        if (scan_plane >= 3 && plane8_ok && plane8_scan_supports(Kp) && nq <= 2 && k <= 4) want = 3;
+        int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) && k <= (size_t)plane_max_k ? 2 : (Kp >= 384 || scan_plane == 1 ? 1 : 0);
+        // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour; the tail
+        // re-ranks up to FIN_NC = 128 of them (one thread each)
+        if (scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && plane8_scan_supports(Kp) && nq <= 2 && k <= (size_t)plane8_max_k) want = 3;
         if (want == 3) {
             const bool have8 = plane8_ready && plane8_n == n_versions;
             if (cs == cudaStreamCaptureStatusNone || have8) {
@@ -573,6 +573,10 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
             else if (sr != -1000) return sr;
         }
     }
+    // the single-plane scans' tail selects its candidates from ALL the CTA lists at once (tail.cuh, selection path: lists
+    // shorter than 16 entries that fit shared memory together); a CTA that holds more than `cap` of a query's window
+    // fails the completeness proof and the query is re-answered from the fp64 rows
+    if (plane >= 2) cap = std::min(cap, 15);
     if (!fp64_only) {                    // an escalation step must not hide which copy of the log the call itself scanned
         last_scan_plane = plane;
         stats.scan_plane_last = (uint64_t)plane;
@@ -946,13 +950,14 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        const bool byte_plane = few && scan_plane >= 3 && plane8_ok && plane8_scan_supports(umma_kpad(K)) && nq <= 2 && k <= 4;
+        const bool byte_plane = few && scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && plane8_scan_supports(umma_kpad(K)) && nq <= 2 &&
+                            k <= (size_t)plane8_max_k;
         if (byte_plane) {
             rc = ensure_plane8();
             if (rc && rc != -1000) return rc;
         }
         if (!(byte_plane && plane8_ready && plane8_n == n_versions) || to_umma) {
-            rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1) || k > 6);
+            rc = ensure_shadow(to_umma || scan_plane == 1 || !plane_scan_supports(umma_kpad(K), 1) || k > (size_t)plane_max_k);
             if (rc && rc != -1000) return rc;
         }
     }
@@ -1050,10 +1055,11 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     if (last_scan_plane == 3) {
         // a store-wide uniform grid resolves some data badly (heavy tails, a few huge coordinates): the measured plane error
         // then makes most proofs fail and every query pays for two scans.  Stop using the plane when that shows.
-        p8_calls += nq;
-        for (size_t i = 0; i < nq; i++) p8_unsafe += (res[i * k].flags & SVDB_CAND_UNSAFE) ? 1 : 0;
-        if (p8_calls >= 8 && p8_unsafe * 4 > p8_calls) {
-            plane8_ok = false;
+        const int cls = k > 4 ? 1 : 0;
+        p8_calls[cls] += nq;
+        for (size_t i = 0; i < nq; i++) p8_unsafe[cls] += (res[i * k].flags & SVDB_CAND_UNSAFE) ? 1 : 0;
+        if (p8_calls[cls] >= 8 && p8_unsafe[cls] * 4 > p8_calls[cls]) {
+            (cls ? plane8_ok_bigk : plane8_ok) = false;
             opt_gen++;                       // captured graphs baked the plane's scan in
         }
     }
@@ -1816,6 +1822,8 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
+    else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);
+    else if (n == "scan.plane8_max_k") e->plane8_max_k = (int)std::max(0l, value);
     else if (n == "umma.debug_keys") e->umma_debug = value != 0;
     else if (n == "umma.resident_queries") e->umma_resident = value != 0;
     else if (n == "scan.shadow") e->scan_plane = value != 0 ? 1 : 0;      // round-1 name: 1 = K11 (hi + lo planes), 0 = fp64 rows

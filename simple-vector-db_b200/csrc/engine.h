@@ -78,6 +78,8 @@ struct svdb_engine {
     // ~0.65 fp64 HBM passes at kd_dim 768 (K2: 1.4 - 4 passes), so it takes over from 3 queries on for kd_dim >= 256; for
     // shorter rows its per-tile epilogue dominates and K2 stays ahead up to 16 queries (set in init(); -1 = not chosen yet).
     int umma_min_q = -1, umma_min_k = 32;
+    // largest k the single-plane scans serve (a coarser key means a wider re-rank window: more rows for the tail to fetch)
+    int plane_max_k = 24, plane8_max_k = 16;
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the hi plane ...
     size_t shadow_lo_n = 0;              // ... and in the lo plane (built when K10 / K11 first ask for it: K12 reads hi only)
@@ -89,7 +91,10 @@ struct svdb_engine {
     svdb::Scratch plane8_par;
     bool plane8_ready = false, plane8_ok = true;
     size_t plane8_n = 0, plane8_mapped_counted = 0;
-    uint64_t p8_calls = 0, p8_unsafe = 0;      // queries K13 answered / could not prove: the engine stops using the plane
+    // queries K13 answered / could not prove, by result size (k <= 4, k > 4: larger k means a wider re-rank window): the engine
+    // stops using the plane for a class whose proofs mostly fail (plane8_ok covers k <= 4 and every k, plane8_ok_bigk only k > 4)
+    uint64_t p8_calls[2] = {0, 0}, p8_unsafe[2] = {0, 0};
+    bool plane8_ok_bigk = true;
                                                // for data its grid resolves badly (nearest_host)
     int ensure_plane8();                 // SVDB_OK, an error, or -1000: not available
     svdb::Scratch qsplit, ubuf, udbg, plane_err, ticket, xlocal;

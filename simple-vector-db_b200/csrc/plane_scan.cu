@@ -282,8 +282,11 @@ cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaS
 // Data a uniform grid resolves badly (heavy tails, a few huge coordinates) shows up as a large measured error: the
 // proof fails, the query is re-answered from the fp64 rows, and the engine stops using the plane (engine.cu).
 // =====================================================================================================================
-template <int TRIPS, int TR>
+// LPR = 32: a warp walks one row per step (8 bytes per lane and 256-coordinate trip).  LPR = 16 / 8 (TRIPS = 1, Kp = 128 / 64):
+// 2 / 4 rows side by side, 32 rows per round, TR / 32 rounds per tile (tiles of 8 KB whatever the row length).
+template <int TRIPS, int TR, int LPR>
 __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_constant__ Plane8ScanArgs p, int nstages, int smem_bytes) {
+    static_assert(LPR == 32 || (TRIPS == 1 && TR % 32 == 0), "packed rows: one trip, whole rounds of 32 rows");
     extern __shared__ __align__(128) unsigned char smem[];
     if (p.tail.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
     const int W = blockDim.x >> 5;
@@ -319,14 +322,15 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         }
     }
 
-    // the query's digits, packed like the plane's bytes: lane l owns coordinates trip * 256 + l * 8 .. + 7
+    // the query's digits, packed like the plane's bytes: lane (j = lane % LPR) owns coordinates trip * 256 + j * 8 .. + 7
     const double lo = p.par->lo, step = p.par->step;
+    const int pj = lane % LPR, pg = lane / LPR;
     uint32_t qa[TRIPS][2], qb[TRIPS][2];
     bool act[TRIPS];
     long long qq = 0;                                   // sum Q_i^2 over the lane's coordinates
 #pragma unroll
     for (int t = 0; t < TRIPS; t++) {
-        const int c0 = t * 256 + lane * 8;
+        const int c0 = t * 256 + pj * 8;
         act[t] = c0 < Kp;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         }
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) qq += __shfl_xor_sync(FULL, qq, m);
+    for (int m = LPR / 2; m >= 1; m >>= 1) qq += __shfl_xor_sync(FULL, qq, m);     // every group of LPR lanes holds the whole query
     const double c2 = (step / 256.0) * (step / 256.0);
 
     WarpList wl;
@@ -353,36 +357,69 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
     uint32_t phase = 0;
     for (u64 t = gw; t < ntiles; t += GW) {
         mbar_wait(my_bar + 8 * s, phase);
-        long long v[TR];
-        const uint32_t sa = my_stage + s * tile_bytes + lane * 8;
-#pragma unroll
-        for (int r = 0; r < TR; r++) {
-            uint32_t s2 = 0, A = 0, B = 0;
-#pragma unroll
-            for (int tr = 0; tr < TRIPS; tr++) {
-                uint32_t w0 = 0, w1 = 0;
-                if (act[tr]) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + r * row_bytes + tr * 256));
-                s2 = __dp4a(w0, w0, s2);
-                s2 = __dp4a(w1, w1, s2);
-                A = __dp4a(w0, qa[tr][0], A);
-                A = __dp4a(w1, qa[tr][1], A);
-                B = __dp4a(w0, qb[tr][0], B);
-                B = __dp4a(w1, qb[tr][1], B);
-            }
-            v[r] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)B;
-        }
-        reduce_rows<TR>(v, lane);
-        __syncwarp();
-        // the stage is consumed: refill it before the (rare) list maintenance
         const u64 tn = t + (u64)nstages * GW;
-        if (lane == 0 && tn < ntiles) issue(tn, s);
-        if (++s == nstages) {
-            s = 0;
-            phase ^= 1;
+        if constexpr (LPR < 32) {
+            constexpr int PR = 32 / LPR;               // rows side by side
+            long long key[TR / 32];
+            const uint32_t sa = my_stage + s * tile_bytes + (uint32_t)pg * row_bytes + (uint32_t)pj * 8;
+#pragma unroll
+            for (int h = 0; h < TR / 32; h++) {
+                long long v[LPR];
+#pragma unroll
+                for (int i = 0; i < LPR; i++) {
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + (uint32_t)(h * 32 + i * PR) * row_bytes));
+                    uint32_t s2 = __dp4a(w0, w0, 0u), A = __dp4a(w0, qa[0][0], 0u), Bq = __dp4a(w0, qb[0][0], 0u);
+                    s2 = __dp4a(w1, w1, s2);
+                    A = __dp4a(w1, qa[0][1], A);
+                    Bq = __dp4a(w1, qb[0][1], Bq);
+                    v[i] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)Bq;
+                }
+                reduce_packed<LPR>(v, lane);
+                key[h] = v[0];
+            }
+            __syncwarp();
+            if (lane == 0 && tn < ntiles) issue(tn, s);
+            if (++s == nstages) {
+                s = 0;
+                phase ^= 1;
+            }
+#pragma unroll
+            for (int h = 0; h < TR / 32; h++) {
+                const u64 row = t * TR + (u64)(h * 32 + pj * PR + pg);
+                wl.offer(row < p.n, (double)(key[h] + qq) * c2, row, lane, p.cap);
+            }
+        } else {
+            long long v[TR];
+            const uint32_t sa = my_stage + s * tile_bytes + lane * 8;
+#pragma unroll
+            for (int r = 0; r < TR; r++) {
+                uint32_t s2 = 0, A = 0, B = 0;
+#pragma unroll
+                for (int tr = 0; tr < TRIPS; tr++) {
+                    uint32_t w0 = 0, w1 = 0;
+                    if (act[tr]) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + r * row_bytes + tr * 256));
+                    s2 = __dp4a(w0, w0, s2);
+                    s2 = __dp4a(w1, w1, s2);
+                    A = __dp4a(w0, qa[tr][0], A);
+                    A = __dp4a(w1, qa[tr][1], A);
+                    B = __dp4a(w0, qb[tr][0], B);
+                    B = __dp4a(w1, qb[tr][1], B);
+                }
+                v[r] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)B;
+            }
+            reduce_rows<TR>(v, lane);
+            __syncwarp();
+            // the stage is consumed: refill it before the (rare) list maintenance
+            if (lane == 0 && tn < ntiles) issue(tn, s);
+            if (++s == nstages) {
+                s = 0;
+                phase ^= 1;
+            }
+            const u64 row = t * TR + RowLane<TR>::row(lane);
+            const bool has = RowLane<TR>::owner(lane) && row < p.n;
+            wl.offer(has, (double)(v[0] + qq) * c2, row, lane, p.cap);
         }
-        const u64 row = t * TR + RowLane<TR>::row(lane);
-        const bool has = RowLane<TR>::owner(lane) && row < p.n;
-        wl.offer(has, (double)(v[0] + qq) * c2, row, lane, p.cap);
     }
 
     cta_merge_emit(wl, mrg, W, warp, lane, p.cap, p.lists + (size_t)blockIdx.x * p.cap);
@@ -484,9 +521,9 @@ cudaError_t launch_plane8_build(const double *src, int ld, int K, int Kp, u64 fi
     return cudaGetLastError();
 }
 
-bool plane8_scan_supports(int Kp) { return Kp >= 256 && Kp % 64 == 0 && Kp <= 1024; }
+bool plane8_scan_supports(int Kp) { return Kp >= 64 && Kp % 64 == 0 && Kp <= 1024; }
 
-template <int TRIPS, int TR>
+template <int TRIPS, int TR, int LPR>
 static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.Kp;
     const int grid = scan_num_lists(t, true);
@@ -503,18 +540,21 @@ static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs 
     const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
     const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
     static SmemOptIn optin;
-    cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR>, smem);
+    cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR, LPR>, smem);
     if (e != cudaSuccess) return e;
-    scan_plane8_kernel<TRIPS, TR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
+    scan_plane8_kernel<TRIPS, TR, LPR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
     if (!plane8_scan_supports(a.Kp) || a.Kp < a.K || !a.x8 || !a.par || a.n == 0) return cudaErrorInvalidValue;
-    if (a.Kp <= 256) return launch_plane8_inst<1, 16>(t, a, st);
-    if (a.Kp <= 512) return launch_plane8_inst<2, 16>(t, a, st);
-    if (a.Kp <= 768) return launch_plane8_inst<3, 8>(t, a, st);
-    return launch_plane8_inst<4, 8>(t, a, st);
+    if (a.Kp == 64) return launch_plane8_inst<1, 128, 8>(t, a, st);
+    if (a.Kp == 128) return launch_plane8_inst<1, 64, 16>(t, a, st);
+    if (a.Kp == 192) return launch_plane8_inst<1, 32, 32>(t, a, st);
+    if (a.Kp <= 256) return launch_plane8_inst<1, 16, 32>(t, a, st);
+    if (a.Kp <= 512) return launch_plane8_inst<2, 16, 32>(t, a, st);
+    if (a.Kp <= 768) return launch_plane8_inst<3, 8, 32>(t, a, st);
+    return launch_plane8_inst<4, 8, 32>(t, a, st);
 }
 
 }  // namespace svdb

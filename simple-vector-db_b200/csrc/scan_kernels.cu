@@ -499,13 +499,15 @@ __global__ void __launch_bounds__(512, 1) scan_exact_kernel(ScanArgs p) {
 // =====================================================================================
 constexpr int FIN_WARPS = 8;
 constexpr size_t FIN_SMEM = fin_head_bytes(FIN_WARPS) + (size_t)32 * 257 * 8;
+// a single-query scan's short lists (selection path of finalize_query): all of them at once, 296 x 15 x 16 bytes
+constexpr size_t FIN_SMEM_ALL_LISTS = fin_head_bytes(FIN_WARPS) + (size_t)96 * 1024;
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const __grid_constant__ FinalArgs p) {
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const __grid_constant__ FinalArgs p, int fsm_bytes) {
     extern __shared__ __align__(128) unsigned char fsm[];
     if (threadIdx.x == 0) fin_bar_init(fsm, FIN_WARPS);
     __syncthreads();
     uint32_t phase = 0;
-    finalize_query(p, blockIdx.x, fsm, (int)FIN_SMEM, phase);
+    finalize_query(p, blockIdx.x, fsm, fsm_bytes, phase);
 }
 
 // =====================================================================================
@@ -772,9 +774,15 @@ cudaError_t launch_scan_exact(const ScanTuning &t, const ScanArgs &a, cudaStream
 
 cudaError_t launch_finalize(const FinalArgs &a, cudaStream_t st) {
     static SmemOptIn optin;
-    cudaError_t e = optin.ensure(finalize_kernel, FIN_SMEM);
+    cudaError_t e = optin.ensure(finalize_kernel, FIN_SMEM_ALL_LISTS);
     if (e != cudaSuccess) return e;
-    finalize_kernel<<<a.nq, FIN_WARPS * 32, FIN_SMEM, st>>>(a);
+    const size_t lists_bytes = (size_t)a.nlists * a.cap * sizeof(Cand);
+    const bool approx = a.sq_mode || a.eps >= 0.0;
+    const size_t smem = approx && a.cap < 16 && fin_head_bytes(FIN_WARPS) + lists_bytes > FIN_SMEM &&
+                                fin_head_bytes(FIN_WARPS) + lists_bytes <= FIN_SMEM_ALL_LISTS
+                            ? FIN_SMEM_ALL_LISTS
+                            : FIN_SMEM;
+    finalize_kernel<<<a.nq, FIN_WARPS * 32, smem, st>>>(a, (int)smem);
     return cudaGetLastError();
 }
 

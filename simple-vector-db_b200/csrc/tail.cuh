@@ -30,10 +30,13 @@ __device__ __forceinline__ Cand ldcg_cand(const Cand *p) {
     return c;
 }
 
-// shared memory finalize_query needs besides the staging / re-rank buffer: [nw][32] Cand, [nw] bounds, 40 words, 32 candidates,
-// and the mbarrier its bulk copies complete on (the caller initialises it: fin_bar_init)
+// shared memory finalize_query needs besides the staging / re-rank buffer: [nw][32] Cand, [nw] bounds, FIN_NC candidate
+// entries + 8 words, FIN_NC candidates, and the mbarrier its bulk copies complete on (the caller initialises it: fin_bar_init)
 // (every part a multiple of 16 bytes: the buffer behind it is the destination of bulk copies)
-__host__ __device__ constexpr size_t fin_head_bytes(int nw) { return (size_t)nw * 32 * 16 + (size_t)((nw + 1) & ~1) * 8 + 40 * 8 + 32 * 16 + 16; }
+constexpr int FIN_NC = 128;                     // candidate slots of the selection path (one thread re-ranks one candidate)
+__host__ __device__ constexpr size_t fin_head_bytes(int nw) {
+    return (size_t)nw * 32 * 16 + (size_t)((nw + 1) & ~1) * 8 + (size_t)(FIN_NC + 8) * 8 + (size_t)FIN_NC * 16 + 16;
+}
 __device__ __forceinline__ uint32_t fin_bar_addr(unsigned char *fsm, int nw) { return smem_u32(fsm + fin_head_bytes(nw) - 16); }
 // one thread, followed by a __syncthreads() before the first finalize_query
 __device__ __forceinline__ void fin_bar_init(unsigned char *fsm, int nw) {
@@ -65,9 +68,9 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     const int NW = blockDim.x >> 5;
     Cand *mrg = reinterpret_cast<Cand *>(fsm);                                        // [NW][32]
     double *wbound = reinterpret_cast<double *>(fsm + (size_t)NW * 32 * sizeof(Cand)); // [NW]
-    u64 *cseq = reinterpret_cast<u64 *>(wbound + ((NW + 1) & ~1));                    // [33] + 4 words of block reductions + tau
-    double *red = reinterpret_cast<double *>(cseq + 34);                              // [4]
-    Cand *cand = reinterpret_cast<Cand *>(cseq + 40);                                 // [32] (selection path)
+    u64 *cseq = reinterpret_cast<u64 *>(wbound + ((NW + 1) & ~1));                    // [FIN_NC] entries, [FIN_NC] counter, [FIN_NC + 1] k-th key
+    double *red = reinterpret_cast<double *>(cseq + FIN_NC + 2);                      // [4] block reductions
+    Cand *cand = reinterpret_cast<Cand *>(cseq + FIN_NC + 8);                         // [FIN_NC] (selection path)
     double *tbuf = reinterpret_cast<double *>(fsm + fin_head_bytes(NW));
     const int tcap = (fsm_bytes - (int)fin_head_bytes(NW)) / 8;                       // doubles in tbuf
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,10 +89,11 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     const int T = blockDim.x;
     double bound = CUDART_INF;                           // the smallest approximate key any scan list may have dropped
     double eq2 = 0.0, qn2 = 0.0, eabs = 0.0, E = 0.0, scale = 0.0;
-    double cd = CUDART_INF;                              // warp 0, lane j < nneed: approximate key and entry of candidate j
+    double cd = CUDART_INF;                              // thread j < nneed: approximate key and entry of candidate j
     u64 cs = SEQ_NONE;
     int nneed = 0;
     bool overflow = false;
+    double d_next = CUDART_INF;                          // warp 0: exact distance of the best candidate that got no lane (rank 32)
 
     // |key - d| bounds -> the largest approximate key a member of the true top-k can have, given the k-th smallest key dk
     auto window = [&](double dk) -> double {
@@ -146,105 +150,86 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
     const int total_c = p.nlists * p.cap;
     const bool select_path = approx && p.cap < 16 && total_c > 0 && (size_t)total_c * sizeof(Cand) <= (size_t)tcap * 8;
     if (select_path) {
-        // ---- 1+2 (approximate keys, k <= 7, all lists fit the buffer -- the single-query tail): SELECTION, not a merge.
-        // One bulk async copy brings every list into shared memory.  k rounds of "smallest key above the previous one"
-        // over all entries (a strided pass + a min-reduction each: no serial inserts) give the k-th smallest key dk; the
-        // candidates are the entries <= window(dk), compacted with one ballot per 32 entries.  Measured before: walking
-        // the 296 lists of a single-query scan by warp-list insertion cost 11-18 of the tail's 27 us.
+        // ---- 1+2 (approximate keys, short lists, all of them fit the buffer -- the single-query tail): SELECTION, not a merge.
+        // One bulk async copy brings every list into shared memory.  ONE strided pass gives every thread the smallest key
+        // among its entries; the k-th smallest of those T minima (rank counting in shared memory) is an upper bound of the
+        // k-th smallest key overall -- they are k distinct entries -- and for k = 1 it is the minimum itself.  Any upper
+        // bound serves: the window only has to contain the true top-k.  The candidates are the entries <= window(that key),
+        // compacted with one ballot per 32 entries into up to FIN_NC slots.  (Measured before: walking the 296 lists of a
+        // single-query scan by warp-list insertion cost 11-18 of the tail's 27 us; k rounds of min-extraction 2.6 us each.)
         if (threadIdx.x == 0) {
             // the lists were written through the generic proxy (by other SMs), the bulk copy reads through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
             const uint32_t bytes = (uint32_t)total_c * sizeof(Cand);
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s(smem_u32(tbuf), L, bytes, bar);
-            cseq[32] = 0;                                // candidate counter
+            cseq[FIN_NC] = 0;                            // candidate counter
+            cseq[FIN_NC + 1] = ~0ull;                    // k-th smallest thread minimum (ord), none yet
         }
         if (p.sq_mode) query_norms();
         mbar_wait(bar, phase);
         phase ^= 1;
         if (dbg && threadIdx.x == 0) dbg[10] = global_timer_ns();
         // keys are compared as integers: ord() maps a double's bits to an unsigned with the same order (negative keys
-        // happen with GEMM-form keys), so a round costs integer compares only -- this CTA runs alone on its SM with one warp
+        // happen with GEMM-form keys), so the pass costs integer compares only -- this CTA runs alone on its SM with one warp
         // per scheduler, every instruction's latency shows
         auto ord = [](u64 bits) -> u64 { return bits ^ ((u64)((long long)bits >> 63) | 0x8000000000000000ull); };
         const ulonglong2 *se = reinterpret_cast<const ulonglong2 *>(sl);       // .x = key bits, .y = entry
-        const int slot0 = (int)threadIdx.x % p.cap, slot_step = T % p.cap;
-        u64 po = 0, ps = 0, ko = 0, sk = SEQ_NONE;                             // previous round's key; the k-th smallest
-        for (int r = 0; r < p.k; r++) {
-            u64 bo = ~0ull, bs = SEQ_NONE;
-            int slot = slot0;
+        u64 *smin = reinterpret_cast<u64 *>(mrg);                              // [T] thread minima
+        u64 bo = ~0ull;
+        {
+            int slot = (int)threadIdx.x % p.cap;
+            const int slot_step = T % p.cap;
 #pragma unroll 4
             for (int i = threadIdx.x; i < total_c; i += T) {
                 const ulonglong2 c = se[i];
                 const u64 o = ord(c.x);
                 const bool valid = c.y != SEQ_NONE;
-                if (r == 0 && valid && slot == p.cap - 1) bound = fmin(bound, __longlong_as_double((long long)c.x));   // that list was full
-                const bool above = r == 0 || o > po || (o == po && c.y > ps);
-                const bool better = o < bo || (o == bo && c.y < bs);
-                if (valid && above && better) {
-                    bo = o;
-                    bs = c.y;
-                }
+                if (valid && slot == p.cap - 1) bound = fmin(bound, __longlong_as_double((long long)c.x));   // that list was full
+                if (valid && o < bo) bo = o;
                 slot += slot_step;
                 if (slot >= p.cap) slot -= p.cap;
             }
+        }
+        smin[threadIdx.x] = bo;
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                const u64 oo = __shfl_xor_sync(FULL, bo, m), os = __shfl_xor_sync(FULL, bs, m);
-                if (oo < bo || (oo == bo && os < bs)) {
-                    bo = oo;
-                    bs = os;
-                }
-                if (r == 0) bound = fmin(bound, shfl_xor_f64(bound, m));
+        for (int m = 16; m >= 1; m >>= 1) bound = fmin(bound, shfl_xor_f64(bound, m));
+        if (lane == 0) {
+            wbound[warp] = bound;
+            cand[warp] = Cand{eq2, (u64)__double_as_longlong(qn2)};
+        }
+        __syncthreads();
+        {
+            int rk = 0;
+            for (int j = 0; j < T; j++) {
+                const u64 o = smin[j];
+                rk += (o < bo || (o == bo && j < (int)threadIdx.x)) ? 1 : 0;
             }
-            if (lane == 0) {
-                mrg[warp] = Cand{__longlong_as_double((long long)bo), bs};     // (ord, entry), not a distance
-                if (r == 0) {
-                    wbound[warp] = bound;
-                    cand[warp] = Cand{eq2, (u64)__double_as_longlong(qn2)};
-                }
-            }
-            __syncthreads();
-            bo = ~0ull;
-            bs = SEQ_NONE;
+            if (rk == p.k - 1) cseq[FIN_NC + 1] = bo;    // exactly one thread
+            double a = 0.0, b2 = 0.0;
+            bound = CUDART_INF;
             for (int w = 0; w < NW; w++) {
-                const Cand c = mrg[w];
-                const u64 oo = (u64)__double_as_longlong(c.d);
-                if (oo < bo || (oo == bo && c.seq < bs)) {
-                    bo = oo;
-                    bs = c.seq;
-                }
+                bound = fmin(bound, wbound[w]);
+                a += cand[w].d;
+                b2 += __longlong_as_double((long long)cand[w].seq);
             }
-            if (r == 0) {
-                double a = 0.0, b2 = 0.0;
-                bound = CUDART_INF;
-                for (int w = 0; w < NW; w++) {
-                    bound = fmin(bound, wbound[w]);
-                    a += cand[w].d;
-                    b2 += __longlong_as_double((long long)cand[w].seq);
-                }
-                if (threadIdx.x == 0) {
-                    red[0] = a;
-                    red[1] = b2;
-                }
-            }
-            __syncthreads();                             // mrg is rewritten by the next round
-            if (bs == SEQ_NONE) break;                   // fewer than r + 1 entries in all
-            po = bo;
-            ps = bs;
-            if (r == p.k - 1) {
-                ko = bo;
-                sk = bs;
+            if (threadIdx.x == 0) {
+                red[0] = a;
+                red[1] = b2;
             }
         }
+        __syncthreads();
+        const u64 ko = cseq[FIN_NC + 1];
+        const u64 sk = ko != ~0ull ? 0ull : SEQ_NONE;    // fewer than k threads saw an entry: every entry is a candidate
         // the k-th smallest key as a distance again (ord is an involution up to the sign test)
         const u64 kbits = (ko >> 63) ? (ko ^ 0x8000000000000000ull) : ~ko;
         const double dk = __longlong_as_double((long long)kbits);
         if (dbg && threadIdx.x == 0) dbg[11] = global_timer_ns();
         error_terms();
-        // with fewer than k entries every entry is a candidate
         const double lim = sk != SEQ_NONE ? window(dk) : CUDART_INF;
         const unsigned below = (1u << lane) - 1u;
+        // one thread re-ranks one candidate; the re-rank buffer must hold at least 32 coordinates of each per round
+        const int nc_max = min(min(FIN_NC, T), tcap / 33);
         for (int base = warp * 32; base < total_c; base += NW * 32) {
             const int i = base + lane;
             Cand c = Cand{CUDART_INF, SEQ_NONE};
@@ -253,9 +238,9 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             const unsigned m = __ballot_sync(FULL, in);
             if (m) {
                 unsigned at = 0;
-                if (lane == 0) at = (unsigned)atomicAdd(reinterpret_cast<unsigned long long *>(cseq + 32), (unsigned long long)__popc(m));
+                if (lane == 0) at = (unsigned)atomicAdd(reinterpret_cast<unsigned long long *>(cseq + FIN_NC), (unsigned long long)__popc(m));
                 at = __shfl_sync(FULL, at, 0) + __popc(m & below);
-                if (in && at < 32u) {
+                if (in && at < (unsigned)nc_max) {
                     cand[at] = c;
                     cseq[at] = c.seq;
                 }
@@ -266,15 +251,15 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             dbg[16] = (unsigned long long)__double_as_longlong(E);
             dbg[17] = (unsigned long long)__double_as_longlong(lim);
             dbg[18] = (unsigned long long)__double_as_longlong(dk);
-            dbg[19] = cseq[32];
+            dbg[19] = cseq[FIN_NC];
             dbg[20] = (unsigned long long)__double_as_longlong(bound);
         }
-        const unsigned found = (unsigned)cseq[32];
-        overflow = found > 32u;                          // more near-ties than lanes: not provable here (-> fp64 / exact rerun)
-        nneed = (int)min(found, 32u);
-        if (warp == 0 && lane < nneed) {
-            cd = cand[lane].d;
-            cs = cand[lane].seq;
+        const unsigned found = (unsigned)cseq[FIN_NC];
+        overflow = found > (unsigned)nc_max;             // more near-ties than slots: not provable here (-> fp64 / exact rerun)
+        nneed = (int)min(found, (unsigned)nc_max);
+        if ((int)threadIdx.x < nneed) {
+            cd = cand[threadIdx.x].d;
+            cs = cand[threadIdx.x].seq;
         }
         if (dbg && threadIdx.x == 0) dbg[1] = dbg[12] = dbg[13] = global_timer_ns();
     } else {
@@ -375,10 +360,10 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             cd = wl.d;
             cs = wl.seq;
             cseq[lane] = wl.seq;
-            if (lane == 0) cseq[32] = (u64)nneed;
+            if (lane == 0) cseq[FIN_NC] = (u64)nneed;
         }
         __syncthreads();
-        nneed = (int)cseq[32];
+        nneed = (int)cseq[FIN_NC];
         if (dbg && threadIdx.x == 0) dbg[13] = global_timer_ns();
     }
 
@@ -431,10 +416,10 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
             }
             __syncthreads();
             if (dbg && threadIdx.x == 0 && c0 == 0) dbg[14] = global_timer_ns();
-            if (warp == 0 && lane < nneed) {
+            if ((int)threadIdx.x < nneed) {
                 // kdtree.c:136, strictly in index order: a chain of `len` dependent rounded adds (the one part of the
                 // reference's loop that cannot be parallelised).  Sixteen squares are fetched ahead of the chain.
-                const uint32_t ta = smem_u32(tbuf + lane * ld);
+                const uint32_t ta = smem_u32(tbuf + threadIdx.x * ld);
                 int i = 0;
                 for (; i + 16 <= len; i += 16) {
                     double v[16];
@@ -444,8 +429,33 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
 #pragma unroll
                     for (int u = 0; u < 16; u++) dex = __dadd_rn(dex, v[u]);
                 }
-                for (; i < len; i++) dex = __dadd_rn(dex, tbuf[lane * ld + i]);
+                for (; i < len; i++) dex = __dadd_rn(dex, tbuf[threadIdx.x * ld + i]);
             }
+            __syncthreads();
+        }
+        if (nneed > 32) {
+            // more candidates than warp 0 has lanes (selection path, wide windows): rank all of them by (exact distance,
+            // entry) and hand the best 32 to warp 0 -- k <= 24 of them are the answer.  The 33rd is kept for the tie test.
+            Cand *all = reinterpret_cast<Cand *>(tbuf), *best = all + FIN_NC;       // [nneed], [33]
+            Cand mine = Cand{CUDART_INF, SEQ_NONE};
+            if ((int)threadIdx.x < nneed && cs != SEQ_NONE && dex < CUDART_INF) mine = Cand{dex, cs};   // kdtree.c:139: non-finite never wins
+            if ((int)threadIdx.x < nneed) all[threadIdx.x] = mine;
+            __syncthreads();
+            if ((int)threadIdx.x < nneed) {
+                int rk = 0;
+                for (int j = 0; j < nneed; j++) {
+                    const Cand c = all[j];
+                    rk += (key_less(c.d, c.seq, mine.d, mine.seq) || (c.d == mine.d && c.seq == mine.seq && j < (int)threadIdx.x)) ? 1 : 0;
+                }
+                if (rk <= 32) best[rk] = mine;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                dex = best[lane].d;
+                cs = best[lane].seq;
+                d_next = best[32].d;
+            }
+            nneed = 32;
             __syncthreads();
         }
     }
@@ -471,6 +481,11 @@ static __device__ __noinline__ void finalize_query(const FinalArgs &p, int qi, u
         const double ek = mk ? __shfl_sync(FULL, dex, __ffs(mk) - 1) : CUDART_INF;
 
         bool unsafe = overflow;                          // more entries inside the window than candidate slots: not provable here
+        {
+            // an exact tie at the minimum that reaches beyond the 32 candidates warp 0 holds cannot be resolved here
+            const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
+            if (m0 && d_next < CUDART_INF && d_next == __shfl_sync(FULL, dex, __ffs(m0) - 1)) unsafe = true;
+        }
         if (approx && bound < CUDART_INF) {
             if (p.sq_mode) {
                 // entries outside the candidate set have key >= bound, hence sqrt(d) >= sqrt(bound)/(1 + gamma) - E
