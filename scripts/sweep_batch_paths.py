@@ -1,6 +1,7 @@
 """Which kernel should answer a call of nq queries?  Times one device-resident call (CUDA events, queries in HBM) through
 each path on the same store and prints one JSON line per nq: K1 (fp64 rows, passes of <= 8 queries), K11 (hi + lo bf16
-planes, passes of <= 8), K12 (hi plane, passes of <= 2), K2 (FP64 DMMA), K10 (tcgen05).  Answers of every path are
+planes, passes of <= 8), K12 (hi plane, passes of <= 2), K13 (one-byte plane, one pass per query, k <= 16), K2 (FP64 DMMA),
+K10 (tcgen05).  Answers of every path are
 compared with K1's; `hbm_pass_ms` is one pass over the fp64 rows at the measured HBM peak.
 
     python scripts/sweep_batch_paths.py [rows] [dim] [k]          # defaults 2000000 768 10
@@ -20,6 +21,7 @@ PATHS = {           # name: (scan.plane, nearest.mma_min_queries, nearest.umma_m
     "K1_fp64_rows": (0, 0, 0),
     "K11_hi_lo_planes": (1, 0, 0),
     "K12_hi_plane": (2, 0, 0),
+    "K13_byte_plane": (3, 0, 0),
     "K2_dmma": (0, 1, 0),
     "K10_tcgen05": (0, 0, 1),
 }
@@ -44,6 +46,7 @@ def main():
             del part
         e.set_stream(torch.cuda.current_stream().cuda_stream)
         e.set_option("nearest.umma_min_kd_dim", 1)
+        e.set_option("scan.plane8_max_queries", 64)
         Qall = torch.rand((1024, D), dtype=torch.float64, device="cuda", generator=g)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for nq in (1, 2, 3, 4, 8, 16, 32, 64, 65, 128, 256, 1024):
@@ -54,7 +57,7 @@ def main():
             line = {"rows": n, "dim": D, "k": k, "nq": nq, "hbm_pass_ms": n * D * 8 / PEAK / 1e6}
             want = None
             for name, (shadow, mma, umma) in PATHS.items():
-                if name in ("K1_fp64_rows", "K11_hi_lo_planes") and nq > 256 or name == "K12_hi_plane" and nq > 64:
+                if name in ("K1_fp64_rows", "K11_hi_lo_planes") and nq > 256 or name in ("K12_hi_plane", "K13_byte_plane") and nq > 64:
                     continue                                   # too many passes: not a contender
                 e.set_option("scan.plane", shadow)
                 e.set_option("nearest.mma_min_queries", mma)

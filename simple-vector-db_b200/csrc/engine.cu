@@ -145,7 +145,6 @@ int svdb_engine::init(const svdb_config &c) {
     K = (int)c.kd_dim;
     Dpad = (int)round_up(D, 16);
     wide = K > tune.thin_max_k;
-    if (umma_min_q < 0) umma_min_q = K >= 256 ? 3 : 32;
     alias = !log_only && !no_log && wide && K == D;
     kstride = alias ? Dpad : (wide ? (int)round_up(K, 2) : K);
 
@@ -460,13 +459,15 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
     const bool use_exact = mode == SVDB_MODE_EXACT || force_exact || !wide;
     int cap = (int)std::min<size_t>(32, k + 8);
     // K10: larger batches go to the tcgen05 tensor cores (split-bf16 keys, same exact re-rank)
-    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_min_q > 0 && nq >= (size_t)umma_min_q &&
+    int umma_from, mma_from;
+    batch_thresholds(k, umma_from, mma_from);
+    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && umma_ok && umma_from > 0 && nq >= (size_t)umma_from &&
         K >= umma_min_k && n_versions < (1ull << 31)) {
         const int r = nearest_umma(d_Q, nq, ldq, k, d_out);
         if (r != -1000) return r;
     }
     // K2: a batch large enough to be compute-bound goes to the FP64 tensor cores
-    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && mma_min_q > 0 && nq >= (size_t)mma_min_q) {
+    if (!use_exact && !fp64_only && mode == SVDB_MODE_AUTO && n_versions && mma_from > 0 && nq >= (size_t)mma_from) {
         const int G = mma_group_size(nq);
         std::string err;
         const int ldp = kstride;
@@ -556,7 +557,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) && k <= (size_t)plane_max_k ? 2 : (Kp >= 384 || scan_plane == 1 ? 1 : 0);
         // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour; the tail
         // re-ranks up to FIN_NC = 128 of them (one thread each)
-        if (scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && plane8_scan_supports(Kp) && nq <= 2 && k <= (size_t)plane8_max_k) want = 3;
+        if (byte_plane_serves(k) && nq <= (size_t)std::max(2, plane8_max_q)) want = 3;
         if (want == 3) {
             const bool have8 = plane8_ready && plane8_n == n_versions;
             if (cs == cudaStreamCaptureStatusNone || have8) {
@@ -795,6 +796,25 @@ int svdb_engine::ensure_shadow(bool need_lo) {
 
 // K13's one-byte plane: created (grid chosen from the rows present) on first use, extended by the entries appended since.
 // -1000: no HBM for it -- K12 keeps serving.
+bool svdb_engine::byte_plane_serves(size_t k) const {
+    return scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && k <= (size_t)plane8_max_k && wide && umma_ok && K >= umma_min_k &&
+           plane8_scan_supports(umma_kpad(K));
+}
+void svdb_engine::batch_thresholds(size_t k, int &uq, int &mq) const {
+    // Measured (profiles/r02_sweep_*.jsonl, ms per call of <= 64 queries, e = rows x padded kd_dim elements):
+    //   K10 ~ 0.25 + 0.73e-9 e   (64-query groups; reads 4 bytes per element once)
+    //   K2  ~ 0.06 + 2.0e-9 e    (<= 16 queries; reads the 8-byte rows once), DMMA-bound beyond
+    //   K13 ~ nq (0.035 + 0.147e-9 e), K12 twice that per element
+    // -> K10 from 3 queries on wide kd-points or large stores (K2 only wins below ~1.5e8 elements, i.e. 1M x 128), and
+    //    K13 passes beat both up to 4 queries per call at every size measured (1M x 128, 2M x 768, 20M x 128).
+    uq = umma_min_q >= 0 ? umma_min_q : ((K >= 256 || n_versions * (u64)umma_kpad(K) > (1ull << 27)) ? 3 : 32);
+    mq = mma_min_q;
+    if (byte_plane_serves(k)) {
+        if (!umma_min_user && uq > 0) uq = std::max(uq, plane8_max_q + 1);
+        if (!mma_min_user && mq > 0) mq = std::max(mq, plane8_max_q + 1);
+    }
+}
+
 int svdb_engine::ensure_plane8() {
     std::string err;
     const int Kp = umma_kpad(K);
@@ -944,14 +964,15 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         rc = mtree_update();
         if (rc) return rc;
     }
-    const bool to_umma = umma_min_q > 0 && nq >= (size_t)umma_min_q;     // K10 serves the call
-    const bool few = !to_umma && (mma_min_q <= 0 || nq < (size_t)mma_min_q);   // the single-query scans (K12 / K11) do
+    int umma_from, mma_from;
+    batch_thresholds(k, umma_from, mma_from);
+    const bool to_umma = umma_from > 0 && nq >= (size_t)umma_from;     // K10 serves the call
+    const bool few = !to_umma && (mma_from <= 0 || nq < (size_t)mma_from);   // the single-query scans (K13 / K12 / K11) do
     if (((scan_plane > 0 && few) || to_umma) && wide && !force_exact && umma_ok && K >= umma_min_k &&
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        const bool byte_plane = few && scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && plane8_scan_supports(umma_kpad(K)) && nq <= 2 &&
-                            k <= (size_t)plane8_max_k;
+        const bool byte_plane = few && byte_plane_serves(k) && nq <= (size_t)std::max(2, plane8_max_q);
         if (byte_plane) {
             rc = ensure_plane8();
             if (rc && rc != -1000) return rc;
@@ -1063,7 +1084,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
             opt_gen++;                       // captured graphs baked the plane's scan in
         }
     }
-    const bool low_precision_first = wide && (last_scan_plane > 0 || nq >= (size_t)std::max(1, mma_min_q));
+    const bool low_precision_first = wide && (last_scan_plane > 0 || nq >= (size_t)std::max(1, mma_from));
     for (size_t i = 0; i < nq && !x; i++) {
         svdb_candidate *r = res + i * k;
         if (!(r[0].flags & SVDB_CAND_UNSAFE)) continue;
@@ -1819,8 +1840,9 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "mtree.tail_max") e->mtree_tail_max = (size_t)std::max(0l, value);
     else if (n == "mtree.tail_min") e->mtree_tail_min = (size_t)std::max(0l, value);
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
-    else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value;
-    else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value;
+    else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value, e->mma_min_user = true;
+    else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value, e->umma_min_user = true;
+    else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value);
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);
     else if (n == "scan.plane8_max_k") e->plane8_max_k = (int)std::max(0l, value);

@@ -80,6 +80,12 @@ struct svdb_engine {
     int umma_min_q = -1, umma_min_k = 32;
     // largest k the single-plane scans serve (a coarser key means a wider re-rank window: more rows for the tail to fetch)
     int plane_max_k = 24, plane8_max_k = 16;
+    // K13 streams an eighth of what K2 reads and a quarter of what K10 reads per pass: repeated passes beat both up to this
+    // many queries per call (cost model in DESIGN.md section 4, from profiles/r02_sweep_batch_paths.jsonl and r02_window_counts_*)
+    int plane8_max_q = 4;
+    bool umma_min_user = false, mma_min_user = false;      // thresholds set through svdb_set_option: taken literally
+    bool byte_plane_serves(size_t k) const;                // K13 usable for a call asking for k neighbours per query
+    void batch_thresholds(size_t k, int &uq, int &mq) const;   // from how many queries K10 / K2 take a call of this k
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the hi plane ...
     size_t shadow_lo_n = 0;              // ... and in the lo plane (built when K10 / K11 first ask for it: K12 reads hi only)

@@ -337,6 +337,7 @@ def test_batched_dmma_path_vs_oracle(port, n, D, K, nq, k, seed):
         e.insert(rows)
         e.flush()
         e.set_option("nearest.umma_min_queries", 0)             # K10 (tests/test_gpu_umma.py) would take the 100-query case
+        e.set_option("nearest.mma_min_queries", 4)              # set explicitly: calls of <= 5 queries default to byte-plane passes
         l0 = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q, k), want, k)
         assert e.stats()["exact_reruns"] == 0

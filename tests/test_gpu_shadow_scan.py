@@ -124,3 +124,60 @@ def test_shadow_scan_follows_inserts_and_extremes(port, plane):
             assert e.stats()["scan_plane_last"] == 3 and e.stats()["exact_reruns"] + e.stats()["fp64_reruns"] == 0
         else:               # low-precision float keys -> K1 (fp64 rows) -> exact
             assert e.stats()["exact_reruns"] + e.stats()["fp64_reruns"] > 0
+
+
+@pytest.mark.parametrize("plane", [2, 3])
+@pytest.mark.parametrize("K,cluster,k,exact_dups", [
+    (256, 60, 10, 0),        # a cluster of near neighbours the plane cannot tell apart: 33..128 candidates, one thread each
+    (128, 100, 16, 0),       # packed rows, almost all slots
+    (768, 45, 4, 0),
+    (256, 70, 5, 40),        # 40 exact duplicates at the minimum among 70 candidates: more ties than warp 0 has lanes
+    (64, 300, 3, 0),         # more candidates than slots: the window overflows, the fp64 rows answer
+])
+def test_plane_tail_with_many_candidates(port, plane, K, cluster, k, exact_dups):
+    """The selection path of the tail (tail.cuh) with more candidates than one warp holds: every candidate is re-ranked
+    by a thread of its own, the best 32 by exact distance go to warp 0.  Rows of a tight cluster differ by less than the
+    plane resolves, so all of them land inside the window; the answers must be the oracle's whatever path that takes."""
+    rng = np.random.Generator(np.random.PCG64(K + cluster))
+    n = 5000
+    rows = rng.random((n, K))
+    q = rng.random(K)
+    centre = q + 0.02 * rng.standard_normal(K)
+    where = rng.choice(n, size=cluster, replace=False)
+    rows[where] = centre + 1e-7 * rng.standard_normal((cluster, K))      # far below a step of either plane
+    if exact_dups:
+        rows[np.sort(where)[:exact_dups]] = centre                        # identical kd-points: the earliest insert wins
+    want = oracle_topk(port, rows, K, [q], k)
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        e.set_option("scan.plane", plane)
+        e.set_option("nearest.umma_min_kd_dim", 1)
+        for _ in range(2):
+            assert_topk_equal(e.nearest(q, k), want, k)
+        st = e.stats()
+        if cluster <= 100 and not exact_dups:
+            assert st["scan_plane_last"] == plane and st["fp64_reruns"] == 0 and st["exact_reruns"] == 0
+        if cluster > 128:
+            assert st["fp64_reruns"] >= 1
+
+
+def test_few_queries_per_call_take_byte_plane_passes(port):
+    """Up to scan.plane8_max_queries (4) queries per call are answered by one K13 pass each -- an eighth of the bytes K2
+    would stream, a quarter of K10's -- unless the caller set the batch thresholds itself."""
+    rows = synth.uniform_rows(41, 20000, 256)
+    Q = synth.uniform_rows(42, 7, 256)
+    want = oracle_topk(port, rows, 256, Q, 3)
+    with B.Engine(256, 256) as e:
+        e.insert(rows)
+        for nq in (3, 4):
+            assert_topk_equal(e.nearest(Q[:nq], 3), want[:nq], 3)
+            assert e.stats()["scan_plane_last"] == 3
+        before = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
+        assert e.stats()["kernels_launched"] - before == 4           # one fused launch per query, nothing else
+        assert_topk_equal(e.nearest(Q, 3), want, 3)                   # 7 queries: the tensor-core path
+        e.set_option("nearest.umma_min_queries", 0)
+        e.set_option("nearest.mma_min_queries", 3)                    # explicit threshold: taken literally
+        before = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
+        assert e.stats()["kernels_launched"] - before == 3           # K2: prep + DMMA scan + finalize, not four K13 passes
