@@ -22,6 +22,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Programmatic dependent launch (griddepcontrol, sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start once every CTA of the kernel in front of it on the stream has executed pdl_launch_dependents() (or exited);
+// pdl_wait() returns when that kernel has COMPLETED and its memory is visible.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// order-sensitive 64-bit mix of a query's raw bits: what a scan that started early re-checks after pdl_wait()
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long bits) {
+    return (h ^ bits) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+}
+__device__ __forceinline__ double ld_cv_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.cv.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void mbar_inval(uint32_t bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }

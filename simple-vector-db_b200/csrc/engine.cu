@@ -322,6 +322,7 @@ int svdb_engine::mtree_update() {
 
 int svdb_engine::flush() {
     if (stage_n == 0) return SVDB_OK;
+    pdl_mark = ~0ull;                          // whatever follows new rows starts fully ordered (engine.h: overlap_steps)
     CK(cudaSetDevice(device));
     const size_t n0 = n_versions, m = stage_n, n1 = n0 + m;
     std::string err;
@@ -610,12 +611,21 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
     // the scan's last CTA finalizes (and exchanges) itself -- every wide scan but the LDG variant and the exact kernel
     const bool fuse = fuse_tail && ticket.p && nlists && !use_exact && (plane > 0 || tune.variant == 0);
 
+    // K13 with a fused tail, outside stream capture: consecutive launches overlap (engine.h: overlap_steps)
+    bool overlap = false;
+    if (plane == 3 && fuse && overlap_steps && nlists > 1) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        overlap = cs == cudaStreamCaptureStatusNone;
+    }
+    const int nl = overlap ? nlists - 1 : nlists;
+
     size_t done = 0;
     while (done < nq) {
         const int nqp = largest_pass(nq - done, limit);
         FinalArgs fa{};
         fa.lists = lists.as<Cand>();
-        fa.nlists = nlists;
+        fa.nlists = nl;
         fa.cap = cap;
         fa.nq = nqp;
         fa.k = (int)k;
@@ -690,7 +700,11 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 pa.cap = cap;
                 pa.lists = lists.as<Cand>();
                 pa.tail = ta;
+                pa.grid = nl;
+                // the scan in front must be one that waits for ITS predecessor before it writes (a chain of K13 launches)
+                pa.pdl = overlap && !profile_scan && stats.kernels_launched == pdl_mark ? 1 : 0;
                 CK(launch_scan_plane8(tune, pa, stream));
+                if (overlap) pdl_mark = stats.kernels_launched + 1;
             } else if (plane == 2) {
                 PlaneScanArgs pa{};
                 pa.xhi = shadow_hi.as<uint16_t>();
@@ -834,6 +848,7 @@ int svdb_engine::ensure_plane8() {
             return -1000;
         }
         unsigned long long *errw = reinterpret_cast<unsigned long long *>(plane8_par.as<unsigned char>() + sizeof(Plane8Par));
+        pdl_mark = ~0ull;                      // the next scan reads what this writes: a fully ordered launch
         CK(launch_plane8_build(kd_ptr(), kstride, K, Kp, plane8_n, n_versions - plane8_n, plane8_par.as<Plane8Par>(), plane8_n == 0,
                                plane8.as<unsigned char>(), errw, tune.num_sms, stream));
         stats.kernels_launched += plane8_n == 0 ? 4 : 1;
@@ -1843,6 +1858,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value, e->mma_min_user = true;
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value, e->umma_min_user = true;
     else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value);
+    else if (n == "scan.overlap_steps") e->overlap_steps = value != 0;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);
     else if (n == "scan.plane8_max_k") e->plane8_max_k = (int)std::max(0l, value);

@@ -83,6 +83,12 @@ struct svdb_engine {
     // K13 streams an eighth of what K2 reads and a quarter of what K10 reads per pass: repeated passes beat both up to this
     // many queries per call (cost model in DESIGN.md section 4, from profiles/r02_sweep_batch_paths.jsonl and r02_window_counts_*)
     int plane8_max_q = 4;
+    // Back-to-back single-query steps (device entry points): the K13 scan of step i+1 is launched with programmatic stream
+    // serialization and starts while the tail of step i (re-rank, proof, exchange) still runs on one SM; it uses one CTA
+    // less than the machine holds so that all of them start at once.  pdl_mark = stats.kernels_launched right after such a
+    // launch: the attribute is only set while nothing else of this engine ran in between (plane builds, inserts, ...).
+    int overlap_steps = 1;
+    uint64_t pdl_mark = ~0ull;
     bool umma_min_user = false, mma_min_user = false;      // thresholds set through svdb_set_option: taken literally
     bool byte_plane_serves(size_t k) const;                // K13 usable for a call asking for k neighbours per query
     void batch_thresholds(size_t k, int &uq, int &mq) const;   // from how many queries K10 / K2 take a call of this k

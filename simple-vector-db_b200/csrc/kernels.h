@@ -144,6 +144,10 @@ struct Plane8ScanArgs {
     int cap;
     Cand *lists;            // [nlists][cap]
     TailArgs tail;
+    int grid;               // CTAs (= lists) to launch; 0: scan_num_lists()
+    int pdl;                // 1: launched with programmatic stream serialization -- the scan may start while the tail of the launch
+                            // in front of it still runs; everything mutable is touched only after pdl_wait(), and the query,
+                            // read before it, is re-checked after it (tail.ticket[3] = "a query changed under a scan")
 };
 bool plane8_scan_supports(int Kp);
 cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st);

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
     uint32_t qa[TRIPS][2], qb[TRIPS][2];
     bool act[TRIPS];
     long long qq = 0;                                   // sum Q_i^2 over the lane's coordinates
+    unsigned long long qhash = 0;                       // of the raw bits this lane read (re-checked after pdl_wait)
 #pragma unroll
     for (int t = 0; t < TRIPS; t++) {
         const int c0 = t * 256 + pj * 8;
@@ -338,7 +339,9 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int c = c0 + h * 4 + j;
-                const unsigned Q = c < p.K ? p8_quant_q(__ldg(p.q + c), lo, step) : 0u;
+                const double qc = c < p.K ? ld_cv_f64(p.q + c) : 0.0;
+                qhash = mix64(qhash, (unsigned long long)__double_as_longlong(qc));
+                const unsigned Q = c < p.K ? p8_quant_q(qc, lo, step) : 0u;
                 wa |= (Q >> 8) << (8 * j);
                 wb |= (Q & 255u) << (8 * j);
                 qq += (long long)Q * Q;
@@ -422,6 +425,23 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         }
     }
 
+    if (p.pdl) {
+        // The rows are read; what follows writes.  Let the next launch on the stream start its own (read-only) scan now,
+        // and touch nothing mutable -- lists, ticket, answers, the exchange -- before the launch in front of this one has
+        // completed.  This scan may itself have started before that launch's completion: the one input a caller can
+        // change between two calls is the query, so it is read again (past the caches) and compared.
+        pdl_launch_dependents();
+        pdl_wait();
+        unsigned long long h2 = 0;
+#pragma unroll
+        for (int t = 0; t < TRIPS; t++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = t * 256 + pj * 8 + j;
+                h2 = mix64(h2, (unsigned long long)__double_as_longlong(c < p.K ? ld_cv_f64(p.q + c) : 0.0));
+            }
+        if (__any_sync(FULL, h2 != qhash) && lane == 0) atomicOr(p.tail.ticket + 3, 1u);
+    }
     cta_merge_emit(wl, mrg, W, warp, lane, p.cap, p.lists + (size_t)blockIdx.x * p.cap);
     if (threadIdx.x == 0)                                // the tail reuses this memory (and brings its own barrier)
         for (int i = 0; i < W * nstages; i++) mbar_inval(smem_u32(bars + i));
@@ -526,7 +546,7 @@ bool plane8_scan_supports(int Kp) { return Kp >= 64 && Kp % 64 == 0 && Kp <= 102
 template <int TRIPS, int TR, int LPR>
 static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.Kp;
-    const int grid = scan_num_lists(t, true);
+    const int grid = a.grid > 0 ? a.grid : scan_num_lists(t, true);
     int W = t.warps < 1 ? 1 : (t.warps > 8 ? 8 : t.warps);
     int NS = t.stages < 2 ? 2 : t.stages;
     while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
@@ -542,6 +562,19 @@ static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs 
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR, LPR>, smem);
     if (e != cudaSuccess) return e;
+    if (a.pdl && a.tail.ticket) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(W * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, scan_plane8_kernel<TRIPS, TR, LPR>, a, NS, (int)smem);
+    }
     scan_plane8_kernel<TRIPS, TR, LPR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
     return cudaGetLastError();
 }

@@ -678,9 +678,14 @@ __device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    __shared__ unsigned s_stale;
     if (threadIdx.x == 0) {
+        unsigned stale;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(stale) : "l"(t.ticket + 3));
+        s_stale = stale;                               // a scan that started early (kernels.h: pdl) saw its query change
         t.ticket[0] = 0;                               // re-armed for the next launch on the stream ...
         t.ticket[2] = 0;                               // ... and so is the tile counter of the scans that hand tiles out dynamically
+        t.ticket[3] = 0;
         if (t.dbg) t.dbg[0] = global_timer_ns();
     }
     if (threadIdx.x == 0) fin_bar_init(smem, blockDim.x >> 5);
@@ -688,6 +693,10 @@ __device__ __forceinline__ void scan_tail(const TailArgs &t, unsigned char *smem
     if (t.dbg && threadIdx.x == 0) t.dbg[9] = global_timer_ns();
     uint32_t phase = 0;
     for (int qi = 0; qi < t.fin.nq; qi++) finalize_query(t.fin, qi, smem, smem_bytes, phase, qi == 0 ? t.dbg : nullptr);
+    if (s_stale) {                                     // answers for a query that is not the caller's: never hand them out as good
+        for (int i = threadIdx.x; i < t.fin.nq * t.fin.k; i += blockDim.x) t.fin.out[i].flags |= SVDB_CAND_UNSAFE;
+        __syncthreads();
+    }
     if (t.dbg && threadIdx.x == 0) t.dbg[2] = global_timer_ns();
     if (t.world <= 1) return;
     const int nrec = t.fin.nq * t.fin.k;

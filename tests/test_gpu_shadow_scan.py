@@ -181,3 +181,54 @@ def test_few_queries_per_call_take_byte_plane_passes(port):
         before = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
         assert e.stats()["kernels_launched"] - before == 3           # K2: prep + DMMA scan + finalize, not four K13 passes
+
+
+def test_back_to_back_device_calls_overlap_safely(port):
+    """Device-resident single-query calls back to back: from the second one on the K13 scan is launched with programmatic
+    stream serialization and may start while the tail of the call before it still runs (option scan.overlap_steps).
+    Answers must be what the oracle says for the query the caller passed -- also when the caller rewrites ONE query buffer
+    between the calls with a kernel of its own on the same stream, the case the scan's re-check of the query exists for:
+    an answer is then either right or flagged SVDB_CAND_UNSAFE, never silently the previous query's."""
+    import torch
+    n, K, k, calls = 60000, 256, 3, 40
+    rows = synth.uniform_rows(51, n, K)
+    Q = synth.uniform_rows(52, calls, K)
+    want = oracle_topk(port, rows, K, Q, k)
+    dev = torch.device("cuda:0")
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        q_all = torch.from_numpy(Q).to(dev)
+        outs = torch.zeros((calls, k, 4), dtype=torch.int64, device=dev)
+        for overlap in (1, 0):
+            e.set_option("scan.overlap_steps", overlap)
+            # (a) every call has its own query and answer buffers; nothing else is enqueued in between
+            outs.zero_()
+            for rep in range(2):
+                for i in range(calls):
+                    e.nearest_device(q_all[i].data_ptr(), 1, K, k, outs[i].data_ptr())
+            torch.cuda.synchronize()
+            got = outs.cpu().numpy().view(np.uint64)
+            for i in range(calls):
+                wseq, widx, wd = want[i]
+                assert not (got[i, :, 3] & B.CAND_UNSAFE).any()
+                np.testing.assert_array_equal(got[i, :, 1].astype(np.int64), wseq)        # svdb_candidate: dist, seq, index, flags
+                np.testing.assert_array_equal(got[i, :, 0], wd.view(np.uint64))
+            # (b) one query buffer, rewritten by a torch kernel right in front of every call
+            qbuf = torch.zeros(K, dtype=torch.float64, device=dev)
+            outs.zero_()
+            for i in range(calls):
+                qbuf.copy_(q_all[i])
+                e.nearest_device(qbuf.data_ptr(), 1, K, k, outs[i].data_ptr())
+            torch.cuda.synchronize()
+            got = outs.cpu().numpy().view(np.uint64)
+            flagged = 0
+            for i in range(calls):
+                wseq, widx, wd = want[i]
+                if (got[i, :, 3] & B.CAND_UNSAFE).any():
+                    flagged += 1
+                    continue
+                np.testing.assert_array_equal(got[i, :, 1].astype(np.int64), wseq)
+                np.testing.assert_array_equal(got[i, :, 0], wd.view(np.uint64))
+            assert flagged <= calls // 4
+        assert e.stats()["scan_plane_last"] == 3
