@@ -667,7 +667,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
             ta.ticket = ticket.as<unsigned>();
             ta.fin = fa;
             if (tail_debug) {
-                if (!tail_dbg.ensure((size_t)(32 + nlists) * 8, err)) return fail(SVDB_ERR_OOM, err);
+                if (!tail_dbg.ensure((size_t)(32 + 3 * nlists) * 8, err)) return fail(SVDB_ERR_OOM, err);
                 ta.dbg = tail_dbg.as<unsigned long long>();
             }
             if (x && exchanged && done == 0 && (size_t)nqp == nq) {      // the whole call is this one pass

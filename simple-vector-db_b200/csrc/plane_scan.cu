@@ -288,7 +288,13 @@ template <int TRIPS, int TR, int LPR>
 __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_constant__ Plane8ScanArgs p, int nstages, int smem_bytes) {
     static_assert(LPR == 32 || (TRIPS == 1 && TR % 32 == 0), "packed rows: one trip, whole rounds of 32 rows");
     extern __shared__ __align__(128) unsigned char smem[];
-    if (p.tail.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
+    if (p.tail.dbg && threadIdx.x == 0) {
+        if (blockIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
+        p.tail.dbg[32 + gridDim.x + blockIdx.x] = global_timer_ns();         // behind the CTAs' finish stamps (tail.cuh)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.tail.dbg[32 + 2 * gridDim.x + blockIdx.x] = smid;
+    }
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Kp = p.Kp;
@@ -558,7 +564,12 @@ static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs 
     if (need(W, NS) > budget) return cudaErrorInvalidValue;
     // the tail wants every CTA's list in shared memory at once (selection path): 296 lists x cap x 16 bytes
     const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
-    const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
+    size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
+    // A launch that may start under the tail of the one in front of it (a.grid = one CTA less than the machine holds) is
+    // placed by the hardware as slots free up, depth-first: 3 of these CTAs fit an SM by registers and shared memory, and
+    // a chain of such launches ended up with 0..3 CTAs per SM and a 35-80 us spread of finish times (profiles/
+    // r02_overlap_probe.txt).  Asking for more than a third of the SM's shared memory keeps it at cps per SM.
+    if (a.grid > 0) smem = std::max(smem, std::min(budget, (size_t)MAX_SMEM / (cps + 1) + 1024));
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR, LPR>, smem);
     if (e != cudaSuccess) return e;
