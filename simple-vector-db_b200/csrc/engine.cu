@@ -613,7 +613,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
 
     // K13 with a fused tail, outside stream capture: consecutive launches overlap (engine.h: overlap_steps)
     bool overlap = false;
-    if (plane == 3 && fuse && overlap_steps && nlists > 1) {
+    if (plane >= 2 && fuse && overlap_steps && nlists > 1 && dyn_tiles == 0) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         overlap = cs == cudaStreamCaptureStatusNone;
@@ -700,7 +700,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 pa.cap = cap;
                 pa.lists = lists.as<Cand>();
                 pa.tail = ta;
-                pa.grid = nl;
+                pa.grid = overlap ? nl : 0;
                 // the scan in front must be one that waits for ITS predecessor before it writes (a chain of K13 launches)
                 pa.pdl = overlap && !profile_scan && stats.kernels_launched == pdl_mark ? 1 : 0;
                 CK(launch_scan_plane8(tune, pa, stream));
@@ -718,7 +718,10 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 pa.lists = lists.as<Cand>();
                 pa.tail = ta;
                 pa.dyn_eighths = dyn_tiles;
+                pa.grid = overlap ? nl : 0;
+                pa.pdl = overlap && !profile_scan && stats.kernels_launched == pdl_mark ? 1 : 0;
                 CK(launch_scan_plane(tune, pa, stream));
+                if (overlap) pdl_mark = stats.kernels_launched + 1;
             } else if (plane == 1) {
                 ShadowScanArgs ha{};
                 ha.xhi = shadow_hi.as<uint16_t>();

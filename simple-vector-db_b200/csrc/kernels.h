@@ -124,6 +124,8 @@ struct PlaneScanArgs {
     int cap;
     Cand *lists;            // [nq][nlists][cap]
     TailArgs tail;
+    int grid;               // CTAs (= lists) to launch; 0: scan_num_lists()
+    int pdl;                // see Plane8ScanArgs
 };
 bool plane_scan_supports(int Kp, int nq);
 double plane_gamma(int Kp);

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
     const int pj = lane % LPR, pg = lane / LPR;
     float qr[NQ][TRIPS][8];
     bool act[TRIPS];
+    unsigned long long qhash = 0;                       // of the raw bits this lane read (re-checked after pdl_wait)
 #pragma unroll
     for (int t = 0; t < TRIPS; t++) {
         const int c0 = t * 256 + pj * 8;
@@ -112,8 +113,11 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
 #pragma unroll
         for (int qi = 0; qi < NQ; qi++)
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                qr[qi][t][j] = c0 + j < p.K ? __double2float_rn(__ldg(p.q + (size_t)qi * p.ldq + c0 + j)) : 0.f;
+            for (int j = 0; j < 8; j++) {
+                const double qc = c0 + j < p.K ? ld_cv_f64(p.q + (size_t)qi * p.ldq + c0 + j) : 0.0;
+                qhash = mix64(qhash, (unsigned long long)__double_as_longlong(qc));
+                qr[qi][t][j] = __double2float_rn(qc);
+            }
     }
 
     WarpList wl[NQ];
@@ -216,6 +220,21 @@ __global__ void __launch_bounds__(256, 2) scan_plane_kernel(const __grid_constan
         for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, (double)key[qi], row, lane, p.cap);
     }
 
+    if (p.pdl) {                                        // see scan_plane8_kernel
+        pdl_launch_dependents();
+        pdl_wait();
+        unsigned long long h2 = 0;
+#pragma unroll
+        for (int t = 0; t < TRIPS; t++)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = t * 256 + pj * 8 + j;
+                    h2 = mix64(h2, (unsigned long long)__double_as_longlong(c < p.K ? ld_cv_f64(p.q + (size_t)qi * p.ldq + c) : 0.0));
+                }
+        if (__any_sync(FULL, h2 != qhash) && lane == 0) atomicOr(p.tail.ticket + 3, 1u);
+    }
     const int nlists = gridDim.x;
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++)
@@ -231,7 +250,7 @@ double plane_gamma(int Kp) { return ((double)Kp / 32.0 + 12.0) * ldexp(1.0, -24)
 template <int NQ, int TRIPS, int LPR, int TR>
 static cudaError_t launch_plane_inst(const ScanTuning &t, const PlaneScanArgs &a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.Kp * 2;
-    const int grid = scan_num_lists(t, true);
+    const int grid = a.grid > 0 ? a.grid : scan_num_lists(t, true);
     int W = t.warps < 1 ? 1 : (t.warps > 8 ? 8 : t.warps);
     int NS = t.stages < 2 ? 2 : t.stages;
     while (NS < 4 && (size_t)NS * TR * row_bytes < 8192) NS++;
@@ -243,10 +262,24 @@ static cudaError_t launch_plane_inst(const ScanTuning &t, const PlaneScanArgs &a
     if (need(W, NS) > budget) return cudaErrorInvalidValue;
     // the tail wants every CTA's list in shared memory at once (selection path): nlists x cap x 16 bytes per query
     const size_t tail_need = a.tail.ticket ? fin_head_bytes(W) + std::max<size_t>(FIN_MIN_TBUF, (size_t)grid * a.cap * sizeof(Cand)) : 0;
-    const size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
+    size_t smem = std::max(need(W, NS), std::min(tail_need, budget));
+    if (a.grid > 0) smem = std::max(smem, std::min(budget, (size_t)MAX_SMEM / (cps + 1) + 1024));    // see launch_plane8_inst
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(scan_plane_kernel<NQ, TRIPS, LPR, TR>, smem);
     if (e != cudaSuccess) return e;
+    if (a.pdl && a.tail.ticket) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(W * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, scan_plane_kernel<NQ, TRIPS, LPR, TR>, a, NS, (int)smem);
+    }
     scan_plane_kernel<NQ, TRIPS, LPR, TR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
     return cudaGetLastError();
 }
