@@ -884,9 +884,9 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         const int nstreams = std::max(1, tune.num_sms / ngroups);
         const size_t nq_pad = (size_t)ngroups * bn;
         if (!qpad.ensure(nq_pad * (size_t)ldp * 8, err) || !qnorm.ensure(nq_pad * 8, err) || !qsplit.ensure(nq_pad * row_bytes, err) ||
-            !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err) || !ubuf.ensure(umma_buf_bytes(ngroups, nstreams, bn) + nq_pad * 4, err))
+            !lists.ensure(nq_pad * (size_t)nstreams * cap * sizeof(Cand), err) || !ubuf.ensure(umma_buf_bytes(ngroups, nstreams, bn) + nq_pad * 4 * (size_t)(1 + nstreams), err))
             return fail(SVDB_ERR_OOM, err);
-        if (umma_debug && !udbg.ensure((size_t)128 * 256 * 4, err)) return fail(SVDB_ERR_OOM, err);
+        if (umma_debug && !udbg.ensure((size_t)(128 * 256 + 16) * 4, err)) return fail(SVDB_ERR_OOM, err);
         CK(launch_prep_queries(d_Q + done * ldq, (int)ldq, K, (int)nqp, (int)nq_pad, qpad.as<double>(), ldp, qnorm.as<double>(), stream));
         uint16_t *qhi = qsplit.as<uint16_t>(), *qlo = qhi + nq_pad * (size_t)Kp;
         CK(launch_split_bf16(qpad.as<double>(), ldp, K, Kp, 0, nq_pad, qhi, qlo, nullptr, tune.num_sms, stream));
@@ -908,7 +908,8 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         ua.lists = lists.as<Cand>();
         ua.bufs = ubuf.p;
         ua.gtau = reinterpret_cast<uint32_t *>(static_cast<char *>(ubuf.p) + umma_buf_bytes(ngroups, nstreams, bn));
-        CK(cudaMemsetAsync(ua.gtau, 0xff, nq_pad * 4, stream));
+        ua.gmin = umma_group_min ? ua.gtau + nq_pad : nullptr;
+        CK(cudaMemsetAsync(ua.gtau, 0xff, nq_pad * 4 * (size_t)(1 + (umma_group_min ? nstreams : 0)), stream));
         ua.dbg_keys = (umma_debug && done == 0) ? udbg.as<float>() : nullptr;
         ua.qres = umma_resident ? umma_resident_stages(bn, Kp) : 0;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1862,6 +1863,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value, e->umma_min_user = true;
     else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value);
     else if (n == "scan.overlap_steps") e->overlap_steps = value != 0;
+    else if (n == "umma.group_min") e->umma_group_min = value != 0;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);
     else if (n == "scan.plane8_max_k") e->plane8_max_k = (int)std::max(0l, value);
@@ -1988,7 +1990,7 @@ int svdb_debug_plane8(svdb_engine *e, double par_out[3], unsigned char *bytes_ou
 int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count) {
     if (!e || !keys_out) return SVDB_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    if (!e->udbg.p || count > (size_t)128 * 256) return e->fail(SVDB_ERR_ARG, "no K10 debug capture (set umma.debug_keys before the call)");
+    if (!e->udbg.p || count > (size_t)128 * 256 + 16) return e->fail(SVDB_ERR_ARG, "no K10 debug capture (set umma.debug_keys before the call)");
     cudaSetDevice(e->device);
     cudaError_t ce = cudaStreamSynchronize(e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpy(keys_out, e->udbg.p, count * 4, cudaMemcpyDeviceToHost);

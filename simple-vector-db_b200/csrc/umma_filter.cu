@@ -60,7 +60,7 @@ constexpr int UF_B_BYTES = UF_NMAX * 128;       // one plane of a query tile
 constexpr int UF_STAGE_BYTES = 2 * UF_A_BYTES + 2 * UF_B_BYTES;     // 96 KB: row hi/lo + query hi/lo of one 64-coordinate chunk
 constexpr int UF_RING_BYTES = UF_STAGES * UF_STAGE_BYTES;           // 192 KB of operand staging either way
 constexpr int UF_THREADS = 384;                  // TMA warp, MMA warp, two idle, eight epilogue warps
-constexpr int UF_TAIL = 256 + 3 * UF_NMAX * 4;                      // barriers + tmem pointer, cnt / tau / qn
+constexpr int UF_TAIL = 256 + 4 * UF_NMAX * 4;                      // barriers + tmem pointer, cnt / tau / qn / smallest key kept
 constexpr int UF_SMEM = UF_RING_BYTES + UF_TAIL + 1024;             // + slack to align the stages to 1024 bytes
 
 // Short kd-points (config 2 / 5 rows: K = 128): a row tile is only one or two 64-coordinate chunks, so with the queries
@@ -148,6 +148,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     unsigned *cnt_s = reinterpret_cast<unsigned *>(tail + 256);
     float *thr_s = reinterpret_cast<float *>(tail + 256 + UF_NMAX * 4);   // per query: tau - |q|^2, tau = cap-th smallest key so far
     float *qn_s = reinterpret_cast<float *>(tail + 256 + 2 * UF_NMAX * 4);
+    uint32_t *lmin_s = reinterpret_cast<uint32_t *>(tail + 256 + 3 * UF_NMAX * 4);   // per query: smallest key this CTA has kept (uf_ord)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bn = p.bn;
@@ -155,6 +156,9 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     const int q0 = group * bn;
     const int nchunks = p.Kp / UF_KC;
     const u64 ntiles = (p.n + UF_M - 1) / UF_M;
+    // option umma.debug_keys: CTA 0 also leaves cycle counts of its three roles in 16 floats behind the key dump (128 x UF_NMAX)
+    const bool prof = p.dbg_keys != nullptr && blockIdx.x == 0;
+    long long clk[6] = {0, 0, 0, 0, 0, 0};
     // resident queries (p.qres stages of rows behind nchunks x [hi | lo] query tiles) or queries streamed with the rows
     const int nst = p.qres > 0 ? p.qres : UF_STAGES;
     const uint32_t qchunk_bytes = 2u * (uint32_t)bn * 128u;
@@ -180,6 +184,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     }
     for (int j = tid; j < UF_NMAX; j += UF_THREADS) {
         cnt_s[j] = 0;
+        lmin_s[j] = 0xffffffffu;
         thr_s[j] = CUDART_INF_F;
         qn_s[j] = j < bn ? (float)p.qnorm[q0 + j] : 0.f;
     }
@@ -201,10 +206,13 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             const uint32_t stage_tx = p.qres > 0 ? 2u * UF_A_BYTES : 2 * UF_A_BYTES + 2 * (uint32_t)bn * 128u;
             int stage = 0;
             uint32_t phase = 0;
+            const long long cstart = prof ? clock64() : 0;
             for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
                 const int row0 = (int)(tile * UF_M);
                 for (int kc = 0; kc < nchunks; kc++) {
+                    const long long c0 = prof ? clock64() : 0;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (prof) clk[0] += clock64() - c0;
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t st = ring0 + stage * stage_bytes;
                     mbar_arrive_expect_tx(full, stage_tx);
@@ -220,6 +228,10 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     }
                 }
             }
+            if (prof) {
+                p.dbg_keys[128 * UF_NMAX + 0] = (float)clk[0] * 1e-3f;                    // producer: waiting for a free smem stage
+                p.dbg_keys[128 * UF_NMAX + 1] = (float)(clock64() - cstart) * 1e-3f;      // producer: whole loop
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -231,12 +243,17 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 mbar_wait(bar_q, 0);
                 tc_fence_after();
             }
+            const long long cstart = prof ? clock64() : 0;
             for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
+                long long c0 = prof ? clock64() : 0;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);      // the epilogue has drained this accumulator stage
+                if (prof) clk[0] += clock64() - c0;
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)as * UF_NMAX;
                 for (int kc = 0; kc < nchunks; kc++) {
+                    c0 = prof ? clock64() : 0;
                     mbar_wait(bar_full + 8 * stage, phase);
+                    if (prof) clk[1] += clock64() - c0;
                     tc_fence_after();
                     const uint32_t st = ring0 + stage * stage_bytes;
                     const uint32_t qb = p.qres > 0 ? sbase + kc * qchunk_bytes : st + 2 * UF_A_BYTES;
@@ -262,6 +279,11 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     aphase ^= 1;
                 }
             }
+            if (prof) {
+                p.dbg_keys[128 * UF_NMAX + 2] = (float)clk[0] * 1e-3f;                    // MMA issuer: waiting for the epilogue (tempty)
+                p.dbg_keys[128 * UF_NMAX + 3] = (float)clk[1] * 1e-3f;                    // MMA issuer: waiting for loads (full)
+                p.dbg_keys[128 * UF_NMAX + 4] = (float)(clock64() - cstart) * 1e-3f;      // MMA issuer: whole loop
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue: keys, thresholds, candidate buffers =====================
@@ -275,10 +297,18 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         uint32_t aphase = 0;
         // |x|^2 of this lane's row of the NEXT tile and the group's shared thresholds are fetched before the wait for the
         // accumulator, not after it: two global round trips per tile came off the epilogue's critical path
-        // (profiles/r02_ncu_umma_filter_1Mx128_q64_*: the F2F behind the norm load and the threshold load were the top
-        // long-scoreboard stalls, and the eight warps wait for each other twice per tile)
+        // (an ncu capture at 1M x 128 showed the F2F behind the norm load and the threshold load as the top long-scoreboard
+        // stalls, and the eight warps wait for each other twice per tile; profiles/r02_K10_role_cycles_before.jsonl)
         const int jmine = wi + 8 * lane;                  // bn / 8 <= 32 queries per warp: lane t looks after query wi + 8 t
         const bool mineok = lane < bn / 8;
+        // Thresholds from the whole group (round 2): every CTA of a query group publishes, per query, the smallest key it has
+        // kept (gmin).  Those are keys of nstreams DISTINCT rows, so the cap-th smallest of them bounds the group's cap-th
+        // smallest key from above -- and sits near the quantile 1 / (rows one CTA has seen), where a CTA's own cap-th smallest
+        // key (what gtau carried before) sits near cap / (rows one CTA has seen): ~cap times fewer survivors to append,
+        // sort and prune.  CTA `stream` looks after the queries stream, stream + nstreams, ... of its group, one per warp.
+        const bool use_gmin = p.gmin != nullptr && p.nstreams >= p.cap;
+        uint32_t pub = 0xffffffffu;                        // what this lane last published for query jmine
+        const int jsel = stream + p.nstreams * wi;        // the query whose group threshold this warp refreshes
         double xn_next = 0.0;
         {
             const u64 r0 = (u64)stream * UF_M + ew * 32 + lane;
@@ -295,11 +325,14 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 const u64 rn = row + (u64)p.nstreams * UF_M;
                 xn_next = (tile + p.nstreams < ntiles && rn < p.n) ? __ldg(p.xnorm + rn) : 0.0;
             }
+            long long c0 = prof ? clock64() : 0;
             mbar_wait(bar_tfull + 8 * as, aphase);
+            if (prof) clk[0] += clock64() - c0, c0 = clock64();
             tc_fence_after();
             const bool dbg = p.dbg_keys != nullptr && blockIdx.x == 0 && tile == (u64)stream;
             for (int c = c_lo; c < c_hi; c++) {
                 uint32_t v[32];
+                long long c1 = prof ? clock64() : 0;
                 tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * UF_NMAX + c * 32), v);
                 float th[32];                                     // thresholds of these 32 queries (constant during the tile)
 #pragma unroll
@@ -308,35 +341,37 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     th[4 * i] = t4.x, th[4 * i + 1] = t4.y, th[4 * i + 2] = t4.z, th[4 * i + 3] = t4.w;
                 }
                 tc_wait_ld();
+                if (prof) clk[3] += clock64() - c1, c1 = clock64();
                 // key < tau  <=>  |x|^2 - 2 acc < tau - |q|^2 =: thr (kept conservative, see uf_thr); NaN passes.
-                // One ballot per key; lane i keeps the mask of the chunk's query i.
-                unsigned mine = 0;
+                // Every lane (= row) collects the pass bits of its own 32 keys: no vote per key.  (The first version took one
+                // ballot per key and transposed the survivors to the query's lane with shuffles: 5 instructions per key on
+                // the fast path and ~600 cycles per chunk for the appends, which are NOT rare -- the threshold only tightens
+                // when a buffer has taken 128 new entries, so ~60 keys per tile survive at any store size;
+                // profiles/r02_K10_role_cycles_before.jsonl.)
+                unsigned pm = 0;
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                    const bool pass = ok && !(fmaf(-2.f, __uint_as_float(v[i]), xn) >= th[i]);
-                    const unsigned m = __ballot_sync(FULL, pass);
-                    if (lane == i) mine = m;
+                    const bool pass = !(fmaf(-2.f, __uint_as_float(v[i]), xn) >= th[i]);
+                    pm |= pass ? (1u << i) : 0u;
                 }
-                const unsigned any = __ballot_sync(FULL, mine != 0);
-                if (any) {                                        // rare after the first tiles, and uniform over the warp
-                    // ONE shared-memory atomic instruction reserves the buffer slots of every query that has survivors
-                    unsigned base_mine = 0;
-                    if (mine) base_mine = atomicAdd(&cnt_s[c * 32 + lane], (unsigned)__popc(mine));
+                if (!ok) pm = 0;
+                if (prof) clk[4] += clock64() - c1, c1 = clock64();
+                if (__any_sync(FULL, pm != 0)) {
+                    // a survivor's own lane reserves its slot (one shared-memory atomic per survivor) and stores it
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        if ((any >> i) & 1u) {
-                            const unsigned m = __shfl_sync(FULL, mine, i);
-                            const unsigned base = __shfl_sync(FULL, base_mine, i);
-                            if ((m >> lane) & 1u) {
-                                const int j = c * 32 + i;
-                                float key = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[j]);
-                                if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;   // NaN / inf: keep it, never drop it
-                                const unsigned pos = base + __popc(m & below);
-                                if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
-                            }
+                        if ((pm >> i) & 1u) {
+                            const int j = c * 32 + i;
+                            float key = fmaf(-2.f, __uint_as_float(v[i]), xn + qn_s[j]);
+                            if (!(fabsf(key) <= FLT_MAX)) key = -FLT_MAX;       // NaN / inf: keep it, never drop it
+                            const unsigned pos = atomicAdd(&cnt_s[j], 1u);
+                            if (pos < (unsigned)UF_BUF) bufs[(size_t)j * UF_BUF + pos] = UfEntry{key, (uint32_t)row};
+                            atomicMin(lmin_s + j, uf_ord(key));
                         }
                     }
+                    __syncwarp();
                 }
+                if (prof) clk[5] += clock64() - c1;
                 if (dbg) {
 #pragma unroll
                     for (int i = 0; i < 32; i++)
@@ -345,6 +380,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
+            if (prof) clk[1] += clock64() - c0, c0 = clock64();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);      // this warp is done with the accumulator stage
             if (++as == 2) {
                 as = 0;
@@ -373,10 +409,54 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     }
                 }
                 __syncwarp();
+                if (use_gmin) {
+                    if (mineok) {
+                        const uint32_t lm = lmin_s[jmine];
+                        if (lm < pub) {
+                            p.gmin[(size_t)(q0 + jmine) * p.nstreams + stream] = lm;
+                            pub = lm;
+                        }
+                    }
+                    if (refresh && jsel < bn) {
+                        // cap-th smallest of the group's published minima of query jsel: 32-step search on the ordered bits
+                        uint32_t val[5];
+                        int have = 0;
+#pragma unroll
+                        for (int t = 0; t < 5; t++) {
+                            const int s2 = lane + 32 * t;
+                            val[t] = s2 < p.nstreams ? __ldcg(p.gmin + (size_t)(q0 + jsel) * p.nstreams + s2) : 0xffffffffu;
+                            have += val[t] != 0xffffffffu;
+                        }
+                        have = __reduce_add_sync(FULL, have);
+                        if (have >= p.cap) {
+                            uint32_t x = 0;
+                            for (int bit = 31; bit >= 0; bit--) {
+                                const uint32_t cand = x | (1u << bit);
+                                int c2 = 0;
+#pragma unroll
+                                for (int t = 0; t < 5; t++) c2 += val[t] < cand;
+                                if (__reduce_add_sync(FULL, c2) < p.cap) x = cand;
+                            }
+                            // everybody (this CTA included: thr_s[jsel] belongs to another warp) picks it up with the next look at gtau
+                            if (lane == 0) atomicMin(p.gtau + q0 + jsel, x);
+                        }
+                    }
+                    __syncwarp();
+                }
                 if (g != 0xffffffffu) thr_s[jmine] = fminf(thr_s[jmine], uf_thr(uf_unord(g), qn_s[jmine]));
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (prof) clk[2] += clock64() - c0;
             it++;
+        }
+        if (prof && wi == 0 && lane == 0) {
+            p.dbg_keys[128 * UF_NMAX + 5] = (float)clk[0] * 1e-3f;                        // epilogue warp 4: waiting for the accumulator
+            p.dbg_keys[128 * UF_NMAX + 6] = (float)clk[1] * 1e-3f;                        //                 keys, thresholds, appends
+            p.dbg_keys[128 * UF_NMAX + 7] = (float)clk[2] * 1e-3f;                         //                 barriers + pruning
+            p.dbg_keys[128 * UF_NMAX + 8] = (float)it;
+            p.dbg_keys[128 * UF_NMAX + 9] = (float)clk[3] * 1e-3f;                         //   of the keys part: tcgen05.ld + thresholds from smem
+            p.dbg_keys[128 * UF_NMAX + 10] = (float)clk[4] * 1e-3f;                         //                     compare, 32 keys per lane
+            p.dbg_keys[128 * UF_NMAX + 11] = (float)clk[5] * 1e-3f;                         //                     appending survivors
         }
         // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
         for (int j = wi; j < bn; j += 8) {

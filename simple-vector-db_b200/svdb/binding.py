@@ -344,6 +344,12 @@ class Engine:
         _check(self.L.svdb_time_scan(self.h, C.c_void_p(q_ptr), nq, ldq, k, iters, C.byref(ms)), "svdb_time_scan")
         return ms.value
 
+    def debug_filter_cycles(self) -> np.ndarray:
+        """16 floats behind the K10 key dump: kilocycles CTA 0 spent per role (csrc/umma_filter.cu, option umma.debug_keys)."""
+        out = np.empty(128 * 256 + 16, dtype=np.float32)
+        _check(self.L.svdb_debug_filter_keys(self.h, C.c_void_p(out.ctypes.data), out.size), "svdb_debug_filter_keys")
+        return out[128 * 256:]
+
     def debug_filter_keys(self, bn: int) -> np.ndarray:
         out = np.empty((128, bn), dtype=np.float32)
         _check(self.L.svdb_debug_filter_keys(self.h, C.c_void_p(out.ctypes.data), out.size), "svdb_debug_filter_keys")
