@@ -558,7 +558,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
         int want = scan_plane >= 2 && plane_scan_supports(Kp, 1) && k <= (size_t)plane_max_k ? 2 : (Kp >= 384 || scan_plane == 1 ? 1 : 0);
         // the byte plane's window is ~1.5 x K12's: at 10M x 768 it holds ~4 candidates per requested neighbour; the tail
         // re-ranks up to FIN_NC = 128 of them (one thread each)
-        if (byte_plane_serves(k) && nq <= (size_t)std::max(2, plane8_max_q)) want = 3;
+        if (nq <= (size_t)byte_plane_max_queries(k)) want = 3;
         if (want == 3) {
             const bool have8 = plane8_ready && plane8_n == n_versions;
             if (cs == cudaStreamCaptureStatusNone || have8) {
@@ -817,18 +817,27 @@ bool svdb_engine::byte_plane_serves(size_t k) const {
     return scan_plane >= 3 && plane8_ok && (k <= 4 || plane8_ok_bigk) && k <= (size_t)plane8_max_k && wide && umma_ok && K >= umma_min_k &&
            plane8_scan_supports(umma_kpad(K));
 }
+// Up to how many queries per call K13 passes answer (0: K13 does not serve this call).  Measured (profiles/r02_sweep_*.jsonl,
+// ms per top-10 call of <= 64 queries, e = rows x padded kd_dim elements):
+//   K13 ~ nq (0.035 + 0.147e-9 e)       one launch per query, an eighth of the fp64 bytes each
+//   K10 ~ 0.13 + 0.9e-9 e               (64-query groups; reads 4 bytes per element once; after the epilogue rework)
+//   K2  ~ 0.06 + 2.0e-9 e               (<= 16 queries; reads the 8-byte rows once), DMMA-bound beyond
+// -> K13 passes win up to 4 queries per call from ~4e7 elements on (1M x 128: 0.18 vs 0.25 / 0.32 ms; 2M x 768: 1.08 vs 1.26 /
+//    2.75; 20M x 128: 1.80 vs 2.00 / 5.4) and up to 2 below (250k x 128: 4 passes 0.15 ms, K2 0.12);
+//    K10 beats K2 from ~7e7 elements on (1M x 128: 0.25 vs 0.32; 500k x 128: 0.20 vs 0.19; 250k x 128: 0.18 vs 0.12).
+int svdb_engine::byte_plane_max_queries(size_t k) const {
+    if (!byte_plane_serves(k)) return 0;
+    const u64 e = n_versions * (u64)umma_kpad(K);
+    if (plane8_max_q_user) return plane8_max_q;           // set through svdb_set_option: taken literally
+    return e >= (40ull << 20) ? plane8_max_q : std::min(2, plane8_max_q);
+}
 void svdb_engine::batch_thresholds(size_t k, int &uq, int &mq) const {
-    // Measured (profiles/r02_sweep_*.jsonl, ms per call of <= 64 queries, e = rows x padded kd_dim elements):
-    //   K10 ~ 0.25 + 0.73e-9 e   (64-query groups; reads 4 bytes per element once)
-    //   K2  ~ 0.06 + 2.0e-9 e    (<= 16 queries; reads the 8-byte rows once), DMMA-bound beyond
-    //   K13 ~ nq (0.035 + 0.147e-9 e), K12 twice that per element
-    // -> K10 from 3 queries on wide kd-points or large stores (K2 only wins below ~1.5e8 elements, i.e. 1M x 128), and
-    //    K13 passes beat both up to 4 queries per call at every size measured (1M x 128, 2M x 768, 20M x 128).
-    uq = umma_min_q >= 0 ? umma_min_q : ((K >= 256 || n_versions * (u64)umma_kpad(K) > (1ull << 27)) ? 3 : 32);
+    uq = umma_min_q >= 0 ? umma_min_q : ((K >= 256 || n_versions * (u64)umma_kpad(K) > (1ull << 26)) ? 3 : 32);
     mq = mma_min_q;
-    if (byte_plane_serves(k)) {
-        if (!umma_min_user && uq > 0) uq = std::max(uq, plane8_max_q + 1);
-        if (!mma_min_user && mq > 0) mq = std::max(mq, plane8_max_q + 1);
+    const int p8 = byte_plane_max_queries(k);
+    if (p8 > 0) {
+        if (!umma_min_user && uq > 0) uq = std::max(uq, p8 + 1);
+        if (!mma_min_user && mq > 0) mq = std::max(mq, p8 + 1);
     }
 }
 
@@ -991,7 +1000,7 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
         n_versions && n_versions < (1ull << 31)) {
         // the shadow K10 / K11 read likewise: building it inside a capture that is later discarded would leave shadow_n
         // ahead of what was actually converted
-        const bool byte_plane = few && byte_plane_serves(k) && nq <= (size_t)std::max(2, plane8_max_q);
+        const bool byte_plane = few && nq <= (size_t)byte_plane_max_queries(k);
         if (byte_plane) {
             rc = ensure_plane8();
             if (rc && rc != -1000) return rc;
@@ -1861,7 +1870,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "tree.max_depth") e->tree_max_depth = (int)value;
     else if (n == "nearest.mma_min_queries") e->mma_min_q = (int)value, e->mma_min_user = true;
     else if (n == "nearest.umma_min_queries") e->umma_min_q = (int)value, e->umma_min_user = true;
-    else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value);
+    else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value), e->plane8_max_q_user = true;
     else if (n == "scan.overlap_steps") e->overlap_steps = value != 0;
     else if (n == "umma.group_min") e->umma_group_min = value != 0;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);

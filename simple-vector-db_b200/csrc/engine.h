@@ -90,8 +90,9 @@ struct svdb_engine {
     int overlap_steps = 1;
     bool umma_group_min = true;          // K10: thresholds from the group's published minima (umma_filter.cu); 0: from gtau alone (A/B)
     uint64_t pdl_mark = ~0ull;
-    bool umma_min_user = false, mma_min_user = false;      // thresholds set through svdb_set_option: taken literally
+    bool umma_min_user = false, mma_min_user = false, plane8_max_q_user = false;      // thresholds set through svdb_set_option: taken literally
     bool byte_plane_serves(size_t k) const;                // K13 usable for a call asking for k neighbours per query
+    int byte_plane_max_queries(size_t k) const;            // ... for calls of up to this many queries (0: not at all)
     void batch_thresholds(size_t k, int &uq, int &mq) const;   // from how many queries K10 / K2 take a call of this k
     bool umma_ok = true, shadow_ready = false;
     size_t shadow_n = 0;                 // log entries present in the hi plane ...

@@ -163,8 +163,9 @@ def test_plane_tail_with_many_candidates(port, plane, K, cluster, k, exact_dups)
 
 def test_few_queries_per_call_take_byte_plane_passes(port):
     """Up to scan.plane8_max_queries (4) queries per call are answered by one K13 pass each -- an eighth of the bytes K2
-    would stream, a quarter of K10's -- unless the caller set the batch thresholds itself."""
-    rows = synth.uniform_rows(41, 20000, 256)
+    would stream, a quarter of K10's -- unless the caller set the batch thresholds itself.  (Stores below 4e7 elements: up
+    to 2; there a pass is all launch latency and one K2 call is cheaper than three.)"""
+    rows = synth.uniform_rows(41, 170000, 256)
     Q = synth.uniform_rows(42, 7, 256)
     want = oracle_topk(port, rows, 256, Q, 3)
     with B.Engine(256, 256) as e:
@@ -176,10 +177,19 @@ def test_few_queries_per_call_take_byte_plane_passes(port):
         assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
         assert e.stats()["kernels_launched"] - before == 4           # one fused launch per query, nothing else
         assert_topk_equal(e.nearest(Q, 3), want, 3)                   # 7 queries: the tensor-core path
+    small = synth.uniform_rows(43, 20000, 256)
+    want_small = oracle_topk(port, small, 256, Q, 3)
+    with B.Engine(256, 256) as e:
+        e.insert(small)
+        assert_topk_equal(e.nearest(Q[:2], 3), want_small[:2], 3)
+        assert e.stats()["scan_plane_last"] == 3
+        before = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q[:3], 3), want_small[:3], 3)     # three queries on a small store: one K10 call
+        assert e.stats()["kernels_launched"] - before != 3
         e.set_option("nearest.umma_min_queries", 0)
         e.set_option("nearest.mma_min_queries", 3)                    # explicit threshold: taken literally
         before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
+        assert_topk_equal(e.nearest(Q[:4], 3), want_small[:4], 3)
         assert e.stats()["kernels_launched"] - before == 3           # K2: prep + DMMA scan + finalize, not four K13 passes
 
 
