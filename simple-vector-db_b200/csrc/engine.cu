@@ -606,7 +606,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
     }
     int limit = std::max(1, tune.nq_per_pass);
     if (plane == 2) limit = plane_scan_supports(Kp, 2) ? std::min(limit, 2) : 1;
-    if (plane == 3) limit = 1;
+    if (plane == 3) limit = plane8_pair && plane8_scan_supports_two(Kp) ? 2 : 1;
     if (nlists && !lists.ensure((size_t)8 * nlists * cap * sizeof(Cand), err)) return fail(SVDB_ERR_OOM, err);
     // the scan's last CTA finalizes (and exchanges) itself -- every wide scan but the LDG variant and the exact kernel
     const bool fuse = fuse_tail && ticket.p && nlists && !use_exact && (plane > 0 || tune.variant == 0);
@@ -697,6 +697,8 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
                 pa.K = K;
                 pa.Kp = Kp;
                 pa.q = fa.q;
+                pa.ldq = qld;
+                pa.nq = nqp;
                 pa.cap = cap;
                 pa.lists = lists.as<Cand>();
                 pa.tail = ta;
@@ -819,7 +821,7 @@ bool svdb_engine::byte_plane_serves(size_t k) const {
 }
 // Up to how many queries per call K13 passes answer (0: K13 does not serve this call).  Measured (profiles/r02_sweep_*.jsonl,
 // ms per top-10 call of <= 64 queries, e = rows x padded kd_dim elements):
-//   K13 ~ nq (0.035 + 0.147e-9 e)       one launch per query, an eighth of the fp64 bytes each
+//   K13 ~ nq (0.035 + 0.147e-9 e)       one launch per query, an eighth of the fp64 bytes each (a pair of queries: 1.5 x one)
 //   K10 ~ 0.13 + 0.9e-9 e               (64-query groups; reads 4 bytes per element once; after the epilogue rework)
 //   K2  ~ 0.06 + 2.0e-9 e               (<= 16 queries; reads the 8-byte rows once), DMMA-bound beyond
 // -> K13 passes win up to 4 queries per call from ~4e7 elements on (1M x 128: 0.18 vs 0.25 / 0.32 ms; 2M x 768: 1.08 vs 1.26 /
@@ -829,6 +831,9 @@ int svdb_engine::byte_plane_max_queries(size_t k) const {
     if (!byte_plane_serves(k)) return 0;
     const u64 e = n_versions * (u64)umma_kpad(K);
     if (plane8_max_q_user) return plane8_max_q;           // set through svdb_set_option: taken literally
+    // two queries share a pass at 1.5 x the time of one (Kp >= 192): on large stores three pairs still beat one K10 call
+    // (10M x 768: 6 queries 4.9 vs 5.6 ms; 2M x 768: 1.0 vs 1.2; 1M x 256: 0.33 vs 0.28 -- there it stays at 4)
+    if (plane8_pair && plane8_scan_supports_two(umma_kpad(K)) && e >= (1ull << 29)) return plane8_max_q + 2;
     return e >= (40ull << 20) ? plane8_max_q : std::min(2, plane8_max_q);
 }
 void svdb_engine::batch_thresholds(size_t k, int &uq, int &mq) const {
@@ -1873,6 +1878,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value), e->plane8_max_q_user = true;
     else if (n == "scan.overlap_steps") e->overlap_steps = value != 0;
     else if (n == "umma.group_min") e->umma_group_min = value != 0;
+    else if (n == "scan.plane8_pair") e->plane8_pair = value != 0;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);
     else if (n == "scan.plane8_max_k") e->plane8_max_k = (int)std::max(0l, value);

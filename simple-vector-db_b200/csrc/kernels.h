@@ -142,9 +142,11 @@ struct Plane8ScanArgs {
     const Plane8Par *par;
     u64 n;
     int K, Kp;
-    const double *q;        // one device query (fp64), K coordinates
+    const double *q;        // device queries (fp64), query i at q + i * ldq; K coordinates each are read
+    int ldq;
+    int nq;                 // 1, or 2 queries sharing the pass (plane8_scan_supports_two)
     int cap;
-    Cand *lists;            // [nlists][cap]
+    Cand *lists;            // [nq][nlists][cap]
     TailArgs tail;
     int grid;               // CTAs (= lists) to launch; 0: scan_num_lists()
     int pdl;                // 1: launched with programmatic stream serialization -- the scan may start while the tail of the launch
@@ -152,6 +154,7 @@ struct Plane8ScanArgs {
                             // read before it, is re-checked after it (tail.ticket[3] = "a query changed under a scan")
 };
 bool plane8_scan_supports(int Kp);
+bool plane8_scan_supports_two(int Kp);
 cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st);
 // rows [first, first+n) of the log -> the byte plane; choose_grid: first take lo / step from the range of those rows.
 // err_bits: running max over the rows of |x - x^|_2 (double bits).

@@ -317,9 +317,11 @@ cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaS
 // =====================================================================================================================
 // LPR = 32: a warp walks one row per step (8 bytes per lane and 256-coordinate trip).  LPR = 16 / 8 (TRIPS = 1, Kp = 128 / 64):
 // 2 / 4 rows side by side, 32 rows per round, TR / 32 rounds per tile (tiles of 8 KB whatever the row length).
-template <int TRIPS, int TR, int LPR>
+// NQ = 2 (LPR = 32 only): two queries share the pass -- the bytes and the u.u dot products are read and formed once, each
+// query adds its own two dp4a per four coordinates (5 instead of 6 per query pair and word).
+template <int NQ, int TRIPS, int TR, int LPR>
 __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_constant__ Plane8ScanArgs p, int nstages, int smem_bytes) {
-    static_assert(LPR == 32 || (TRIPS == 1 && TR % 32 == 0), "packed rows: one trip, whole rounds of 32 rows");
+    static_assert(LPR == 32 || (TRIPS == 1 && TR % 32 == 0 && NQ == 1), "packed rows: one trip, whole rounds of 32 rows, one query");
     extern __shared__ __align__(128) unsigned char smem[];
     if (p.tail.dbg && threadIdx.x == 0) {
         if (blockIdx.x == 0) p.tail.dbg[6] = global_timer_ns();
@@ -364,37 +366,42 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
     // the query's digits, packed like the plane's bytes: lane (j = lane % LPR) owns coordinates trip * 256 + j * 8 .. + 7
     const double lo = p.par->lo, step = p.par->step;
     const int pj = lane % LPR, pg = lane / LPR;
-    uint32_t qa[TRIPS][2], qb[TRIPS][2];
+    uint32_t qa[NQ][TRIPS][2], qb[NQ][TRIPS][2];
     bool act[TRIPS];
-    long long qq = 0;                                   // sum Q_i^2 over the lane's coordinates
+    long long qq[NQ];                                   // sum Q_i^2 over the lane's coordinates
     unsigned long long qhash = 0;                       // of the raw bits this lane read (re-checked after pdl_wait)
 #pragma unroll
-    for (int t = 0; t < TRIPS; t++) {
-        const int c0 = t * 256 + pj * 8;
-        act[t] = c0 < Kp;
+    for (int qi = 0; qi < NQ; qi++) {
+        qq[qi] = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t wa = 0, wb = 0;
+        for (int t = 0; t < TRIPS; t++) {
+            const int c0 = t * 256 + pj * 8;
+            act[t] = c0 < Kp;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int c = c0 + h * 4 + j;
-                const double qc = c < p.K ? ld_cv_f64(p.q + c) : 0.0;
-                qhash = mix64(qhash, (unsigned long long)__double_as_longlong(qc));
-                const unsigned Q = c < p.K ? p8_quant_q(qc, lo, step) : 0u;
-                wa |= (Q >> 8) << (8 * j);
-                wb |= (Q & 255u) << (8 * j);
-                qq += (long long)Q * Q;
+            for (int h = 0; h < 2; h++) {
+                uint32_t wa = 0, wb = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = c0 + h * 4 + j;
+                    const double qc = c < p.K ? ld_cv_f64(p.q + (size_t)qi * p.ldq + c) : 0.0;
+                    qhash = mix64(qhash, (unsigned long long)__double_as_longlong(qc));
+                    const unsigned Q = c < p.K ? p8_quant_q(qc, lo, step) : 0u;
+                    wa |= (Q >> 8) << (8 * j);
+                    wb |= (Q & 255u) << (8 * j);
+                    qq[qi] += (long long)Q * Q;
+                }
+                qa[qi][t][h] = wa;
+                qb[qi][t][h] = wb;
             }
-            qa[t][h] = wa;
-            qb[t][h] = wb;
         }
-    }
 #pragma unroll
-    for (int m = LPR / 2; m >= 1; m >>= 1) qq += __shfl_xor_sync(FULL, qq, m);     // every group of LPR lanes holds the whole query
+        for (int m = LPR / 2; m >= 1; m >>= 1) qq[qi] += __shfl_xor_sync(FULL, qq[qi], m);     // every group of LPR lanes holds the whole query
+    }
     const double c2 = (step / 256.0) * (step / 256.0);
 
-    WarpList wl;
-    wl.reset();
+    WarpList wl[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) wl[qi].reset();
     int s = 0;
     uint32_t phase = 0;
     for (u64 t = gw; t < ntiles; t += GW) {
@@ -411,10 +418,10 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
                 for (int i = 0; i < LPR; i++) {
                     uint32_t w0, w1;
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + (uint32_t)(h * 32 + i * PR) * row_bytes));
-                    uint32_t s2 = __dp4a(w0, w0, 0u), A = __dp4a(w0, qa[0][0], 0u), Bq = __dp4a(w0, qb[0][0], 0u);
+                    uint32_t s2 = __dp4a(w0, w0, 0u), A = __dp4a(w0, qa[0][0][0], 0u), Bq = __dp4a(w0, qb[0][0][0], 0u);
                     s2 = __dp4a(w1, w1, s2);
-                    A = __dp4a(w1, qa[0][1], A);
-                    Bq = __dp4a(w1, qb[0][1], Bq);
+                    A = __dp4a(w1, qa[0][0][1], A);
+                    Bq = __dp4a(w1, qb[0][0][1], Bq);
                     v[i] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)Bq;
                 }
                 reduce_packed<LPR>(v, lane);
@@ -429,28 +436,36 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
 #pragma unroll
             for (int h = 0; h < TR / 32; h++) {
                 const u64 row = t * TR + (u64)(h * 32 + pj * PR + pg);
-                wl.offer(row < p.n, (double)(key[h] + qq) * c2, row, lane, p.cap);
+                wl[0].offer(row < p.n, (double)(key[h] + qq[0]) * c2, row, lane, p.cap);
             }
         } else {
-            long long v[TR];
+            long long v[NQ][TR];
             const uint32_t sa = my_stage + s * tile_bytes + lane * 8;
 #pragma unroll
             for (int r = 0; r < TR; r++) {
-                uint32_t s2 = 0, A = 0, B = 0;
+                uint32_t s2 = 0, A[NQ], B[NQ];
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) A[qi] = 0, B[qi] = 0;
 #pragma unroll
                 for (int tr = 0; tr < TRIPS; tr++) {
                     uint32_t w0 = 0, w1 = 0;
                     if (act[tr]) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + r * row_bytes + tr * 256));
                     s2 = __dp4a(w0, w0, s2);
                     s2 = __dp4a(w1, w1, s2);
-                    A = __dp4a(w0, qa[tr][0], A);
-                    A = __dp4a(w1, qa[tr][1], A);
-                    B = __dp4a(w0, qb[tr][0], B);
-                    B = __dp4a(w1, qb[tr][1], B);
+#pragma unroll
+                    for (int qi = 0; qi < NQ; qi++) {
+                        A[qi] = __dp4a(w0, qa[qi][tr][0], A[qi]);
+                        A[qi] = __dp4a(w1, qa[qi][tr][1], A[qi]);
+                        B[qi] = __dp4a(w0, qb[qi][tr][0], B[qi]);
+                        B[qi] = __dp4a(w1, qb[qi][tr][1], B[qi]);
+                    }
                 }
-                v[r] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)B;
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++)
+                    v[qi][r] = 65536ll * (long long)s2 - 131072ll * (long long)A[qi] - 512ll * (long long)B[qi];
             }
-            reduce_rows<TR>(v, lane);
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) reduce_rows<TR>(v[qi], lane);
             __syncwarp();
             // the stage is consumed: refill it before the (rare) list maintenance
             if (lane == 0 && tn < ntiles) issue(tn, s);
@@ -460,7 +475,8 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
             }
             const u64 row = t * TR + RowLane<TR>::row(lane);
             const bool has = RowLane<TR>::owner(lane) && row < p.n;
-            wl.offer(has, (double)(v[0] + qq) * c2, row, lane, p.cap);
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) wl[qi].offer(has, (double)(v[qi][0] + qq[qi]) * c2, row, lane, p.cap);
         }
     }
 
@@ -473,15 +489,20 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         pdl_wait();
         unsigned long long h2 = 0;
 #pragma unroll
-        for (int t = 0; t < TRIPS; t++)
+        for (int qi = 0; qi < NQ; qi++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int c = t * 256 + pj * 8 + j;
-                h2 = mix64(h2, (unsigned long long)__double_as_longlong(c < p.K ? ld_cv_f64(p.q + c) : 0.0));
-            }
+            for (int t = 0; t < TRIPS; t++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = t * 256 + pj * 8 + j;
+                    h2 = mix64(h2, (unsigned long long)__double_as_longlong(c < p.K ? ld_cv_f64(p.q + (size_t)qi * p.ldq + c) : 0.0));
+                }
         if (__any_sync(FULL, h2 != qhash) && lane == 0) atomicOr(p.tail.ticket + 3, 1u);
     }
-    cta_merge_emit(wl, mrg, W, warp, lane, p.cap, p.lists + (size_t)blockIdx.x * p.cap);
+    const int nlists = gridDim.x;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+        cta_merge_emit(wl[qi], mrg, W, warp, lane, p.cap, p.lists + ((size_t)qi * nlists + blockIdx.x) * p.cap);
     if (threadIdx.x == 0)                                // the tail reuses this memory (and brings its own barrier)
         for (int i = 0; i < W * nstages; i++) mbar_inval(smem_u32(bars + i));
     scan_tail(p.tail, smem, smem_bytes);
@@ -582,7 +603,7 @@ cudaError_t launch_plane8_build(const double *src, int ld, int K, int Kp, u64 fi
 
 bool plane8_scan_supports(int Kp) { return Kp >= 64 && Kp % 64 == 0 && Kp <= 1024; }
 
-template <int TRIPS, int TR, int LPR>
+template <int NQ, int TRIPS, int TR, int LPR>
 static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.Kp;
     const int grid = a.grid > 0 ? a.grid : scan_num_lists(t, true);
@@ -601,10 +622,10 @@ static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs 
     // A launch that may start under the tail of the one in front of it (a.grid = one CTA less than the machine holds) is
     // placed by the hardware as slots free up, depth-first: 3 of these CTAs fit an SM by registers and shared memory, and
     // a chain of such launches ended up with 0..3 CTAs per SM and a 35-80 us spread of finish times (profiles/
-    // r02_overlap_probe.txt).  Asking for more than a third of the SM's shared memory keeps it at cps per SM.
+    // r02_overlap_probe_before_smem_pad.txt).  Asking for more than a third of the SM's shared memory keeps it at cps per SM.
     if (a.grid > 0) smem = std::max(smem, std::min(budget, (size_t)MAX_SMEM / (cps + 1) + 1024));
     static SmemOptIn optin;
-    cudaError_t e = optin.ensure(scan_plane8_kernel<TRIPS, TR, LPR>, smem);
+    cudaError_t e = optin.ensure(scan_plane8_kernel<NQ, TRIPS, TR, LPR>, smem);
     if (e != cudaSuccess) return e;
     if (a.pdl && a.tail.ticket) {
         cudaLaunchConfig_t cfg{};
@@ -617,21 +638,31 @@ static cudaError_t launch_plane8_inst(const ScanTuning &t, const Plane8ScanArgs 
         at.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = &at;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, scan_plane8_kernel<TRIPS, TR, LPR>, a, NS, (int)smem);
+        return cudaLaunchKernelEx(&cfg, scan_plane8_kernel<NQ, TRIPS, TR, LPR>, a, NS, (int)smem);
     }
-    scan_plane8_kernel<TRIPS, TR, LPR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
+    scan_plane8_kernel<NQ, TRIPS, TR, LPR><<<grid, W * 32, smem, st>>>(a, NS, (int)smem);
     return cudaGetLastError();
 }
 
+bool plane8_scan_supports_two(int Kp) { return Kp >= 192 && Kp % 64 == 0 && Kp <= 1024; }
+
 cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cudaStream_t st) {
     if (!plane8_scan_supports(a.Kp) || a.Kp < a.K || !a.x8 || !a.par || a.n == 0) return cudaErrorInvalidValue;
-    if (a.Kp == 64) return launch_plane8_inst<1, 128, 8>(t, a, st);
-    if (a.Kp == 128) return launch_plane8_inst<1, 64, 16>(t, a, st);
-    if (a.Kp == 192) return launch_plane8_inst<1, 32, 32>(t, a, st);
-    if (a.Kp <= 256) return launch_plane8_inst<1, 16, 32>(t, a, st);
-    if (a.Kp <= 512) return launch_plane8_inst<2, 16, 32>(t, a, st);
-    if (a.Kp <= 768) return launch_plane8_inst<3, 8, 32>(t, a, st);
-    return launch_plane8_inst<4, 8, 32>(t, a, st);
+    if (a.nq == 2) {
+        if (!plane8_scan_supports_two(a.Kp)) return cudaErrorInvalidValue;
+        if (a.Kp <= 256) return launch_plane8_inst<2, 1, 16, 32>(t, a, st);
+        if (a.Kp <= 512) return launch_plane8_inst<2, 2, 8, 32>(t, a, st);
+        if (a.Kp <= 768) return launch_plane8_inst<2, 3, 8, 32>(t, a, st);
+        return launch_plane8_inst<2, 4, 4, 32>(t, a, st);
+    }
+    if (a.nq != 1) return cudaErrorInvalidValue;
+    if (a.Kp == 64) return launch_plane8_inst<1, 1, 128, 8>(t, a, st);
+    if (a.Kp == 128) return launch_plane8_inst<1, 1, 64, 16>(t, a, st);
+    if (a.Kp == 192) return launch_plane8_inst<1, 1, 32, 32>(t, a, st);
+    if (a.Kp <= 256) return launch_plane8_inst<1, 1, 16, 32>(t, a, st);
+    if (a.Kp <= 512) return launch_plane8_inst<1, 2, 16, 32>(t, a, st);
+    if (a.Kp <= 768) return launch_plane8_inst<1, 3, 8, 32>(t, a, st);
+    return launch_plane8_inst<1, 4, 8, 32>(t, a, st);
 }
 
 }  // namespace svdb

@@ -28,6 +28,9 @@ from test_gpu_parity import assert_topk_equal, oracle_topk  # noqa: E402
     (8000, 64, 64, 1, 10, 7),          # K12: four rows packed to a warp step
     (8003, 64, 64, 2, 3, 17),          # K13: four rows packed to a warp step, ragged last tile of 128 rows
     (70001, 128, 128, 1, 4, 18),       # K13: two rows packed, several 64-row tiles per warp
+    (9001, 500, 500, 2, 3, 19),        # K13: a pair of queries per pass, two trips
+    (5003, 1024, 1024, 2, 1, 20),      # K13: a pair, four trips, 4-row tiles
+    (9002, 256, 256, 2, 16, 21),       # K13: a pair, one trip, the largest k it serves
     (8001, 192, 192, 2, 2, 8),         # K12: one trip, 24 of 32 lanes
     (3000, 1000, 1000, 1, 10, 9),      # K12: four trips
     (2000, 1100, 1100, 1, 5, 10),      # beyond K12's register-resident query: K11 serves plane 2 as well
@@ -175,7 +178,15 @@ def test_few_queries_per_call_take_byte_plane_passes(port):
             assert e.stats()["scan_plane_last"] == 3
         before = e.stats()["kernels_launched"]
         assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
-        assert e.stats()["kernels_launched"] - before == 4           # one fused launch per query, nothing else
+        assert e.stats()["kernels_launched"] - before == 2           # two queries share a pass: two fused launches, nothing else
+        before = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q[:3], 3), want[:3], 3)
+        assert e.stats()["kernels_launched"] - before == 2           # a pair and a single
+        e.set_option("scan.plane8_pair", 0)
+        before = e.stats()["kernels_launched"]
+        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
+        assert e.stats()["kernels_launched"] - before == 4           # A/B switch: one launch per query
+        e.set_option("scan.plane8_pair", 1)
         assert_topk_equal(e.nearest(Q, 3), want, 3)                   # 7 queries: the tensor-core path
     small = synth.uniform_rows(43, 20000, 256)
     want_small = oracle_topk(port, small, 256, Q, 3)
