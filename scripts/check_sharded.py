@@ -79,7 +79,15 @@ def main():
                 # ONE query per call: the whole step is a single scan launch whose last CTA re-ranks, stores to the peers,
                 # waits and merges (scan_tail) -- through the host entry point and through the device entry point
                 ones = [idx.nearest(Q[i:i + 1], k) for i in range(4)]
+                # TWO queries per call: where the kd-points are wide enough the pair shares one scan (K13, NQ = 2) whose tail
+                # exchanges and merges both answers
+                pairs = [idx.nearest(Q[i:i + 2], k) for i in (0, 2)]
                 qd = Q.to(dev)
+                pairs_dev = []
+                for i in (0, 2):
+                    r = idx.nearest_device(qd[i:i + 2], k).clone()
+                    torch.cuda.synchronize()
+                    pairs_dev.append(r.cpu().numpy().view(B.candidate_dtype).reshape(2, k))
                 ones_dev = []
                 for i in range(4):
                     r = idx.nearest_device(qd[i:i + 1], k).clone()
@@ -97,7 +105,13 @@ def main():
                     single_dev = all((o["flags"][0, 0] & (B.CAND_TIE | B.CAND_UNSAFE)) or
                                      (np.array_equal(o["seq"][0], wseq[i]) and np.array_equal(o["dist"][0].view(np.uint64), wdist[i].view(np.uint64)))
                                      for i, o in enumerate(ones_dev))
-                    same = same and single and single_dev
+                    pair_ok = all(np.array_equal(o["seq"], wseq[i:i + 2]) and np.array_equal(o["index"], widx[i:i + 2]) and
+                                  np.array_equal(o["dist"].view(np.uint64), wdist[i:i + 2].view(np.uint64)) for i, o in zip((0, 2), pairs))
+                    pair_ok = pair_ok and all(all((o["flags"][j, 0] & (B.CAND_TIE | B.CAND_UNSAFE)) or
+                                                  (np.array_equal(o["seq"][j], wseq[i + j]) and
+                                                   np.array_equal(o["dist"][j].view(np.uint64), wdist[i + j].view(np.uint64))) for j in range(2))
+                                              for i, o in zip((0, 2), pairs_dev))
+                    same = same and single and single_dev and pair_ok
                     # ... and against the CPU oracle itself (flat (distance, seq) order is the reference's answer wherever
                     # the minimum is not shared by distinct points: the non-lattice cases)
                     oracle_ok = None
@@ -117,7 +131,7 @@ def main():
                     ok &= bool(same)
                     report.append({"rows": n, "dim": D, "kd_dim": K, "k": k, "lattice_levels": levels, "phase": phase,
                                    "layout": "replicated kd log, queries split" if idx.replicated else "row shards",
-                                   "identical_to_single_gpu": bool(same), "single_query_calls_identical": bool(single and single_dev),
+                                   "identical_to_single_gpu": bool(same), "single_query_calls_identical": bool(single and single_dev), "two_query_calls_identical": bool(pair_ok),
                                    "identical_to_cpu_oracle": oracle_ok, "tie_events": idx.engine.stats()["tie_events"],
                                    "tie_levels": idx.engine.stats()["tie_levels"]})
         if ref is not None:
