@@ -151,3 +151,59 @@ def test_k13_byte_plane_key_bound(kind, K, seed):
     d2 = ((x2[:, None, :] - q[None, :, :]) ** 2).sum(-1)
     key2, E2, _ = k13_keys(x2, q, lo, step)
     check_sqrt_form(key2, d2, E2, gamma)
+
+
+# ---- two selection shortcuts the kernels take: both only need an UPPER bound of an order statistic --------------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_kth_smallest_of_thread_minima_bounds_the_kth_smallest(seed):
+    """tail.cuh, selection path: every thread keeps the smallest key among the entries it looked at; the k-th smallest of
+    those T minima stands in for the k-th smallest key overall.  They are k distinct entries, so it can only be larger --
+    which only widens the re-rank window -- and for k = 1 it is the minimum itself."""
+    rng = np.random.default_rng(seed)
+    T = 128
+    for total, k in ((2664, 1), (2664, 4), (4440, 10), (4440, 24), (300, 24), (40, 24)):
+        keys = rng.random(total) if seed % 2 else np.round(rng.random(total), 2)          # with and without ties
+        valid = rng.random(total) < (0.9 if total > 100 else 0.5)
+        mins = np.full(T, np.inf)
+        for t in range(T):
+            mine = keys[t::T][valid[t::T]]
+            if mine.size:
+                mins[t] = mine.min()
+        kth_of_minima = np.sort(mins)[k - 1]
+        v = np.sort(keys[valid])
+        if v.size >= k and np.isfinite(kth_of_minima):
+            assert kth_of_minima >= v[k - 1]
+            if k == 1:
+                assert kth_of_minima == v[0]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cap_th_smallest_of_group_minima_bounds_the_groups_cap_th_smallest(seed):
+    """umma_filter.cu (K10): every CTA of a query group publishes the smallest key it has kept; CTAs own disjoint rows, so the
+    cap-th smallest of the published minima is the key of a row with at least cap - 1 rows below it: an upper bound of the
+    group's cap-th smallest key (what the filter may use as a threshold), and a far tighter one than the smallest of the CTAs'
+    own cap-th smallest keys, which is what the thresholds came from before."""
+    rng = np.random.default_rng(seed)
+    streams, cap = 37, 24
+    for rows_per_cta in (128, 1280, 20000):
+        keys = rng.standard_normal((streams, rows_per_cta)) ** 2
+        truth = np.sort(keys.ravel())[cap - 1]
+        from_minima = np.sort(keys.min(axis=1))[cap - 1]
+        own_cap_th = np.sort(keys, axis=1)[:, cap - 1].min()
+        assert from_minima >= truth
+        assert own_cap_th >= truth
+        if rows_per_cta >= 1280:
+            # keys that pass the threshold (= survivors to append, sort, prune): several times fewer
+            assert (keys < from_minima).sum() * 3 < (keys < own_cap_th).sum()
+
+
+def test_k13_pair_shares_the_squares():
+    """scan_plane8_kernel<NQ = 2>: sum u^2 is formed once per row and used for both queries of the pair."""
+    rng = np.random.default_rng(3)
+    x = rng.random((50, 300))
+    q = rng.random((2, 300))
+    lo, step = k13_grid(x)
+    both, _, _ = k13_keys(x, q, lo, step)
+    for j in range(2):
+        one, _, _ = k13_keys(x, q[j:j + 1], lo, step)
+        assert np.array_equal(both[:, j], one[:, 0])
