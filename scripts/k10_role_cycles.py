@@ -2,7 +2,7 @@
 waiting and working (csrc/umma_filter.cu, option umma.debug_keys): the TMA producer (waiting for a free stage), the MMA issuer
 (waiting for the epilogue / for loads) and epilogue warp 4 (waiting for the accumulator, tcgen05.ld + thresholds, the
 compares, appending survivors, barriers + pruning).  One JSON line, kilocycles.
-    python scripts/k10_role_cycles.py [rows] [dim] [queries] [umma.group_min]"""
+    python scripts/k10_role_cycles.py [rows] [dim] [queries] [umma.group_min] [umma.sparse_checks]"""
 import json
 import os
 import sys
@@ -21,6 +21,7 @@ def main():
     D = int(sys.argv[2]) if len(sys.argv) > 2 else 128
     nq = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     gm = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    sp = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     k = 10
     g = torch.Generator(device="cuda").manual_seed(5)
     with B.Engine(D, D) as e:
@@ -34,6 +35,7 @@ def main():
         e.set_option("nearest.umma_min_queries", 1)
         e.set_option("nearest.umma_min_kd_dim", 1)
         e.set_option("umma.group_min", gm)
+        e.set_option("umma.sparse_checks", sp)
         Q = torch.rand((nq, D), dtype=torch.float64, device="cuda", generator=g)
         out = torch.zeros((nq, k, 4), dtype=torch.int64, device="cuda")
         for _ in range(3):
@@ -42,7 +44,7 @@ def main():
         e.nearest_device(Q.data_ptr(), nq, D, k, out.data_ptr())
         torch.cuda.synchronize()
         v = e.debug_filter_cycles()[:12]
-        print(json.dumps({"rows": n, "dim": D, "nq": nq, "group_min": gm, "kilocycles": {a: float(b) for a, b in zip(NAMES, v)}}))
+        print(json.dumps({"rows": n, "dim": D, "nq": nq, "group_min": gm, "sparse_checks": sp, "kilocycles": {a: float(b) for a, b in zip(NAMES, v)}}))
 
 
 if __name__ == "__main__":

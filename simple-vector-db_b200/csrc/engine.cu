@@ -923,6 +923,7 @@ int svdb_engine::nearest_umma(const double *d_Q, size_t nq, size_t ldq, size_t k
         ua.bufs = ubuf.p;
         ua.gtau = reinterpret_cast<uint32_t *>(static_cast<char *>(ubuf.p) + umma_buf_bytes(ngroups, nstreams, bn));
         ua.gmin = umma_group_min ? ua.gtau + nq_pad : nullptr;
+        ua.sparse_checks = umma_sparse_checks && umma_group_min ? 1 : 0;
         CK(cudaMemsetAsync(ua.gtau, 0xff, nq_pad * 4 * (size_t)(1 + (umma_group_min ? nstreams : 0)), stream));
         ua.dbg_keys = (umma_debug && done == 0) ? udbg.as<float>() : nullptr;
         ua.qres = umma_resident ? umma_resident_stages(bn, Kp) : 0;
@@ -1878,6 +1879,7 @@ int svdb_set_option(svdb_engine *e, const char *name, long value) {
     else if (n == "scan.plane8_max_queries") e->plane8_max_q = (int)std::max(0l, value), e->plane8_max_q_user = true;
     else if (n == "scan.overlap_steps") e->overlap_steps = value != 0;
     else if (n == "umma.group_min") e->umma_group_min = value != 0;
+    else if (n == "umma.sparse_checks") e->umma_sparse_checks = value != 0;
     else if (n == "scan.plane8_pair") e->plane8_pair = value != 0;
     else if (n == "nearest.umma_min_kd_dim") e->umma_min_k = (int)std::max(1l, value);
     else if (n == "scan.plane_max_k") e->plane_max_k = (int)std::max(0l, value);

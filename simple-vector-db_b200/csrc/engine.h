@@ -89,6 +89,7 @@ struct svdb_engine {
     // launch: the attribute is only set while nothing else of this engine ran in between (plane builds, inserts, ...).
     int overlap_steps = 1;
     bool plane8_pair = true;             // K13: two queries of a call share a pass where the kernel supports it (Kp >= 192); 0: one each (A/B)
+    bool umma_sparse_checks = true;      // K10: prune check / threshold refresh every fourth tile once thresholds are tight (0: every tile, A/B)
     bool umma_group_min = true;          // K10: thresholds from the group's published minima (umma_filter.cu); 0: from gtau alone (A/B)
     uint64_t pdl_mark = ~0ull;
     bool umma_min_user = false, mma_min_user = false, plane8_max_q_user = false;      // thresholds set through svdb_set_option: taken literally

@@ -202,6 +202,7 @@ struct UmmaArgs {
     Cand *lists;            // [ngroups*bn][nstreams][cap]
     void *bufs;             // umma_buf_bytes(ngroups, nstreams, bn) of scratch
     uint32_t *gtau;         // [ngroups*bn] words, all 0xffffffff at launch: per query the smallest cap-th key published so far
+    int sparse_checks;      // 1: the per-tile bookkeeping between the CTA barriers runs every fourth tile once thresholds are tight
     uint32_t *gmin;         // [ngroups*bn][nstreams] words behind gtau, all 0xffffffff at launch: per query and CTA of its group the
                             // smallest key that CTA has kept so far (NULL: thresholds from gtau alone)
     float *dbg_keys;        // NULL, or [128][bn]: the keys of rows 0..127 against the first query group (diagnostics)

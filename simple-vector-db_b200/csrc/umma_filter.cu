@@ -308,6 +308,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         // sort and prune.  CTA `stream` looks after the queries stream, stream + nstreams, ... of its group, one per warp.
         const bool use_gmin = p.gmin != nullptr && p.nstreams >= p.cap;
         uint32_t pub = 0xffffffffu;                        // what this lane last published for query jmine
+        bool ovf_mine = false;                            // query jmine's buffer overflowed between two checks: unprovable
         const int jsel = stream + p.nstreams * wi;        // the query whose group threshold this warp refreshes
         double xn_next = 0.0;
         {
@@ -315,7 +316,16 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             if (stream < ntiles && r0 < p.n) xn_next = __ldg(p.xnorm + r0);
         }
         for (u64 tile = stream; tile < ntiles; tile += p.nstreams) {
-            const bool refresh = it < 16 || (it & 3) == 0;
+            // The bookkeeping between the two CTA barriers below (prune check, publishing minima, threshold refresh) runs after
+            // every tile while the thresholds are still loose, then after every fourth: the barriers were 2.1-4.4 of the
+            // 5.6-9.4 kcycles a tile cost at kd_dim 128 (profiles/r02_K10_role_cycles_ab.jsonl).  A buffer that nevertheless
+            // fills up between two checks (rows arriving in order of decreasing distance, say) loses nothing silently: its
+            // query is emitted as unprovable (ovf_mine below) and re-answered by the caller's next rung.
+            const bool sect = p.sparse_checks == 0 || it < 8 || (it & 3) == 3;
+            const bool refresh = sect;
+            // the group threshold (a 32-step search, ~2.7 kcycles) tightens with the logarithm of the rows seen: computed after
+            // tiles 0..7, then whenever the tile count reaches a power of two, and every 64th tile
+            const bool select = sect && (p.sparse_checks == 0 ? (it < 16 || (it & 3) == 0) : (it < 8 || ((it + 1) & it) == 0 || (it & 63) == 63));
             uint32_t g = 0xffffffffu;
             if (refresh && mineok) g = __ldcg(p.gtau + q0 + jmine);
             const u64 row = tile * UF_M + ew * 32 + lane;
@@ -386,16 +396,19 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 as = 0;
                 aphase ^= 1;
             }
-            // ---- prune the buffers that could overflow during the next tile (warp wi owns queries wi, wi+8, ...) ----
+            // ---- prune the buffers that could overflow before the next check (warp wi owns queries wi, wi+8, ...) ----
+            if (sect) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             {
                 // g: the smallest cap-th key any CTA of this query group had published when this tile began: an upper bound
                 // of the group's cap-th smallest key, so keys above it are nobody's candidates (the CTAs converge as one)
-                unsigned m = __ballot_sync(FULL, mineok && cnt_s[jmine] > (unsigned)(UF_BUF - UF_M));
+                const unsigned cmine = mineok ? cnt_s[jmine] : 0u;
+                if (cmine > (unsigned)UF_BUF) ovf_mine = true;           // entries were lost
+                unsigned m = __ballot_sync(FULL, cmine > (unsigned)(p.sparse_checks && it >= 8 ? UF_BUF / 4 : UF_BUF - UF_M));
                 while (m) {
                     const int j = wi + 8 * (__ffs(m) - 1);
                     m &= m - 1;
-                    const unsigned cnt = cnt_s[j];
+                    const unsigned cnt = min(cnt_s[j], (unsigned)UF_BUF);
                     float tau;
                     bool dropped;
                     const unsigned kept = uf_prune(bufs + (size_t)j * UF_BUF, cnt, p.cap, lane, tau, dropped);
@@ -417,7 +430,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                             pub = lm;
                         }
                     }
-                    if (refresh && jsel < bn) {
+                    if (select && jsel < bn) {
                         // cap-th smallest of the group's published minima of query jsel: 32-step search on the ordered bits
                         uint32_t val[5];
                         int have = 0;
@@ -446,6 +459,7 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 if (g != 0xffffffffu) thr_s[jmine] = fminf(thr_s[jmine], uf_thr(uf_unord(g), qn_s[jmine]));
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             if (prof) clk[2] += clock64() - c0;
             it++;
         }
@@ -459,16 +473,20 @@ umma_filter_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             p.dbg_keys[128 * UF_NMAX + 11] = (float)clk[5] * 1e-3f;                         //                     appending survivors
         }
         // ---- emit: the cap smallest keys of every query of the group, ascending, for finalize_kernel ----
+        if (mineok && cnt_s[jmine] > (unsigned)UF_BUF) ovf_mine = true;
         for (int j = wi; j < bn; j += 8) {
             UfEntry *b = bufs + (size_t)j * UF_BUF;
             float tau;
             bool dropped;
-            const unsigned kept = uf_prune(b, cnt_s[j], p.cap, lane, tau, dropped);
+            const unsigned kept = uf_prune(b, min(cnt_s[j], (unsigned)UF_BUF), p.cap, lane, tau, dropped);
             __syncwarp();
+            // a buffer that lost entries cannot vouch for anything: all its keys become -FLT_MAX, which makes the list's bound
+            // -FLT_MAX and the completeness proof of this query fail in finalize (SVDB_CAND_UNSAFE -> re-answered)
+            const bool ovf = __shfl_sync(FULL, ovf_mine, (j - wi) >> 3);
             u64 v = ~0ull;                                        // (key, row) in one word; empty slots sort last
             if ((unsigned)lane < kept) {
                 const UfEntry e = b[lane];
-                v = ((u64)uf_ord(e.key) << 32) | e.row;
+                v = ((u64)uf_ord(ovf ? -FLT_MAX : e.key) << 32) | e.row;
             }
             v = uf_sort32(v, lane);
             if (lane < p.cap) {

@@ -165,3 +165,28 @@ def test_umma_on_row_shards_and_merge(port):
     assert_topk_equal((res["seq"], res["dist"], res["seq"]), want, k)
     for e in shards:
         e.close()
+
+
+@pytest.mark.parametrize("sparse", [1, 0])
+def test_umma_rows_in_order_of_decreasing_distance(port, sparse):
+    """The order of rows that defeats every running threshold: each tile is closer to the queries than all tiles before it, so
+    every key passes.  With the bookkeeping between the CTA barriers running only every fourth tile (umma.sparse_checks) the
+    append buffers overflow between two checks; the filter must then say so -- the query comes back unprovable and is
+    re-answered by the next rung -- and never lose a neighbour silently.  With a check after every tile nothing overflows."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    n, K, nq, k = 148 * 128 * 13 + 5, 64, 48, 5
+    c = rng.random(K)
+    rows = rng.random((n, K))
+    rows = rows[np.argsort(-((rows - c) ** 2).sum(1), kind="stable")]
+    Q = c + 1e-3 * rng.standard_normal((nq, K))
+    want = oracle_topk(port, rows, K, Q, k)
+    with B.Engine(K, K) as e:
+        e.insert(rows)
+        umma_on(e)
+        e.set_option("umma.sparse_checks", sparse)
+        assert_topk_equal(e.nearest(Q, k), want, k)
+        st = e.stats()
+        if sparse:
+            assert st["fp64_reruns"] + st["exact_reruns"] > 0       # the overflow was noticed, not papered over
+        else:
+            assert st["fp64_reruns"] + st["exact_reruns"] == 0
