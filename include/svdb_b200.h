@@ -270,19 +270,27 @@ typedef struct svdb_stats {
     uint64_t mtree_levels;       /* its internal levels after the last build (2^levels leaves of <= 32 points) */
     uint64_t mtree_rows;         /* log entries it covers; later ones are scanned as a tail */
     uint64_t fp64_reruns;        /* queries a low-precision path flagged and the fp64 scan (K1) re-answered */
-    uint64_t scan_plane_last;    /* what the last scan pass read: 0 fp64 rows (K1 / exact), 1 hi + lo bf16 planes (K11), 2 hi plane (K12) */
+    uint64_t scan_plane_last;    /* what the last scan pass read: 0 fp64 rows (K1 / exact), 1 hi + lo bf16 planes (K11), 2 hi plane (K12),
+                                    3 one-byte plane (K13) */
     uint64_t tree_dropped;       /* 1: the reference-shaped tree was deeper than "tree.max_depth" (degenerate insertion
                                     order, e.g. sorted input) and has been dropped: distinct kd-points at exactly equal
                                     minimal distance now resolve to the lowest seq, not to the reference's traversal order */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
 /* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
- * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never),
+ * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never; default: chosen per
+ * call from the store's size), "nearest.mma_min_queries" (same for the FP64 DMMA path K2),
  * "nearest.umma_min_kd_dim",
- * "scan.plane" (which copy of the log calls of 1-3 queries scan: 2 = the bf16 hi plane of the split-bf16 shadow, K12, 2 bytes
- * per coordinate -- the default; 1 = hi + lo planes, K11, 4 bytes; 0 = the fp64 rows, K1, 8 bytes.  Same answers on every
- * setting: the survivors are re-ranked from the fp64 rows in the reference's operation order and whatever cannot be proven
- * complete is re-answered from the fp64 rows), "scan.shadow" (round-1 name: 1 = scan.plane 1, 0 = scan.plane 0),
+ * "scan.plane" (which copy of the log calls of few queries may scan: 3 = a one-byte plane, K13, exact integer keys, 1 byte per
+ * coordinate -- the default; 2 = the bf16 hi plane of the split-bf16 shadow, K12, 2 bytes; 1 = hi + lo planes, K11, 4 bytes;
+ * 0 = the fp64 rows, K1, 8 bytes.  Same answers on every setting: the survivors are re-ranked from the fp64 rows in the
+ * reference's operation order and whatever cannot be proven complete is re-answered from the fp64 rows),
+ * "scan.plane8_max_k" / "scan.plane_max_k" (largest k the one-byte / bf16 plane serves: 16 / 24),
+ * "scan.plane8_max_queries" (calls of up to this many queries are K13 passes), "scan.plane8_pair" (two queries share a pass),
+ * "scan.overlap_steps" (1, default: on the device entry points the scan of a single-query call may start, by programmatic
+ * dependent launch, while the tail of the call before it still runs; a query buffer that changed under such a scan is
+ * detected and the answers come back flagged SVDB_CAND_UNSAFE),
+ * "scan.shadow" (round-1 name: 1 = scan.plane 1, 0 = scan.plane 0),
  * "scan.fuse_tail" (1, default: the scan's last CTA runs the re-rank and the cross-shard exchange itself),
  * "nearest.mtree" (AUTO may use the median tree), "mtree.lanes" (32/16/8 lanes per query), "mtree.tail_max";
  * "log.index_base": added to the index every log entry written from now on reports (a shard whose local
@@ -296,7 +304,8 @@ int svdb_time_scan(svdb_engine *e, const double *d_Q, size_t nq, size_t ldq, siz
 int svdb_take_scan_time(svdb_engine *e, float *total_ms, uint64_t *launches);
 /* Diagnostics of the tcgen05 batch path (K10): after a batch call made with option "umma.debug_keys" = 1, copies
  * the approximate keys of log rows 0..127 against the first bn queries of that call ([128][bn] floats, bn = 64,
- * 128 or 256 by batch size) to keys_out -- tests use it to check the key error bound. */
+ * 128 or 256 by batch size) to keys_out -- tests use it to check the key error bound.  With count = 128 * 256 + 16 the
+ * last 16 floats are kilocycles CTA 0 spent per role (producer / MMA issuer / epilogue; scripts/k10_role_cycles.py). */
 int svdb_debug_filter_keys(svdb_engine *e, float *keys_out, size_t count);
 /* Diagnostics of the fused scan tail: with option "scan.tail_debug" = 1 the last fused scan launch leaves %globaltimer
  * stamps (ns): [0] the last CTA took its ticket, [1] CTA lists merged, [2] re-rank done, [3] answers stored to the peers,
