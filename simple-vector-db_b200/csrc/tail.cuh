@@ -49,12 +49,15 @@ constexpr int FIN_MIN_TBUF = 32 * 33 * 8;      // room for 32 candidates x 32 co
 // finalize of ONE query by the whole CTA (blockDim.x = nw * 32, nw <= 16).  fsm: fsm_bytes of shared memory the
 // caller does not need any more (>= fin_head_bytes(nw) + FIN_MIN_TBUF, 128-byte aligned, its mbarrier initialised by
 // fin_bar_init; `phase` = that barrier's phase, 0 at first).  Ends with a __syncthreads().
-//   1. every warp merges a slice of the per-CTA lists into its register list, the slices are merged through shared
-//      memory -> the 32 best approximate keys, plus `bound`, the smallest approximate key any list may have dropped;
+//   1. the candidates: either (short lists of approximate keys that fit shared memory together -- the single-plane scans)
+//      SELECTED from all lists at once: an upper bound of the k-th smallest key from one pass, then every entry inside the
+//      error window of it, up to FIN_NC of them; or (long lists, exact keys) MERGED: every warp merges a slice of the
+//      per-CTA lists into its register list, the slices are merged through shared memory -> the 32 best approximate keys.
+//      Either way `bound` is the smallest approximate key any list may have dropped;
 //   2. only candidates whose approximate key is within the error margin of the k-th can belong to the exact top-k;
-//      those (normally exactly k) are recomputed in the reference's operation order: the warps fetch each candidate
-//      row coalesced and form the rounded squares t_i = (x_i - q_i)^2 in shared memory, then one lane per candidate
-//      adds them strictly in index order (the serial chain the reference has);
+//      those are recomputed in the reference's operation order: the warps fetch each candidate row coalesced and form
+//      the rounded squares t_i = (x_i - q_i)^2 in shared memory, then one thread per candidate adds them strictly in
+//      index order (the serial chain the reference has); with more than 32 candidates the best 32 by exact distance go on;
 //   3. rank by (exact distance, seq), emit top-k, prove completeness against `bound`.
 // =====================================================================================
 __device__ __forceinline__ unsigned long long global_timer_ns() {
