@@ -277,7 +277,10 @@ typedef struct svdb_stats {
                                     minimal distance now resolve to the lowest seq, not to the reference's traversal order */
 } svdb_stats;
 int svdb_get_stats(const svdb_engine *e, svdb_stats *out);
-/* Tuning knobs (name/value), e.g. "scan.variant", "scan.warps", "scan.stages", "scan.ctas_per_sm";
+/* Tuning knobs (name/value).  K1's launch shape: "scan.variant" (0 TMA ring, 1 plain loads), "scan.warps", "scan.stages",
+ * "scan.ctas_per_sm", "scan.tile_rows", "scan.assign" (tile order), "scan.nq_per_pass" (queries sharing an fp64 pass, <= 8);
+ * "scan.force_exact" (1: every query through the exact-order scan K1'), "nearest.tree_max_k" (largest k the reference-shaped
+ * tree K6 answers), "host.graphs" (0: the host entry points launch directly instead of replaying captured CUDA graphs);
  * "nearest.umma_min_queries" (batches of at least this many queries take the tcgen05 path K10; 0 = never; default: chosen per
  * call from the store's size), "nearest.mma_min_queries" (same for the FP64 DMMA path K2),
  * "nearest.umma_min_kd_dim",

@@ -87,3 +87,14 @@ def test_dropin_without_gpu_keeps_reference_sentinels(lib, capfd):
     api.lib.vector_db_update(db, 5, api.make_vector(np.ones(3), own=False))   # out of range: silent no-op
     api.lib.vector_db_delete(db, 5)
     api.lib.vector_db_free(db)
+
+
+def test_every_engine_option_is_documented():
+    """Every name svdb_set_option accepts appears in the public header, INTEGRATION.md or DESIGN.md."""
+    import re
+    src = open(os.path.join(ROOT, "simple-vector-db_b200", "csrc", "engine.cu")).read()
+    names = sorted(set(re.findall(r'n == "([a-z0-9_.]+)"', src)))
+    assert len(names) > 30
+    docs = "".join(open(os.path.join(ROOT, f)).read() for f in ("include/svdb_b200.h", "INTEGRATION.md", "DESIGN.md"))
+    missing = [n for n in names if n not in docs]
+    assert not missing, missing
