@@ -613,7 +613,7 @@ int svdb_engine::nearest_local(const double *d_Q, size_t nq, size_t ldq, size_t 
 
     // K13 with a fused tail, outside stream capture: consecutive launches overlap (engine.h: overlap_steps)
     bool overlap = false;
-    if (plane >= 2 && fuse && overlap_steps && nlists > 1 && dyn_tiles == 0) {
+    if (plane >= 2 && fuse && overlap_steps && !in_host_call && nlists > 1 && dyn_tiles == 0) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cs);
         overlap = cs == cudaStreamCaptureStatusNone;
@@ -987,6 +987,14 @@ int svdb_engine::nearest_host(const double *Q, size_t nq, size_t ldq, size_t k, 
     if (nq == 0) return SVDB_OK;
     if (!Q || ldq < (size_t)K) return fail(SVDB_ERR_ARG, "bad query buffer");
     CK(cudaSetDevice(device));
+    // A host call copies its queries in, waits for the answers and copies them out: nothing of it can overlap with the call
+    // before or after it, so its launches are plain ones (the overlap of engine.h: overlap_steps is for the device entry
+    // points, where consecutive calls queue up on the stream with the queries already resident).
+    struct HostCall {
+        bool &f;
+        explicit HostCall(bool &flag) : f(flag) { f = true; }
+        ~HostCall() { f = false; }
+    } host_call_guard(in_host_call);
     std::string err;
     if (!hq.ensure(nq * (size_t)K * 8, err) || !qraw.ensure(nq * (size_t)K * 8, err) ||
         !outc.ensure((nq * k + 1) * sizeof(svdb_candidate), err) || !hout.ensure(nq * k * sizeof(svdb_candidate), err))

@@ -88,6 +88,7 @@ struct svdb_engine {
     // less than the machine holds so that all of them start at once.  pdl_mark = stats.kernels_launched right after such a
     // launch: the attribute is only set while nothing else of this engine ran in between (plane builds, inserts, ...).
     int overlap_steps = 1;
+    bool in_host_call = false;           // set for the duration of nearest_host (host buffers in and out): plain launches
     bool plane8_pair = true;             // K13: two queries of a call share a pass where the kernel supports it (Kp >= 192); 0: one each (A/B)
     bool umma_sparse_checks = true;      // K10: prune check / threshold refresh every fourth tile once thresholds are tight (0: every tile, A/B)
     bool umma_group_min = true;          // K10: thresholds from the group's published minima (umma_filter.cu); 0: from gtau alone (A/B)

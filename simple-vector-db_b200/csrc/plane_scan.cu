@@ -315,8 +315,8 @@ cudaError_t launch_scan_plane(const ScanTuning &t, const PlaneScanArgs &a, cudaS
 // Data a uniform grid resolves badly (heavy tails, a few huge coordinates) shows up as a large measured error: the
 // proof fails, the query is re-answered from the fp64 rows, and the engine stops using the plane (engine.cu).
 // =====================================================================================================================
-// LPR = 32: a warp walks one row per step (8 bytes per lane and 256-coordinate trip).  LPR = 16 / 8 (TRIPS = 1, Kp = 128 / 64):
-// 2 / 4 rows side by side, 32 rows per round, TR / 32 rounds per tile (tiles of 8 KB whatever the row length).
+// LPR = 32: a warp walks one row per step (8 bytes per lane and 256-coordinate trip).  LPR = 8 / 4 (TRIPS = 1, Kp = 128 / 64):
+// 16 bytes per lane, 4 / 8 rows side by side, 32 rows per round, TR / 32 rounds per tile (tiles of 8 KB whatever the row length).
 // NQ = 2 (LPR = 32 only): two queries share the pass -- the bytes and the u.u dot products are read and formed once, each
 // query adds its own two dp4a per four coordinates (5 instead of 6 per query pair and word).
 template <int NQ, int TRIPS, int TR, int LPR>
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
     // the query's digits, packed like the plane's bytes: lane (j = lane % LPR) owns coordinates trip * 256 + j * 8 .. + 7
     const double lo = p.par->lo, step = p.par->step;
     const int pj = lane % LPR, pg = lane / LPR;
-    uint32_t qa[NQ][TRIPS][2], qb[NQ][TRIPS][2];
+    constexpr int CPL = LPR < 32 ? 16 : 8;              // coordinates (= bytes of the plane) per lane and trip
+    uint32_t qa[NQ][TRIPS][CPL / 4], qb[NQ][TRIPS][CPL / 4];
     bool act[TRIPS];
     long long qq[NQ];                                   // sum Q_i^2 over the lane's coordinates
     unsigned long long qhash = 0;                       // of the raw bits this lane read (re-checked after pdl_wait)
@@ -375,10 +376,10 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         qq[qi] = 0;
 #pragma unroll
         for (int t = 0; t < TRIPS; t++) {
-            const int c0 = t * 256 + pj * 8;
+            const int c0 = t * 256 + pj * CPL;
             act[t] = c0 < Kp;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < CPL / 4; h++) {
                 uint32_t wa = 0, wb = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -410,18 +411,21 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
         if constexpr (LPR < 32) {
             constexpr int PR = 32 / LPR;               // rows side by side
             long long key[TR / 32];
-            const uint32_t sa = my_stage + s * tile_bytes + (uint32_t)pg * row_bytes + (uint32_t)pj * 8;
+            const uint32_t sa = my_stage + s * tile_bytes + (uint32_t)pg * row_bytes + (uint32_t)pj * 16;
 #pragma unroll
             for (int h = 0; h < TR / 32; h++) {
                 long long v[LPR];
 #pragma unroll
                 for (int i = 0; i < LPR; i++) {
-                    uint32_t w0, w1;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sa + (uint32_t)(h * 32 + i * PR) * row_bytes));
-                    uint32_t s2 = __dp4a(w0, w0, 0u), A = __dp4a(w0, qa[0][0][0], 0u), Bq = __dp4a(w0, qb[0][0][0], 0u);
-                    s2 = __dp4a(w1, w1, s2);
-                    A = __dp4a(w1, qa[0][0][1], A);
-                    Bq = __dp4a(w1, qb[0][0][1], Bq);
+                    const uint4 w4 = pl_lds128(sa + (uint32_t)(h * 32 + i * PR) * row_bytes);
+                    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                    uint32_t s2 = 0, A = 0, Bq = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        s2 = __dp4a(w[u], w[u], s2);
+                        A = __dp4a(w[u], qa[0][0][u], A);
+                        Bq = __dp4a(w[u], qb[0][0][u], Bq);
+                    }
                     v[i] = 65536ll * (long long)s2 - 131072ll * (long long)A - 512ll * (long long)Bq;
                 }
                 reduce_packed<LPR>(v, lane);
@@ -493,8 +497,8 @@ __global__ void __launch_bounds__(256, 2) scan_plane8_kernel(const __grid_consta
 #pragma unroll
             for (int t = 0; t < TRIPS; t++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int c = t * 256 + pj * 8 + j;
+                for (int j = 0; j < CPL; j++) {
+                    const int c = t * 256 + pj * CPL + j;
                     h2 = mix64(h2, (unsigned long long)__double_as_longlong(c < p.K ? ld_cv_f64(p.q + (size_t)qi * p.ldq + c) : 0.0));
                 }
         if (__any_sync(FULL, h2 != qhash) && lane == 0) atomicOr(p.tail.ticket + 3, 1u);
@@ -656,8 +660,8 @@ cudaError_t launch_scan_plane8(const ScanTuning &t, const Plane8ScanArgs &a, cud
         return launch_plane8_inst<2, 4, 4, 32>(t, a, st);
     }
     if (a.nq != 1) return cudaErrorInvalidValue;
-    if (a.Kp == 64) return launch_plane8_inst<1, 1, 128, 8>(t, a, st);
-    if (a.Kp == 128) return launch_plane8_inst<1, 1, 64, 16>(t, a, st);
+    if (a.Kp == 64) return launch_plane8_inst<1, 1, 128, 4>(t, a, st);
+    if (a.Kp == 128) return launch_plane8_inst<1, 1, 64, 8>(t, a, st);
     if (a.Kp == 192) return launch_plane8_inst<1, 1, 32, 32>(t, a, st);
     if (a.Kp <= 256) return launch_plane8_inst<1, 1, 16, 32>(t, a, st);
     if (a.Kp <= 512) return launch_plane8_inst<1, 2, 16, 32>(t, a, st);

@@ -165,27 +165,32 @@ def test_plane_tail_with_many_candidates(port, plane, K, cluster, k, exact_dups)
 
 
 def test_few_queries_per_call_take_byte_plane_passes(port):
-    """Up to scan.plane8_max_queries (4) queries per call are answered by one K13 pass each -- an eighth of the bytes K2
-    would stream, a quarter of K10's -- unless the caller set the batch thresholds itself.  (Stores below 4e7 elements: up
-    to 2; there a pass is all launch latency and one K2 call is cheaper than three.)"""
+    """Up to scan.plane8_max_queries (4) queries per call are answered by K13 passes, two queries to a pass -- an eighth of
+    the bytes K2 would stream, a quarter of K10's -- unless the caller set the batch thresholds itself.  (Stores below 4e7
+    elements: up to 2; there a pass is all launch latency and one K2 / K10 call is cheaper than three.)"""
     rows = synth.uniform_rows(41, 170000, 256)
     Q = synth.uniform_rows(42, 7, 256)
     want = oracle_topk(port, rows, 256, Q, 3)
+
+    def launches(e, q, w):
+        """scan launches of one call: what it launched minus one per query that had to be re-answered from the fp64 rows"""
+        s0 = e.stats()
+        assert_topk_equal(e.nearest(q, 3), w, 3)
+        s1 = e.stats()
+        return (s1["kernels_launched"] - s0["kernels_launched"]) - (s1["fp64_reruns"] - s0["fp64_reruns"]), s1
+
     with B.Engine(256, 256) as e:
         e.insert(rows)
         for nq in (3, 4):
             assert_topk_equal(e.nearest(Q[:nq], 3), want[:nq], 3)
             assert e.stats()["scan_plane_last"] == 3
-        before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
-        assert e.stats()["kernels_launched"] - before == 2           # two queries share a pass: two fused launches, nothing else
-        before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:3], 3), want[:3], 3)
-        assert e.stats()["kernels_launched"] - before == 2           # a pair and a single
+        n, st = launches(e, Q[:4], want[:4])
+        assert n == 2, st                                             # two queries share a pass: two fused launches, nothing else
+        n, st = launches(e, Q[:3], want[:3])
+        assert n == 2, st                                             # a pair and a single
         e.set_option("scan.plane8_pair", 0)
-        before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:4], 3), want[:4], 3)
-        assert e.stats()["kernels_launched"] - before == 4           # A/B switch: one launch per query
+        n, st = launches(e, Q[:4], want[:4])
+        assert n == 4, st                                             # A/B switch: one launch per query
         e.set_option("scan.plane8_pair", 1)
         assert_topk_equal(e.nearest(Q, 3), want, 3)                   # 7 queries: the tensor-core path
     small = synth.uniform_rows(43, 20000, 256)
@@ -194,14 +199,12 @@ def test_few_queries_per_call_take_byte_plane_passes(port):
         e.insert(small)
         assert_topk_equal(e.nearest(Q[:2], 3), want_small[:2], 3)
         assert e.stats()["scan_plane_last"] == 3
-        before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:3], 3), want_small[:3], 3)     # three queries on a small store: one K10 call
-        assert e.stats()["kernels_launched"] - before != 3
+        n, st = launches(e, Q[:3], want_small[:3])                    # three queries on a small store: one K10 call
+        assert n > 3, st                                              # query prep + planes + filter + finalize
         e.set_option("nearest.umma_min_queries", 0)
         e.set_option("nearest.mma_min_queries", 3)                    # explicit threshold: taken literally
-        before = e.stats()["kernels_launched"]
-        assert_topk_equal(e.nearest(Q[:4], 3), want_small[:4], 3)
-        assert e.stats()["kernels_launched"] - before == 3           # K2: prep + DMMA scan + finalize, not four K13 passes
+        n, st = launches(e, Q[:4], want_small[:4])
+        assert n == 3, st                                             # K2: prep + DMMA scan + finalize, not K13 passes
 
 
 def test_back_to_back_device_calls_overlap_safely(port):
