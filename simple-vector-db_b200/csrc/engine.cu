@@ -822,7 +822,7 @@ bool svdb_engine::byte_plane_serves(size_t k) const {
 // Up to how many queries per call K13 passes answer (0: K13 does not serve this call).  Measured (profiles/r02_sweep_*.jsonl,
 // ms per top-10 call of <= 64 queries, e = rows x padded kd_dim elements):
 //   K13 ~ nq (0.035 + 0.147e-9 e)       one launch per query, an eighth of the fp64 bytes each (a pair of queries: 1.5 x one)
-//   K10 ~ 0.13 + 0.9e-9 e               (64-query groups; reads 4 bytes per element once; after the epilogue rework)
+//   K10 ~ 0.15 + 0.72e-9 e              (64-query groups; reads 4 bytes per element once)
 //   K2  ~ 0.06 + 2.0e-9 e               (<= 16 queries; reads the 8-byte rows once), DMMA-bound beyond
 // -> K13 passes win up to 4 queries per call from ~4e7 elements on (1M x 128: 0.18 vs 0.25 / 0.32 ms; 2M x 768: 1.08 vs 1.26 /
 //    2.75; 20M x 128: 1.80 vs 2.00 / 5.4) and up to 2 below (250k x 128: 4 passes 0.15 ms, K2 0.12);
