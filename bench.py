@@ -570,7 +570,7 @@ def ours(args):
 
     rows_per_rank = idx.hi - idx.lo
     # the roofline is stated on the bytes of the copy of the log the timed launches actually streamed (engine stat
-    # scan_plane_last: 2 = bf16 hi plane, K12, the default; 1 = hi + lo planes, K11; 0 = the fp64 rows, K1)
+    # scan_plane_last: 3 = one-byte plane, K13, the default; 2 = bf16 hi plane, K12; 1 = hi + lo planes, K11; 0 = the fp64 rows, K1)
     algo_bytes = plane_bytes(plane_used, rows_per_rank, K)
     peak, peak_src = measured_peak_gbs()
     achieved = algo_bytes / (scan_ms_avg / 1e3) / 1e9 if scan_ms_avg > 0 else 0.0
