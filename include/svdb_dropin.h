@@ -73,6 +73,12 @@ KDTree *kdtree_create(size_t dimension);
 void kdtree_insert(KDTree *tree, const double *point, size_t index);
 void kdtree_free(KDTree *tree);
 size_t kdtree_nearest(KDTree *tree, const double *point);
+/* One documented difference in kdtree_nearest: between DISTINCT kd-points at exactly equal minimal distance the reference
+ * returns whichever its insertion-order tree reaches first (kdtree.c:139, :147-159), and this library reproduces that by
+ * keeping a tree of the same shape on the GPU -- up to a depth of 8192 (option "tree.max_depth").  Input inserted in
+ * monotone order (points along a line) makes the reference's tree a list; past that depth the shape is dropped
+ * (svdb_stats.tree_dropped = 1) and such exact ties resolve to the earliest insert instead.  Unique minima and copies of
+ * one point are unaffected. */
 
 /* -- include/vector_database.h:39-135 -- */
 VectorDatabase *vector_db_init(size_t initial_capacity, size_t dimension);
