@@ -43,3 +43,28 @@ def test_reference_callers_compile_and_link_against_the_dropin(tmp_path):
     assert wanted == L1_API, f"callers did not pick these from the library: {sorted(L1_API - wanted)}"
     ldd = subprocess.run(["ldd", exe], capture_output=True, text=True, check=True).stdout
     assert "libsvdb_b200.so" in ldd and "not found" not in ldd
+
+
+def test_link_line_patch_applies_to_the_reference_makefile(tmp_path):
+    """integration/link_line.patch is the whole binding a maintainer adds: the reference's Makefile stops compiling its own
+    vector_database.c / kdtree.c and links libsvdb_b200.so instead.  Applied to a scratch copy, `make -n` must show exactly that."""
+    import shutil
+    import subprocess
+    if not os.path.exists(os.path.join(REF, "Makefile")):
+        pytest.skip("reference tree not present")
+    if shutil.which("patch") is None or shutil.which("make") is None:
+        pytest.skip("patch / make not installed")
+    shutil.copy(os.path.join(REF, "Makefile"), tmp_path / "Makefile")
+    os.makedirs(tmp_path / "src")
+    for name in ("get_handler", "post_handler", "put_handler", "delete_handler", "compare_handler", "main", "vector_database", "kdtree"):
+        (tmp_path / "src" / (name + ".c")).write_text("")
+    patch = os.path.join(ROOT, "integration", "link_line.patch")
+    subprocess.run(["patch", "-p1", "-i", patch], cwd=tmp_path, check=True, capture_output=True)
+    out = subprocess.run(["make", "-n", "SVDB_B200=" + ROOT], cwd=tmp_path, check=True, capture_output=True, text=True).stdout
+    link = [line for line in out.splitlines() if "-o executable/vector_db_server" in line]
+    assert len(link) == 1
+    assert "-lsvdb_b200" in link[0] and os.path.join(ROOT, "simple-vector-db_b200", "lib") in link[0]
+    assert "kdtree.o" not in link[0] and "vector_database.o" not in link[0]
+    assert "src/kdtree.c" not in out and "src/vector_database.c" not in out
+    for name in ("get_handler", "post_handler", "put_handler", "delete_handler", "compare_handler", "main"):
+        assert f"src/{name}.c" in out
