@@ -220,7 +220,7 @@ def store_chunks(dev, lo: int, hi: int, N: int, D: int):
 
 PLANE_KERNEL = {0: "scan_wide_kernel<TR,1> (K1, fp64 rows)", 1: "scan_shadow_kernel<1> (K11, hi + lo bf16 planes of the shadow)",
                 2: "scan_plane_kernel<1,TRIPS,32,TR> (K12, bf16 hi plane of the shadow)",
-                3: "scan_plane8_kernel<TRIPS,TR> (K13, one-byte plane, exact integer keys)"}
+                3: "scan_plane8_kernel<NQ,TRIPS,TR,LPR> (K13, one-byte plane, exact integer keys)"}
 
 
 def plane_bytes(plane: int, rows: int, K: int) -> int:
