@@ -207,3 +207,40 @@ def test_k13_pair_shares_the_squares():
     for j in range(2):
         one, _, _ = k13_keys(x, q[j:j + 1], lo, step)
         assert np.array_equal(both[:, j], one[:, 0])
+
+
+def test_device_quantisers_equal_the_numpy_model(tmp_path):
+    """The two expressions that put rows and queries on K13's grids (csrc/common.cuh: p8_quant_x, p8_quant_q) are plain C:
+    compiled here for the host from the very source text the kernels include and compared with the numpy model the bound
+    tests above are written in -- rounding mode, clamps, NaN and infinities included."""
+    import ctypes
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "simple-vector-db_b200", "csrc", "common.cuh")).read()
+    fns = re.findall(r"__device__ __forceinline__ (unsigned p8_quant_[xq]\(double v, double lo, double step\) \{.*?\n\})", src, re.S)
+    assert len(fns) == 2
+    c = "#include <math.h>\n" + "\n".join("static " + f for f in fns) + """
+void quant(const double *v, int n, double lo, double step, unsigned *ux, unsigned *uq) {
+    for (int i = 0; i < n; i++) { ux[i] = p8_quant_x(v[i], lo, step); uq[i] = p8_quant_q(v[i], lo, step); }
+}
+"""
+    (tmp_path / "q.c").write_text(c)
+    so = str(tmp_path / "q.so")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", str(tmp_path / "q.c"), "-o", so, "-lm"], check=True)
+    lib = ctypes.CDLL(so)
+    rng = np.random.default_rng(5)
+    for lo, step in ((0.0, 1.0 / 255.0), (-3.7, 0.031), (1000.0, 1e-3), (0.25, 7.0)):
+        v = np.concatenate([lo + step * 255.0 * rng.random(4000), lo + step * (rng.integers(0, 512, 500) / 2.0),      # incl. exact halves
+                            lo + step * 300.0 * rng.standard_normal(500), [np.nan, np.inf, -np.inf, lo, lo - step, lo + 255 * step, 1e300, -1e300]])
+        ux = np.zeros(len(v), np.uint32)
+        uq = np.zeros(len(v), np.uint32)
+        lib.quant(v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(v), ctypes.c_double(lo), ctypes.c_double(step),
+                  ux.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), uq.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)))
+        with np.errstate(invalid="ignore"):
+            tx = np.rint((v - lo) / step)
+            tq = np.rint(256.0 * ((v - lo) / step))
+        wx = np.where(np.isnan(tx), 0, np.clip(tx, 0, 255)).astype(np.uint32)
+        wq = np.where(np.isnan(tq), 0, np.clip(tq, 0, 65535)).astype(np.uint32)
+        assert np.array_equal(ux, wx) and np.array_equal(uq, wq)
