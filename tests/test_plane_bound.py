@@ -244,3 +244,32 @@ void quant(const double *v, int n, double lo, double step, unsigned *ux, unsigne
         wx = np.where(np.isnan(tx), 0, np.clip(tx, 0, 255)).astype(np.uint32)
         wq = np.where(np.isnan(tq), 0, np.clip(tq, 0, 65535)).astype(np.uint32)
         assert np.array_equal(ux, wx) and np.array_equal(uq, wq)
+
+
+def test_bound_coefficients_in_the_sources_are_the_ones_the_tests_use(tmp_path):
+    """plane_gamma (K12), umma_eabs_coef (K10) and shadow_eps (K11) are one-line host functions next to their kernels; the
+    numpy bound tests restate them.  Compiled from the source text and compared, so that the two cannot drift apart."""
+    import ctypes
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "simple-vector-db_b200", "csrc")
+    bodies = []
+    for fname, sig in (("plane_scan.cu", r"double plane_gamma\(int Kp\) \{[^\n]*\}"), ("umma_filter.cu", r"double umma_eabs_coef\(int K\) \{[^\n]*\}"),
+                       ("scan_kernels.cu", r"double shadow_eps\(int K\) \{[^\n]*\}")):
+        m = re.search(sig, open(os.path.join(csrc, fname)).read())
+        assert m, sig
+        bodies.append(m.group(0))
+    (tmp_path / "c.c").write_text("#include <math.h>\n" + "\n".join(bodies) + "\n")
+    so = str(tmp_path / "c.so")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", str(tmp_path / "c.c"), "-o", so, "-lm"], check=True)
+    lib = ctypes.CDLL(so)
+    for f in (lib.plane_gamma, lib.umma_eabs_coef, lib.shadow_eps):
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_int]
+    for K in (64, 100, 128, 320, 768, 1024):
+        Kp = -(-K // 64) * 64
+        assert lib.plane_gamma(Kp) == (Kp / 32.0 + 12.0) * 2.0 ** -24 == k12_terms(np.zeros((1, K)), np.zeros((1, K)), Kp)[1]
+        assert lib.umma_eabs_coef(K) == 3.2 * 2.0 ** -16 + (3.0 * K / 16.0) * 2.0 ** -21 + 8.0 * 2.0 ** -20
+        assert lib.shadow_eps(K) == 2.0 ** -13 + (K / 32.0 + 12.0) * 2.0 ** -24
