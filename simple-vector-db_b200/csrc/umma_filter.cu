@@ -30,12 +30,14 @@
 //   warp 1   : MMA issuer    -- one lane issues 12 tcgen05.mma (M=128, N=bn, K=16) per stage into one of two TMEM
 //              accumulator stages; tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 4-11: epilogue     -- tcgen05.ld 32 lanes x 32 columns, |x|^2 - 2 acc against the query's threshold (tau - |q|^2, in
-//              shared memory), one ballot per key; the rare survivors of a warp are appended to the (CTA, query) buffer
-//              in global memory, their slots reserved by ONE shared-memory atomic instruction per warp and chunk;
-//              the CTAs of a query group share the smallest cap-th key any of them has seen (one u32 per query in global
-//              memory, atomicMin / refreshed every few tiles), so their thresholds converge as one;
-//              when a buffer may overflow in the next tile a warp prunes it to the `cap` smallest (bitwise selection of
-//              the cap-th smallest key, uf_prune) and tightens the threshold.  Buffers never overflow: <= 128 keys arrive per tile, pruning starts at 128 of 256.
+//              shared memory); every lane (= row) collects the pass bits of its 32 keys, a survivor's own lane reserves its
+//              slot in the (CTA, query) buffer in global memory with one shared-memory atomic and stores it there;
+//              thresholds come from the whole query group: every CTA publishes the smallest key it has kept per query,
+//              the cap-th smallest of those (keys of distinct rows) bounds the group's cap-th smallest key and is handed
+//              round through one u32 per query in global memory (atomicMin / looked at every few tiles);
+//              between two CTA barriers -- after every tile at first, then after every fourth -- a warp prunes the buffers
+//              it owns that are filling up to the `cap` smallest (bitwise selection of the cap-th smallest key, uf_prune).
+//              A buffer that overflows between two checks is emitted as unprovable (-> SVDB_CAND_UNSAFE), never truncated.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <float.h>
